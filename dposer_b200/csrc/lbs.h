@@ -1,0 +1,53 @@
+// Internal layout of the LBS handle (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+struct dpb_lbs {
+  int device = 0;
+  int sm_count = 0;
+  int V = 0, J = 0, S = 0, P = 0, n_extra = 0, n_lmk = 0, n_out = 0;
+  int max_depth = 0;
+  int nnz = 0;                    // ELL width of the skinning weights
+  std::vector<int> parents_h;
+  // device tensors
+  float* v_template = nullptr;    // [V,3]
+  float* shapedirs = nullptr;     // [V,3,S]
+  float* posedirs = nullptr;      // [P,3V]
+  float* j_template = nullptr;    // [J,3]     J_regressor . v_template
+  float* j_shapedirs = nullptr;   // [J,3,S]   J_regressor . shapedirs
+  int32_t* parents = nullptr;     // [J]
+  int32_t* depth = nullptr;       // [J]
+  int32_t* ell_idx = nullptr;     // [nnz,V]
+  float* ell_w = nullptr;         // [nnz,V]
+  int32_t* extra_vids = nullptr;  // [n_extra]
+  int32_t* lmk_faces = nullptr;   // [n_lmk,3]
+  float* lmk_bary = nullptr;      // [n_lmk,3]
+  // joints-only mode: compact list of the vertices the extra joints / landmarks need
+  int n_need = 0;
+  int32_t* need_vids = nullptr;   // [n_need] sorted unique vertex ids
+  int32_t* extra_pos = nullptr;   // [n_extra] position of extra_vids[i] in need_vids
+  int32_t* lmk_pos = nullptr;     // [n_lmk,3]
+  // tensor-core pose-blend operands (lbs_tc.cu)
+  bool tc_ready = false;
+  int kext = 0;                   // extended K (multiple of 64)
+  __half* dirs16 = nullptr;       // [3V_pad, kext] K-major fp16 hi/lo-split blend basis
+  CUtensorMap tm_dirs;
+  int n_cols_pad = 0;
+};
+
+namespace dpb {
+// per-pose workspace layout shared by forward and backward
+struct LbsWs {
+  float* A;       // [B,J,12]  skinning transforms (rotation | translation)
+  float* feat;    // [B,P]     pose feature (R - I), joints 1..J-1
+  float* G;       // [B,J,12]  global transforms (kept for backward)
+  float* jrest;   // [B,J,3]
+  float* compact; // [B,n_need,3] (joints-only mode)
+};
+size_t lbs_ws_bytes(const dpb_lbs* h, int64_t B, bool compact);
+bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_bytes, LbsWs* out);
+}  // namespace dpb

@@ -1,0 +1,238 @@
+// fp32 engine of the score network: time-path table, tiled SGEMM with per-row time bias,
+// GroupNorm+SiLU(+residual).  This is the exact path (fp32 FFMA, fp32 accumulate); the
+// tcgen05 engine in score_tc.cu is the throughput path and is validated against this one
+// on the device as well as against the CPU oracle.
+//
+// Math follows ScoreModelFC.forward (reference lib/algorithms/advanced/model.py:141-196).
+#include "score.h"
+
+namespace dpb {
+
+// ------------------------------------------------------------------ time path
+// grid: ceil(n / TT_LABELS) CTAs, 256 threads.  Each CTA handles TT_LABELS labels so the
+// 11.5 MB of time-path weights are read once per TT_LABELS labels.
+constexpr int TT_LABELS = 8;
+
+struct PtrPack {
+  const float* t_w[5];
+  const float* t_b[5];
+  const float* lin_b[5];
+};
+
+__global__ void __launch_bounds__(256) time_table_kernel(
+    const float* __restrict__ labels, int n, const float* __restrict__ freqs,
+    const float* __restrict__ temb_w, const float* __restrict__ temb_b,
+    const PtrPack p, float* __restrict__ table) {
+  __shared__ float emb0[TT_LABELS][E];
+  __shared__ float emb1[TT_LABELS][E];
+  const int l0 = blockIdx.x * TT_LABELS;
+  const int nl = min(TT_LABELS, n - l0);
+  // sinusoidal embedding: [sin(label*f_k) | cos(label*f_k)]  (model.py:37-51)
+  for (int i = threadIdx.x; i < TT_LABELS * E; i += blockDim.x) {
+    int li = i / E, c = i % E;
+    float v = 0.f;
+    if (li < nl) {
+      float arg = labels[l0 + li] * freqs[c % (E / 2)];
+      v = (c < E / 2) ? sinf(arg) : cosf(arg);
+    }
+    emb0[li][c] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shared_time_embed: temb = SiLU(W_s emb0 + b_s)   (model.py:124-127,164)
+  for (int o = warp; o < E; o += 8) {
+    float acc[TT_LABELS];
+#pragma unroll
+    for (int li = 0; li < TT_LABELS; ++li) acc[li] = 0.f;
+    const float* wr = temb_w + (size_t)o * E;
+    for (int k = lane; k < E; k += 32) {
+      float w = wr[k];
+#pragma unroll
+      for (int li = 0; li < TT_LABELS; ++li) acc[li] = fmaf(w, emb0[li][k], acc[li]);
+    }
+#pragma unroll
+    for (int li = 0; li < TT_LABELS; ++li) {
+      float v = acc[li];
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0) {
+        v += temb_b[o];
+        emb1[li][o] = v / (1.0f + expf(-v));
+      }
+    }
+  }
+  __syncthreads();
+  // five projections W_lt temb + b_lt, with the x-path bias b_l folded in
+  for (int o = warp; o < NL * H; o += 8) {
+    const int layer = o / H, c = o % H;
+    float acc[TT_LABELS];
+#pragma unroll
+    for (int li = 0; li < TT_LABELS; ++li) acc[li] = 0.f;
+    const float* wr = p.t_w[layer] + (size_t)c * E;
+    for (int k = lane; k < E; k += 32) {
+      float w = wr[k];
+#pragma unroll
+      for (int li = 0; li < TT_LABELS; ++li) acc[li] = fmaf(w, emb1[li][k], acc[li]);
+    }
+#pragma unroll
+    for (int li = 0; li < TT_LABELS; ++li) {
+      float v = acc[li];
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0 && li < nl)
+        table[((size_t)(l0 + li) * NL + layer) * H + c] = (v + p.t_b[layer][c]) + p.lin_b[layer][c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ SGEMM  C = A W^T + bias
+// A [M,K] row-major, W [N,K] row-major, C [M,N].  64x64 tile, BK=16, 256 threads, 4x4 micro-tile.
+// bias: table + layer*H, row -> entry t_index[m] (stride NL*H) or entry 0; bias==nullptr -> none.
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_bias_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                         float* __restrict__ C, int64_t M, int N, int K,
+                                                         const float* __restrict__ bias,
+                                                         const int32_t* __restrict__ t_index, int bias_stride,
+                                                         const float* __restrict__ col_bias) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int tx = tid & 15, ty = tid >> 4;  // micro-tile: rows ty*4.., cols tx*4..
+  // loader mapping: each thread loads one float4 of A and one of W per k-tile
+  const int lr = tid >> 2, lk = (tid & 3) * 4;  // row 0..63, k offset 0,4,8,12
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + lr < M) a = *reinterpret_cast<const float4*>(A + (m0 + lr) * K + k0 + lk);
+    float4 w = *reinterpret_cast<const float4*>(W + (size_t)(n0 + lr) * K + k0 + lk);
+    As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
+    Ws[lk + 0][lr] = w.x; Ws[lk + 1][lr] = w.y; Ws[lk + 2][lr] = w.z; Ws[lk + 3][lr] = w.w;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 wv = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      float ar[4] = {av.x, av.y, av.z, av.w}, wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const float* brow = nullptr;
+    if (bias) brow = bias + (size_t)(t_index ? t_index[m] : 0) * bias_stride;
+    float4 o;
+    float* op = &o.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      float v = acc[i][j];
+      if (brow) v += brow[n];
+      if (col_bias) v += col_bias[n];
+      op[j] = v;
+    }
+    *reinterpret_cast<float4*>(C + m * N + n0 + tx * 4) = o;
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm(32x32) + SiLU (+ residual)
+// one CTA (256 threads) per row; thread owns 4 consecutive channels; a group = 8 consecutive lanes.
+__global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta,
+                                                      const float* residual, float* out, int64_t M) {
+  // residual and out may alias (in-place residual update of the stream h)
+  const int64_t m = blockIdx.x;
+  if (m >= M) return;
+  const int c = threadIdx.x * 4;
+  float4 v = *reinterpret_cast<const float4*>(in + m * H + c);
+  float s = (v.x + v.y) + (v.z + v.w);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  const float mean = s * (1.0f / GROUP);
+  float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+  float q = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  q += __shfl_xor_sync(0xffffffffu, q, 1);
+  q += __shfl_xor_sync(0xffffffffu, q, 2);
+  q += __shfl_xor_sync(0xffffffffu, q, 4);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / GROUP) + GN_EPS);  // biased variance, eps 1e-5
+  float4 g = *reinterpret_cast<const float4*>(gamma + c);
+  float4 b = *reinterpret_cast<const float4*>(beta + c);
+  float y[4] = {dx * rstd * g.x + b.x, dy * rstd * g.y + b.y, dz * rstd * g.z + b.z, dw * rstd * g.w + b.w};
+  float4 o;
+  float* op = &o.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) op[i] = y[i] / (1.0f + expf(-y[i]));
+  if (residual) {
+    float4 r = *reinterpret_cast<const float4*>(residual + m * H + c);
+    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+  }
+  *reinterpret_cast<float4*>(out + m * H + c) = o;
+}
+
+// x [B,63] -> xpad [B,64]
+__global__ void pad_x_kernel(const float* __restrict__ x, float* __restrict__ xp, int64_t B) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * DP) return;
+  int64_t r = i / DP;
+  int c = (int)(i % DP);
+  xp[i] = (c < D) ? x[r * D + c] : 0.f;
+}
+
+int simt_time_table(dpb_score* h, const float* labels, int n, float* table, cudaStream_t st) {
+  if (n <= 0) return DPB_OK;
+  // pointer tables live in constant kernel-parameter space (no device allocation in the call)
+  PtrPack p;
+  for (int l = 0; l < NL; ++l) { p.t_w[l] = h->t_w[l]; p.t_b[l] = h->t_b[l]; p.lin_b[l] = h->lin_b[l]; }
+  int grid = (n + TT_LABELS - 1) / TT_LABELS;
+  time_table_kernel<<<grid, 256, 0, st>>>(labels, n, h->emb_freqs, h->temb_w, h->temb_b, p, table);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+size_t simt_forward_ws_bytes(int64_t B) {
+  // xpad [B,64] + three [B,1024] fp32 buffers
+  return align_up((size_t)B * DP * 4, 256) + 3 * align_up((size_t)B * H * 4, 256) + 1024;
+}
+
+int simt_forward_raw(dpb_score* h, const float* x, const float* table, const int32_t* t_index, float* raw,
+                     int64_t B, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (B <= 0) return DPB_OK;
+  WsCarver c(ws, ws_bytes);
+  float* xp = c.take<float>((size_t)B * DP);
+  float* pre = c.take<float>((size_t)B * H);   // pre-activation scratch
+  float* hbuf = c.take<float>((size_t)B * H);  // residual stream
+  float* tbuf = c.take<float>((size_t)B * H);  // block intermediate
+  if (!c.ok() || ws == nullptr) return fail(DPB_ENOMEM, "score forward: workspace too small");
+  const int stride = NL * H;
+  dim3 gemm_grid(H / BN, (unsigned)((B + BM - 1) / BM));
+  {
+    int64_t n = B * DP;
+    pad_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, xp, B);
+  }
+  // pre_dense + pre_gnorm + act   (model.py:166-169)
+  sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(xp, h->pre_w, pre, B, H, DP, table, t_index, stride, nullptr);
+  gn_silu_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[0], h->gn_b[0], nullptr, hbuf, B);
+  for (int blk = 0; blk < 2; ++blk) {  // model.py:172-187
+    int l1 = 1 + 2 * blk, l2 = 2 + 2 * blk;
+    sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(hbuf, h->blk_w[l1 - 1], pre, B, H, H, table + (size_t)l1 * H,
+                                                 t_index, stride, nullptr);
+    gn_silu_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[l1], h->gn_b[l1], nullptr, tbuf, B);
+    sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(tbuf, h->blk_w[l2 - 1], pre, B, H, H, table + (size_t)l2 * H,
+                                                 t_index, stride, nullptr);
+    gn_silu_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[l2], h->gn_b[l2], hbuf, hbuf, B);
+  }
+  // post_dense (model.py:189), N padded to 64
+  dim3 post_grid(DP / BN, (unsigned)((B + BM - 1) / BM));
+  sgemm_bias_kernel<<<post_grid, 256, 0, st>>>(hbuf, h->post_w, raw, B, DP, H, nullptr, nullptr, 0, h->post_b);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+}  // namespace dpb

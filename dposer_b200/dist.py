@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing: one process per GPU, rows sharded contiguously exactly like the reference's
+``DistributedEvalSampler`` (lib/dataset/EvaSampler.py:77-106); the only collectives are the result
+all-gather and metric all-reduce that replace ``dist.gather_object`` (run/completion.py:300-305).
+Backend nccl on GPUs, gloo in the CPU tests."""
+import os
+
+import torch
+import torch.distributed as dist
+
+from .misc import shard_range
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment (no-op for a single process)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def my_shard(total, units=1):
+    """(start, count) of this rank's contiguous rows; ``units`` keeps groups of rows (e.g. 60-frame
+    sequences) on one rank by sharding whole units."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    assert total % units == 0
+    s, n = shard_range(total // units, world, rank)
+    return s * units, n * units
+
+
+def all_gather_rows(local, total):
+    """Concatenate ragged row shards from all ranks in rank order -> [total, ...] on every rank."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    counts = [shard_range(total, world, r)[1] for r in range(world)]
+    pad = max(counts)
+    buf = local.new_zeros((pad,) + tuple(local.shape[1:]))
+    buf[:local.shape[0]] = local
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+
+
+def all_reduce_sum(t):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+def max_over_ranks(value, device):
+    """Max of a python float over ranks (timing rule: report the slowest rank)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])

@@ -1,0 +1,192 @@
+"""DPoser prior loss with the reference's call surface.
+
+Replaces ``DPoserComp`` (run/completion.py:95-207), ``MotionDenoise.DPoser_loss``
+(run/motion_denoising.py:125-143) and ``DPoser`` (run/smplify.py:17-115).  One call into
+``dpb_prior_loss`` does perturb -> score net -> one-step denoise -> weighted squared error
+and its closed-form gradient (x0_hat is detached in the reference, so no backward through
+the network exists).  The returned loss is an autograd scalar whose backward scales the
+kernel-produced gradient.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import utils as mutils
+from .misc import linear_interpolation
+
+N_POSES = 21
+
+
+class _PriorLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, owner, t, weighted, divisor, z, seed):
+        model = owner.model
+        ps = mutils.prior_scalars(owner.sde, model, t, owner.continuous)
+        table = owner._table(t, ps['label'])
+        xd = x0.detach().to(torch.float32).contiguous()
+        L.require_cuda(xd, 'x_0')
+        B = xd.shape[0]
+        loss = torch.empty(1, dtype=torch.float32, device=xd.device)
+        grad = torch.empty_like(xd)
+        h = model.handle()
+        ws = model.workspace(B, xd.device)
+        zz = None if z is None else z.detach().to(torch.float32).contiguous()
+        L.check(L.load().dpb_prior_loss(h.ptr, L.ptr(xd), L.ptr(table), ps['alpha'], ps['std'], ps['inv_sigma_std'],
+                                        int(bool(weighted)), float(divisor), L.ptr(zz), seed, 0, L.ptr(loss),
+                                        L.ptr(grad), None, B, model.engine, L.ptr(ws), ws.numel(),
+                                        L.current_stream(xd.device)))
+        ctx.save_for_backward(grad)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None, None, None, None
+
+
+class _PriorBase:
+    """Shared machinery: cached per-t time tables and the fused loss call."""
+
+    def _init_prior(self, model, sde, continuous, batch_size):
+        self.model, self.sde, self.continuous, self.batch_size = model, sde, continuous, batch_size
+        self.score_fn = mutils.get_score_fn(sde, model, train=False, continuous=continuous)
+        self.rsde = sde.reverse(self.score_fn, False)
+        self.loss_fn = nn.MSELoss(reduction='none')
+        self._tables = {}
+
+    def _table(self, t, label):
+        key = float(t)
+        tb = self._tables.get(key)
+        if tb is None:
+            tb = self.model.time_table(label)
+            self._tables[key] = tb
+        return tb
+
+    @staticmethod
+    def _host_t(vec_t):
+        """The batch-uniform time as a python float (one tiny D2H read when given a device tensor)."""
+        if isinstance(vec_t, (float, int)):
+            return float(vec_t)
+        return float(vec_t.reshape(-1)[0])
+
+    def _fused_loss(self, x_0, t, weighted, divisor, z=None):
+        seed = mutils.host_seed() if z is None else 0
+        return _PriorLossFn.apply(x_0, self, t, weighted, divisor, z, seed)
+
+    # the un-fused pieces keep the reference's names for callers that use them directly
+    def one_step_denoise(self, x_t, t):
+        """run/completion.py:105-110."""
+        drift, diffusion, alpha, sigma_2, score = self.rsde.sde(x_t, t, guide=True)
+        x_0_hat = (x_t.detach() + sigma_2[:, None] * score) / alpha
+        return x_0_hat.detach(), alpha / torch.sqrt(sigma_2)[:, None]
+
+    def multi_step_denoise(self, x_t, t, t_end, N=10):
+        """run/completion.py:112-129 (DDIM); N score evaluations on the GPU kernels."""
+        time_traj = linear_interpolation(t, t_end, N + 1)
+        cur = x_t.detach()
+        for i in range(N):
+            a_c, s_c = self.sde.return_alpha_sigma(time_traj[i])
+            a_b, s_b = self.sde.return_alpha_sigma(time_traj[i + 1])
+            eps_hat = -self.score_fn(cur, time_traj[i], None, None) * s_c[:, None]
+            cur = a_b / a_c * (cur - s_c[:, None] * eps_hat) + s_b[:, None] * eps_hat
+        alpha, sigma = self.sde.return_alpha_sigma(time_traj[0])
+        return cur.detach(), alpha / sigma[:, None]
+
+    def _ddim_loss(self, x_0, vec_t, weighted, divisor, n, z=None):
+        """multi_denoise=True branch: only the final squared error is differentiable w.r.t. x_0."""
+        z = torch.randn_like(x_0) if z is None else z
+        mean, std = self.sde.marginal_prob(x_0, vec_t)
+        x0_hat, snr = self.multi_step_denoise(mean + std[:, None] * z, vec_t, t_end=vec_t / (2 * n), N=n)
+        w = 0.5 * torch.sqrt(1 + snr) if weighted else 0.5
+        sq = w * self.loss_fn(x_0, x0_hat)
+        return sq.mean() if divisor is None else sq.sum() / divisor
+
+
+class DPoserComp(_PriorBase):
+    """run/completion.py:95-207."""
+
+    def __init__(self, diffusion_model, sde, continuous, batch_size=1):
+        self._init_prior(diffusion_model, sde, continuous, batch_size)
+        self.data_loss = nn.MSELoss(reduction='mean')
+
+    def loss(self, x_0, vec_t, weighted=False, multi_denoise=False, z=None):
+        """mean over B*63 of w (x0 - sg[x0_hat])^2  (run/completion.py:131-149)."""
+        if multi_denoise:
+            return self._ddim_loss(x_0, vec_t, weighted, None, 10, z)
+        return self._fused_loss(x_0, self._host_t(vec_t), bool(weighted), float(x_0.numel()), z)
+
+    def get_loss_weights(self):
+        return {'data': lambda cst, it: 100 * cst / (1 + it), 'dposer': lambda cst, it: 0.1 * cst * (it + 1)}
+
+    @staticmethod
+    def backward_step(loss_dict, weight_dict, it):
+        return torch.stack([weight_dict[k](loss_dict[k], it) for k in loss_dict]).sum()
+
+    def optimize(self, observation, mask, time_strategy='3', lr=0.1, sample_trun=5.0, sample_time=900,
+                 iterations=2, steps_per_iter=100):
+        """run/completion.py:167-207: Adam on the pose with data + DPoser losses."""
+        total_steps = iterations * steps_per_iter
+        opti_variable = observation.clone().detach()
+        opti_variable.requires_grad = True
+        optimizer = torch.optim.Adam([opti_variable], lr, betas=(0.9, 0.999))
+        weight_dict = self.get_loss_weights()
+        timesteps = mutils.timestep_grid(self.sde, 1e-3)           # host copy: no per-step device read
+        for it in range(iterations):
+            for i in range(steps_per_iter):
+                step = it * steps_per_iter + i
+                optimizer.zero_grad()
+                if time_strategy == '1':
+                    quan_t = int(torch.randint(self.sde.N, [1]))
+                elif time_strategy == '2':
+                    quan_t = int(sample_time)
+                elif time_strategy == '3':
+                    quan_t = self.sde.N - math.floor(
+                        torch.tensor(total_steps - step - 1) * (self.sde.N / (sample_trun * total_steps))) - 2
+                else:
+                    raise NotImplementedError('unsupported time sampling strategy')
+                t = float(timesteps[quan_t])
+                # the reference passes quan_t into `weighted` (run/completion.py:196): weighted iff quan_t != 0
+                loss_dict = {'dposer': self.loss(opti_variable, t, quan_t),
+                             'data': self.data_loss(opti_variable * mask, observation * mask)}
+                self.backward_step(loss_dict, weight_dict, it).backward()
+                optimizer.step()
+        return (observation * mask + opti_variable * (1.0 - mask)).detach()
+
+
+class MotionPrior(_PriorBase):
+    """The prior part of ``MotionDenoise`` (run/motion_denoising.py:63-143)."""
+
+    def __init__(self, diffusion_model, sde, continuous=True, batch_size=1):
+        self._init_prior(diffusion_model, sde, continuous, batch_size)
+
+    def DPoser_loss(self, x_0, vec_t, quan_t=None, weighted=False, multi_denoise=False, z=None):
+        """sum_all(w (x0 - sg[x0_hat])^2) / batch_size  (run/motion_denoising.py:125-143)."""
+        if multi_denoise:
+            return self._ddim_loss(x_0, vec_t, weighted, self.batch_size, 10, z)
+        return self._fused_loss(x_0, self._host_t(vec_t), bool(weighted), float(self.batch_size), z)
+
+
+class DPoser(nn.Module, _PriorBase):
+    """run/smplify.py:17-115 -- SMPLify pose prior: normalise, weighted loss, sum / batch_size."""
+
+    def __init__(self, batch_size=32, config_path='', args=None, model=None, sde=None, normalizer=None,
+                 continuous=True):
+        nn.Module.__init__(self)
+        if model is None or sde is None or normalizer is None:
+            raise NotImplementedError('checkpoint / config loading is out of scope: pass model=, sde=, normalizer=')
+        self.device = getattr(args, 'device', None)
+        self.Normalizer = normalizer
+        sde.N = getattr(args, 'sde_N', sde.N)
+        self._init_prior(model, sde, continuous, batch_size)
+        self.timesteps = mutils.timestep_grid(sde, 1e-3)
+
+    def DPoser_loss(self, x_0, vec_t, multi_denoise=False, z=None):
+        if multi_denoise:
+            return self._ddim_loss(x_0, vec_t, True, self.batch_size, 5, z)
+        return self._fused_loss(x_0, self._host_t(vec_t), True, float(self.batch_size), z)
+
+    def forward(self, poses, betas, quan_t):
+        poses = self.Normalizer.offline_normalize(poses[:, :N_POSES * 3], from_axis=True)
+        return self.DPoser_loss(poses, float(self.timesteps[int(quan_t)]))

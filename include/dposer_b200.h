@@ -1,0 +1,222 @@
+/*
+ * dposer_b200 -- C ABI of the B200-native DPoser hot path (libdposer_b200.so).
+ *
+ * The reference (moonbow721/DPoser) has no FFI layer: its boundary is a set of Python
+ * callables.  Each entry point below names the reference callable whose
+ * arithmetic it replaces (paths relative to the reference checkout); INTEGRATION.md shows
+ * the ctypes stub a reference maintainer would add at that call site.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - every function returns 0 on success or a negative DPB_E* code; dpb_last_error()
+ *     returns a thread-local message for the last failure on the calling thread.
+ *   - "host" pointers are read during the call; "device" pointers are caller-owned device
+ *     buffers (e.g. torch tensors) on the handle's device; nothing is allocated in hot calls:
+ *     scratch comes from the caller through (ws, ws_bytes), sized by the *_workspace_bytes query.
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*;
+ *     torch.cuda.current_stream().cuda_stream); no entry point synchronises the host.
+ *   - handles are immutable after creation and may be used from any host thread.
+ *   - there is no CPU fallback: on a machine without a B200-class GPU every compute entry
+ *     point fails with DPB_ECUDA.
+ */
+#ifndef DPOSER_B200_H_
+#define DPOSER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPB_VERSION 100 /* 0.1.0 */
+
+#define DPB_OK 0
+#define DPB_EINVAL (-1)       /* bad argument (maps to ValueError / AssertionError in the Python mirror) */
+#define DPB_ECUDA (-2)        /* CUDA runtime / driver failure, or no sm_100 device */
+#define DPB_ENOMEM (-3)       /* workspace too small or allocation failure */
+#define DPB_EUNSUPPORTED (-4) /* feature not available (maps to NotImplementedError) */
+
+/* network geometry (configs/subvp/amass_scorefc_continuous.py:36-45 + defaults) */
+#define DPB_POSE_DIM 63
+#define DPB_HIDDEN 1024
+#define DPB_EMBED 512
+#define DPB_NUM_DENSE 5 /* pre_dense, b1_dense1, b1_dense2, b2_dense1, b2_dense2 */
+
+/* precision / engine selector (flags bits 0..3) */
+#define DPB_ENGINE_MASK 0xF
+#define DPB_ENGINE_AUTO 0  /* tcgen05 path when t is batch-uniform and B >= 64, else fp32 */
+#define DPB_ENGINE_FP32 1  /* fp32 FFMA kernels, fp32 accumulate (exact path, <=2e-5 rel.) */
+#define DPB_ENGINE_TC 2    /* tcgen05 tensor cores: fp16 operands (bf16 hi/lo split for the
+                              63-wide input layer), fp32 TMEM accumulators (<=1e-3 rel.) */
+
+typedef struct dpb_score dpb_score_t;
+typedef struct dpb_lbs dpb_lbs_t;
+
+int dpb_version(void);
+const char* dpb_last_error(void);
+/* fills sm_count / cc_major / cc_minor of `device`; DPB_ECUDA when there is no usable GPU */
+int dpb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Score network  (replaces ScoreModelFC.forward, lib/algorithms/advanced/model.py:141-196,
+ * and the score_fn wrapper, lib/algorithms/advanced/utils.py:141-163)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  /* all HOST fp32 pointers, nn.Linear layout [out, in] row-major; state_dict key in comments */
+  const float* pre_w;        /* pre_dense.weight        [1024, 63]   */
+  const float* pre_b;        /* pre_dense.bias          [1024]       */
+  const float* pre_t_w;      /* pre_dense_t.weight      [1024, 512]  */
+  const float* pre_t_b;      /* pre_dense_t.bias        [1024]       */
+  const float* pre_gn_w;     /* pre_gnorm.weight        [1024]       */
+  const float* pre_gn_b;     /* pre_gnorm.bias          [1024]       */
+  const float* temb_w;       /* shared_time_embed.0.weight [512,512] */
+  const float* temb_b;       /* shared_time_embed.0.bias   [512]     */
+  const float* blk_w[4];     /* b1_dense1, b1_dense2, b2_dense1, b2_dense2 .weight [1024,1024] */
+  const float* blk_b[4];     /* ... .bias [1024] */
+  const float* blk_t_w[4];   /* b{1,2}_dense{1,2}_t.weight [1024,512] */
+  const float* blk_t_b[4];   /* ... .bias [1024] */
+  const float* blk_gn_w[4];  /* b{1,2}_gnorm{1,2}.weight [1024] */
+  const float* blk_gn_b[4];  /* ... .bias [1024] */
+  const float* post_w;       /* post_dense.weight [63,1024] */
+  const float* post_b;       /* post_dense.bias   [63] */
+  const float* emb_freqs;    /* [256] exp(-k ln(1e4)/255) evaluated by the host in fp32 (model.py:41-43) */
+} dpb_score_weights;
+
+int dpb_score_create(dpb_score_t** h, const dpb_score_weights* w, int device);
+int dpb_score_destroy(dpb_score_t* h);
+
+/* Time path, hoisted (model.py:161-167,174,181 with utils.py:152): for each of n labels
+ * (= t*999, fp32, DEVICE) computes temb = SiLU(W_s [sin|cos](label f_k) + b_s) and the five
+ * projections W_lt temb + b_lt + b_l.  table is DEVICE fp32 [n, 5, 1024]. */
+int dpb_score_time_table(dpb_score_t* h, const float* labels, int n, float* table, void* stream);
+
+size_t dpb_score_workspace_bytes(dpb_score_t* h, int64_t B, int flags);
+
+/* out[B,63] = post_dense(...)(x) * scale.
+ *   x         DEVICE fp32 [B,63]
+ *   table     DEVICE fp32 [n,5,1024] from dpb_score_time_table
+ *   t_index   DEVICE int32 [B] row -> table entry, or NULL (every row uses entry 0)
+ *   row_scale DEVICE fp32 [B] or NULL (then `scale` is used for every row).  The caller folds
+ *             1/sigmas[floor(label)] (model.py:159,192-194) and -1/std(t) (utils.py:162) here.
+ */
+int dpb_score_forward(dpb_score_t* h, const float* x, const float* table, const int32_t* t_index,
+                      const float* row_scale, float scale, float* out, int64_t B, int flags,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused PC sampler  (replaces pc_sampler's hot loop, lib/algorithms/advanced/sampling.py:456-461,
+ * EulerMaruyamaPredictor.update_fn :182-188, imputation :413-422, RSDE.sde sde_lib.py:98-106)
+ * ---------------------------------------------------------------------------------------- */
+#define DPB_COEF_STRIDE 8
+/* coef[i] = {a, b, c, alpha, std, 0, 0, 0}:  x_mean = a*x + b*raw ;  x = x_mean + c*z ;
+ * imputation x = x*(1-m) + (alpha*obs + std*z')*m.  `raw` is the post_dense output BEFORE the
+ * sigma division; the host builds a,b,c with the reference's own fp32 torch expressions. */
+typedef struct {
+  int n_steps;             /* steps executed by this call */
+  const float* coef;       /* DEVICE fp32 [n_steps, DPB_COEF_STRIDE] */
+  const float* time_table; /* DEVICE fp32 [n_steps, 5, 1024] */
+} dpb_step_tables;
+
+#define DPB_SAMPLER_IMPUTE (1 << 4)      /* args.task == 'completion' */
+#define DPB_SAMPLER_NOISE_GIVEN (1 << 5) /* consume caller-supplied Gaussian draws (parity mode) */
+
+/*   x_io      DEVICE fp32 [B,63] in: x_T (or z), out: x after the last step
+ *   obs,mask  DEVICE fp32 [B,63] (only with DPB_SAMPLER_IMPUTE)
+ *   noise     DEVICE fp32: with NOISE_GIVEN, [n_steps, K, B, 63] where K=1 (predictor draw) or
+ *             K=3 with IMPUTE (draw after corrector, predictor draw, draw after predictor --
+ *             the reference's order, sampling.py:459-460).  Otherwise NULL: Philox4x32-10
+ *             keyed by (seed, row, step+step_offset, column).
+ *   traj      DEVICE fp32 [n_steps,B,63] or NULL;  x_mean DEVICE fp32 [B,63] or NULL.
+ */
+int dpb_sampler_run(dpb_score_t* h, float* x_io, const dpb_step_tables* tbl, const float* obs,
+                    const float* mask, const float* noise, uint64_t seed, uint64_t step_offset,
+                    float* traj, float* x_mean, int64_t B, int flags, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* Langevin corrector pieces (sampling.py:282-302): batch sums of row norms, then the update.
+ * sums DEVICE fp32[2] must be zeroed by the caller; norms: sums[0]+=sum_b||grad_b||, sums[1]+=sum_b||noise_b||.
+ * update: step = (snr*(sums[1]/Bglobal)/(sums[0]/Bglobal))^2 * 2*alpha ; x_mean = x + step*grad ;
+ *         x = x_mean + sqrt(2 step)*noise. */
+int dpb_langevin_norms(const float* grad, const float* noise, float* sums, int64_t B, void* stream);
+int dpb_langevin_update(float* x_io, float* x_mean, const float* grad, const float* noise,
+                        const float* sums, float snr, float alpha, int64_t B, void* stream);
+/* fills out[n] with N(0,1) draws of the library's Philox stream (row-major [B,63] addressing) */
+int dpb_normal_fill(float* out, int64_t B, uint64_t seed, uint64_t step, int slot, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DPoser prior loss  (replaces DPoserComp.loss run/completion.py:131-149,
+ * MotionDenoise.DPoser_loss run/motion_denoising.py:125-143, DPoser.DPoser_loss run/smplify.py:94-107)
+ * ---------------------------------------------------------------------------------------- */
+/* x_t = alpha*x0 + std*z ; raw = net(x_t) ; x0_hat = (x_t + std^2 * (-raw*inv_sigma_std))/alpha ;
+ * loss = sum_all( w (x0-x0_hat)^2 ) / divisor, w = 0.5 or 0.5*sqrt(1+alpha/std) ;
+ * grad = 2 w (x0-x0_hat)/divisor  (x0_hat is detached in the reference).
+ *   table      DEVICE fp32 [1,5,1024] time table of this t
+ *   z          DEVICE fp32 [B,63] Gaussian draw or NULL (Philox with seed/step)
+ *   loss_out   DEVICE fp32 [1] (overwritten), grad_out DEVICE fp32 [B,63] or NULL
+ *   row_loss   DEVICE fp32 [B] or NULL: per-row sums of w (x0-x0_hat)^2 (for per-problem normalisation)
+ */
+int dpb_prior_loss(dpb_score_t* h, const float* x0, const float* table, float alpha, float std,
+                   float inv_sigma_std, int weighted, float divisor, const float* z, uint64_t seed,
+                   uint64_t step, float* loss_out, float* grad_out, float* row_loss, int64_t B,
+                   int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Linear blend skinning (replaces smplx==0.1.28 lbs()/SMPL.forward/SMPLX.forward as called from
+ * lib/body_model/body_model.py:75-88 and lib/body_model/smpl.py:67-78)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int V, J, S;                 /* vertices, joints, shape(+expression) components; P = (J-1)*9 */
+  const float* v_template;     /* HOST [V,3]    */
+  const float* shapedirs;      /* HOST [V,3,S]  */
+  const float* posedirs;       /* HOST [P,3V]   */
+  const float* J_regressor;    /* HOST [J,V]    */
+  const float* lbs_weights;    /* HOST [V,J]    */
+  const int32_t* parents;      /* HOST [J], parents[0] = -1, parents[i] < i */
+  int n_extra;                 /* extra vertex joints (VertexJointSelector) */
+  const int32_t* extra_vids;   /* HOST [n_extra] */
+  int n_lmk;                   /* barycentric landmarks (SMPL-X static face landmarks) */
+  const int32_t* lmk_faces;    /* HOST [n_lmk,3] vertex ids of each landmark's face */
+  const float* lmk_bary;       /* HOST [n_lmk,3] */
+} dpb_body_tensors;
+
+#define DPB_LBS_ENGINE_FP32 1 /* fp32 FFMA pose-blend (exact) */
+#define DPB_LBS_ENGINE_TC 2   /* tcgen05 pose-blend, fp16 hi/lo-split operands, fp32 accumulate */
+
+int dpb_lbs_create(dpb_lbs_t** h, const dpb_body_tensors* m, int device);
+int dpb_lbs_destroy(dpb_lbs_t* h);
+int dpb_lbs_num_joints_out(dpb_lbs_t* h); /* J + n_extra + n_lmk */
+size_t dpb_lbs_workspace_bytes(dpb_lbs_t* h, int64_t B, int flags);
+
+/*   betas DEVICE [B,S], full_pose DEVICE [B,J*3] axis-angle (global_orient first), transl DEVICE [B,3] or NULL
+ *   verts DEVICE [B,V,3] or NULL (joints-only: skins only the vertices the extra joints need)
+ *   joints DEVICE [B, J+n_extra+n_lmk, 3]
+ *   ws keeps the per-pose skinning transforms / rotations needed by dpb_lbs_backward when the same
+ *   workspace is handed to it afterwards. */
+int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* full_pose, const float* transl,
+                    float* verts, float* joints, int64_t B, int flags, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* Vector-Jacobian product of dpb_lbs_forward w.r.t. full_pose, betas, transl.
+ *   g_verts DEVICE [B,V,3] or NULL, g_joints DEVICE [B,J+n_extra+n_lmk,3] or NULL
+ *   g_pose DEVICE [B,J*3], g_betas DEVICE [B,S], g_transl DEVICE [B,3] (each may be NULL) */
+int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* full_pose, const float* g_verts,
+                     const float* g_joints, float* g_pose, float* g_betas, float* g_transl, int64_t B,
+                     int flags, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Metrics (replaces average_pairwise_distance lib/utils/metric.py:8-37 and the per-sample
+ * reductions of Evaler.eval_bodys lib/dataset/AMASS.py:275-298)
+ * ---------------------------------------------------------------------------------------- */
+/* sum over i in [row0,row0+nrows), j in [0,B), j != i of mean_k ||joints[i,k]-joints[j,k]|| ;
+ * out DEVICE fp32[1] is ACCUMULATED into (zero it first; divide by B(B-1) afterwards). */
+int dpb_apd_partial(const float* joints, int64_t B, int n_joints, int64_t row0, int64_t nrows,
+                    float* out, void* stream);
+/* out[b] = 1000 * mean_{k in idx} ||a[b,idx[k]] - c[b,idx[k]]||  (idx DEVICE int32[n_idx] or NULL = all) */
+int dpb_mean_point_error(const float* a, const float* c, int64_t B, int n_points, const int32_t* idx,
+                         int n_idx, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPOSER_B200_H_ */

@@ -1,0 +1,180 @@
+"""CPU: host-side logic of the product package (tables, masks, shards, drop-in surface) and the
+C-ABI library: it must load and export every symbol include/dposer_b200.h declares.  No compute
+call is made here (there is no CPU fallback to call)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+from dposer_b200 import _lib as L
+from dposer_b200 import misc, sde_lib, synthetic, utils as mutils
+from oracle import score_ref as S
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'dposer_b200.h')).read()
+    declared = sorted(set(re.findall(r'\b(dpb_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(declared) >= 20
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/dposer_b200.h but not exported'
+    assert sorted(L.EXPORTS) == declared
+    assert lib.dpb_version() == 100
+
+
+def test_no_cpu_fallback_fails_loudly():
+    m = synthetic.make_score_model()
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 63), torch.ones(2))
+    from dposer_b200.body_model import BodyModel
+    bm = BodyModel(synthetic.make_body_tensors('smpl'), batch_size=2, model_type='smpl')
+    with pytest.raises(RuntimeError):
+        bm(pose_body=torch.zeros(2, 69))
+    # the library itself reports the missing device instead of computing on the host
+    sm = ctypes.c_int()
+    assert L.load().dpb_device_info(0, ctypes.byref(sm), None, None) == L.ECUDA
+
+
+def test_state_dict_surface_matches_reference_keys():
+    m = synthetic.make_score_model()
+    keys = set(m.state_dict().keys())
+    expect = {'sigmas'}
+    for n in ['pre_dense', 'pre_dense_t', 'pre_dense_cond', 'pre_gnorm', 'shared_time_embed.0', 'post_dense'] + \
+             [f'b{b}_{k}' for b in (1, 2) for k in ('dense1', 'dense1_t', 'gnorm1', 'dense2', 'dense2_t', 'gnorm2')]:
+        expect |= {n + '.weight', n + '.bias'}
+    assert keys == expect
+    assert sum(p.numel() for p in m.parameters()) == 8277567
+    fp = golden('weights_fingerprint.npz')
+    sd = m.state_dict()
+    for k in fp.files:
+        assert sd[k].double().abs().sum().item() == float(fp[k]), k
+
+
+def test_em_coefficients_reproduce_the_reference_update(oracle_sd):
+    """a*x + b*raw + c*z must equal EulerMaruyamaPredictor.update_fn on the oracle (fp32 rounding only)."""
+    model = synthetic.make_score_model()
+    g = torch.Generator().manual_seed(0)
+    for N, pf in [(1000, False), (500, False), (1000, True)]:
+        sde, osde = sde_lib.subVPSDE(0.1, 20., N), S.SubVP(0.1, 20., N)
+        ts = mutils.timestep_grid(sde, 1e-3)
+        coef, labels = mutils.em_coefficients(sde, model, ts, pf)
+        assert np.array_equal(labels.long().numpy(), (ts * 999).long().numpy())
+        for i in [0, N // 2, N - 1]:
+            x = torch.randn(4, 63, generator=g)
+            z = torch.randn(4, 63, generator=g)
+            vt = torch.ones(4) * ts[i]
+            raw = S.score_model_forward(oracle_sd, x, vt * 999, scale_by_sigma=False)
+            xr, xmr = S.em_step(oracle_sd, osde, x, vt, z, pf)
+            a, b, c = coef[i, 0], coef[i, 1], coef[i, 2]
+            xm = a * x + b * raw
+            assert (xm - xmr).abs().max() <= 2e-6 * xmr.abs().max()
+            assert ((xm + c * z) - xr).abs().max() <= 2e-6 * xr.abs().max()
+            mean, std = osde.marginal(torch.ones(1, 1), ts[i:i + 1])
+            assert coef[i, 3] == mean[0, 0] and coef[i, 4] == std[0]
+
+
+def test_prior_scalars_match_oracle():
+    model = synthetic.make_score_model()
+    sde, osde = sde_lib.subVPSDE(0.1, 20., 1000), S.SubVP()
+    ts = mutils.timestep_grid(sde, 1e-3)
+    for q in [0, 400, 799, 998]:
+        ps = mutils.prior_scalars(sde, model, float(ts[q]))
+        a, s = osde.alpha_sigma(ts[q:q + 1])
+        assert ps['alpha'] == float(a[0, 0]) and ps['std'] == float(s[0])
+        sig = S.sigma_table()[(ts[q] * 999).long()]
+        np.testing.assert_allclose(ps['inv_sigma_std'], float(1 / (sig * s[0])), rtol=1e-6)
+
+
+def test_masks_parts_shards_schedules_bit_exact():
+    g = golden('int_tables.npz')
+    for part in ['legs', 'arms', 'trunk', 'hands', 'left_leg', 'right_leg', 'left_arm', 'right_arm']:
+        assert getattr(misc.BodyPartIndices, part) == g[f'part_{part}'].tolist()
+        mask, obs = misc.create_mask(torch.zeros(3, 63), part=part)
+        assert np.array_equal(np.nonzero(mask[0].numpy() == 0)[0], g[f'maskzero_{part}'])
+        assert (obs[:, mask[0] == 1] == 0).all()
+    for N, total, trun, off, nm in [(1000, 200, 5.0, 2, 'completion'), (500, 180, 4.0, 2, 'denoise'),
+                                    (500, 500, 20.0, 5, 'smplify')]:
+        assert misc.quan_t_schedule(N, total, trun, off) == g[f'quan_t_{nm}'].tolist()
+    for total, world, r, first, n in g['shards'].tolist():
+        st, cnt = misc.shard_range(total, world, r)
+        assert cnt == n and (n == 0 or st == first)
+    # shards tile the range exactly, in rank order
+    for total, world in [(500, 8), (65536, 8), (40960, 3), (5, 8)]:
+        pos = 0
+        for r in range(world):
+            st, cnt = misc.shard_range(total, world, r)
+            assert st == pos
+            pos += cnt
+        assert pos == total
+
+
+def test_create_mask_same_draws_as_reference_rng():
+    """With the same torch seed the noise fill equals the reference's (same randn_like call order)."""
+    g = golden('sampler_golden.npz')
+    norm = misc.Posenormalizer(None, device='cpu', normalize=True, min_max=False, rot_rep='axis')
+    poses = norm.offline_normalize(synthetic.toy_poses()[:5])
+    torch.manual_seed(3)
+    mask, obs = misc.create_mask(poses, part='legs')
+    assert np.array_equal(mask.numpy(), g['comp8_mask']) and np.array_equal(obs.numpy(), g['comp8_obs'])
+
+
+def test_normalizer_roundtrip_and_stats():
+    norm = misc.Posenormalizer(None, device='cpu', normalize=True, min_max=False, rot_rep='axis')
+    toy = synthetic.toy_poses()
+    x = norm.offline_normalize(toy)
+    assert (norm.offline_denormalize(x) - toy).abs().max() < 1e-6
+    g = golden('score_golden.npz')
+    gen = torch.Generator().manual_seed(5)
+    x7 = norm.offline_normalize(toy[:7]) + 0.3 * torch.randn(7, 63, generator=gen)
+    assert np.array_equal(x7.numpy(), g['x'])
+    with pytest.raises(NotImplementedError):
+        misc.Posenormalizer(None, device='cpu', rot_rep='rot6d')
+
+
+def test_sde_objects_match_oracle_scalars():
+    sde, osde = sde_lib.subVPSDE(0.1, 20., 1000), S.SubVP()
+    t = torch.linspace(1, 1e-3, 1000)
+    x = torch.randn(1000, 3)
+    assert torch.equal(sde.sde(x, t)[1], osde.sde(x, t)[1])
+    assert torch.equal(sde.marginal_prob(x, t)[1], osde.marginal(x, t)[1])
+    assert torch.equal(sde.return_alpha_sigma(t)[0], osde.alpha_sigma(t)[0])
+    k = golden('known_answers.npz')
+    assert np.array_equal(sde.alphas.numpy(), k['sde_alphas'])
+    with pytest.raises(NotImplementedError):
+        mutils.get_score_fn(object(), None)
+    # reverse() keeps the reference surface
+    r = sde.reverse(lambda x, t, c, m: torch.zeros_like(x), probability_flow=True)
+    d, g_ = r.sde(x[:4], t[:4])
+    assert d.shape == (4, 3) and float(g_) == 0.0 and r.N == 1000 and r.T == 1
+
+
+def test_sampling_fn_argument_errors():
+    from dposer_b200 import sampling
+    cfg = synthetic.default_config()
+    cfg.sampling.method = 'bogus'
+    with pytest.raises(ValueError):
+        sampling.get_sampling_fn(cfg, sde_lib.subVPSDE(), (2, 63), lambda x: x, 1e-3, device='cpu')
+    cfg.sampling.method = 'pc'
+    cfg.sampling.predictor = 'ancestral_sampling'
+    with pytest.raises(NotImplementedError):
+        sampling.get_sampling_fn(cfg, sde_lib.subVPSDE(), (2, 63), lambda x: x, 1e-3, device='cpu')
+
+
+def test_body_model_wrapper_shapes_and_joint_map():
+    from dposer_b200 import body_model as bmod
+    g = golden('int_tables.npz')
+    assert bmod.JOINT_MAP_49 == g['smplx_joint_map49'].tolist()
+    assert bmod.SMPLX_PARENTS[:22] == bmod.SMPL_PARENTS[:22] and len(bmod.SMPLX_PARENTS) == 55
+    # first 22 parents are what lib/body_model/utils.py:180-205 (get_smpl_skeleton) implies
+    assert bmod.SMPL_PARENTS[:22] == [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19]
+    with pytest.raises(ValueError):
+        bmod.BodyModel(synthetic.make_body_tensors('smpl'), model_type='smplx')
+    m = bmod.SMPLX(synthetic.make_body_tensors('smplx'))
+    assert m.mean_poses.shape == (72,) and m.mean_shape.shape == (10,)
+    assert torch.isfinite(m.mean_poses).all()
