@@ -1,7 +1,632 @@
-// tcgen05 engine (placeholder).
+// tcgen05 engine of the score network: ONE persistent, warp-specialised kernel that runs every
+// layer of every sampler step for a 128-row tile of poses.
+//
+//   warp 0      TMA producer, weight (B-operand) tiles   [N x 64] fp16, SWIZZLE_128B
+//   warp 1      tcgen05.mma issuer (one thread), fp32 accumulators in TMEM (2 x 256 columns)
+//   warp 2      TMEM allocator, then TMA producer of activation (A-operand) tiles [128 x 64]
+//   warps 4-11  epilogue: tcgen05.ld 32x32b -> +time bias -> GroupNorm(32 ch, thread-local stats)
+//               -> SiLU (-> +residual) -> fp16 -> per-CTA activation scratch (L2 resident);
+//               last layer: Euler-Maruyama update / imputation / Philox noise (sampler),
+//               scaled output (forward) or loss + closed-form gradient (prior loss)
+//
+// Numerics: fp16 operands with fp32 accumulation for the four 1024x1024 layers and post_dense;
+// the 63-wide input layer uses a bf16 hi/lo split of x and W_pre expressed as a K-extension
+// ([x_hi | x_lo | x_hi] . [W_hi | W_hi | W_lo]^T, K = 192) so it keeps ~16 mantissa bits and the
+// fp32 range of x.  Math follows ScoreModelFC.forward (reference model.py:141-196), the EM update
+// sampling.py:182-188 and imputation :413-422; identical formulas / Philox addressing as sampler.cu.
+#include <cudaTypedefs.h>
+
+#include <vector>
+
+#include "ptx.cuh"
 #include "score.h"
+
 namespace dpb {
-int tc_prepare(dpb_score* h, const dpb_score_weights*) { h->tc_ready = false; return DPB_OK; }
-void tc_release(dpb_score*) {}
-int tc_launch(dpb_score*, const TcJob&, cudaStream_t) { return fail(DPB_EUNSUPPORTED, "tcgen05 engine not built"); }
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr int BLOCK_K = 64;  // 64 x 2 B = one 128-byte swizzle row
+constexpr int CHUNK_N = 256;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TILE_M * BLOCK_K * 2;   // 16 KB
+constexpr int B_BYTES = CHUNK_N * BLOCK_K * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int POST_B_BYTES = DP * BLOCK_K * 2;  // 8 KB (N = 64)
+constexpr int XA_K = 192;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int PAR_BYTES = 3 * H * 4;
+constexpr int NUM_BARS = 2 * STAGES + 5;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PAR_BYTES + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
+constexpr uint32_t IDESC_F16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 0);
+constexpr uint32_t IDESC_BF16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 1);
+constexpr uint32_t IDESC_F16_64 = ptx::umma_idesc_f16(TILE_M, DP, 0);
+
+struct KParams {
+  int mode, n_steps, impute, noise_k, n_tiles;
+  long long B;
+  const float* x_in;
+  float* x_io;
+  const float* table;
+  const float* coef;
+  const float* gn;
+  const float* post_b;
+  const float* row_scale;
+  float scale;
+  float* out;
+  const float* obs;
+  const float* mask;
+  const float* noise;
+  unsigned long long seed, step_offset;
+  float* traj;
+  float* x_mean;
+  float alpha, sd, inv_sigma_std, inv_div, wgt;
+  const float* z;
+  float* loss_out;
+  float* grad_out;
+  float* row_loss;
+  __half* act_h;
+  __half* act_t;
+  __nv_bfloat16* xa;
+};
+
+__device__ __forceinline__ int layer_nk(int layer) { return layer == 0 ? XA_K / BLOCK_K : H / BLOCK_K; }
+__device__ __forceinline__ int layer_chunks(int layer) { return layer == 5 ? 1 : H / CHUNK_N; }
+
+// x[32] (fp32, columns hf*32..hf*32+31 of one row) -> [hi | lo | hi] bf16 segments of the xa row
+__device__ __forceinline__ void write_xa(__nv_bfloat16* row, int hf, const float* x) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  uint4* p0 = reinterpret_cast<uint4*>(row + hf * 32);
+  uint4* p1 = reinterpret_cast<uint4*>(row + 64 + hf * 32);
+  uint4* p2 = reinterpret_cast<uint4*>(row + 128 + hf * 32);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 h = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+    uint4 l = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+    p0[i] = h;
+    p1[i] = l;
+    p2[i] = h;
+  }
+}
+
+// Gaussian draws for this thread's 32 columns: caller-supplied plane or Philox (slot, step)
+__device__ __forceinline__ void draw32(const float* plane, long long row, int hf, unsigned long long seed,
+                                       uint32_t step, uint32_t slot, float* z) {
+  if (plane) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      int col = hf * 32 + i;
+      z[i] = col < D ? plane[row * D + col] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) normal4(seed, (uint64_t)row, step, slot, (uint32_t)(hf * 8 + j), z + 4 * j);
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUtensorMap tm_xa,
+                const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_t,
+                const __grid_constant__ CUtensorMap tm_pre, const __grid_constant__ CUtensorMap tm_w0,
+                const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+                const __grid_constant__ CUtensorMap tm_w3, const __grid_constant__ CUtensorMap tm_post) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  float* par = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [tb | gamma | beta] x 1024
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + PAR_BYTES;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t act_bar = bar_base + 8u * (2 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + PAR_BYTES + NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 2);   // A producer + W producer (each arrive.expect_tx)
+      ptx::mbar_init(empty_bar(s), 1);  // tcgen05.commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar(b), 1);   // tcgen05.commit
+      ptx::mbar_init(tempty_bar(b), 8);  // one lane of each epilogue warp
+    }
+    ptx::mbar_init(act_bar, 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_pre); ptx::prefetch_tmap(&tm_w0); ptx::prefetch_tmap(&tm_w1);
+    ptx::prefetch_tmap(&tm_w2); ptx::prefetch_tmap(&tm_w3); ptx::prefetch_tmap(&tm_post);
+  }
+  if (warp == 2) {
+    if (lane == 0) { ptx::prefetch_tmap(&tm_xa); ptx::prefetch_tmap(&tm_h); ptx::prefetch_tmap(&tm_t); }
+    __syncwarp();
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int slot_row0 = blockIdx.x * TILE_M;  // this CTA's rows in the scratch buffers
+
+  if (warp == 0) {
+    // ======================= weight producer =======================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+        for (int step = 0; step < p.n_steps; ++step)
+          for (int layer = 0; layer < 6; ++layer) {
+            const CUtensorMap* tm = layer == 0 ? &tm_pre : layer == 1 ? &tm_w0 : layer == 2 ? &tm_w1
+                                  : layer == 3 ? &tm_w2 : layer == 4 ? &tm_w3 : &tm_post;
+            const uint32_t bytes = layer == 5 ? POST_B_BYTES : B_BYTES;
+            const int nk = layer_nk(layer), nc = layer_chunks(layer);
+            for (int chunk = 0; chunk < nc; ++chunk)
+              for (int k = 0; k < nk; ++k) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);
+                ptx::tma_load_2d(smem_base + stage * STAGE_BYTES + A_BYTES, tm, full_bar(stage), k * BLOCK_K,
+                                 chunk * CHUNK_N);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+          }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, chunk_ctr = 0, tph = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+        for (int step = 0; step < p.n_steps; ++step)
+          for (int layer = 0; layer < 6; ++layer) {
+            const uint32_t idesc = layer == 0 ? IDESC_BF16_256 : layer == 5 ? IDESC_F16_64 : IDESC_F16_256;
+            const int nk = layer_nk(layer), nc = layer_chunks(layer);
+            for (int chunk = 0; chunk < nc; ++chunk) {
+              const uint32_t buf = chunk_ctr & 1;
+              ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
+              ptx::tc_fence_after();
+              const uint32_t taddr = tmem_base + buf * CHUNK_N;
+              for (int k = 0; k < nk; ++k) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
+                const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
+                const uint64_t bdesc = ptx::umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_K / 16; ++kk)  // UMMA_K = 16: advance 32 B inside the swizzle row
+                  ptx::mma_f16_ss(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                ptx::mma_commit(empty_bar(stage));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+              ptx::mma_commit(tfull_bar(buf));
+              tph ^= 1u << buf;
+              ++chunk_ctr;
+            }
+          }
+    }
+  } else if (warp == 2) {
+    // ======================= activation producer =======================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+        for (int step = 0; step < p.n_steps; ++step)
+          for (int layer = 0; layer < 6; ++layer) {
+            // layer input: xa | H | T | H | T | H
+            const CUtensorMap* tm = layer == 0 ? &tm_xa : (layer == 2 || layer == 4) ? &tm_t : &tm_h;
+            const int nk = layer_nk(layer), nc = layer_chunks(layer);
+            ptx::mbar_wait(act_bar, aph);  // the epilogue finished writing this layer's input
+            aph ^= 1;
+            for (int chunk = 0; chunk < nc; ++chunk)
+              for (int k = 0; k < nk; ++k) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
+                ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), k * BLOCK_K, slot_row0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+          }
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue =======================
+    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    const int hf = (warp - 4) >> 2;  // which half of the chunk's column groups
+    const int et = threadIdx.x - 128;
+    const int r_in = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t chunk_ctr = 0, tph = 0;
+    auto signal_act = [&]() {
+      __threadfence();
+      ptx::fence_proxy_async_global();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(act_bar);
+    };
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const long long row = (long long)tile * TILE_M + r_in;
+      const bool valid = row < p.B;
+      const size_t srow = (size_t)(slot_row0 + r_in);
+      __half* hrow = p.act_h + srow * H;
+      __half* trow = p.act_t + srow * H;
+      __nv_bfloat16* xarow = p.xa + srow * XA_K;
+      // ---------------- tile prologue: first-layer operand of step 0
+      {
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = 0.f;
+        if (valid) {
+          if (p.mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              int col = hf * 32 + i;
+              if (col < D) x[i] = p.x_io[row * D + col];
+            }
+            if (p.impute) {  // imputation that follows the (none) corrector of step 0, sampling.py:459
+              float zc[32];
+              draw32(p.noise ? p.noise : nullptr, row, hf, p.seed, (uint32_t)p.step_offset, 0, zc);
+              const float al = p.coef[3], sd = p.coef[4];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                int col = hf * 32 + i;
+                if (col < D) {
+                  float m = p.mask[row * D + col];
+                  x[i] = x[i] * (1.0f - m) + (al * p.obs[row * D + col] + zc[i] * sd) * m;
+                  p.x_io[row * D + col] = x[i];
+                }
+              }
+            }
+          } else if (p.mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              int col = hf * 32 + i;
+              if (col < D) x[i] = p.x_in[row * D + col];
+            }
+          } else {  // prior loss: x_t = alpha x0 + std z
+            float z[32];
+            draw32(p.z, row, hf, p.seed, (uint32_t)p.step_offset, 3, z);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              int col = hf * 32 + i;
+              if (col < D) x[i] = p.alpha * p.x_in[row * D + col] + p.sd * z[i];
+            }
+          }
+        }
+        write_xa(xarow, hf, x);
+        signal_act();
+      }
+      for (int step = 0; step < p.n_steps; ++step) {
+        // ---------------- hidden layers 0..4
+        for (int layer = 0; layer < 5; ++layer) {
+          ptx::named_bar_sync(1, EPI_THREADS);  // everyone is done with the previous layer's parameters
+          {
+            const float4* tb = reinterpret_cast<const float4*>(p.table + ((size_t)step * NL + layer) * H);
+            const float4* gm = reinterpret_cast<const float4*>(p.gn + (size_t)(layer * 2) * H);
+            const float4* bt = reinterpret_cast<const float4*>(p.gn + (size_t)(layer * 2 + 1) * H);
+            reinterpret_cast<float4*>(par)[et] = tb[et];
+            reinterpret_cast<float4*>(par + H)[et] = gm[et];
+            reinterpret_cast<float4*>(par + 2 * H)[et] = bt[et];
+          }
+          ptx::named_bar_sync(1, EPI_THREADS);
+          const bool to_h = (layer == 0 || layer == 2 || layer == 4);
+          const bool residual = (layer == 2 || layer == 4);
+          __half* drow = to_h ? hrow : trow;
+          for (int chunk = 0; chunk < H / CHUNK_N; ++chunk) {
+            const uint32_t buf = chunk_ctr & 1;
+            ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int gi = 0; gi < 4; ++gi) {
+              const int g = hf * 4 + gi;
+              const int col0 = chunk * CHUNK_N + g * 32;
+              uint32_t vr[32];
+              ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g * 32, vr);
+              ptx::tmem_ld_wait();
+              if (gi == 3) {  // last TMEM read of this warp for the buffer: hand it back to the MMA warp
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+              }
+              float v[32];
+              float s = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 t4 = *reinterpret_cast<const float4*>(par + col0 + i);
+                v[i] = __uint_as_float(vr[i]) + t4.x;
+                v[i + 1] = __uint_as_float(vr[i + 1]) + t4.y;
+                v[i + 2] = __uint_as_float(vr[i + 2]) + t4.z;
+                v[i + 3] = __uint_as_float(vr[i + 3]) + t4.w;
+                s += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+              }
+              const float mean = s * (1.0f / GROUP);
+              float qv = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                v[i] -= mean;
+                qv = fmaf(v[i], v[i], qv);
+              }
+              const float rstd = rsqrtf(qv * (1.0f / GROUP) + GN_EPS);
+              uint32_t res[16];
+              if (residual) {
+                const uint4* rp = reinterpret_cast<const uint4*>(drow + col0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  uint4 r4 = rp[i];
+                  res[4 * i] = r4.x; res[4 * i + 1] = r4.y; res[4 * i + 2] = r4.z; res[4 * i + 3] = r4.w;
+                }
+              }
+              uint32_t packed[16];
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 g4 = *reinterpret_cast<const float4*>(par + H + col0 + i);
+                float4 b4 = *reinterpret_cast<const float4*>(par + 2 * H + col0 + i);
+                float y0 = fmaf(v[i] * rstd, g4.x, b4.x), y1 = fmaf(v[i + 1] * rstd, g4.y, b4.y);
+                float y2 = fmaf(v[i + 2] * rstd, g4.z, b4.z), y3 = fmaf(v[i + 3] * rstd, g4.w, b4.w);
+                y0 = __fdividef(y0, 1.0f + __expf(-y0));
+                y1 = __fdividef(y1, 1.0f + __expf(-y1));
+                y2 = __fdividef(y2, 1.0f + __expf(-y2));
+                y3 = __fdividef(y3, 1.0f + __expf(-y3));
+                if (residual) {
+                  float2 r01 = __half22float2(*reinterpret_cast<const __half2*>(&res[i / 2]));
+                  float2 r23 = __half22float2(*reinterpret_cast<const __half2*>(&res[i / 2 + 1]));
+                  y0 += r01.x; y1 += r01.y; y2 += r23.x; y3 += r23.y;
+                }
+                __half2 p01 = __floats2half2_rn(y0, y1), p23 = __floats2half2_rn(y2, y3);
+                packed[i / 2] = *reinterpret_cast<uint32_t*>(&p01);
+                packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&p23);
+              }
+              uint4* dp = reinterpret_cast<uint4*>(drow + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                dp[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            }
+            tph ^= 1u << buf;
+            ++chunk_ctr;
+          }
+          signal_act();  // this layer's output (next layer's A operand) is in the scratch
+        }
+        // ---------------- post_dense + mode-specific tail
+        {
+          const uint32_t buf = chunk_ctr & 1;
+          ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+          ptx::tc_fence_after();
+          uint32_t vr[32];
+          ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + hf * 32, vr);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+          tph ^= 1u << buf;
+          ++chunk_ctr;
+          float raw[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = __uint_as_float(vr[i]) + __ldg(p.post_b + hf * 32 + i);
+          const bool last = (step + 1 == p.n_steps);
+          if (p.mode == 0) {
+            if (valid) {
+              const float sc = p.row_scale ? p.row_scale[row] : p.scale;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                int col = hf * 32 + i;
+                if (col < D) p.out[row * D + col] = raw[i] * sc;
+              }
+            }
+          } else if (p.mode == 1) {
+            float x[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = 0.f;
+            if (valid) {
+              const float* cf = p.coef + (size_t)step * DPB_COEF_STRIDE;
+              const float a = cf[0], b = cf[1], c = cf[2], al = cf[3], sd = cf[4];
+              const uint32_t gstep = (uint32_t)(p.step_offset + (unsigned long long)step);
+              const size_t plane = (size_t)p.B * D;
+              const float* nz = p.noise ? p.noise + (size_t)step * p.noise_k * plane : nullptr;
+              float zp[32];
+              draw32(nz ? nz + (p.noise_k == 3 ? plane : 0) : nullptr, row, hf, p.seed, gstep, 1, zp);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                int col = hf * 32 + i;
+                if (col < D) {
+                  float xm = a * p.x_io[row * D + col] + b * raw[i];  // sampling.py:185-186 in affine form
+                  x[i] = xm + c * zp[i];
+                  if (last && p.x_mean) p.x_mean[row * D + col] = xm;
+                }
+              }
+              if (p.impute) {
+                float zi[32];
+                draw32(nz ? nz + 2 * plane : nullptr, row, hf, p.seed, gstep, 2, zi);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  int col = hf * 32 + i;
+                  if (col < D) {
+                    float m = p.mask[row * D + col];
+                    x[i] = x[i] * (1.0f - m) + (al * p.obs[row * D + col] + zi[i] * sd) * m;
+                  }
+                }
+              }
+              if (p.traj) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  int col = hf * 32 + i;
+                  if (col < D) p.traj[((size_t)step * p.B + row) * D + col] = x[i];
+                }
+              }
+              if (!last && p.impute) {  // imputation in the corrector slot of the NEXT step precedes its score eval
+                float zc[32];
+                const float* nz1 = p.noise ? p.noise + (size_t)(step + 1) * p.noise_k * plane : nullptr;
+                draw32(nz1, row, hf, p.seed, gstep + 1, 0, zc);
+                const float al1 = cf[DPB_COEF_STRIDE + 3], sd1 = cf[DPB_COEF_STRIDE + 4];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  int col = hf * 32 + i;
+                  if (col < D) {
+                    float m = p.mask[row * D + col];
+                    x[i] = x[i] * (1.0f - m) + (al1 * p.obs[row * D + col] + zc[i] * sd1) * m;
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                int col = hf * 32 + i;
+                if (col < D) p.x_io[row * D + col] = x[i];
+              }
+            }
+            if (!last) {
+              write_xa(xarow, hf, x);
+              signal_act();
+            }
+          } else {  // prior loss
+            float acc = 0.f;
+            if (valid) {
+              float z[32];
+              draw32(p.z, row, hf, p.seed, (uint32_t)p.step_offset, 3, z);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                int col = hf * 32 + i;
+                if (col < D) {
+                  float x0 = p.x_in[row * D + col];
+                  float xt = p.alpha * x0 + p.sd * z[i];
+                  float score = -raw[i] * p.inv_sigma_std;
+                  float x0h = (xt + (p.sd * p.sd) * score) / p.alpha;
+                  float d = x0 - x0h;
+                  acc = fmaf(p.wgt * d, d, acc);
+                  if (p.grad_out) p.grad_out[row * D + col] = 2.0f * p.wgt * d * p.inv_div;
+                }
+              }
+              if (p.row_loss) atomicAdd(p.row_loss + row, acc);
+            }
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) atomicAdd(p.loss_out, acc * p.inv_div);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major [rows, inner] 16-bit tensor, box {box_inner, box_rows}, 128-byte swizzle
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64_t inner, uint64_t rows,
+                 uint32_t box_inner, uint32_t box_rows, size_t elem_bytes) {
+  auto enc = encode_fn();
+  if (!enc) return fail(DPB_ECUDA, "cuTensorMapEncodeTiled is unavailable from the driver");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * elem_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DPB_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return DPB_OK;
+}
+
+int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
+  h->tc_ready = false;
+  // fp16 copies of the square layers and post_dense (zero row 63), bf16 hi/hi/lo split of pre_dense
+  std::vector<__half> buf((size_t)H * H);
+  for (int l = 0; l < 4; ++l) {
+    for (size_t i = 0; i < (size_t)H * H; ++i) buf[i] = __float2half_rn(w->blk_w[l][i]);
+    DPB_CUDA_CHECK(cudaMalloc((void**)&h->w16[l], buf.size() * sizeof(__half)));
+    DPB_CUDA_CHECK(cudaMemcpy(h->w16[l], buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  std::vector<__half> post((size_t)DP * H, __float2half_rn(0.f));
+  for (size_t i = 0; i < (size_t)D * H; ++i) post[i] = __float2half_rn(w->post_w[i]);
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->post16, post.size() * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMemcpy(h->post16, post.data(), post.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  std::vector<__nv_bfloat16> pre((size_t)H * tc::XA_K, __float2bfloat16_rn(0.f));
+  for (int o = 0; o < H; ++o)
+    for (int k = 0; k < D; ++k) {
+      float v = w->pre_w[(size_t)o * D + k];
+      __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      pre[(size_t)o * tc::XA_K + k] = hi;         // pairs with x_hi
+      pre[(size_t)o * tc::XA_K + 64 + k] = hi;    // pairs with x_lo
+      pre[(size_t)o * tc::XA_K + 128 + k] = lo;   // pairs with x_hi
+    }
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->pre_split, pre.size() * sizeof(__nv_bfloat16)));
+  DPB_CUDA_CHECK(cudaMemcpy(h->pre_split, pre.data(), pre.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  // per-CTA activation scratch (one 128-row slot per SM)
+  h->tc_slots = h->sm_count;
+  const size_t rows = (size_t)h->tc_slots * tc::TILE_M;
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_h, rows * H * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_t, rows * H * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->xa, rows * tc::XA_K * sizeof(__nv_bfloat16)));
+  DPB_CUDA_CHECK(cudaMemset(h->act_h, 0, rows * H * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMemset(h->act_t, 0, rows * H * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMemset(h->xa, 0, rows * tc::XA_K * sizeof(__nv_bfloat16)));
+  int rc = DPB_OK;
+  for (int l = 0; l < 4 && rc == DPB_OK; ++l)
+    rc = make_tmap_2d(&h->tm_w[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->w16[l], H, H, tc::BLOCK_K, tc::CHUNK_N, 2);
+  if (rc == DPB_OK) rc = make_tmap_2d(&h->tm_post, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->post16, H, DP, tc::BLOCK_K, DP, 2);
+  if (rc == DPB_OK)
+    rc = make_tmap_2d(&h->tm_pre, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, h->pre_split, tc::XA_K, H, tc::BLOCK_K, tc::CHUNK_N, 2);
+  if (rc == DPB_OK)
+    rc = make_tmap_2d(&h->tm_act_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->act_h, H, rows, tc::BLOCK_K, tc::TILE_M, 2);
+  if (rc == DPB_OK)
+    rc = make_tmap_2d(&h->tm_act_t, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->act_t, H, rows, tc::BLOCK_K, tc::TILE_M, 2);
+  if (rc == DPB_OK)
+    rc = make_tmap_2d(&h->tm_xa, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, h->xa, tc::XA_K, rows, tc::BLOCK_K, tc::TILE_M, 2);
+  if (rc != DPB_OK) return rc;
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(tc::score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      tc::SMEM_BYTES));
+  h->tc_ready = true;
+  return DPB_OK;
+}
+
+void tc_release(dpb_score* h) {
+  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->act_t, h->xa};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  h->tc_ready = false;
+}
+
+int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
+  tc::KParams p{};
+  p.mode = j.mode;
+  p.n_steps = j.n_steps;
+  p.impute = j.impute;
+  p.noise_k = j.noise_k;
+  p.B = j.B;
+  p.n_tiles = (int)((j.B + tc::TILE_M - 1) / tc::TILE_M);
+  p.x_in = j.x_in; p.x_io = j.x_io; p.table = j.table; p.coef = j.coef;
+  p.gn = h->gn_packed; p.post_b = h->post_b;
+  p.row_scale = j.row_scale; p.scale = j.scale; p.out = j.out;
+  p.obs = j.obs; p.mask = j.mask; p.noise = j.noise;
+  p.seed = j.seed; p.step_offset = j.step_offset; p.traj = j.traj; p.x_mean = j.x_mean;
+  p.alpha = j.alpha; p.sd = j.std; p.inv_sigma_std = j.inv_sigma_std;
+  p.inv_div = j.divisor > 0.f ? 1.0f / j.divisor : 0.f;
+  p.wgt = j.scale;  // prior loss: api.cu passes the weight through `scale`
+  p.z = j.z; p.loss_out = j.loss_out; p.grad_out = j.grad_out; p.row_loss = j.row_loss;
+  p.act_h = h->act_h; p.act_t = h->act_t; p.xa = h->xa;
+  if (j.mode == 2 && j.row_loss) DPB_CUDA_CHECK(cudaMemsetAsync(j.row_loss, 0, sizeof(float) * j.B, st));
+  const int grid = p.n_tiles < h->tc_slots ? p.n_tiles : h->tc_slots;
+  tc::score_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, h->tm_xa, h->tm_act_h, h->tm_act_t, h->tm_pre,
+                                                                    h->tm_w[0], h->tm_w[1], h->tm_w[2], h->tm_w[3],
+                                                                    h->tm_post);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
 }  // namespace dpb
