@@ -149,8 +149,14 @@ class ScoreModelFC(nn.Module):
                                               L.current_stream(h.device)))
         return table
 
-    def raw_forward(self, x, labels, row_mult=None, uniform=None):
-        """post_dense(...)(x) * row_mult (row_mult: None | [B] tensor).  uniform=True skips the unique() sync."""
+    def raw_forward(self, x, labels, row_mult=None):
+        """post_dense(...)(x) * row_mult.
+
+        ``labels`` ([B] or [1], = t*999) and ``row_mult`` (None | [B] | [1]) are small schedule vectors: they
+        are brought to the HOST once (a [B]-float copy) so that (a) the batch-uniform case is detected without
+        a device reduction and (b) every schedule scalar is the CPU-fp32 value the reference would compute
+        (``1 - exp(2 lmc)`` loses ~5e-4 relative at t=1e-3 to a single ulp of exp, so the device's exp must
+        not be used for it).  The time path is evaluated once per distinct label."""
         h = self.handle()
         L.require_cuda(x, 'batch')
         x = x.detach().to(torch.float32).contiguous()
@@ -158,26 +164,38 @@ class ScoreModelFC(nn.Module):
         out = torch.empty(B, L.POSE_DIM, dtype=torch.float32, device=x.device)
         if B == 0:
             return out
-        labels = labels.detach().to(device=x.device, dtype=torch.float32)
-        if uniform is None:
-            uniform = labels.numel() == 1 or bool((labels == labels[0]).all())
+        labels = labels.detach().to(device='cpu', dtype=torch.float32).reshape(-1)
+        mult = None if row_mult is None else row_mult.detach().to(device='cpu', dtype=torch.float32).reshape(-1)
+        uniform = labels.numel() == 1 or bool((labels == labels[0]).all())
+        scale, rs, idx = 1.0, None, None
         if uniform:
-            table, idx = self.time_table(labels.reshape(-1)[:1]), None
+            table = self.time_table(labels[:1])
+            if mult is not None:
+                if mult.numel() == 1 or bool((mult == mult[0]).all()):
+                    scale = float(mult[0])
+                else:
+                    rs = mult.to(x.device)
         else:
             uniq, inv = torch.unique(labels, return_inverse=True)
-            table, idx = self.time_table(uniq), inv.to(torch.int32).contiguous()
-        rs = None if row_mult is None else row_mult.detach().to(torch.float32).contiguous()
+            table, idx = self.time_table(uniq), inv.to(device=x.device, dtype=torch.int32).contiguous()
+            rs = None if mult is None else mult.expand(B).contiguous().to(x.device)
         ws = self.workspace(B, x.device)
-        L.check(L.load().dpb_score_forward(h.ptr, L.ptr(x), L.ptr(table), L.ptr(idx), L.ptr(rs), 1.0, L.ptr(out), B,
-                                           self.engine, L.ptr(ws), ws.numel(), L.current_stream(x.device)))
+        L.check(L.load().dpb_score_forward(h.ptr, L.ptr(x), L.ptr(table), L.ptr(idx), L.ptr(rs), scale, L.ptr(out),
+                                           B, self.engine, L.ptr(ws), ws.numel(), L.current_stream(x.device)))
         return out
 
     def forward(self, batch, t, condition=None, mask=None):
         """batch [B,63], t [B] (labels, i.e. t*999 when called through score_fn) -> [B,63]  (model.py:141-196)."""
         if self.training:
             raise NotImplementedError('dposer_b200.ScoreModelFC is inference-only (dropout/training are out of scope)')
+        t = t.detach().to('cpu', torch.float32)
         row_mult = None
         if self.config.model.scale_by_sigma:
-            used_sigmas = self.sigmas[t.long()]            # model.py:159 (int64 gather, bit-exact)
+            used_sigmas = self._sigmas_host()[t.long()]    # model.py:159 (int64 gather, bit-exact)
             row_mult = 1.0 / used_sigmas
         return self.raw_forward(batch, t, row_mult)
+
+    def _sigmas_host(self):
+        if getattr(self, '_sig_cpu', None) is None or self._sig_cpu[1] != self.sigmas._version:
+            self._sig_cpu = (self.sigmas.detach().cpu(), self.sigmas._version)
+        return self._sig_cpu[0]

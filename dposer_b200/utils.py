@@ -34,15 +34,16 @@ def get_score_fn(sde, model, train=False, continuous=False):
     if _is_vp(sde):
         def score_fn(x, t, condition=None, mask=None):
             model.eval()
+            t = t.detach().to('cpu', torch.float32)       # schedule scalars are evaluated on the host (fp32)
             if continuous or isinstance(sde, sde_lib.subVPSDE):
                 labels = t * 999
                 std = sde.marginal_prob(torch.zeros_like(t)[:, None], t)[1]
             else:
                 labels = t * (sde.N - 1)
-                std = sde.sqrt_1m_alphas_cumprod.to(labels.device)[labels.long()]
+                std = sde.sqrt_1m_alphas_cumprod[labels.long()]
             mult = -1.0 / std
             if model.config.model.scale_by_sigma:
-                mult = mult / model.sigmas[labels.long()]
+                mult = mult / model._sigmas_host()[labels.long()]
             return model.raw_forward(x, labels, mult)
     elif isinstance(sde, sde_lib.VESDE):
         def score_fn(x, t, condition=None, mask=None):
@@ -77,7 +78,7 @@ def sigma_at(model, labels):
     """sigmas[floor(label)] (model.py:159) on the CPU copy of the buffer; 1 if scale_by_sigma is off."""
     if not model.config.model.scale_by_sigma:
         return torch.ones_like(labels)
-    return model.sigmas.detach().cpu()[labels.long()]
+    return model._sigmas_host()[labels.long()]
 
 
 def em_coefficients(sde, model, t, probability_flow=False, continuous=True):
