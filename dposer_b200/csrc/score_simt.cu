@@ -9,9 +9,11 @@
 namespace dpb {
 
 // ------------------------------------------------------------------ time path
-// grid: ceil(n / TT_LABELS) CTAs, 256 threads.  Each CTA handles TT_LABELS labels so the
-// 11.5 MB of time-path weights are read once per TT_LABELS labels.
+// grid: (ceil(n / TT_LABELS), TT_SPLIT) CTAs of 256 threads.  A CTA handles TT_LABELS labels (weights are
+// read once per TT_LABELS labels); blockIdx.y selects 1/TT_SPLIT of the 5x1024 projection outputs.  The
+// 512x512 shared embed is recomputed by every split (cheap) so a single label still spreads over TT_SPLIT SMs.
 constexpr int TT_LABELS = 8;
+constexpr int TT_SPLIT = 16;
 
 struct PtrPack {
   const float* t_w[5];
@@ -62,7 +64,9 @@ __global__ void __launch_bounds__(256) time_table_kernel(
   }
   __syncthreads();
   // five projections W_lt temb + b_lt, with the x-path bias b_l folded in
-  for (int o = warp; o < NL * H; o += 8) {
+  constexpr int PER_SPLIT = NL * H / TT_SPLIT;
+  for (int oo = warp; oo < PER_SPLIT; oo += 8) {
+    const int o = blockIdx.y * PER_SPLIT + oo;
     const int layer = o / H, c = o % H;
     float acc[TT_LABELS];
 #pragma unroll
@@ -190,7 +194,7 @@ int simt_time_table(dpb_score* h, const float* labels, int n, float* table, cuda
   // pointer tables live in constant kernel-parameter space (no device allocation in the call)
   PtrPack p;
   for (int l = 0; l < NL; ++l) { p.t_w[l] = h->t_w[l]; p.t_b[l] = h->t_b[l]; p.lin_b[l] = h->lin_b[l]; }
-  int grid = (n + TT_LABELS - 1) / TT_LABELS;
+  dim3 grid((n + TT_LABELS - 1) / TT_LABELS, TT_SPLIT);
   time_table_kernel<<<grid, 256, 0, st>>>(labels, n, h->emb_freqs, h->temb_w, h->temb_b, p, table);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
