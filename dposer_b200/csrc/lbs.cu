@@ -286,8 +286,10 @@ size_t lbs_ws_bytes(const dpb_lbs* h, int64_t B, bool compact) {
   n += align_up((size_t)B * h->J * 12 * 4, 256) * 2;  // A, G
   n += align_up((size_t)B * h->P * 4, 256);
   n += align_up((size_t)B * h->J * 3 * 4, 256);
-  if (compact) n += align_up((size_t)B * h->n_need * 3 * 4, 256);
-  return n + 1024;
+  n += align_up((size_t)B * h->n_need * 3 * 4, 256) * (compact ? 2 : 1);   // compact verts + gextra
+  n += align_up((size_t)B * h->J * 12 * 4, 256) + align_up((size_t)B * h->P * 4, 256) +
+       align_up((size_t)B * (h->S + 3) * 4, 256);
+  return n + 2048;
 }
 
 bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_bytes, LbsWs* out) {
@@ -296,6 +298,10 @@ bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_by
   out->G = c.take<float>((size_t)B * h->J * 12);
   out->feat = c.take<float>((size_t)B * h->P);
   out->jrest = c.take<float>((size_t)B * h->J * 3);
+  out->gA = c.take<float>((size_t)B * h->J * 12);
+  out->gfeat = c.take<float>((size_t)B * h->P);
+  out->gextra = c.take<float>((size_t)B * h->n_need * 3 + 1);
+  out->gbeta = c.take<float>((size_t)B * (h->S + 3));
   out->compact = compact ? c.take<float>((size_t)B * h->n_need * 3) : nullptr;
   return ws != nullptr && c.ok();
 }
@@ -382,6 +388,8 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
   need.erase(std::unique(need.begin(), need.end()), need.end());
   std::map<int32_t, int32_t> pos;
   for (size_t i = 0; i < need.size(); ++i) pos[need[i]] = (int32_t)i;
+  std::vector<int32_t> nidx(V, -1);
+  for (size_t i = 0; i < need.size(); ++i) nidx[need[i]] = (int32_t)i;
   std::vector<int32_t> epos(std::max(m->n_extra, 1)), lpos(std::max(m->n_lmk * 3, 1));
   for (int i = 0; i < m->n_extra; ++i) epos[i] = pos[m->extra_vids[i]];
   for (int i = 0; i < m->n_lmk * 3; ++i) lpos[i] = pos[m->lmk_faces[i]];
@@ -404,6 +412,7 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
   UP(need_vids, need.data(), need.size());
   UP(extra_pos, epos.data(), m->n_extra);
   UP(lmk_pos, lpos.data(), m->n_lmk * 3);
+  UP(need_index, nidx.data(), V);
 #undef UP
   if (rc == DPB_OK) rc = lbs_tc_prepare(h, m);
   if (rc != DPB_OK) { dpb_lbs_destroy(h); return rc; }
@@ -417,7 +426,7 @@ extern "C" int dpb_lbs_destroy(dpb_lbs_t* h) {
   lbs_tc_release(h);
   void* ptrs[] = {h->v_template, h->shapedirs, h->posedirs, h->j_template, h->j_shapedirs, h->parents, h->depth,
                   h->ell_idx, h->ell_w, h->extra_vids, h->lmk_faces, h->lmk_bary, h->need_vids, h->extra_pos,
-                  h->lmk_pos};
+                  h->lmk_pos, h->need_index};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return DPB_OK;

@@ -31,6 +31,7 @@ struct dpb_lbs {
   int32_t* need_vids = nullptr;   // [n_need] sorted unique vertex ids
   int32_t* extra_pos = nullptr;   // [n_extra] position of extra_vids[i] in need_vids
   int32_t* lmk_pos = nullptr;     // [n_lmk,3]
+  int32_t* need_index = nullptr;  // [V] position in need_vids or -1
   // tensor-core pose-blend operands (lbs_tc.cu)
   bool tc_ready = false;
   int kext = 0;                   // extended K (multiple of 64)
@@ -47,6 +48,11 @@ struct LbsWs {
   float* G;       // [B,J,12]  global transforms (kept for backward)
   float* jrest;   // [B,J,3]
   float* compact; // [B,n_need,3] (joints-only mode)
+  // backward scratch
+  float* gA;      // [B,J,12]   dL/dA
+  float* gfeat;   // [B,P]      dL/dfeat
+  float* gextra;  // [B,n_need,3] joint grads scattered onto the vertices that produce them
+  float* gbeta;   // [B,S+3]    vertex-path part of dL/dbetas | dL/dtransl
 };
 size_t lbs_ws_bytes(const dpb_lbs* h, int64_t B, bool compact);
 bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_bytes, LbsWs* out);

@@ -1,0 +1,404 @@
+// Linear blend skinning, backward (vector-Jacobian product w.r.t. full_pose, betas, transl).
+//
+//   scatter kernel   joint cotangents of the extra vertex joints / landmarks -> the vertices that produce them
+//   vertex kernel    recomputes v_posed (same blend as the forward), then for every (pose, vertex):
+//                      dL/dA[j] += w (g (x) [v_posed;1]),  g_vposed = T_R^T g,  dL/dtransl += g
+//                    and the transposed blend  dL/dfeat = posedirs . g_vposed,  dL/dbeta = shapedirs^T g_vposed
+//                    as an in-CTA [poses x 384] x [384 x (P+S)] product (warp per k, coalesced rows)
+//   pose kernel      warp per pose: dL/dA -> dL/dG, reverse sweep of the kinematic tree (children push into
+//                    their parent), Rodrigues backward, rest-joint cotangents -> dL/dbeta
+//
+// This is the adjoint of lbs.cu (smplx 0.1.28 lbs(); reference call sites lib/body_model/body_model.py:75-88,
+// run/motion_denoising.py:255-268, run/smplify.py:243-258 where autograd differentiates the smplx ops).
+#include "lbs.h"
+
+namespace dpb {
+
+constexpr int BW_TP = 8;
+constexpr int BW_TV = 128;
+
+__global__ void lbs_scatter_joint_grads(const float* __restrict__ g_joints, int n_out, int J, int n_extra, int n_lmk,
+                                        const int32_t* __restrict__ extra_pos, const int32_t* __restrict__ lmk_pos,
+                                        const float* __restrict__ lmk_bary, int n_need, float* __restrict__ gextra,
+                                        int64_t B) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = n_extra + n_lmk * 3;
+  if (i >= B * per) return;
+  const int64_t b = i / per;
+  const int k = (int)(i % per);
+  int q, src;
+  float w = 1.f;
+  if (k < n_extra) {
+    q = extra_pos[k];
+    src = J + k;
+  } else {
+    const int l = (k - n_extra) / 3, f = (k - n_extra) % 3;
+    q = lmk_pos[l * 3 + f];
+    w = lmk_bary[l * 3 + f];
+    src = J + n_extra + l;
+  }
+  const float* g = g_joints + ((size_t)b * n_out + src) * 3;
+  float* o = gextra + ((size_t)b * n_need + q) * 3;
+  atomicAdd(o + 0, w * g[0]);
+  atomicAdd(o + 1, w * g[1]);
+  atomicAdd(o + 2, w * g[2]);
+}
+
+__global__ void __launch_bounds__(BW_TV) lbs_vertex_bwd_kernel(
+    const float* __restrict__ betas, const float* __restrict__ feat, const float* __restrict__ A,
+    const float* __restrict__ v_template, const float* __restrict__ shapedirs, const float* __restrict__ posedirs,
+    const int32_t* __restrict__ ell_idx, const float* __restrict__ ell_w, const int32_t* __restrict__ vlist,
+    const int32_t* __restrict__ need_index, int n_verts, int n_need, int V, int J, int S, int P, int nnz,
+    const float* __restrict__ g_verts, const float* __restrict__ gextra, float* __restrict__ gA,
+    float* __restrict__ gfeat, float* __restrict__ gbt, int64_t B) {
+  extern __shared__ float smem[];
+  float* feat_s = smem;                              // [P][TP]
+  float* beta_s = feat_s + (size_t)P * BW_TP;        // [S][TP]
+  float* A_s = beta_s + (size_t)S * BW_TP;           // [TP][J][12]
+  float* gA_s = A_s + (size_t)BW_TP * J * 12;        // [TP][J][12]
+  float* gvp_s = gA_s + (size_t)BW_TP * J * 12;      // [TP][3*TV]
+  float* gtr_s = gvp_s + (size_t)BW_TP * 3 * BW_TV;  // [TP][3]
+  const int64_t b0 = (int64_t)blockIdx.y * BW_TP;
+  const int np = (int)min((int64_t)BW_TP, B - b0);
+  for (int i = threadIdx.x; i < P * BW_TP; i += BW_TV) {
+    int k = i / BW_TP, p = i % BW_TP;
+    feat_s[i] = p < np ? feat[(b0 + p) * P + k] : 0.f;
+  }
+  for (int i = threadIdx.x; i < S * BW_TP; i += BW_TV) {
+    int k = i / BW_TP, p = i % BW_TP;
+    beta_s[i] = p < np ? betas[(b0 + p) * S + k] : 0.f;
+  }
+  for (int i = threadIdx.x; i < BW_TP * J * 12; i += BW_TV) {
+    A_s[i] = i < np * J * 12 ? A[b0 * J * 12 + i] : 0.f;
+    gA_s[i] = 0.f;
+  }
+  for (int i = threadIdx.x; i < BW_TP * 3 * BW_TV; i += BW_TV) gvp_s[i] = 0.f;
+  if (threadIdx.x < BW_TP * 3) gtr_s[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int v0 = blockIdx.x * BW_TV;
+  const int vi = v0 + threadIdx.x;
+  if (vi < n_verts) {
+    const int v = vlist ? vlist[vi] : vi;
+    float acc[BW_TP][3];
+#pragma unroll
+    for (int p = 0; p < BW_TP; ++p) {
+      acc[p][0] = v_template[v * 3 + 0];
+      acc[p][1] = v_template[v * 3 + 1];
+      acc[p][2] = v_template[v * 3 + 2];
+    }
+    for (int k = 0; k < S; ++k) {
+      float s0 = shapedirs[(v * 3 + 0) * S + k], s1 = shapedirs[(v * 3 + 1) * S + k], s2 = shapedirs[(v * 3 + 2) * S + k];
+#pragma unroll
+      for (int p = 0; p < BW_TP; ++p) {
+        float bv = beta_s[k * BW_TP + p];
+        acc[p][0] = fmaf(s0, bv, acc[p][0]);
+        acc[p][1] = fmaf(s1, bv, acc[p][1]);
+        acc[p][2] = fmaf(s2, bv, acc[p][2]);
+      }
+    }
+    const float* pd = posedirs + (size_t)v * 3;
+    const size_t pstride = (size_t)V * 3;
+    for (int k = 0; k < P; ++k) {
+      float d0 = pd[k * pstride + 0], d1 = pd[k * pstride + 1], d2 = pd[k * pstride + 2];
+#pragma unroll
+      for (int p = 0; p < BW_TP; ++p) {
+        float fv = feat_s[k * BW_TP + p];
+        acc[p][0] = fmaf(d0, fv, acc[p][0]);
+        acc[p][1] = fmaf(d1, fv, acc[p][1]);
+        acc[p][2] = fmaf(d2, fv, acc[p][2]);
+      }
+    }
+    const int q = vlist ? vi : (need_index ? need_index[v] : -1);
+#pragma unroll
+    for (int p = 0; p < BW_TP; ++p) {
+      if (p >= np) break;
+      float g[3] = {0.f, 0.f, 0.f};
+      if (g_verts) {
+        const float* gv = g_verts + ((size_t)(b0 + p) * V + v) * 3;
+        g[0] = gv[0]; g[1] = gv[1]; g[2] = gv[2];
+      }
+      if (q >= 0 && gextra) {
+        const float* ge = gextra + ((size_t)(b0 + p) * n_need + q) * 3;
+        g[0] += ge[0]; g[1] += ge[1]; g[2] += ge[2];
+      }
+      if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
+      float TR[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) TR[e] = 0.f;
+      const float x = acc[p][0], y = acc[p][1], z = acc[p][2];
+      for (int n = 0; n < nnz; ++n) {
+        const float w = ell_w[(size_t)n * V + v];
+        if (w == 0.f) continue;
+        const int j = ell_idx[(size_t)n * V + v];
+        const float* Ap = A_s + ((size_t)p * J + j) * 12;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) TR[e] = fmaf(w, Ap[e], TR[e]);
+        float* gp = gA_s + ((size_t)p * J + j) * 12;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float wg = w * g[i];
+          atomicAdd(gp + i * 3 + 0, wg * x);
+          atomicAdd(gp + i * 3 + 1, wg * y);
+          atomicAdd(gp + i * 3 + 2, wg * z);
+          atomicAdd(gp + 9 + i, wg);
+        }
+      }
+      atomicAdd(gtr_s + p * 3 + 0, g[0]);
+      atomicAdd(gtr_s + p * 3 + 1, g[1]);
+      atomicAdd(gtr_s + p * 3 + 2, g[2]);
+      // g_vposed = T_R^T g
+      gvp_s[(p * BW_TV + threadIdx.x) * 3 + 0] = TR[0] * g[0] + TR[3] * g[1] + TR[6] * g[2];
+      gvp_s[(p * BW_TV + threadIdx.x) * 3 + 1] = TR[1] * g[0] + TR[4] * g[1] + TR[7] * g[2];
+      gvp_s[(p * BW_TV + threadIdx.x) * 3 + 2] = TR[2] * g[0] + TR[5] * g[1] + TR[8] * g[2];
+    }
+  }
+  __syncthreads();
+  // transposed blend: warp per k over the P pose-blend rows and the S shape-blend rows
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncol = min(BW_TV, n_verts - v0) * 3;
+  for (int k = warp; k < P + S; k += BW_TV / 32) {
+    float part[BW_TP];
+#pragma unroll
+    for (int p = 0; p < BW_TP; ++p) part[p] = 0.f;
+    for (int col = lane; col < ncol; col += 32) {
+      const int lv = col / 3, c = col % 3;
+      const int v = vlist ? vlist[v0 + lv] : v0 + lv;
+      const float d = k < P ? posedirs[(size_t)k * V * 3 + (size_t)v * 3 + c]
+                            : shapedirs[((size_t)v * 3 + c) * S + (k - P)];
+#pragma unroll
+      for (int p = 0; p < BW_TP; ++p) part[p] = fmaf(d, gvp_s[p * 3 * BW_TV + col], part[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < BW_TP; ++p)
+      for (int o = 16; o > 0; o >>= 1) part[p] += __shfl_xor_sync(0xffffffffu, part[p], o);
+    if (lane < np) {
+      float val = 0.f;
+#pragma unroll
+      for (int p = 0; p < BW_TP; ++p) val = (lane == p) ? part[p] : val;
+      if (val != 0.f) {
+        if (k < P) atomicAdd(gfeat + (b0 + lane) * P + k, val);
+        else atomicAdd(gbt + (b0 + lane) * (S + 3) + (k - P), val);
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < np * J * 12; i += BW_TV)
+    if (gA_s[i] != 0.f) atomicAdd(gA + b0 * J * 12 + i, gA_s[i]);
+  if (threadIdx.x < np * 3) {
+    const int p = threadIdx.x / 3, c = threadIdx.x % 3;
+    atomicAdd(gbt + (b0 + p) * (S + 3) + S + c, gtr_s[threadIdx.x]);
+  }
+}
+
+// d(loss)/d(axis-angle) from d(loss)/d(R) for R = I + sin(a) K + (1-cos(a)) K^2, a = ||r + 1e-8||, K = skew(r/a)
+__device__ __forceinline__ void rodrigues_bwd(const float* __restrict__ r, const float* __restrict__ gR, float* gr) {
+  const float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;
+  const float a = sqrtf(ex * ex + ey * ey + ez * ez);
+  const float x = r[0] / a, y = r[1] / a, z = r[2] / a;
+  float s, c;
+  sincosf(a, &s, &c);
+  const float oc = 1.0f - c;
+  const float K[9] = {0.f, -z, y, z, 0.f, -x, -y, x, 0.f};
+  const float K2[9] = {-(z * z) - y * y, x * y, x * z, x * y, -(z * z) - x * x, y * z, x * z, y * z, -(y * y) - x * x};
+  float ga = 0.f;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) ga += gR[e] * (c * K[e] + s * K2[e]);
+  // gK = s gR + (1-c)(gR K^T + K^T gR)
+  float gK[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t += gR[i * 3 + k] * K[j * 3 + k] + K[k * 3 + i] * gR[k * 3 + j];
+      gK[i * 3 + j] = s * gR[i * 3 + j] + oc * t;
+    }
+  const float gd[3] = {gK[7] - gK[5], gK[2] - gK[6], gK[3] - gK[1]};
+  const float dot = gd[0] * r[0] + gd[1] * r[1] + gd[2] * r[2];
+  const float ia = 1.0f / a, ia3 = ia * ia * ia;
+  gr[0] = gd[0] * ia - dot * ex * ia3 + ga * ex * ia;
+  gr[1] = gd[1] * ia - dot * ey * ia3 + ga * ey * ia;
+  gr[2] = gd[2] * ia - dot * ez * ia3 + ga * ez * ia;
+}
+
+__device__ __forceinline__ void rodrigues_fwd(const float* __restrict__ p, float* R) {
+  float bx = p[0] + 1e-8f, by = p[1] + 1e-8f, bz = p[2] + 1e-8f;
+  float angle = sqrtf(bx * bx + by * by + bz * bz);
+  float x = p[0] / angle, y = p[1] / angle, z = p[2] / angle;
+  float s, c;
+  sincosf(angle, &s, &c);
+  float oc = 1.0f - c;
+  R[0] = 1.0f + oc * (-(z * z) - y * y); R[1] = s * (-z) + oc * (x * y); R[2] = s * y + oc * (x * z);
+  R[3] = s * z + oc * (x * y); R[4] = 1.0f + oc * (-(z * z) - x * x); R[5] = s * (-x) + oc * (y * z);
+  R[6] = s * (-y) + oc * (x * z); R[7] = s * x + oc * (y * z); R[8] = 1.0f + oc * (-(y * y) - x * x);
+}
+
+// one warp per pose, 4 poses per CTA; smem per warp: gG [J][12] + gJ [J][3]
+__global__ void __launch_bounds__(128) lbs_pose_bwd_kernel(
+    const float* __restrict__ pose, const float* __restrict__ G, const float* __restrict__ jrest,
+    const float* __restrict__ gA, const float* __restrict__ gfeat, const float* __restrict__ gbt,
+    const float* __restrict__ g_joints, const float* __restrict__ j_shapedirs, const int32_t* __restrict__ parents,
+    const int32_t* __restrict__ depth, int J, int S, int max_depth, int n_out, float* __restrict__ g_pose,
+    float* __restrict__ g_betas, float* __restrict__ g_transl, int64_t B) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 4 + warp;
+  if (b >= B) return;
+  float* gG = smem + (size_t)warp * J * 15;
+  float* gJ = gG + (size_t)J * 12;
+  const int P = (J - 1) * 9;
+  float gt[3] = {0.f, 0.f, 0.f};
+  for (int j = lane; j < J; j += 32) {
+    const float* a = gA + (b * J + j) * 12;
+    const float* g = G + (b * J + j) * 12;
+    const float* jr = jrest + (b * J + j) * 3;
+    float gj[3] = {0.f, 0.f, 0.f};
+    if (g_joints) {
+      const float* q = g_joints + ((size_t)b * n_out + j) * 3;
+      gj[0] = q[0]; gj[1] = q[1]; gj[2] = q[2];
+      gt[0] += gj[0]; gt[1] += gj[1]; gt[2] += gj[2];
+    }
+    // A_R = G_R, A_t = G_t - G_R jrest
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gG[j * 12 + i * 3 + k] = a[i * 3 + k] - a[9 + i] * jr[k];
+      gG[j * 12 + 9 + i] = a[9 + i] + gj[i];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gJ[j * 3 + k] = -(g[0 * 3 + k] * a[9] + g[1 * 3 + k] * a[10] + g[2 * 3 + k] * a[11]);
+  }
+  __syncwarp();
+  // reverse sweep: children (depth d) push into their parents
+  for (int d = max_depth; d >= 1; --d) {
+    for (int j = lane; j < J; j += 32) {
+      if (depth[j] != d) continue;
+      const int p = parents[j];
+      float R[9];
+      rodrigues_fwd(pose + (b * J + j) * 3, R);
+      const float* gp = G + (b * J + p) * 12;
+      float rel[3], gg[12];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) rel[k] = jrest[(b * J + j) * 3 + k] - jrest[(b * J + p) * 3 + k];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) gg[e] = gG[j * 12 + e];
+      // parent: gG_R,p += gG_R,j R_j^T + gG_t,j (x) rel ; gG_t,p += gG_t,j
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float t = gg[i * 3 + 0] * R[k * 3 + 0] + gg[i * 3 + 1] * R[k * 3 + 1] + gg[i * 3 + 2] * R[k * 3 + 2] +
+                    gg[9 + i] * rel[k];
+          atomicAdd(gG + p * 12 + i * 3 + k, t);
+        }
+        atomicAdd(gG + p * 12 + 9 + i, gg[9 + i]);
+      }
+      // own local transform: g_R_j = G_R,p^T gG_R,j (kept in place), g_rel = G_R,p^T gG_t,j
+      float gl[12];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          gl[i * 3 + k] = gp[0 * 3 + i] * gg[0 * 3 + k] + gp[1 * 3 + i] * gg[1 * 3 + k] + gp[2 * 3 + i] * gg[2 * 3 + k];
+        gl[9 + i] = gp[0 * 3 + i] * gg[9] + gp[1 * 3 + i] * gg[10] + gp[2 * 3 + i] * gg[11];
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) gG[j * 12 + e] = gl[e];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        atomicAdd(gJ + j * 3 + k, gl[9 + k]);
+        atomicAdd(gJ + p * 3 + k, -gl[9 + k]);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {  // root: M_0 = G_0, rel_0 = jrest_0
+    gJ[0] += gG[9]; gJ[1] += gG[10]; gJ[2] += gG[11];
+  }
+  __syncwarp();
+  // Rodrigues backward (gG[j][0..8] now holds dL/dR_j of the local rotation)
+  for (int j = lane; j < J; j += 32) {
+    float gR[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) gR[e] = gG[j * 12 + e] + (j > 0 ? gfeat[b * P + (j - 1) * 9 + e] : 0.f);
+    float gr[3];
+    rodrigues_bwd(pose + (b * J + j) * 3, gR, gr);
+    if (g_pose) {
+      g_pose[(b * J + j) * 3 + 0] = gr[0];
+      g_pose[(b * J + j) * 3 + 1] = gr[1];
+      g_pose[(b * J + j) * 3 + 2] = gr[2];
+    }
+  }
+  if (g_betas) {
+    for (int s = 0; s < S; ++s) {
+      float part = 0.f;
+      for (int j = lane; j < J; j += 32)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) part = fmaf(j_shapedirs[(j * 3 + c) * S + s], gJ[j * 3 + c], part);
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) g_betas[b * S + s] = part + gbt[b * (S + 3) + s];
+    }
+  }
+  if (g_transl) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      for (int o = 16; o > 0; o >>= 1) gt[c] += __shfl_xor_sync(0xffffffffu, gt[c], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g_transl[b * 3 + c] = gt[c] + gbt[b * (S + 3) + S + c];
+    }
+  }
+}
+
+}  // namespace dpb
+
+using namespace dpb;
+
+extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* full_pose, const float* g_verts,
+                                const float* g_joints, float* g_pose, float* g_betas, float* g_transl, int64_t B,
+                                int flags, void* ws, size_t ws_bytes, void* stream) {
+  (void)flags;
+  if (!h) return fail(DPB_EINVAL, "dpb_lbs_backward: null handle");
+  DPB_REQUIRE(betas && full_pose, "dpb_lbs_backward: betas and full_pose are required");
+  DPB_REQUIRE(g_verts || g_joints, "dpb_lbs_backward: need g_verts and/or g_joints");
+  if (B <= 0) return DPB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LbsWs w;
+  if (!lbs_carve(h, B, false, ws, ws_bytes, &w)) return fail(DPB_ENOMEM, "dpb_lbs_backward: workspace too small");
+  const int J = h->J, S = h->S, P = h->P;
+  DPB_CUDA_CHECK(cudaMemsetAsync(w.gA, 0, (size_t)B * J * 12 * 4, st));
+  DPB_CUDA_CHECK(cudaMemsetAsync(w.gfeat, 0, (size_t)B * P * 4, st));
+  DPB_CUDA_CHECK(cudaMemsetAsync(w.gbeta, 0, (size_t)B * (S + 3) * 4, st));
+  const int per = h->n_extra + h->n_lmk * 3;
+  const bool have_extra = g_joints && per > 0 && h->n_need > 0;
+  if (have_extra) {
+    DPB_CUDA_CHECK(cudaMemsetAsync(w.gextra, 0, (size_t)B * h->n_need * 3 * 4, st));
+    int64_t n = B * per;
+    lbs_scatter_joint_grads<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g_joints, h->n_out, J, h->n_extra, h->n_lmk,
+                                                                          h->extra_pos, h->lmk_pos, h->lmk_bary,
+                                                                          h->n_need, w.gextra, B);
+    DPB_CUDA_CHECK(cudaGetLastError());
+  }
+  const bool full = g_verts != nullptr;
+  const int n_verts = full ? h->V : h->n_need;
+  if (full || have_extra) {
+    size_t smem = ((size_t)P * BW_TP + (size_t)S * BW_TP + 2 * (size_t)BW_TP * J * 12 + (size_t)BW_TP * 3 * BW_TV +
+                   BW_TP * 3) * 4;
+    DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_vertex_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((n_verts + BW_TV - 1) / BW_TV, (unsigned)((B + BW_TP - 1) / BW_TP));
+    DPB_REQUIRE(grid.y <= 65535u, "dpb_lbs_backward: batch too large for one call (max 65535*8 poses)");
+    lbs_vertex_bwd_kernel<<<grid, BW_TV, smem, st>>>(betas, w.feat, w.A, h->v_template, h->shapedirs, h->posedirs,
+                                                     h->ell_idx, h->ell_w, full ? nullptr : h->need_vids,
+                                                     full ? h->need_index : nullptr, n_verts, h->n_need, h->V, J, S,
+                                                     P, h->nnz, g_verts, have_extra ? w.gextra : nullptr, w.gA,
+                                                     w.gfeat, w.gbeta, B);
+    DPB_CUDA_CHECK(cudaGetLastError());
+  }
+  size_t psmem = (size_t)4 * J * 15 * 4;
+  lbs_pose_bwd_kernel<<<(unsigned)((B + 3) / 4), 128, psmem, st>>>(full_pose, w.G, w.jrest, w.gA, w.gfeat, w.gbeta,
+                                                                    g_joints, h->j_shapedirs, h->parents, h->depth, J,
+                                                                    S, h->max_depth, h->n_out, g_pose, g_betas,
+                                                                    g_transl, B);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}

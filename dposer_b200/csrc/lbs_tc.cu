@@ -10,7 +10,3 @@ int lbs_tc_vertices(dpb_lbs* h, const float*, const float*, const LbsWs&, float*
 }
 }  // namespace dpb
 
-extern "C" int dpb_lbs_backward(dpb_lbs_t*, const float*, const float*, const float*, const float*, float*, float*,
-                                float*, int64_t, int, void*, size_t, void*) {
-  return dpb::fail(DPB_EUNSUPPORTED, "dpb_lbs_backward: not implemented yet");
-}

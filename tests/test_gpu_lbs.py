@@ -92,3 +92,45 @@ def test_smplify_wrapper_joints():
     _, j_ref = lbs_ref.body_forward(m, torch.cat([betas, torch.zeros(B, 10)], 1), full, transl)
     assert out.joints.shape == (B, 49, 3)
     assert (out.joints.cpu() - j_ref[:, smpl.joint_map]).abs().max() < TOL_M
+
+
+@pytest.mark.parametrize('mt,B,use_verts', [('smpl', 5, True), ('smpl', 19, False), ('smplx', 6, True),
+                                            ('smplx', 9, False)])
+def test_lbs_backward_vs_autograd_oracle(mt, B, use_verts):
+    """dpb_lbs_backward (VJP wrt pose, betas, transl) against torch autograd through the CPU oracle."""
+    m = synthetic.make_body_tensors(mt)
+    inp = synthetic.lbs_inputs(B, mt, seed=5)
+    if mt == 'smplx':   # exercise hands / jaw / eyes too
+        g0 = torch.Generator().manual_seed(9)
+        inp['pose_hand'] = torch.randn(B, 90, generator=g0) * 0.2
+        inp['pose_jaw'] = torch.randn(B, 3, generator=g0) * 0.2
+        inp['pose_eye'] = torch.randn(B, 6, generator=g0) * 0.2
+        inp['expression'] = torch.randn(B, 10, generator=g0)
+    g = torch.Generator().manual_seed(17)
+    nj = 45 if mt == 'smpl' else 127
+    V = m['v_template'].shape[0]
+    gv = torch.randn(B, V, 3, generator=g) / V
+    gj = torch.randn(B, nj, 3, generator=g)
+    # ---- oracle autograd
+    leaf = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    if mt == 'smpl':
+        pose = torch.cat([leaf['root_orient'], leaf['pose_body']], 1)
+        shape = leaf['betas']
+    else:
+        pose = torch.cat([leaf['root_orient'], leaf['pose_body'], leaf['pose_jaw'], leaf['pose_eye'],
+                          leaf['pose_hand']], 1)
+        shape = torch.cat([leaf['betas'], leaf['expression']], 1)
+    v_ref, j_ref = lbs_ref.body_forward(m, shape, pose, leaf['trans'])
+    loss = (j_ref * gj).sum() + ((v_ref * gv).sum() if use_verts else 0.0)
+    loss.backward()
+    # ---- device
+    bm = BodyModel(m, num_betas=10, batch_size=B, model_type=mt).cuda()
+    dl = {k: v.clone().cuda().requires_grad_(True) for k, v in inp.items()}
+    out = bm(need_verts=use_verts, **dl)
+    l2 = (out.Jtr * gj.cuda()).sum() + ((out.v * gv.cuda()).sum() if use_verts else 0.0)
+    l2.backward()
+    for k in inp:
+        ref, got = leaf[k].grad, dl[k].grad.cpu()
+        scale = ref.abs().max().clamp_min(1e-6)
+        err = (got - ref).abs().max() / scale
+        assert err < 2e-4, (k, float(err))
