@@ -36,7 +36,7 @@ constexpr int XA_K = 192;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int PAR_BYTES = 3 * H * 4;
-constexpr int NUM_BARS = 2 * STAGES + 5;
+constexpr int NUM_BARS = 2 * STAGES + 9;  // full, empty, tfull[2], tempty[2], xa, act[4]
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PAR_BYTES + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
 constexpr uint32_t IDESC_F16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 0);
 constexpr uint32_t IDESC_BF16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 1);
@@ -69,6 +69,15 @@ struct KParams {
   __half* act_t;
   __nv_bfloat16* xa;
 };
+
+__device__ __forceinline__ uint4 ld_global_v4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_global_v4(uint4* p, uint4 v) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ int layer_nk(int layer) { return layer == 0 ? XA_K / BLOCK_K : H / BLOCK_K; }
 __device__ __forceinline__ int layer_chunks(int layer) { return layer == 5 ? 1 : H / CHUNK_N; }
@@ -119,7 +128,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
                 const __grid_constant__ CUtensorMap tm_w3, const __grid_constant__ CUtensorMap tm_post) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for SWIZZLE_128B; offset arithmetic on the __shared__ array keeps ld/st.shared
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = ptx::smem_u32(smem);
   float* par = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [tb | gamma | beta] x 1024
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + PAR_BYTES;
@@ -127,7 +137,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-  const uint32_t act_bar = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t xa_bar = bar_base + 8u * (2 * STAGES + 4);                                // first-layer operand ready
+  auto act_bar = [&](uint32_t c) { return bar_base + 8u * (2 * STAGES + 5 + c); };       // column chunk c of a hidden layer ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + PAR_BYTES + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,7 +151,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       ptx::mbar_init(tfull_bar(b), 1);   // tcgen05.commit
       ptx::mbar_init(tempty_bar(b), 8);  // one lane of each epilogue warp
     }
-    ptx::mbar_init(act_bar, 8);
+    ptx::mbar_init(xa_bar, 8);
+    for (int c = 0; c < 4; ++c) ptx::mbar_init(act_bar(c), 8);
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -214,22 +226,29 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   } else if (warp == 2) {
     // ======================= activation producer =======================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, aph = 0;
+      uint32_t stage = 0, phase = 0, xph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
         for (int step = 0; step < p.n_steps; ++step)
           for (int layer = 0; layer < 6; ++layer) {
             // layer input: xa | H | T | H | T | H
             const CUtensorMap* tm = layer == 0 ? &tm_xa : (layer == 2 || layer == 4) ? &tm_t : &tm_h;
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
-            ptx::mbar_wait(act_bar, aph);  // the epilogue finished writing this layer's input
-            aph ^= 1;
+            if (layer == 0) {
+              ptx::mbar_wait(xa_bar, xph);  // prologue / previous step's tail wrote the x operand
+              xph ^= 1;
+            }
             for (int chunk = 0; chunk < nc; ++chunk)
               for (int k = 0; k < nk; ++k) {
+                // K-slabs 4c..4c+3 of this layer's input are column chunk c of the previous layer's output:
+                // wait for exactly that chunk (first pass only), so the next layer starts while the previous
+                // layer's last chunks are still in the epilogue
+                if (layer > 0 && chunk == 0 && (k & 3) == 0) ptx::mbar_wait(act_bar(k >> 2), aph);
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                 ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
                 ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), k * BLOCK_K, slot_row0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
+            if (layer > 0) aph ^= 1;
           }
     }
   } else if (warp >= 4) {
@@ -240,11 +259,11 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     const int r_in = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t chunk_ctr = 0, tph = 0;
-    auto signal_act = [&]() {
+    auto signal = [&](uint32_t bar) {  // generic-proxy global writes -> visible to the TMA (async proxy) reads
       __threadfence();
       ptx::fence_proxy_async_global();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(act_bar);
+      if (lane == 0) ptx::mbar_arrive(bar);
     };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long row = (long long)tile * TILE_M + r_in;
@@ -296,7 +315,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           }
         }
         write_xa(xarow, hf, x);
-        signal_act();
+        signal(xa_bar);
       }
       for (int step = 0; step < p.n_steps; ++step) {
         // ---------------- hidden layers 0..4
@@ -318,6 +337,12 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             const uint32_t buf = chunk_ctr & 1;
             ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
             ptx::tc_fence_after();
+            uint4 rnext[4];
+            if (residual) {  // prefetch the first group's residual (L2 latency) before waiting on TMEM
+              const uint4* rp = reinterpret_cast<const uint4*>(drow + chunk * CHUNK_N + hf * 128);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rnext[i] = ld_global_v4(rp + i);
+            }
 #pragma unroll 1
             for (int gi = 0; gi < 4; ++gi) {
               const int g = hf * 4 + gi;
@@ -351,11 +376,14 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               const float rstd = rsqrtf(qv * (1.0f / GROUP) + GN_EPS);
               uint32_t res[16];
               if (residual) {
-                const uint4* rp = reinterpret_cast<const uint4*>(drow + col0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  uint4 r4 = rp[i];
-                  res[4 * i] = r4.x; res[4 * i + 1] = r4.y; res[4 * i + 2] = r4.z; res[4 * i + 3] = r4.w;
+                  res[4 * i] = rnext[i].x; res[4 * i + 1] = rnext[i].y; res[4 * i + 2] = rnext[i].z; res[4 * i + 3] = rnext[i].w;
+                }
+                if (gi < 3) {  // next group's residual goes in flight under this group's math
+                  const uint4* rp = reinterpret_cast<const uint4*>(drow + col0 + 32);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) rnext[i] = ld_global_v4(rp + i);
                 }
               }
               uint32_t packed[16];
@@ -381,12 +409,12 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               uint4* dp = reinterpret_cast<uint4*>(drow + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                dp[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                st_global_v4(dp + i, make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]));
             }
             tph ^= 1u << buf;
             ++chunk_ctr;
+            signal(act_bar(chunk));  // columns [256 chunk, 256 chunk + 256) of this layer's output are in the scratch
           }
-          signal_act();  // this layer's output (next layer's A operand) is in the scratch
         }
         // ---------------- post_dense + mode-specific tail
         {
@@ -476,7 +504,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             }
             if (!last) {
               write_xa(xarow, hf, x);
-              signal_act();
+              signal(xa_bar);
             }
           } else {  // prior loss
             float acc = 0.f;
