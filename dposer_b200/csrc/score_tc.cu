@@ -28,6 +28,7 @@ constexpr int TILE_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int CHUNK_N = 256;
 constexpr int STAGES = 4;
+constexpr int CLUSTER = 2;   // CTAs (different row tiles) that share every weight tile through TMA multicast
 constexpr int A_BYTES = TILE_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_BYTES = CHUNK_N * BLOCK_K * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -121,7 +122,7 @@ __device__ __forceinline__ void draw32(const float* plane, long long row, int hf
   }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUtensorMap tm_xa,
                 const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_t,
                 const __grid_constant__ CUtensorMap tm_pre, const __grid_constant__ CUtensorMap tm_w0,
@@ -145,7 +146,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), 2);   // A producer + W producer (each arrive.expect_tx)
-      ptx::mbar_init(empty_bar(s), 1);  // tcgen05.commit
+      ptx::mbar_init(empty_bar(s), CLUSTER);  // tcgen05.commit of every CTA in the cluster (weights are shared)
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tfull_bar(b), 1);   // tcgen05.commit
@@ -166,15 +167,21 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) ptx::cluster_sync();  // peers' barriers are initialised before anyone multicasts / arrives remotely
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int slot_row0 = blockIdx.x * TILE_M;  // this CTA's rows in the scratch buffers
+  const uint32_t crank = CLUSTER > 1 ? ptx::cluster_ctarank() : 0;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
+  // every CTA of a cluster runs the same number of rounds (ghost tiles beyond n_tiles keep feeding the shared
+  // weight pipeline; all their rows are >= B so nothing is written)
+  const int rounds = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     // ======================= weight producer =======================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+      for (int rnd = 0; rnd < rounds; ++rnd)
         for (int step = 0; step < p.n_steps; ++step)
           for (int layer = 0; layer < 6; ++layer) {
             const CUtensorMap* tm = layer == 0 ? &tm_pre : layer == 1 ? &tm_w0 : layer == 2 ? &tm_w1
@@ -183,10 +190,15 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
             for (int chunk = 0; chunk < nc; ++chunk)
               for (int k = 0; k < nk; ++k) {
-                ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-                ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);
-                ptx::tma_load_2d(smem_base + stage * STAGE_BYTES + A_BYTES, tm, full_bar(stage), k * BLOCK_K,
-                                 chunk * CHUNK_N);
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1);  // every CTA of the cluster has consumed this stage
+                ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);  // whole tile: own part + the peers' multicasts
+                const int part_rows = (layer == 5 ? DP : CHUNK_N) / CLUSTER;
+                const uint32_t dst = smem_base + stage * STAGE_BYTES + A_BYTES + crank * part_rows * (BLOCK_K * 2);
+                if (CLUSTER > 1)
+                  ptx::tma_load_2d_mcast(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N + crank * part_rows,
+                                         CMASK);
+                else
+                  ptx::tma_load_2d(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
           }
@@ -195,7 +207,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     // ======================= MMA issuer =======================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, chunk_ctr = 0, tph = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+      for (int rnd = 0; rnd < rounds; ++rnd)
         for (int step = 0; step < p.n_steps; ++step)
           for (int layer = 0; layer < 6; ++layer) {
             const uint32_t idesc = layer == 0 ? IDESC_BF16_256 : layer == 5 ? IDESC_F16_64 : IDESC_F16_256;
@@ -214,7 +226,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
 #pragma unroll
                 for (int kk = 0; kk < BLOCK_K / 16; ++kk)  // UMMA_K = 16: advance 32 B inside the swizzle row
                   ptx::mma_f16_ss(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-                ptx::mma_commit(empty_bar(stage));
+                if (CLUSTER > 1) ptx::mma_commit_mcast(empty_bar(stage), CMASK);
+                else ptx::mma_commit(empty_bar(stage));
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
               ptx::mma_commit(tfull_bar(buf));
@@ -227,7 +240,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     // ======================= activation producer =======================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, xph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+      for (int rnd = 0; rnd < rounds; ++rnd)
         for (int step = 0; step < p.n_steps; ++step)
           for (int layer = 0; layer < 6; ++layer) {
             // layer input: xa | H | T | H | T | H
@@ -265,7 +278,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar);
     };
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int rnd = 0; rnd < rounds; ++rnd) {
+      const int tile = blockIdx.x + rnd * (int)gridDim.x;
       const long long row = (long long)tile * TILE_M + r_in;
       const bool valid = row < p.B;
       const size_t srow = (size_t)(slot_row0 + r_in);
@@ -534,6 +548,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     }
   }
   __syncthreads();
+  if (CLUSTER > 1) ptx::cluster_sync();  // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -606,10 +621,13 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
   DPB_CUDA_CHECK(cudaMemset(h->xa, 0, rows * tc::XA_K * sizeof(__nv_bfloat16)));
   int rc = DPB_OK;
   for (int l = 0; l < 4 && rc == DPB_OK; ++l)
-    rc = make_tmap_2d(&h->tm_w[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->w16[l], H, H, tc::BLOCK_K, tc::CHUNK_N, 2);
-  if (rc == DPB_OK) rc = make_tmap_2d(&h->tm_post, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->post16, H, DP, tc::BLOCK_K, DP, 2);
+    rc = make_tmap_2d(&h->tm_w[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->w16[l], H, H, tc::BLOCK_K,
+                      tc::CHUNK_N / tc::CLUSTER, 2);
+  if (rc == DPB_OK) rc = make_tmap_2d(&h->tm_post, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->post16, H, DP, tc::BLOCK_K,
+                                    DP / tc::CLUSTER, 2);
   if (rc == DPB_OK)
-    rc = make_tmap_2d(&h->tm_pre, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, h->pre_split, tc::XA_K, H, tc::BLOCK_K, tc::CHUNK_N, 2);
+    rc = make_tmap_2d(&h->tm_pre, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, h->pre_split, tc::XA_K, H, tc::BLOCK_K,
+                      tc::CHUNK_N / tc::CLUSTER, 2);
   if (rc == DPB_OK)
     rc = make_tmap_2d(&h->tm_act_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->act_h, H, rows, tc::BLOCK_K, tc::TILE_M, 2);
   if (rc == DPB_OK)
@@ -649,7 +667,10 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   p.z = j.z; p.loss_out = j.loss_out; p.grad_out = j.grad_out; p.row_loss = j.row_loss;
   p.act_h = h->act_h; p.act_t = h->act_t; p.xa = h->xa;
   if (j.mode == 2 && j.row_loss) DPB_CUDA_CHECK(cudaMemsetAsync(j.row_loss, 0, sizeof(float) * j.B, st));
-  const int grid = p.n_tiles < h->tc_slots ? p.n_tiles : h->tc_slots;
+  // grid: a multiple of the cluster size, at most one CTA per scratch slot
+  int grid = (p.n_tiles + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
+  const int max_grid = h->tc_slots / tc::CLUSTER * tc::CLUSTER;
+  if (grid > max_grid) grid = max_grid;
   tc::score_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, h->tm_xa, h->tm_act_h, h->tm_act_t, h->tm_pre,
                                                                     h->tm_w[0], h->tm_w[1], h->tm_w[2], h->tm_w[3],
                                                                     h->tm_post);
