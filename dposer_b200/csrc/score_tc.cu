@@ -16,6 +16,7 @@
 // sampling.py:182-188 and imputation :413-422; identical formulas / Philox addressing as sampler.cu.
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "ptx.cuh"
@@ -28,6 +29,7 @@ constexpr int TILE_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int CHUNK_N = 256;
 constexpr int STAGES = 4;
+constexpr int NSUB = 2;      // row tiles in flight per CTA: one tile's epilogue overlaps the other tile's MMAs
 constexpr int CLUSTER = 2;   // CTAs (different row tiles) that share every weight tile through TMA multicast
 constexpr int A_BYTES = TILE_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_BYTES = CHUNK_N * BLOCK_K * 2;  // 32 KB
@@ -37,7 +39,7 @@ constexpr int XA_K = 192;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int PAR_BYTES = 3 * H * 4;
-constexpr int NUM_BARS = 2 * STAGES + 9;  // full, empty, tfull[2], tempty[2], xa, act[4]
+constexpr int NUM_BARS = 2 * STAGES + 4 + NSUB * 5;  // full, empty, tfull[2], tempty[2], xa[NSUB], act[NSUB][4]
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PAR_BYTES + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
 constexpr uint32_t IDESC_F16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 0);
 constexpr uint32_t IDESC_BF16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 1);
@@ -45,6 +47,7 @@ constexpr uint32_t IDESC_F16_64 = ptx::umma_idesc_f16(TILE_M, DP, 0);
 
 struct KParams {
   int mode, n_steps, impute, noise_k, n_tiles;
+  int debug;  // timing experiments only (DPB_TC_DEBUG): 1 = skip hidden-layer epilogue math, 2 = skip MMAs
   long long B;
   const float* x_in;
   float* x_io;
@@ -78,6 +81,93 @@ __device__ __forceinline__ uint4 ld_global_v4(const uint4* p) {
 }
 __device__ __forceinline__ void st_global_v4(uint4* p, uint4 v) {
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 on sm_100) and MUFU approximations
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One thread, one row, one GroupNorm group (32 consecutive channels):  acc + time bias -> GroupNorm -> SiLU
+// (-> + residual) -> 32 fp16 values.  Reductions use four independent partial sums (short dependency chains);
+// the elementwise math is packed two channels per instruction.
+__device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* tb, const float* gm, const float* bt,
+                                              bool residual, const uint4* res, uint4* out) {
+  float2 v[16];
+  float2 s[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float4 t4 = *reinterpret_cast<const float4*>(tb + 2 * i);
+    v[i] = add2(make_float2(__uint_as_float(vr[2 * i]), __uint_as_float(vr[2 * i + 1])), make_float2(t4.x, t4.y));
+    v[i + 1] = add2(make_float2(__uint_as_float(vr[2 * i + 2]), __uint_as_float(vr[2 * i + 3])), make_float2(t4.z, t4.w));
+    s[(i >> 1) & 3] = add2(s[(i >> 1) & 3], add2(v[i], v[i + 1]));
+  }
+  const float2 st = add2(add2(s[0], s[1]), add2(s[2], s[3]));
+  const float mean = (st.x + st.y) * (1.0f / GROUP);
+  const float2 nm = make_float2(-mean, -mean);
+  float2 q[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = add2(v[i], nm);
+    q[i & 3] = fma2(v[i], v[i], q[i & 3]);
+  }
+  const float2 qt = add2(add2(q[0], q[1]), add2(q[2], q[3]));
+  const float rstd = rsqrtf((qt.x + qt.y) * (1.0f / GROUP) + GN_EPS);
+  const float2 r2 = make_float2(rstd, rstd);
+  const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f);
+  const float2 one = make_float2(1.0f, 1.0f);
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float4 g4 = *reinterpret_cast<const float4*>(gm + 2 * i);
+    const float4 b4 = *reinterpret_cast<const float4*>(bt + 2 * i);
+    float2 y0 = fma2(v[i], mul2(r2, make_float2(g4.x, g4.y)), make_float2(b4.x, b4.y));
+    float2 y1 = fma2(v[i + 1], mul2(r2, make_float2(g4.z, g4.w)), make_float2(b4.z, b4.w));
+    // SiLU: y / (1 + 2^(-y log2 e))
+    float2 e0 = mul2(y0, nl2e), e1 = mul2(y1, nl2e);
+    e0 = make_float2(ex2_approx(e0.x), ex2_approx(e0.y));
+    e1 = make_float2(ex2_approx(e1.x), ex2_approx(e1.y));
+    e0 = add2(e0, one);
+    e1 = add2(e1, one);
+    y0 = mul2(y0, make_float2(rcp_approx(e0.x), rcp_approx(e0.y)));
+    y1 = mul2(y1, make_float2(rcp_approx(e1.x), rcp_approx(e1.y)));
+    if (residual) {
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
+      y0 = add2(y0, __half22float2(*reinterpret_cast<const __half2*>(&rw[i])));
+      y1 = add2(y1, __half22float2(*reinterpret_cast<const __half2*>(&rw[i + 1])));
+    }
+    __half2 p0 = __floats2half2_rn(y0.x, y0.y), p1 = __floats2half2_rn(y1.x, y1.y);
+    pk[i] = *reinterpret_cast<uint32_t*>(&p0);
+    pk[i + 1] = *reinterpret_cast<uint32_t*>(&p1);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
 }
 
 __device__ __forceinline__ int layer_nk(int layer) { return layer == 0 ? XA_K / BLOCK_K : H / BLOCK_K; }
@@ -138,8 +228,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + b); };
   auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-  const uint32_t xa_bar = bar_base + 8u * (2 * STAGES + 4);                                // first-layer operand ready
-  auto act_bar = [&](uint32_t c) { return bar_base + 8u * (2 * STAGES + 5 + c); };       // column chunk c of a hidden layer ready
+  auto xa_bar = [&](uint32_t sub) { return bar_base + 8u * (2 * STAGES + 4 + sub); };     // first-layer operand of tile `sub` ready
+  auto act_bar = [&](uint32_t sub, uint32_t c) {                                          // column chunk c of a hidden layer ready
+    return bar_base + 8u * (2 * STAGES + 4 + NSUB + sub * 4 + c);
+  };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + PAR_BYTES + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -152,8 +244,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       ptx::mbar_init(tfull_bar(b), 1);   // tcgen05.commit
       ptx::mbar_init(tempty_bar(b), 8);  // one lane of each epilogue warp
     }
-    ptx::mbar_init(xa_bar, 8);
-    for (int c = 0; c < 4; ++c) ptx::mbar_init(act_bar(c), 8);
+    for (int sub = 0; sub < NSUB; ++sub) {
+      ptx::mbar_init(xa_bar(sub), 8);
+      for (int c = 0; c < 4; ++c) ptx::mbar_init(act_bar(sub, c), 8);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -170,12 +264,14 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   if (CLUSTER > 1) ptx::cluster_sync();  // peers' barriers are initialised before anyone multicasts / arrives remotely
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int slot_row0 = blockIdx.x * TILE_M;  // this CTA's rows in the scratch buffers
+  const int slot_row0 = blockIdx.x * NSUB * TILE_M;  // this CTA's rows in the scratch buffers (NSUB slots)
   const uint32_t crank = CLUSTER > 1 ? ptx::cluster_ctarank() : 0;
   constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
   // every CTA of a cluster runs the same number of rounds (ghost tiles beyond n_tiles keep feeding the shared
   // weight pipeline; all their rows are >= B so nothing is written)
-  const int rounds = (p.n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  // a CTA works on NSUB row tiles at once: tiles NSUB*g .. NSUB*g+NSUB-1 of tile group g = blockIdx.x + rnd*gridDim.x
+  const int n_groups = (p.n_tiles + NSUB - 1) / NSUB;
+  const int rounds = (n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
     // ======================= weight producer =======================
@@ -189,6 +285,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             const uint32_t bytes = layer == 5 ? POST_B_BYTES : B_BYTES;
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
             for (int chunk = 0; chunk < nc; ++chunk)
+             for (int sub = 0; sub < NSUB; ++sub)
               for (int k = 0; k < nk; ++k) {
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1);  // every CTA of the cluster has consumed this stage
                 ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);  // whole tile: own part + the peers' multicasts
@@ -212,7 +309,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           for (int layer = 0; layer < 6; ++layer) {
             const uint32_t idesc = layer == 0 ? IDESC_BF16_256 : layer == 5 ? IDESC_F16_64 : IDESC_F16_256;
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
-            for (int chunk = 0; chunk < nc; ++chunk) {
+            for (int cs = 0; cs < nc * NSUB; ++cs) {   // (chunk, sub) pairs; chunk_ctr & 1 == sub
               const uint32_t buf = chunk_ctr & 1;
               ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
               ptx::tc_fence_after();
@@ -223,6 +320,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
                 const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
                 const uint64_t bdesc = ptx::umma_desc_sw128(a_addr + A_BYTES);
+                if (!(p.debug & 2))
 #pragma unroll
                 for (int kk = 0; kk < BLOCK_K / 16; ++kk)  // UMMA_K = 16: advance 32 B inside the swizzle row
                   ptx::mma_f16_ss(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
@@ -246,22 +344,23 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             // layer input: xa | H | T | H | T | H
             const CUtensorMap* tm = layer == 0 ? &tm_xa : (layer == 2 || layer == 4) ? &tm_t : &tm_h;
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
-            if (layer == 0) {
-              ptx::mbar_wait(xa_bar, xph);  // prologue / previous step's tail wrote the x operand
-              xph ^= 1;
-            }
             for (int chunk = 0; chunk < nc; ++chunk)
+             for (int sub = 0; sub < NSUB; ++sub) {
+              if (layer == 0 && chunk == 0) ptx::mbar_wait(xa_bar(sub), xph);  // prologue / previous step's tail wrote x
               for (int k = 0; k < nk; ++k) {
                 // K-slabs 4c..4c+3 of this layer's input are column chunk c of the previous layer's output:
                 // wait for exactly that chunk (first pass only), so the next layer starts while the previous
                 // layer's last chunks are still in the epilogue
-                if (layer > 0 && chunk == 0 && (k & 3) == 0) ptx::mbar_wait(act_bar(k >> 2), aph);
+                if (layer > 0 && chunk == 0 && (k & 3) == 0) ptx::mbar_wait(act_bar(sub, k >> 2), aph);
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                 ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
-                ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), k * BLOCK_K, slot_row0);
+                ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), k * BLOCK_K,
+                                 slot_row0 + sub * TILE_M);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
-            if (layer > 0) aph ^= 1;
+             }
+            if (layer == 0) xph ^= 1;
+            else aph ^= 1;
           }
     }
   } else if (warp >= 4) {
@@ -279,15 +378,13 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       if (lane == 0) ptx::mbar_arrive(bar);
     };
     for (int rnd = 0; rnd < rounds; ++rnd) {
-      const int tile = blockIdx.x + rnd * (int)gridDim.x;
-      const long long row = (long long)tile * TILE_M + r_in;
-      const bool valid = row < p.B;
-      const size_t srow = (size_t)(slot_row0 + r_in);
-      __half* hrow = p.act_h + srow * H;
-      __half* trow = p.act_t + srow * H;
-      __nv_bfloat16* xarow = p.xa + srow * XA_K;
+      const long long tile0 = (long long)(blockIdx.x + rnd * (int)gridDim.x) * NSUB;
       // ---------------- tile prologue: first-layer operand of step 0
-      {
+#pragma unroll 1
+      for (int sub = 0; sub < NSUB; ++sub) {
+        const long long row = (tile0 + sub) * TILE_M + r_in;
+        const bool valid = row < p.B;
+        __nv_bfloat16* xarow = p.xa + (size_t)(slot_row0 + sub * TILE_M + r_in) * XA_K;
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = 0.f;
@@ -329,7 +426,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           }
         }
         write_xa(xarow, hf, x);
-        signal(xa_bar);
+        signal(xa_bar(sub));
       }
       for (int step = 0; step < p.n_steps; ++step) {
         // ---------------- hidden layers 0..4
@@ -346,92 +443,53 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           ptx::named_bar_sync(1, EPI_THREADS);
           const bool to_h = (layer == 0 || layer == 2 || layer == 4);
           const bool residual = (layer == 2 || layer == 4);
-          __half* drow = to_h ? hrow : trow;
-          for (int chunk = 0; chunk < H / CHUNK_N; ++chunk) {
+#pragma unroll 1
+          for (int cs = 0; cs < (H / CHUNK_N) * NSUB; ++cs) {
+            const int chunk = cs / NSUB, sub = cs % NSUB;
+            __half* drow = (to_h ? p.act_h : p.act_t) + (size_t)(slot_row0 + sub * TILE_M + r_in) * H;
             const uint32_t buf = chunk_ctr & 1;
             ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
             ptx::tc_fence_after();
-            uint4 rnext[4];
-            if (residual) {  // prefetch the first group's residual (L2 latency) before waiting on TMEM
-              const uint4* rp = reinterpret_cast<const uint4*>(drow + chunk * CHUNK_N + hf * 128);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) rnext[i] = ld_global_v4(rp + i);
-            }
+            // two column groups per iteration: both TMEM loads and both residual loads are in flight before any
+            // math, and the two independent instruction streams interleave (ILP for the 8-warp epilogue)
 #pragma unroll 1
-            for (int gi = 0; gi < 4; ++gi) {
-              const int g = hf * 4 + gi;
-              const int col0 = chunk * CHUNK_N + g * 32;
-              uint32_t vr[32];
-              ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g * 32, vr);
+            for (int gp = 0; gp < 2; ++gp) {
+              const int g0 = hf * 4 + gp * 2;
+              const int col0 = chunk * CHUNK_N + g0 * 32;
+              uint32_t vr0[32], vr1[32];
+              ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g0 * 32, vr0);
+              ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g0 * 32 + 32, vr1);
+              uint4 r0[4], r1[4];
+              if (residual) {
+                const uint4* rp = reinterpret_cast<const uint4*>(drow + col0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { r0[i] = ld_global_v4(rp + i); r1[i] = ld_global_v4(rp + 4 + i); }
+              }
               ptx::tmem_ld_wait();
-              if (gi == 3) {  // last TMEM read of this warp for the buffer: hand it back to the MMA warp
+              if (gp == 1) {  // last TMEM read of this warp for the buffer: hand it back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
               }
-              float v[32];
-              float s = 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 t4 = *reinterpret_cast<const float4*>(par + col0 + i);
-                v[i] = __uint_as_float(vr[i]) + t4.x;
-                v[i + 1] = __uint_as_float(vr[i + 1]) + t4.y;
-                v[i + 2] = __uint_as_float(vr[i + 2]) + t4.z;
-                v[i + 3] = __uint_as_float(vr[i + 3]) + t4.w;
-                s += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
-              }
-              const float mean = s * (1.0f / GROUP);
-              float qv = 0.f;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                v[i] -= mean;
-                qv = fmaf(v[i], v[i], qv);
-              }
-              const float rstd = rsqrtf(qv * (1.0f / GROUP) + GN_EPS);
-              uint32_t res[16];
-              if (residual) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  res[4 * i] = rnext[i].x; res[4 * i + 1] = rnext[i].y; res[4 * i + 2] = rnext[i].z; res[4 * i + 3] = rnext[i].w;
-                }
-                if (gi < 3) {  // next group's residual goes in flight under this group's math
-                  const uint4* rp = reinterpret_cast<const uint4*>(drow + col0 + 32);
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) rnext[i] = ld_global_v4(rp + i);
-                }
-              }
-              uint32_t packed[16];
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 g4 = *reinterpret_cast<const float4*>(par + H + col0 + i);
-                float4 b4 = *reinterpret_cast<const float4*>(par + 2 * H + col0 + i);
-                float y0 = fmaf(v[i] * rstd, g4.x, b4.x), y1 = fmaf(v[i + 1] * rstd, g4.y, b4.y);
-                float y2 = fmaf(v[i + 2] * rstd, g4.z, b4.z), y3 = fmaf(v[i + 3] * rstd, g4.w, b4.w);
-                y0 = __fdividef(y0, 1.0f + __expf(-y0));
-                y1 = __fdividef(y1, 1.0f + __expf(-y1));
-                y2 = __fdividef(y2, 1.0f + __expf(-y2));
-                y3 = __fdividef(y3, 1.0f + __expf(-y3));
-                if (residual) {
-                  float2 r01 = __half22float2(*reinterpret_cast<const __half2*>(&res[i / 2]));
-                  float2 r23 = __half22float2(*reinterpret_cast<const __half2*>(&res[i / 2 + 1]));
-                  y0 += r01.x; y1 += r01.y; y2 += r23.x; y3 += r23.y;
-                }
-                __half2 p01 = __floats2half2_rn(y0, y1), p23 = __floats2half2_rn(y2, y3);
-                packed[i / 2] = *reinterpret_cast<uint32_t*>(&p01);
-                packed[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&p23);
-              }
+              if (p.debug & 1) continue;
+              uint4 o0[4], o1[4];
+              gn_silu_group(vr0, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o0);
+              gn_silu_group(vr1, par + col0 + 32, par + H + col0 + 32, par + 2 * H + col0 + 32, residual, r1, o1);
               uint4* dp = reinterpret_cast<uint4*>(drow + col0);
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                st_global_v4(dp + i, make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]));
+              for (int i = 0; i < 4; ++i) { st_global_v4(dp + i, o0[i]); st_global_v4(dp + 4 + i, o1[i]); }
             }
             tph ^= 1u << buf;
             ++chunk_ctr;
-            signal(act_bar(chunk));  // columns [256 chunk, 256 chunk + 256) of this layer's output are in the scratch
+            signal(act_bar(sub, chunk));  // columns [256 chunk, 256 chunk + 256) of this tile's layer output are written
           }
         }
         // ---------------- post_dense + mode-specific tail
-        {
+#pragma unroll 1
+        for (int sub = 0; sub < NSUB; ++sub) {
+          const long long row = (tile0 + sub) * TILE_M + r_in;
+          const bool valid = row < p.B;
+          __nv_bfloat16* xarow = p.xa + (size_t)(slot_row0 + sub * TILE_M + r_in) * XA_K;
           const uint32_t buf = chunk_ctr & 1;
           ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
           ptx::tc_fence_after();
@@ -518,7 +576,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             }
             if (!last) {
               write_xa(xarow, hf, x);
-              signal(xa_bar);
+              signal(xa_bar(sub));
             }
           } else {  // prior loss
             float acc = 0.f;
@@ -611,7 +669,7 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->pre_split, pre.size() * sizeof(__nv_bfloat16)));
   DPB_CUDA_CHECK(cudaMemcpy(h->pre_split, pre.data(), pre.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   // per-CTA activation scratch (one 128-row slot per SM)
-  h->tc_slots = h->sm_count;
+  h->tc_slots = h->sm_count * tc::NSUB;
   const size_t rows = (size_t)h->tc_slots * tc::TILE_M;
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_h, rows * H * sizeof(__half)));
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_t, rows * H * sizeof(__half)));
@@ -666,10 +724,15 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   p.wgt = j.scale;  // prior loss: api.cu passes the weight through `scale`
   p.z = j.z; p.loss_out = j.loss_out; p.grad_out = j.grad_out; p.row_loss = j.row_loss;
   p.act_h = h->act_h; p.act_t = h->act_t; p.xa = h->xa;
+  {
+    const char* dbg = getenv("DPB_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   if (j.mode == 2 && j.row_loss) DPB_CUDA_CHECK(cudaMemsetAsync(j.row_loss, 0, sizeof(float) * j.B, st));
   // grid: a multiple of the cluster size, at most one CTA per scratch slot
-  int grid = (p.n_tiles + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
-  const int max_grid = h->tc_slots / tc::CLUSTER * tc::CLUSTER;
+  const int n_groups = (p.n_tiles + tc::NSUB - 1) / tc::NSUB;
+  int grid = (n_groups + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
+  const int max_grid = (h->tc_slots / tc::NSUB) / tc::CLUSTER * tc::CLUSTER;
   if (grid > max_grid) grid = max_grid;
   tc::score_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, h->tm_xa, h->tm_act_h, h->tm_act_t, h->tm_pre,
                                                                     h->tm_w[0], h->tm_w[1], h->tm_w[2], h->tm_w[3],
