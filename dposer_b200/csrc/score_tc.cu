@@ -29,7 +29,7 @@ constexpr int TILE_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int CHUNK_N = 256;
 constexpr int STAGES = 4;
-constexpr int NSUB = 2;      // row tiles in flight per CTA: one tile's epilogue overlaps the other tile's MMAs
+constexpr int NSUB = 1;      // row tiles in flight per CTA: one tile's epilogue overlaps the other tile's MMAs
 constexpr int CLUSTER = 2;   // CTAs (different row tiles) that share every weight tile through TMA multicast
 constexpr int A_BYTES = TILE_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_BYTES = CHUNK_N * BLOCK_K * 2;  // 32 KB
