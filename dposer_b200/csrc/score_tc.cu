@@ -28,7 +28,7 @@ namespace tc {
 constexpr int TILE_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int CHUNK_N = 256;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int NSUB = 1;      // row tiles in flight per CTA: one tile's epilogue overlaps the other tile's MMAs
 constexpr int CLUSTER = 2;   // CTAs (different row tiles) that share every weight tile through TMA multicast
 constexpr int A_BYTES = TILE_M * BLOCK_K * 2;   // 16 KB
@@ -39,8 +39,15 @@ constexpr int XA_K = 192;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int PAR_BYTES = 3 * H * 4;
-constexpr int NUM_BARS = 2 * STAGES + 4 + NSUB * 5;  // full, empty, tfull[2], tempty[2], xa[NSUB], act[NSUB][4]
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PAR_BYTES + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
+constexpr int STG_BYTES = TILE_M * 128;          // one [128 rows x 64 fp16] SWIZZLE_128B box of outgoing activations
+constexpr int STG_TOTAL = 4 * STG_BYTES;         // 2 column halves (hf) x 2 buffers
+constexpr int NUM_BARS = 2 * STAGES + 4 + NSUB * 5 + 8;  // full, empty, tfull[2], tempty[2], xa, act[4], sfull[2][2], sempty[2][2]
+constexpr int OFF_PAR = STAGES * STAGE_BYTES;
+constexpr int OFF_STG = OFF_PAR + PAR_BYTES;     // 1024-aligned: 3*49152 + 12288 = 159744
+constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
+constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
+static_assert(OFF_STG % 1024 == 0, "staging boxes must be 1024-byte aligned for SWIZZLE_128B");
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr uint32_t IDESC_F16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 0);
 constexpr uint32_t IDESC_BF16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 1);
 constexpr uint32_t IDESC_F16_64 = ptx::umma_idesc_f16(TILE_M, DP, 0);
@@ -74,10 +81,14 @@ struct KParams {
   __nv_bfloat16* xa;
 };
 
+// L2-only load: the scratch is written by TMA stores (async proxy), which do not update this SM's L1
 __device__ __forceinline__ uint4 ld_global_v4(const uint4* p) {
   uint4 r;
-  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void st_global_v4(uint4* p, uint4 v) {
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -222,8 +233,9 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   // 1024-byte alignment for SWIZZLE_128B; offset arithmetic on the __shared__ array keeps ld/st.shared
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = ptx::smem_u32(smem);
-  float* par = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [tb | gamma | beta] x 1024
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES + PAR_BYTES;
+  float* par = reinterpret_cast<float*>(smem + OFF_PAR);  // [tb | gamma | beta] x 1024
+  const uint32_t stg_base = smem_base + OFF_STG;
+  const uint32_t bar_base = smem_base + OFF_BAR;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
   auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + b); };
@@ -232,7 +244,9 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   auto act_bar = [&](uint32_t sub, uint32_t c) {                                          // column chunk c of a hidden layer ready
     return bar_base + 8u * (2 * STAGES + 4 + NSUB + sub * 4 + c);
   };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + PAR_BYTES + NUM_BARS * 8);
+  auto sfull_bar = [&](uint32_t hf, uint32_t b) { return bar_base + 8u * (2 * STAGES + 4 + NSUB * 5 + hf * 2 + b); };
+  auto sempty_bar = [&](uint32_t hf, uint32_t b) { return bar_base + 8u * (2 * STAGES + 4 + NSUB * 5 + 4 + hf * 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -246,8 +260,13 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     }
     for (int sub = 0; sub < NSUB; ++sub) {
       ptx::mbar_init(xa_bar(sub), 8);
-      for (int c = 0; c < 4; ++c) ptx::mbar_init(act_bar(sub, c), 8);
+      for (int c = 0; c < 4; ++c) ptx::mbar_init(act_bar(sub, c), 1);  // the store warp, after the chunk's TMA stores completed
     }
+    for (int hf = 0; hf < 2; ++hf)
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(sfull_bar(hf, b), 4);   // the four epilogue warps (row quarters) that fill one box
+        ptx::mbar_init(sempty_bar(hf, b), 1);  // the store warp, once the TMA store has read the box
+      }
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -363,6 +382,43 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             else aph ^= 1;
           }
     }
+  } else if (warp == 3) {
+    // ======================= activation store warp =======================
+    // Epilogue warps stage each [128 x 64] fp16 box in shared memory (swizzled); this warp turns boxes into
+    // TMA stores (full 128-byte lines into the L2-resident scratch) and publishes a column chunk to the
+    // activation producer once its stores have completed.
+    if (lane == 0) {
+      uint32_t cnt[2] = {0, 0};
+      uint32_t last_bar = 0;      // sempty barrier of the most recent store that has not been handed back yet
+      bool last_released = true;
+      for (int rnd = 0; rnd < rounds; ++rnd)
+        for (int step = 0; step < p.n_steps; ++step)
+          for (int layer = 0; layer < 5; ++layer) {
+            const CUtensorMap* tm = (layer == 0 || layer == 2 || layer == 4) ? &tm_h : &tm_t;
+            for (int cs = 0; cs < (H / CHUNK_N) * NSUB; ++cs) {
+              const int chunk = cs / NSUB, sub = cs % NSUB;
+              for (int gp = 0; gp < 2; ++gp)
+                for (int hf = 0; hf < 2; ++hf) {
+                  const uint32_t b = cnt[hf] & 1, ph = (cnt[hf] >> 1) & 1;
+                  ptx::mbar_wait(sfull_bar(hf, b), ph);
+                  ptx::tma_store_2d(tm, stg_base + (hf * 2 + b) * STG_BYTES, chunk * CHUNK_N + hf * 128 + gp * 64,
+                                    slot_row0 + sub * TILE_M);
+                  ptx::tma_store_commit();
+                  if (!last_released) {  // the previous store has finished READING its box: hand that box back
+                    ptx::tma_store_wait_read<1>();
+                    ptx::mbar_arrive(last_bar);
+                  }
+                  last_bar = sempty_bar(hf, b);
+                  last_released = false;
+                  ++cnt[hf];
+                }
+              ptx::tma_store_wait<0>();  // this chunk's stores are complete (visible to the TMA loads that follow)
+              ptx::mbar_arrive(last_bar);
+              last_released = true;
+              ptx::mbar_arrive(act_bar(sub, chunk));
+            }
+          }
+    }
   } else if (warp >= 4) {
     // ======================= epilogue =======================
     const int q = warp & 3;          // TMEM lane quarter this warp may read
@@ -370,7 +426,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     const int et = threadIdx.x - 128;
     const int r_in = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t chunk_ctr = 0, tph = 0;
+    uint32_t chunk_ctr = 0, tph = 0, scnt = 0;
     auto signal = [&](uint32_t bar) {  // generic-proxy global writes -> visible to the TMA (async proxy) reads
       __threadfence();
       ptx::fence_proxy_async_global();
@@ -471,17 +527,28 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
               }
-              if (p.debug & 1) continue;
-              uint4 o0[4], o1[4];
-              gn_silu_group(vr0, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o0);
-              gn_silu_group(vr1, par + col0 + 32, par + H + col0 + 32, par + 2 * H + col0 + 32, residual, r1, o1);
-              uint4* dp = reinterpret_cast<uint4*>(drow + col0);
+              uint4 o[8];
+              if (p.debug & 1) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { st_global_v4(dp + i, o0[i]); st_global_v4(dp + 4 + i, o1[i]); }
+                for (int i = 0; i < 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
+              } else {
+                gn_silu_group(vr0, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o);
+                gn_silu_group(vr1, par + col0 + 32, par + H + col0 + 32, par + 2 * H + col0 + 32, residual, r1, o + 4);
+              }
+              // stage this row's 64 fp16 (128 B) in the SWIZZLE_128B box of my column half; the store warp
+              // ships the box with one TMA store (full lines, asynchronous) -- no per-row global stores
+              const uint32_t sb = scnt & 1;
+              ptx::mbar_wait(sempty_bar(hf, sb), ((scnt >> 1) & 1) ^ 1);
+              const uint32_t rbase = stg_base + (hf * 2 + sb) * STG_BYTES + r_in * 128;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) st_shared_v4(rbase + ((j ^ (r_in & 7)) << 4), o[j]);
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(sfull_bar(hf, sb));
+              ++scnt;
             }
             tph ^= 1u << buf;
             ++chunk_ctr;
-            signal(act_bar(sub, chunk));  // columns [256 chunk, 256 chunk + 256) of this tile's layer output are written
           }
         }
         // ---------------- post_dense + mode-specific tail
