@@ -112,7 +112,7 @@ class LbsCore:
         lf = t.get('lmk_faces')
         self.n_lmk = 0 if lf is None else int(lf.shape[0])
         self.n_out = self.J + len(self.extra_vids) + self.n_lmk
-        self.engine = L.ENGINE_FP32
+        self.engine = L.ENGINE_AUTO       # tcgen05 blend for batches >= 64, fp32 blend otherwise (ENGINE_FP32 forces exact)
         self._handles = {}
         self._ws = {}
 

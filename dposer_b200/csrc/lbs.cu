@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(LBS_TV) lbs_vertex_kernel(
     const float* __restrict__ A, const float* __restrict__ v_template, const float* __restrict__ shapedirs,
     const float* __restrict__ posedirs, const int32_t* __restrict__ ell_idx, const float* __restrict__ ell_w,
     const int32_t* __restrict__ vlist, int n_verts, int V, int J, int S, int P, int nnz,
-    float* __restrict__ out, int64_t B) {
+    const float* vp_in, float* out, int64_t B) {
+  // vp_in != nullptr: the blend (v_posed) was already produced by the tcgen05 engine -- skin it in place
+  // (vp_in == out, S = P = 0 passed by the caller); otherwise blend here in fp32.
   extern __shared__ float smem[];
   float* feat_s = smem;                       // [P][TP]  (k-major so 4 poses load as one float4)
   float* beta_s = feat_s + (size_t)P * LBS_TP;  // [S][TP]
@@ -188,11 +190,19 @@ __global__ void __launch_bounds__(LBS_TV) lbs_vertex_kernel(
   if (vi >= n_verts) return;
   const int v = vlist ? vlist[vi] : vi;
   float acc[LBS_TP][3];
+  if (vp_in) {
 #pragma unroll
-  for (int p = 0; p < LBS_TP; ++p) {
-    acc[p][0] = v_template[v * 3 + 0];
-    acc[p][1] = v_template[v * 3 + 1];
-    acc[p][2] = v_template[v * 3 + 2];
+    for (int p = 0; p < LBS_TP; ++p) {
+      const float* s = vp_in + ((size_t)(b0 + (p < np ? p : 0)) * n_verts + vi) * 3;
+      acc[p][0] = s[0]; acc[p][1] = s[1]; acc[p][2] = s[2];
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < LBS_TP; ++p) {
+      acc[p][0] = v_template[v * 3 + 0];
+      acc[p][1] = v_template[v * 3 + 1];
+      acc[p][2] = v_template[v * 3 + 2];
+    }
   }
   // shape blend: v_shaped = v_template + shapedirs . beta
   for (int k = 0; k < S; ++k) {
@@ -289,6 +299,7 @@ size_t lbs_ws_bytes(const dpb_lbs* h, int64_t B, bool compact) {
   n += align_up((size_t)B * h->n_need * 3 * 4, 256) * (compact ? 2 : 1);   // compact verts + gextra
   n += align_up((size_t)B * h->J * 12 * 4, 256) + align_up((size_t)B * h->P * 4, 256) +
        align_up((size_t)B * (h->S + 3) * 4, 256);
+  n += lbs_tc_ws_bytes(h, B);
   return n + 2048;
 }
 
@@ -303,11 +314,15 @@ bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_by
   out->gextra = c.take<float>((size_t)B * h->n_need * 3 + 1);
   out->gbeta = c.take<float>((size_t)B * (h->S + 3));
   out->compact = compact ? c.take<float>((size_t)B * h->n_need * 3) : nullptr;
+  out->featop = nullptr;
+  if (h->tc_ready && !compact) {
+    c.off = align_up(c.off, 1024);
+    out->featop = reinterpret_cast<__half*>(c.base + c.off);
+    c.off += lbs_tc_ws_bytes(h, B) - 1024;
+  }
   return ws != nullptr && c.ok();
 }
 
-int lbs_tc_vertices(dpb_lbs* h, const float* betas, const float* transl, const LbsWs& w, float* verts, int64_t B,
-                    cudaStream_t st);  // lbs_tc.cu
 
 }  // namespace dpb
 
@@ -464,10 +479,22 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
   const int n_verts = compact ? h->n_need : h->V;
   float* vout = compact ? w.compact : verts;
   if (n_verts > 0) {
-    if (!compact && engine == DPB_LBS_ENGINE_TC) {
-      if (!h->tc_ready) return fail(DPB_EUNSUPPORTED, "dpb_lbs_forward: tensor-core engine unavailable");
-      int rc = lbs_tc_vertices(h, betas, transl, w, verts, B, st);
+    const bool use_tc = !compact && h->tc_ready && w.featop &&
+                        (engine == DPB_LBS_ENGINE_TC || (engine == DPB_ENGINE_AUTO && B >= 64));
+    if (!compact && engine == DPB_LBS_ENGINE_TC && !use_tc)
+      return fail(DPB_EUNSUPPORTED, "dpb_lbs_forward: tensor-core engine unavailable");
+    if (use_tc) {
+      // blend on tcgen05 (writes v_posed into verts), then skin in place with the transforms from the pose kernel
+      int rc = lbs_tc_blend(h, betas, w.feat, w.featop, verts, B, st);
       if (rc != DPB_OK) return rc;
+      size_t smem = ((size_t)LBS_TP * h->J * 12 + LBS_TP * 3) * 4;
+      DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((n_verts + LBS_TV - 1) / LBS_TV, (unsigned)((B + LBS_TP - 1) / LBS_TP));
+      DPB_REQUIRE(grid.y <= 65535u, "dpb_lbs_forward: batch too large for one call (max 65535*16 poses)");
+      lbs_vertex_kernel<<<grid, LBS_TV, smem, st>>>(betas, transl, w.feat, w.A, h->v_template, h->shapedirs,
+                                                    h->posedirs, h->ell_idx, h->ell_w, nullptr, n_verts, h->V, h->J,
+                                                    0, 0, h->nnz, verts, verts, B);
+      DPB_CUDA_CHECK(cudaGetLastError());
     } else {
       size_t smem = ((size_t)h->P * LBS_TP + (size_t)h->S * LBS_TP + (size_t)LBS_TP * h->J * 12 + LBS_TP * 3) * 4;
       DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -476,7 +503,7 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
       lbs_vertex_kernel<<<grid, LBS_TV, smem, st>>>(betas, transl, w.feat, w.A, h->v_template, h->shapedirs,
                                                     h->posedirs, h->ell_idx, h->ell_w,
                                                     compact ? h->need_vids : nullptr, n_verts, h->V, h->J, h->S, h->P,
-                                                    h->nnz, vout, B);
+                                                    h->nnz, nullptr, vout, B);
       DPB_CUDA_CHECK(cudaGetLastError());
     }
   }

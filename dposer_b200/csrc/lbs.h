@@ -53,7 +53,11 @@ struct LbsWs {
   float* gfeat;   // [B,P]      dL/dfeat
   float* gextra;  // [B,n_need,3] joint grads scattered onto the vertices that produce them
   float* gbeta;   // [B,S+3]    vertex-path part of dL/dbetas | dL/dtransl
+  __half* featop; // [B_pad, kext] fp16 [hi | lo] blend operand of the tcgen05 engine (nullptr if unavailable)
 };
 size_t lbs_ws_bytes(const dpb_lbs* h, int64_t B, bool compact);
 bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_bytes, LbsWs* out);
+size_t lbs_tc_ws_bytes(const dpb_lbs* h, int64_t B);
+int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* featop, float* verts, int64_t B,
+                 cudaStream_t st);
 }  // namespace dpb

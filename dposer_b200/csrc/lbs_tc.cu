@@ -1,12 +1,309 @@
-// tcgen05 pose-blend engine for LBS (placeholder until the tensor-core kernel lands).
+// tcgen05 blend engine for LBS:  v_posed[b, v, :] = v_template[v] + shapedirs[v] . beta_b + posedirs[:, v]^T . feat_b
+// as ONE tensor-core GEMM with M = vertices (TMEM lane = vertex = epilogue thread, so the stores of a pose's
+// vertices are coalesced), N = 64 poses, K = shape + pose-feature components.
+//
+// Precision: single-pass fp16 misses the 1e-5 m bound (measured 1.6e-5 m max on the SMPL-sized synthetic model),
+// so both operands are split x = x_hi + x_lo (fp16 each) and the three significant products
+// hi*hi + hi*lo + lo*hi are accumulated in fp32 (measured 4e-7 m).  The split is a data layout, not extra
+// storage traffic: operands are stored once as [hi | lo] along K and the MMA issuer pairs K-steps.
+//
+//   warp 0  TMA producer: streams blend-basis slabs [128 vertices x 64 k] (A operand, L2 resident);
+//           loads the pose group's operand [64 poses x K2] once per group (B operand, SMEM resident)
+//   warp 1  tcgen05.mma issuer (M=128, N=64), accumulators D_x | D_y | D_z double-buffered in TMEM
+//   warp 2  TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld -> + v_template -> v_posed written into the vertex buffer
+// The skinning itself (blend of the per-joint transforms and their application) runs in lbs_vertex_kernel
+// (lbs.cu) in place on that buffer.  Reference semantics: smplx 0.1.28 lbs().
+#include <cudaTypedefs.h>
+
+#include <vector>
+
 #include "lbs.h"
+#include "ptx.cuh"
 
 namespace dpb {
-int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) { (void)m; h->tc_ready = false; return DPB_OK; }
-void lbs_tc_release(dpb_lbs* h) { (void)h; }
-int lbs_tc_vertices(dpb_lbs* h, const float*, const float*, const LbsWs&, float*, int64_t, cudaStream_t) {
-  (void)h;
-  return fail(DPB_EUNSUPPORTED, "LBS tensor-core engine not built");
-}
-}  // namespace dpb
 
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64_t inner, uint64_t rows,
+                 uint32_t box_inner, uint32_t box_rows, size_t elem_bytes);  // score_tc.cu
+
+namespace ltc {
+
+constexpr int TILE_V = 128;   // vertices per block (MMA M)
+constexpr int NP = 64;        // poses per group (MMA N)
+constexpr int BK = 64;        // fp16 per 128-byte swizzle row
+constexpr int A_SLAB = TILE_V * BK * 2;  // 16 KB
+constexpr int B_SLAB = NP * BK * 2;      // 8 KB
+constexpr int NUM_THREADS = 256;
+constexpr int MAX_STAGES = 8;
+constexpr uint32_t IDESC = ptx::umma_idesc_f16(TILE_V, NP, 0);
+
+struct KParams {
+  int V, V_pad, n_vt;       // vertices, padded vertices, vertex tiles
+  int ksteps_half;          // K16 steps of the hi (= lo) part: Kp / 16
+  int n_slabs;              // 64-wide slabs of [hi | lo]: 2*Kp / 64
+  int stages;
+  int64_t B;
+  int n_groups;             // ceil(B / NP)
+  const float* v_template;  // [V,3]
+  float* verts;             // [B,V,3]
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUtensorMap tm_dirs,
+                    const __grid_constant__ CUtensorMap tm_feat) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t b_base = smem_base;                              // resident pose-group operand: n_slabs x 8 KB
+  const uint32_t a_base = smem_base + p.n_slabs * B_SLAB;         // ring of A slabs
+  const uint32_t bar_base = a_base + p.stages * A_SLAB;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * MAX_STAGES + b); };
+  auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * MAX_STAGES + 2 + b); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t bempty_bar = bar_base + 8u * (2 * MAX_STAGES + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.n_slabs * B_SLAB + p.stages * A_SLAB + (2 * MAX_STAGES + 6) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar(b), 1);
+      ptx::mbar_init(tempty_bar(b), 4);
+    }
+    ptx::mbar_init(bfull_bar, 1);
+    ptx::mbar_init(bempty_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int half = p.ksteps_half;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tm_dirs);
+      ptx::prefetch_tmap(&tm_feat);
+      uint32_t stage = 0, phase = 0, gph = 0;
+      for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+        ptx::mbar_wait(bempty_bar, gph ^ 1);  // previous group's MMAs are done with the resident operand
+        ptx::mbar_arrive_expect_tx(bfull_bar, (uint32_t)p.n_slabs * B_SLAB);
+        for (int i = 0; i < p.n_slabs; ++i) ptx::tma_load_2d(b_base + i * B_SLAB, &tm_feat, bfull_bar, i * BK, grp * NP);
+        gph ^= 1;
+        for (int vt = 0; vt < p.n_vt; ++vt)
+          for (int c = 0; c < 3; ++c)
+            for (int i = 0; i < p.n_slabs; ++i) {
+              ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+              ptx::mbar_arrive_expect_tx(full_bar(stage), A_SLAB);
+              ptx::tma_load_2d(a_base + stage * A_SLAB, &tm_dirs, full_bar(stage), i * BK, c * p.V_pad + vt * TILE_V);
+              if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, gph = 0, blk = 0, tph = 0;
+      for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+        ptx::mbar_wait(bfull_bar, gph);
+        gph ^= 1;
+        ptx::tc_fence_after();
+        for (int vt = 0; vt < p.n_vt; ++vt) {
+          const uint32_t buf = blk & 1;
+          ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
+          ptx::tc_fence_after();
+          for (int c = 0; c < 3; ++c) {
+            const uint32_t taddr = tmem_base + buf * (3 * NP) + c * NP;
+            uint32_t first = 1;
+            for (int i = 0; i < p.n_slabs; ++i) {
+              ptx::mbar_wait(full_bar(stage), phase);
+              ptx::tc_fence_after();
+              const uint32_t a_addr = a_base + stage * A_SLAB;
+#pragma unroll
+              for (int j = 0; j < BK / 16; ++j) {
+                const int g = i * (BK / 16) + j;  // K16 step inside [hi | lo]
+                const uint64_t adesc = ptx::umma_desc_sw128(a_addr) + 2 * j;
+                auto bdesc = [&](int step) {
+                  return ptx::umma_desc_sw128(b_base + (step >> 2) * B_SLAB) + 2 * (step & 3);
+                };
+                if (g < half) {  // basis_hi x (feat_hi + feat_lo)
+                  ptx::mma_f16_ss(taddr, adesc, bdesc(g), IDESC, first ? 0u : 1u);
+                  ptx::mma_f16_ss(taddr, adesc, bdesc(half + g), IDESC, 1u);
+                  first = 0;
+                } else {         // basis_lo x feat_hi
+                  ptx::mma_f16_ss(taddr, adesc, bdesc(g - half), IDESC, 1u);
+                }
+              }
+              ptx::mma_commit(empty_bar(stage));
+              if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          ptx::mma_commit(tfull_bar(buf));
+          tph ^= 1u << buf;
+          ++blk;
+        }
+        ptx::mma_commit(bempty_bar);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t blk = 0, tph = 0;
+    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+      const int64_t b0 = (int64_t)grp * NP;
+      for (int vt = 0; vt < p.n_vt; ++vt) {
+        const int v = vt * TILE_V + q * 32 + lane;
+        const bool vok = v < p.V;
+        float vt3[3] = {0.f, 0.f, 0.f};
+        if (vok) {
+          vt3[0] = p.v_template[v * 3 + 0];
+          vt3[1] = p.v_template[v * 3 + 1];
+          vt3[2] = p.v_template[v * 3 + 2];
+        }
+        const uint32_t buf = blk & 1;
+        ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int hp = 0; hp < NP / 32; ++hp) {  // 32 poses at a time: x, y, z of each
+          uint32_t dx[32], dy[32], dz[32];
+          const uint32_t t0 = tmem_base + lane_addr + buf * (3 * NP) + hp * 32;
+          ptx::tmem_ld_32x32(t0, dx);
+          ptx::tmem_ld_32x32(t0 + NP, dy);
+          ptx::tmem_ld_32x32(t0 + 2 * NP, dz);
+          ptx::tmem_ld_wait();
+          if (hp == NP / 32 - 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+          }
+          if (vok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int64_t b = b0 + hp * 32 + i;
+              if (b < p.B) {
+                float* o = p.verts + ((size_t)b * p.V + v) * 3;
+                o[0] = __uint_as_float(dx[i]) + vt3[0];
+                o[1] = __uint_as_float(dy[i]) + vt3[1];
+                o[2] = __uint_as_float(dz[i]) + vt3[2];
+              }
+            }
+          }
+        }
+        tph ^= 1u << buf;
+        ++blk;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// [betas | feat] -> fp16 [hi | lo] operand rows (zero padded); one thread per (pose, k)
+__global__ void lbs_featop_kernel(const float* __restrict__ betas, const float* __restrict__ feat, int S, int P, int Kp,
+                                  __half* __restrict__ op, int64_t B, int64_t B_pad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B_pad * Kp) return;
+  const int64_t b = i / Kp;
+  const int k = (int)(i % Kp);
+  float x = 0.f;
+  if (b < B) {
+    if (k < S) x = betas[b * S + k];
+    else if (k < S + P) x = feat[b * P + (k - S)];
+  }
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  op[b * (2 * Kp) + k] = hi;
+  op[b * (2 * Kp) + Kp + k] = lo;
+}
+
+}  // namespace ltc
+
+int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
+  h->tc_ready = false;
+  const int V = h->V, S = h->S, P = h->P;
+  const int Kp = (S + P + 31) / 32 * 32;   // hi (= lo) width: multiple of 32 so that [hi | lo] is whole 64-wide slabs
+  const int K2 = 2 * Kp;
+  const int V_pad = (V + ltc::TILE_V - 1) / ltc::TILE_V * ltc::TILE_V;
+  const int n_slabs = K2 / ltc::BK;
+  if ((size_t)n_slabs * ltc::B_SLAB + 2 * ltc::A_SLAB + 2048 > 232448) return DPB_OK;  // model too wide: fp32 engine only
+  // blend basis, vertex-major per coordinate: row (c*V_pad + v) = [shapedirs[v,c,:] | posedirs[:,3v+c]] as [hi | lo]
+  std::vector<__half> basis((size_t)3 * V_pad * K2, __float2half_rn(0.f));
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < V; ++v) {
+      __half* row = basis.data() + ((size_t)c * V_pad + v) * K2;
+      for (int k = 0; k < S + P; ++k) {
+        const float x = k < S ? m->shapedirs[((size_t)v * 3 + c) * S + k]
+                              : m->posedirs[(size_t)(k - S) * V * 3 + (size_t)v * 3 + c];
+        const __half hi = __float2half_rn(x);
+        row[k] = hi;
+        row[Kp + k] = __float2half_rn(x - __half2float(hi));
+      }
+    }
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->dirs16, basis.size() * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMemcpy(h->dirs16, basis.data(), basis.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  int rc = make_tmap_2d(&h->tm_dirs, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->dirs16, K2, (uint64_t)3 * V_pad, ltc::BK,
+                        ltc::TILE_V, 2);
+  if (rc != DPB_OK) return rc;
+  h->kext = K2;
+  h->n_cols_pad = V_pad;
+  h->tc_ready = true;
+  return DPB_OK;
+}
+
+void lbs_tc_release(dpb_lbs* h) {
+  if (h->dirs16) cudaFree(h->dirs16);
+  h->dirs16 = nullptr;
+  h->tc_ready = false;
+}
+
+size_t lbs_tc_ws_bytes(const dpb_lbs* h, int64_t B) {
+  if (!h->tc_ready) return 0;
+  const int64_t B_pad = (B + ltc::NP - 1) / ltc::NP * ltc::NP;
+  return align_up((size_t)B_pad * h->kext * sizeof(__half), 1024) + 1024;
+}
+
+// writes v_posed (template + shape blend + pose blend) into verts[B,V,3]
+int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* featop, float* verts, int64_t B,
+                 cudaStream_t st) {
+  const int K2 = h->kext, Kp = K2 / 2;
+  const int64_t B_pad = (B + ltc::NP - 1) / ltc::NP * ltc::NP;
+  {
+    const int64_t n = B_pad * Kp;
+    ltc::lbs_featop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(betas, feat, h->S, h->P, Kp, featop, B, B_pad);
+    DPB_CUDA_CHECK(cudaGetLastError());
+  }
+  CUtensorMap tm_feat;
+  int rc = make_tmap_2d(&tm_feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, featop, K2, (uint64_t)B_pad, ltc::BK, ltc::NP, 2);
+  if (rc != DPB_OK) return rc;
+  ltc::KParams p{};
+  p.V = h->V;
+  p.V_pad = h->n_cols_pad;
+  p.n_vt = h->n_cols_pad / ltc::TILE_V;
+  p.ksteps_half = Kp / 16;
+  p.n_slabs = K2 / ltc::BK;
+  p.B = B;
+  p.n_groups = (int)(B_pad / ltc::NP);
+  p.v_template = h->v_template;
+  p.verts = verts;
+  const size_t fixed = (size_t)p.n_slabs * ltc::B_SLAB + (2 * ltc::MAX_STAGES + 6) * 8 + 16 + 1024;
+  int stages = (int)((232448 - fixed) / ltc::A_SLAB);
+  if (stages > ltc::MAX_STAGES) stages = ltc::MAX_STAGES;
+  if (stages < 2) return fail(DPB_EUNSUPPORTED, "lbs tc: not enough shared memory for the operand ring");
+  p.stages = stages;
+  const size_t smem = fixed + (size_t)stages * ltc::A_SLAB;
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.n_groups < h->sm_count ? p.n_groups : h->sm_count;
+  ltc::lbs_blend_tc_kernel<<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+}  // namespace dpb

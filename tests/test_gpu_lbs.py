@@ -16,12 +16,15 @@ def _oracle(model, inputs, mt):
     return lbs_ref.body_forward(model, shape, pose, inputs['trans'])
 
 
-@pytest.mark.parametrize('mt,B', [('smpl', 1), ('smpl', 37), ('smpl', 256), ('smplx', 1), ('smplx', 48)])
-def test_lbs_forward_vs_oracle(mt, B):
+@pytest.mark.parametrize('mt,B,engine', [('smpl', 1, 1), ('smpl', 37, 1), ('smpl', 256, 1), ('smplx', 1, 1),
+                                         ('smplx', 48, 1), ('smpl', 37, 2), ('smpl', 300, 2), ('smplx', 100, 2)])
+def test_lbs_forward_vs_oracle(mt, B, engine):
+    """engine 1 = fp32 blend, engine 2 = tcgen05 blend (fp16 hi/lo split operands, fp32 accumulate)."""
     m = synthetic.make_body_tensors(mt)
     inp = synthetic.lbs_inputs(B, mt)
     v_ref, j_ref = _oracle(m, inp, mt)
     bm = BodyModel(m, num_betas=10, batch_size=B, model_type=mt).cuda()
+    bm.core.engine = engine
     with torch.no_grad():
         out = bm(**{k: v.cuda() for k, v in inp.items()})
     assert out.v.shape == v_ref.shape and out.Jtr.shape == j_ref.shape
