@@ -315,10 +315,14 @@ bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_by
   out->gbeta = c.take<float>((size_t)B * (h->S + 3));
   out->compact = compact ? c.take<float>((size_t)B * h->n_need * 3) : nullptr;
   out->featop = nullptr;
+  out->skinop = nullptr;
   if (h->tc_ready && !compact) {
     c.off = align_up(c.off, 1024);
     out->featop = reinterpret_cast<__half*>(c.base + c.off);
-    c.off += lbs_tc_ws_bytes(h, B) - 1024;
+    const int64_t B_pad = (B + 63) / 64 * 64;
+    c.off += align_up((size_t)B_pad * h->kext * sizeof(__half), 1024);
+    out->skinop = reinterpret_cast<__half*>(c.base + c.off);
+    c.off += align_up((size_t)B_pad * 12 * 2 * h->jp * sizeof(__half), 1024);
   }
   return ws != nullptr && c.ok();
 }
@@ -487,6 +491,10 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
       // blend on tcgen05 (writes v_posed into verts), then skin in place with the transforms from the pose kernel
       int rc = lbs_tc_blend(h, betas, w.feat, w.featop, verts, B, st);
       if (rc != DPB_OK) return rc;
+      if (lbs_tc_skin_fits(h)) {
+        rc = lbs_tc_skin(h, w.A, transl, w.skinop, verts, B, st);
+        if (rc != DPB_OK) return rc;
+      } else {
       size_t smem = ((size_t)LBS_TP * h->J * 12 + LBS_TP * 3) * 4;
       DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid((n_verts + LBS_TV - 1) / LBS_TV, (unsigned)((B + LBS_TP - 1) / LBS_TP));
@@ -495,6 +503,7 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
                                                     h->posedirs, h->ell_idx, h->ell_w, nullptr, n_verts, h->V, h->J,
                                                     0, 0, h->nnz, verts, verts, B);
       DPB_CUDA_CHECK(cudaGetLastError());
+      }
     } else {
       size_t smem = ((size_t)h->P * LBS_TP + (size_t)h->S * LBS_TP + (size_t)LBS_TP * h->J * 12 + LBS_TP * 3) * 4;
       DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -38,6 +38,9 @@ struct dpb_lbs {
   __half* dirs16 = nullptr;       // [3V_pad, kext] K-major fp16 hi/lo-split blend basis
   CUtensorMap tm_dirs;
   int n_cols_pad = 0;
+  int jp = 0;                     // joints padded to 32
+  __half* wop16 = nullptr;        // [V_pad, 2*jp] fp16 [hi | lo] skinning weights
+  CUtensorMap tm_wop;
 };
 
 namespace dpb {
@@ -54,10 +57,14 @@ struct LbsWs {
   float* gextra;  // [B,n_need,3] joint grads scattered onto the vertices that produce them
   float* gbeta;   // [B,S+3]    vertex-path part of dL/dbetas | dL/dtransl
   __half* featop; // [B_pad, kext] fp16 [hi | lo] blend operand of the tcgen05 engine (nullptr if unavailable)
+  __half* skinop; // [B_pad*12, 2*jp] fp16 [hi | lo] per-pose transform operand of the tcgen05 skinning
 };
 size_t lbs_ws_bytes(const dpb_lbs* h, int64_t B, bool compact);
 bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_bytes, LbsWs* out);
 size_t lbs_tc_ws_bytes(const dpb_lbs* h, int64_t B);
 int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* featop, float* verts, int64_t B,
                  cudaStream_t st);
+int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop, float* verts, int64_t B,
+                cudaStream_t st);
+bool lbs_tc_skin_fits(const dpb_lbs* h);
 }  // namespace dpb

@@ -224,6 +224,196 @@ __global__ void lbs_featop_kernel(const float* __restrict__ betas, const float* 
   op[b * (2 * Kp) + Kp + k] = lo;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Skinning on tensor cores:  T[v, (b,e)] = sum_j w[v,j] A[b,j,e]  (e = 12 entries of the 3x4 transform) as a GEMM
+// with M = 128 vertices (lane = vertex = epilogue thread), N = 16 poses x 12 entries, K = joints; fp16 hi/lo
+// 3-product split as in the blend.  The epilogue applies T to the blended vertex (read back from the vertex
+// buffer, coalesced) and stores the skinned vertex in place.  CUDA-core skinning is shared-memory bound
+// (4 x 48 B of transform per (pose, vertex) through LDS); here the blend of transforms costs 6 MMAs per 2048 pairs.
+constexpr int SK_POSES = 16;               // poses per MMA (N = 192)
+constexpr int SK_N = SK_POSES * 12;
+constexpr int SK_GROUP = 64;               // poses whose transform operand stays resident (4 chunks)
+constexpr int SK_WSTAGES = 3;
+constexpr uint32_t SK_IDESC = ptx::umma_idesc_f16(TILE_V, SK_N, 0);
+
+struct SkinParams {
+  int V, n_vt, jsteps;      // jsteps: K16 steps of the hi (= lo) part = Jp/16
+  int n_slabs;              // 64-wide slabs of [hi | lo] = 2*Jp/64
+  int64_t B;
+  int n_groups;
+  const float* transl;      // [B,3] or nullptr
+  float* verts;             // [B,V,3] in: v_posed, out: skinned vertices
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__ CUtensorMap tm_w,
+                   const __grid_constant__ CUtensorMap tm_s) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const int chunks = SK_GROUP / SK_POSES;
+  const uint32_t s_slab = SK_N * BK * 2;                           // 24 KB: one chunk, one 64-wide slab
+  const uint32_t s_bytes = chunks * p.n_slabs * s_slab;            // resident transform operand of the pose group
+  const uint32_t w_bytes = p.n_slabs * A_SLAB;                     // one vertex tile of weights
+  const uint32_t s_base = smem_base;
+  const uint32_t w_base = smem_base + s_bytes;
+  const uint32_t bar_base = w_base + SK_WSTAGES * w_bytes;
+  auto wfull = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto wempty = [&](uint32_t s) { return bar_base + 8u * (SK_WSTAGES + s); };
+  auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * SK_WSTAGES + b); };
+  auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * SK_WSTAGES + 2 + b); };
+  const uint32_t sfull = bar_base + 8u * (2 * SK_WSTAGES + 4);
+  const uint32_t sempty = bar_base + 8u * (2 * SK_WSTAGES + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + s_bytes + SK_WSTAGES * w_bytes + (2 * SK_WSTAGES + 6) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SK_WSTAGES; ++s) { ptx::mbar_init(wfull(s), 1); ptx::mbar_init(wempty(s), 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4); }
+    ptx::mbar_init(sfull, 1);
+    ptx::mbar_init(sempty, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, gph = 0;
+      for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+        ptx::mbar_wait(sempty, gph ^ 1);
+        ptx::mbar_arrive_expect_tx(sfull, s_bytes);
+        for (int c = 0; c < chunks; ++c)
+          for (int i = 0; i < p.n_slabs; ++i)
+            ptx::tma_load_2d(s_base + (c * p.n_slabs + i) * s_slab, &tm_s, sfull, i * BK,
+                             (grp * SK_GROUP + c * SK_POSES) * 12);
+        gph ^= 1;
+        for (int vt = 0; vt < p.n_vt; ++vt) {
+          ptx::mbar_wait(wempty(stage), phase ^ 1);
+          ptx::mbar_arrive_expect_tx(wfull(stage), w_bytes);
+          for (int i = 0; i < p.n_slabs; ++i)
+            ptx::tma_load_2d(w_base + stage * w_bytes + i * A_SLAB, &tm_w, wfull(stage), i * BK, vt * TILE_V);
+          if (++stage == SK_WSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, gph = 0, blk = 0, tph = 0;
+      const int js = p.jsteps;
+      for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+        ptx::mbar_wait(sfull, gph);
+        gph ^= 1;
+        for (int vt = 0; vt < p.n_vt; ++vt) {
+          ptx::mbar_wait(wfull(stage), phase);
+          ptx::tc_fence_after();
+          const uint32_t wa = w_base + stage * w_bytes;
+          auto wdesc = [&](int step) { return ptx::umma_desc_sw128(wa + (step >> 2) * A_SLAB) + 2 * (step & 3); };
+          for (int c = 0; c < chunks; ++c) {
+            const uint32_t buf = blk & 1;
+            ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * 256;
+            const uint32_t sa = s_base + c * p.n_slabs * s_slab;
+            auto sdesc = [&](int step) { return ptx::umma_desc_sw128(sa + (step >> 2) * s_slab) + 2 * (step & 3); };
+            for (int g = 0; g < js; ++g) {   // w_hi x (A_hi + A_lo), then w_lo x A_hi
+              ptx::mma_f16_ss(taddr, wdesc(g), sdesc(g), SK_IDESC, g ? 1u : 0u);
+              ptx::mma_f16_ss(taddr, wdesc(g), sdesc(js + g), SK_IDESC, 1u);
+              ptx::mma_f16_ss(taddr, wdesc(js + g), sdesc(g), SK_IDESC, 1u);
+            }
+            ptx::mma_commit(tfull_bar(buf));
+            tph ^= 1u << buf;
+            ++blk;
+          }
+          ptx::mma_commit(wempty(stage));
+          if (++stage == SK_WSTAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(sempty);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t blk = 0, tph = 0;
+    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+      for (int vt = 0; vt < p.n_vt; ++vt) {
+        const int v = vt * TILE_V + q * 32 + lane;
+        const bool vok = v < p.V;
+        for (int c = 0; c < chunks; ++c) {
+          const int64_t b0 = (int64_t)grp * SK_GROUP + c * SK_POSES;
+          // blended vertices of this thread's vertex for the chunk's poses: in flight before the TMEM wait
+          float vp[SK_POSES][3];
+#pragma unroll
+          for (int i = 0; i < SK_POSES; ++i) {
+            const bool ok = vok && (b0 + i) < p.B;
+            const float* s = p.verts + ((size_t)(ok ? b0 + i : 0) * p.V + (ok ? v : 0)) * 3;
+            vp[i][0] = s[0]; vp[i][1] = s[1]; vp[i][2] = s[2];
+          }
+          const uint32_t buf = blk & 1;
+          ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int h8 = 0; h8 < 2; ++h8) {   // 8 poses (96 columns) at a time
+            uint32_t t[96];
+            const uint32_t t0 = tmem_base + lane_addr + buf * 256 + h8 * 96;
+            ptx::tmem_ld_32x32(t0, t);
+            ptx::tmem_ld_32x32(t0 + 32, t + 32);
+            ptx::tmem_ld_32x32(t0 + 64, t + 64);
+            ptx::tmem_ld_wait();
+            if (h8 == 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int pi = h8 * 8 + i;
+              const int64_t b = b0 + pi;
+              if (vok && b < p.B) {
+                const float* T = reinterpret_cast<const float*>(t) + i * 12;
+                const float x = vp[pi][0], y = vp[pi][1], z = vp[pi][2];
+                float tx = 0.f, ty = 0.f, tz = 0.f;
+                if (p.transl) { tx = p.transl[b * 3]; ty = p.transl[b * 3 + 1]; tz = p.transl[b * 3 + 2]; }
+                float* o = p.verts + ((size_t)b * p.V + v) * 3;
+                o[0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
+                o[1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
+                o[2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
+              }
+            }
+          }
+          tph ^= 1u << buf;
+          ++blk;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// per-pose transforms A[b,j,12] -> operand rows (b*12 + e) = [A[b,:,e] hi (Jp) | lo (Jp)] fp16
+__global__ void lbs_skinop_kernel(const float* __restrict__ A, int J, int Jp, __half* __restrict__ op, int64_t B,
+                                  int64_t B_pad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B_pad * 12 * Jp) return;
+  const int j = (int)(i % Jp);
+  const int64_t r = i / Jp;          // row = b*12 + e
+  const int64_t b = r / 12;
+  const int e = (int)(r % 12);
+  float x = 0.f;
+  if (b < B && j < J) x = A[(b * J + j) * 12 + e];
+  const __half hi = __float2half_rn(x);
+  op[r * (2 * Jp) + j] = hi;
+  op[r * (2 * Jp) + Jp + j] = __float2half_rn(x - __half2float(hi));
+}
+
 }  // namespace ltc
 
 int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
@@ -254,20 +444,78 @@ int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   if (rc != DPB_OK) return rc;
   h->kext = K2;
   h->n_cols_pad = V_pad;
+  // skinning-weight operand: row v = [w[v,:] hi (Jp) | lo (Jp)], Jp = joints padded to 32
+  const int J = h->J, Jp = (J + 31) / 32 * 32;
+  std::vector<__half> wop((size_t)V_pad * 2 * Jp, __float2half_rn(0.f));
+  for (int v = 0; v < V; ++v)
+    for (int j = 0; j < J; ++j) {
+      const float x = m->lbs_weights[(size_t)v * J + j];
+      const __half hi = __float2half_rn(x);
+      wop[(size_t)v * 2 * Jp + j] = hi;
+      wop[(size_t)v * 2 * Jp + Jp + j] = __float2half_rn(x - __half2float(hi));
+    }
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->wop16, wop.size() * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMemcpy(h->wop16, wop.data(), wop.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  rc = make_tmap_2d(&h->tm_wop, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->wop16, 2 * Jp, (uint64_t)V_pad, ltc::BK,
+                    ltc::TILE_V, 2);
+  if (rc != DPB_OK) return rc;
+  h->jp = Jp;
   h->tc_ready = true;
   return DPB_OK;
 }
 
 void lbs_tc_release(dpb_lbs* h) {
   if (h->dirs16) cudaFree(h->dirs16);
+  if (h->wop16) cudaFree(h->wop16);
   h->dirs16 = nullptr;
+  h->wop16 = nullptr;
   h->tc_ready = false;
 }
 
 size_t lbs_tc_ws_bytes(const dpb_lbs* h, int64_t B) {
   if (!h->tc_ready) return 0;
   const int64_t B_pad = (B + ltc::NP - 1) / ltc::NP * ltc::NP;
-  return align_up((size_t)B_pad * h->kext * sizeof(__half), 1024) + 1024;
+  return align_up((size_t)B_pad * h->kext * sizeof(__half), 1024) +
+         align_up((size_t)B_pad * 12 * 2 * h->jp * sizeof(__half), 1024) + 1024;
+}
+
+bool lbs_tc_skin_fits(const dpb_lbs* h) {
+  const int n_slabs = 2 * h->jp / ltc::BK;
+  const size_t smem = (size_t)(ltc::SK_GROUP / ltc::SK_POSES) * n_slabs * ltc::SK_N * ltc::BK * 2 +
+                      (size_t)ltc::SK_WSTAGES * n_slabs * ltc::A_SLAB + 2048;
+  return h->tc_ready && smem <= 232448;
+}
+
+// skins verts[B,V,3] (holding v_posed) in place with the per-pose transforms A[B,J,12]
+int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop, float* verts, int64_t B,
+                cudaStream_t st) {
+  const int Jp = h->jp;
+  const int64_t B_pad = (B + ltc::SK_GROUP - 1) / ltc::SK_GROUP * ltc::SK_GROUP;
+  {
+    const int64_t n = B_pad * 12 * Jp;
+    ltc::lbs_skinop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, h->J, Jp, skinop, B, B_pad);
+    DPB_CUDA_CHECK(cudaGetLastError());
+  }
+  CUtensorMap tm_s;
+  int rc = make_tmap_2d(&tm_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, skinop, 2 * Jp, (uint64_t)B_pad * 12, ltc::BK, ltc::SK_N, 2);
+  if (rc != DPB_OK) return rc;
+  ltc::SkinParams p{};
+  p.V = h->V;
+  p.n_vt = h->n_cols_pad / ltc::TILE_V;
+  p.jsteps = Jp / 16;
+  p.n_slabs = 2 * Jp / ltc::BK;
+  p.B = B;
+  p.n_groups = (int)(B_pad / ltc::SK_GROUP);
+  p.transl = transl;
+  p.verts = verts;
+  const size_t smem = (size_t)(ltc::SK_GROUP / ltc::SK_POSES) * p.n_slabs * ltc::SK_N * ltc::BK * 2 +
+                      (size_t)ltc::SK_WSTAGES * p.n_slabs * ltc::A_SLAB + (2 * ltc::SK_WSTAGES + 6) * 8 + 16 + 1024;
+  if (smem > 232448) return fail(DPB_EUNSUPPORTED, "lbs tc skin: transform operand does not fit shared memory");
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.n_groups < h->sm_count ? p.n_groups : h->sm_count;
+  ltc::lbs_skin_tc_kernel<<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_wop, tm_s);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
 }
 
 // writes v_posed (template + shape blend + pose blend) into verts[B,V,3]

@@ -36,7 +36,7 @@ def test_lbs_forward_vs_oracle(mt, B, engine):
     with torch.no_grad():
         out2 = bm(need_verts=False, **{k: v.cuda() for k, v in inp.items()})
     assert out2.v is None
-    assert (out2.Jtr - out.Jtr).abs().max() < 1e-6
+    assert (out2.Jtr - out.Jtr).abs().max() < 5e-6     # extra joints: fp32 blend (compact) vs tcgen05 blend
 
 
 def test_lbs_large_rotations_and_defaults():
