@@ -33,7 +33,7 @@ constexpr int NP = 64;        // poses per group (MMA N)
 constexpr int BK = 64;        // fp16 per 128-byte swizzle row
 constexpr int A_SLAB = TILE_V * BK * 2;  // 16 KB
 constexpr int B_SLAB = NP * BK * 2;      // 8 KB
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int MAX_STAGES = 8;
 constexpr uint32_t IDESC = ptx::umma_idesc_f16(TILE_V, NP, 0);
 
@@ -73,7 +73,7 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tfull_bar(b), 1);
-      ptx::mbar_init(tempty_bar(b), 4);
+      ptx::mbar_init(tempty_bar(b), 8);
     }
     ptx::mbar_init(bfull_bar, 1);
     ptx::mbar_init(bempty_bar, 1);
@@ -168,28 +168,36 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
         const uint32_t buf = blk & 1;
         ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
         ptx::tc_fence_after();
-#pragma unroll 1
-        for (int hp = 0; hp < NP / 32; ++hp) {  // 32 poses at a time: x, y, z of each
+        {  // this warp's 32 poses (warps 4-7: poses 0-31, warps 8-11: poses 32-63): x, y, z of each
+          const int hp = (warp - 4) >> 2;
           uint32_t dx[32], dy[32], dz[32];
           const uint32_t t0 = tmem_base + lane_addr + buf * (3 * NP) + hp * 32;
           ptx::tmem_ld_32x32(t0, dx);
           ptx::tmem_ld_32x32(t0 + NP, dy);
           ptx::tmem_ld_32x32(t0 + 2 * NP, dz);
           ptx::tmem_ld_wait();
-          if (hp == NP / 32 - 1) {
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
-          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
           if (vok) {
+            const int64_t bb = b0 + hp * 32;
+            float* o = p.verts + ((size_t)bb * p.V + v) * 3;
+            const size_t pstride = (size_t)p.V * 3;
+            if (bb + 32 <= p.B) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int64_t b = b0 + hp * 32 + i;
-              if (b < p.B) {
-                float* o = p.verts + ((size_t)b * p.V + v) * 3;
+              for (int i = 0; i < 32; ++i, o += pstride) {
                 o[0] = __uint_as_float(dx[i]) + vt3[0];
                 o[1] = __uint_as_float(dy[i]) + vt3[1];
                 o[2] = __uint_as_float(dz[i]) + vt3[2];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i, o += pstride) {
+                if (bb + i < p.B) {
+                  o[0] = __uint_as_float(dx[i]) + vt3[0];
+                  o[1] = __uint_as_float(dy[i]) + vt3[1];
+                  o[2] = __uint_as_float(dz[i]) + vt3[2];
+                }
               }
             }
           }
@@ -270,7 +278,7 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < SK_WSTAGES; ++s) { ptx::mbar_init(wfull(s), 1); ptx::mbar_init(wempty(s), 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 4); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar(b), 1); ptx::mbar_init(tempty_bar(b), 8); }
     ptx::mbar_init(sfull, 1);
     ptx::mbar_init(sempty, 1);
     ptx::fence_barrier_init();
@@ -345,44 +353,45 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
         const bool vok = v < p.V;
         for (int c = 0; c < chunks; ++c) {
           const int64_t b0 = (int64_t)grp * SK_GROUP + c * SK_POSES;
-          // blended vertices of this thread's vertex for the chunk's poses: in flight before the TMEM wait
-          float vp[SK_POSES][3];
+          // this warp's 8 poses of the chunk (warps 4-7: poses 0-7, warps 8-11: poses 8-15); the blended
+          // vertices are requested before the TMEM wait so their latency hides behind it
+          const int h8 = (warp - 4) >> 2;
+          const int64_t bb = b0 + h8 * 8;
+          const bool full = vok && (bb + 8 <= p.B);
+          const size_t pstride = (size_t)p.V * 3;
+          float* o = p.verts + ((size_t)(vok && bb < p.B ? bb : 0) * p.V + (vok ? v : 0)) * 3;
+          float vp[8][3];
 #pragma unroll
-          for (int i = 0; i < SK_POSES; ++i) {
-            const bool ok = vok && (b0 + i) < p.B;
-            const float* s = p.verts + ((size_t)(ok ? b0 + i : 0) * p.V + (ok ? v : 0)) * 3;
+          for (int i = 0; i < 8; ++i) {
+            const float* s = o + (size_t)((full || (vok && bb + i < p.B)) ? i : 0) * pstride;
             vp[i][0] = s[0]; vp[i][1] = s[1]; vp[i][2] = s[2];
           }
           const uint32_t buf = blk & 1;
           ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
           ptx::tc_fence_after();
-#pragma unroll 1
-          for (int h8 = 0; h8 < 2; ++h8) {   // 8 poses (96 columns) at a time
-            uint32_t t[96];
-            const uint32_t t0 = tmem_base + lane_addr + buf * 256 + h8 * 96;
-            ptx::tmem_ld_32x32(t0, t);
-            ptx::tmem_ld_32x32(t0 + 32, t + 32);
-            ptx::tmem_ld_32x32(t0 + 64, t + 64);
-            ptx::tmem_ld_wait();
-            if (h8 == 1) {
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
-            }
+          uint32_t t[96];
+          const uint32_t t0 = tmem_base + lane_addr + buf * 256 + h8 * 96;
+          ptx::tmem_ld_32x32(t0, t);
+          ptx::tmem_ld_32x32(t0 + 32, t + 32);
+          ptx::tmem_ld_32x32(t0 + 64, t + 64);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int pi = h8 * 8 + i;
-              const int64_t b = b0 + pi;
-              if (vok && b < p.B) {
-                const float* T = reinterpret_cast<const float*>(t) + i * 12;
-                const float x = vp[pi][0], y = vp[pi][1], z = vp[pi][2];
-                float tx = 0.f, ty = 0.f, tz = 0.f;
-                if (p.transl) { tx = p.transl[b * 3]; ty = p.transl[b * 3 + 1]; tz = p.transl[b * 3 + 2]; }
-                float* o = p.verts + ((size_t)b * p.V + v) * 3;
-                o[0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
-                o[1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
-                o[2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
+          for (int i = 0; i < 8; ++i) {
+            if (full || (vok && bb + i < p.B)) {
+              const float* T = reinterpret_cast<const float*>(t) + i * 12;
+              const float x = vp[i][0], y = vp[i][1], z = vp[i][2];
+              float tx = 0.f, ty = 0.f, tz = 0.f;
+              if (p.transl) {
+                const float* tr = p.transl + (bb + i) * 3;
+                tx = tr[0]; ty = tr[1]; tz = tr[2];
               }
+              float* w = o + (size_t)i * pstride;
+              w[0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
+              w[1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
+              w[2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
             }
           }
           tph ^= 1u << buf;

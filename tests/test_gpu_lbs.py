@@ -71,7 +71,8 @@ def test_lbs_full_size_batch_properties():
         sub = {k: v[idx] for k, v in inp.items()}
         bm_s = BodyModel(m, batch_size=5, model_type='smpl').cuda()
         o2 = bm_s(**sub)
-        assert torch.equal(out.v[idx], o2.v) and torch.equal(out.Jtr[idx], o2.Jtr)
+        # the 5-row call takes the fp32 blend, the 65 536-row call the tcgen05 blend: equal to well below 1e-5 m
+        assert (out.v[idx] - o2.v).abs().max() < 3e-6 and (out.Jtr[idx] - o2.Jtr).abs().max() < 3e-6
         sub2 = dict(sub)
         sub2['trans'] = sub['trans'] + 1.0
         o3 = bm_s(**sub2)
