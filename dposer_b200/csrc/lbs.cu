@@ -319,7 +319,7 @@ bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_by
   if (h->tc_ready && !compact) {
     c.off = align_up(c.off, 1024);
     out->featop = reinterpret_cast<__half*>(c.base + c.off);
-    const int64_t B_pad = (B + 63) / 64 * 64;
+    const int64_t B_pad = (B + 127) / 128 * 128;
     c.off += align_up((size_t)B_pad * h->kext * sizeof(__half), 1024);
     out->skinop = reinterpret_cast<__half*>(c.base + c.off);
     c.off += align_up((size_t)B_pad * 12 * 2 * h->jp * sizeof(__half), 1024);

@@ -29,13 +29,11 @@ int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64
 namespace ltc {
 
 constexpr int TILE_V = 128;   // vertices per block (MMA M)
-constexpr int NP = 64;        // poses per group (MMA N)
 constexpr int BK = 64;        // fp16 per 128-byte swizzle row
 constexpr int A_SLAB = TILE_V * BK * 2;  // 16 KB
-constexpr int B_SLAB = NP * BK * 2;      // 8 KB
 constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int MAX_STAGES = 8;
-constexpr uint32_t IDESC = ptx::umma_idesc_f16(TILE_V, NP, 0);
+constexpr int PAD_POSES = 128;     // operand rows are padded to whole pose groups of either size
 
 struct KParams {
   int V, V_pad, n_vt;       // vertices, padded vertices, vertex tiles
@@ -48,13 +46,19 @@ struct KParams {
   float* verts;             // [B,V,3]
 };
 
+// One accumulation unit = (pose group, vertex tile, coordinate c): D_c[v, pose] over all K, N = NP poses per MMA.
+// NP = 128 when the group's operand fits shared memory (SMPL), 64 otherwise (SMPL-X): with N = 64 an MMA is only
+// 32 tensor cycles and the single issuing thread becomes the limiter, so the wider group is preferred.
+template <int NP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUtensorMap tm_dirs,
                     const __grid_constant__ CUtensorMap tm_feat) {
+  constexpr int B_SLAB = NP * BK * 2;
+  constexpr uint32_t IDESC = ptx::umma_idesc_f16(TILE_V, NP, 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = ptx::smem_u32(smem);
-  const uint32_t b_base = smem_base;                              // resident pose-group operand: n_slabs x 8 KB
+  const uint32_t b_base = smem_base;                              // resident pose-group operand: n_slabs slabs
   const uint32_t a_base = smem_base + p.n_slabs * B_SLAB;         // ring of A slabs
   const uint32_t bar_base = a_base + p.stages * A_SLAB;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
@@ -79,7 +83,7 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
     ptx::mbar_init(bempty_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 256);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -108,109 +112,90 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, gph = 0, blk = 0, tph = 0;
+      uint32_t stage = 0, phase = 0, gph = 0, unit = 0, tph = 0;
+      const uint64_t adesc0 = ptx::umma_desc_sw128(a_base), bdesc0 = ptx::umma_desc_sw128(b_base);
+      auto bdesc = [&](int step) { return bdesc0 + (uint64_t)((step >> 2) * (B_SLAB >> 4) + 2 * (step & 3)); };
       for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
         ptx::mbar_wait(bfull_bar, gph);
         gph ^= 1;
         ptx::tc_fence_after();
-        for (int vt = 0; vt < p.n_vt; ++vt) {
-          const uint32_t buf = blk & 1;
-          ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
-          ptx::tc_fence_after();
+        for (int vt = 0; vt < p.n_vt; ++vt)
           for (int c = 0; c < 3; ++c) {
-            const uint32_t taddr = tmem_base + buf * (3 * NP) + c * NP;
-            uint32_t first = 1;
+            const uint32_t buf = unit & 1;
+            ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * NP;
+            uint32_t acc = 0;
             for (int i = 0; i < p.n_slabs; ++i) {
               ptx::mbar_wait(full_bar(stage), phase);
               ptx::tc_fence_after();
-              const uint32_t a_addr = a_base + stage * A_SLAB;
+              const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_SLAB >> 4));
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j) {
                 const int g = i * (BK / 16) + j;  // K16 step inside [hi | lo]
-                const uint64_t adesc = ptx::umma_desc_sw128(a_addr) + 2 * j;
-                auto bdesc = [&](int step) {
-                  return ptx::umma_desc_sw128(b_base + (step >> 2) * B_SLAB) + 2 * (step & 3);
-                };
                 if (g < half) {  // basis_hi x (feat_hi + feat_lo)
-                  ptx::mma_f16_ss(taddr, adesc, bdesc(g), IDESC, first ? 0u : 1u);
-                  ptx::mma_f16_ss(taddr, adesc, bdesc(half + g), IDESC, 1u);
-                  first = 0;
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g), IDESC, acc);
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(half + g), IDESC, 1u);
+                  acc = 1;
                 } else {         // basis_lo x feat_hi
-                  ptx::mma_f16_ss(taddr, adesc, bdesc(g - half), IDESC, 1u);
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g - half), IDESC, 1u);
                 }
               }
               ptx::mma_commit(empty_bar(stage));
               if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
             }
+            ptx::mma_commit(tfull_bar(buf));
+            tph ^= 1u << buf;
+            ++unit;
           }
-          ptx::mma_commit(tfull_bar(buf));
-          tph ^= 1u << buf;
-          ++blk;
-        }
         ptx::mma_commit(bempty_bar);
       }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
+    const int hh = (warp - 4) >> 2;   // which half of the group's poses this warp stores
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t blk = 0, tph = 0;
+    const size_t pstride = (size_t)p.V * 3;
+    uint32_t unit = 0, tph = 0;
     for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-      const int64_t b0 = (int64_t)grp * NP;
+      const int64_t bb = (int64_t)grp * NP + hh * (NP / 2);
       for (int vt = 0; vt < p.n_vt; ++vt) {
         const int v = vt * TILE_V + q * 32 + lane;
         const bool vok = v < p.V;
-        float vt3[3] = {0.f, 0.f, 0.f};
-        if (vok) {
-          vt3[0] = p.v_template[v * 3 + 0];
-          vt3[1] = p.v_template[v * 3 + 1];
-          vt3[2] = p.v_template[v * 3 + 2];
-        }
-        const uint32_t buf = blk & 1;
-        ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
-        ptx::tc_fence_after();
-        {  // this warp's 32 poses (warps 4-7: poses 0-31, warps 8-11: poses 32-63): x, y, z of each
-          const int hp = (warp - 4) >> 2;
-          uint32_t dx[32], dy[32], dz[32];
-          const uint32_t t0 = tmem_base + lane_addr + buf * (3 * NP) + hp * 32;
-          ptx::tmem_ld_32x32(t0, dx);
-          ptx::tmem_ld_32x32(t0 + NP, dy);
-          ptx::tmem_ld_32x32(t0 + 2 * NP, dz);
+        for (int c = 0; c < 3; ++c) {
+          const float vtc = vok ? p.v_template[v * 3 + c] : 0.f;
+          const uint32_t buf = unit & 1;
+          ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+          ptx::tc_fence_after();
+          uint32_t d[NP / 2];
+#pragma unroll
+          for (int k = 0; k < NP / 64; ++k)
+            ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * NP + hh * (NP / 2) + k * 32, d + k * 32);
           ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
-          if (vok) {
-            const int64_t bb = b0 + hp * 32;
-            float* o = p.verts + ((size_t)bb * p.V + v) * 3;
-            const size_t pstride = (size_t)p.V * 3;
-            if (bb + 32 <= p.B) {
+          if (vok && bb < p.B) {
+            float* o = p.verts + ((size_t)bb * p.V + v) * 3 + c;
+            if (bb + NP / 2 <= p.B) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i, o += pstride) {
-                o[0] = __uint_as_float(dx[i]) + vt3[0];
-                o[1] = __uint_as_float(dy[i]) + vt3[1];
-                o[2] = __uint_as_float(dz[i]) + vt3[2];
-              }
+              for (int i = 0; i < NP / 2; ++i, o += pstride) *o = __uint_as_float(d[i]) + vtc;
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i, o += pstride) {
-                if (bb + i < p.B) {
-                  o[0] = __uint_as_float(dx[i]) + vt3[0];
-                  o[1] = __uint_as_float(dy[i]) + vt3[1];
-                  o[2] = __uint_as_float(dz[i]) + vt3[2];
-                }
-              }
+              for (int i = 0; i < NP / 2; ++i, o += pstride)
+                if (bb + i < p.B) *o = __uint_as_float(d[i]) + vtc;
             }
           }
+          tph ^= 1u << buf;
+          ++unit;
         }
-        tph ^= 1u << buf;
-        ++blk;
       }
     }
   }
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -408,8 +393,10 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
 }
 
 // per-pose transforms A[b,j,12] -> operand rows (b*12 + e) = [A[b,:,e] hi (Jp) | lo (Jp)] fp16
-__global__ void lbs_skinop_kernel(const float* __restrict__ A, int J, int Jp, __half* __restrict__ op, int64_t B,
-                                  int64_t B_pad) {
+// If J < Jp the spare joint slot J carries the translation: its weight is 1 for every vertex (lbs_tc_prepare) and
+// its "transform" is [0 | transl], so T_t already includes + transl and the epilogue does not add it.
+__global__ void lbs_skinop_kernel(const float* __restrict__ A, const float* __restrict__ transl, int J, int Jp,
+                                  __half* __restrict__ op, int64_t B, int64_t B_pad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B_pad * 12 * Jp) return;
   const int j = (int)(i % Jp);
@@ -418,6 +405,7 @@ __global__ void lbs_skinop_kernel(const float* __restrict__ A, int J, int Jp, __
   const int e = (int)(r % 12);
   float x = 0.f;
   if (b < B && j < J) x = A[(b * J + j) * 12 + e];
+  else if (b < B && j == J && e >= 9 && transl) x = transl[b * 3 + (e - 9)];
   const __half hi = __float2half_rn(x);
   op[r * (2 * Jp) + j] = hi;
   op[r * (2 * Jp) + Jp + j] = __float2half_rn(x - __half2float(hi));
@@ -432,7 +420,7 @@ int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   const int K2 = 2 * Kp;
   const int V_pad = (V + ltc::TILE_V - 1) / ltc::TILE_V * ltc::TILE_V;
   const int n_slabs = K2 / ltc::BK;
-  if ((size_t)n_slabs * ltc::B_SLAB + 2 * ltc::A_SLAB + 2048 > 232448) return DPB_OK;  // model too wide: fp32 engine only
+  if ((size_t)n_slabs * (64 * ltc::BK * 2) + 2 * ltc::A_SLAB + 2048 > 232448) return DPB_OK;  // too wide: fp32 engine only
   // blend basis, vertex-major per coordinate: row (c*V_pad + v) = [shapedirs[v,c,:] | posedirs[:,3v+c]] as [hi | lo]
   std::vector<__half> basis((size_t)3 * V_pad * K2, __float2half_rn(0.f));
   for (int c = 0; c < 3; ++c)
@@ -463,6 +451,8 @@ int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
       wop[(size_t)v * 2 * Jp + j] = hi;
       wop[(size_t)v * 2 * Jp + Jp + j] = __float2half_rn(x - __half2float(hi));
     }
+  if (J < Jp)
+    for (int v = 0; v < V; ++v) wop[(size_t)v * 2 * Jp + J] = __float2half_rn(1.0f);   // translation slot
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->wop16, wop.size() * sizeof(__half)));
   DPB_CUDA_CHECK(cudaMemcpy(h->wop16, wop.data(), wop.size() * sizeof(__half), cudaMemcpyHostToDevice));
   rc = make_tmap_2d(&h->tm_wop, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->wop16, 2 * Jp, (uint64_t)V_pad, ltc::BK,
@@ -483,7 +473,7 @@ void lbs_tc_release(dpb_lbs* h) {
 
 size_t lbs_tc_ws_bytes(const dpb_lbs* h, int64_t B) {
   if (!h->tc_ready) return 0;
-  const int64_t B_pad = (B + ltc::NP - 1) / ltc::NP * ltc::NP;
+  const int64_t B_pad = (B + ltc::PAD_POSES - 1) / ltc::PAD_POSES * ltc::PAD_POSES;
   return align_up((size_t)B_pad * h->kext * sizeof(__half), 1024) +
          align_up((size_t)B_pad * 12 * 2 * h->jp * sizeof(__half), 1024) + 1024;
 }
@@ -502,7 +492,7 @@ int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop,
   const int64_t B_pad = (B + ltc::SK_GROUP - 1) / ltc::SK_GROUP * ltc::SK_GROUP;
   {
     const int64_t n = B_pad * 12 * Jp;
-    ltc::lbs_skinop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, h->J, Jp, skinop, B, B_pad);
+    ltc::lbs_skinop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, transl, h->J, Jp, skinop, B, B_pad);
     DPB_CUDA_CHECK(cudaGetLastError());
   }
   CUtensorMap tm_s;
@@ -515,7 +505,7 @@ int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop,
   p.n_slabs = 2 * Jp / ltc::BK;
   p.B = B;
   p.n_groups = (int)(B_pad / ltc::SK_GROUP);
-  p.transl = transl;
+  p.transl = h->J < Jp ? nullptr : transl;   // folded into the GEMM through the spare joint slot when there is one
   p.verts = verts;
   const size_t smem = (size_t)(ltc::SK_GROUP / ltc::SK_POSES) * p.n_slabs * ltc::SK_N * ltc::BK * 2 +
                       (size_t)ltc::SK_WSTAGES * p.n_slabs * ltc::A_SLAB + (2 * ltc::SK_WSTAGES + 6) * 8 + 16 + 1024;
@@ -531,34 +521,43 @@ int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop,
 int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* featop, float* verts, int64_t B,
                  cudaStream_t st) {
   const int K2 = h->kext, Kp = K2 / 2;
-  const int64_t B_pad = (B + ltc::NP - 1) / ltc::NP * ltc::NP;
+  const int64_t B_pad = (B + ltc::PAD_POSES - 1) / ltc::PAD_POSES * ltc::PAD_POSES;
   {
     const int64_t n = B_pad * Kp;
     ltc::lbs_featop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(betas, feat, h->S, h->P, Kp, featop, B, B_pad);
     DPB_CUDA_CHECK(cudaGetLastError());
   }
+  const int n_slabs = K2 / ltc::BK;
+  const size_t bars = (2 * ltc::MAX_STAGES + 6) * 8 + 16 + 1024;
+  // 128-pose groups when their operand leaves room for >= 4 ring stages
+  const int np = ((size_t)n_slabs * 128 * ltc::BK * 2 + 4 * ltc::A_SLAB + bars <= 232448) ? 128 : 64;
   CUtensorMap tm_feat;
-  int rc = make_tmap_2d(&tm_feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, featop, K2, (uint64_t)B_pad, ltc::BK, ltc::NP, 2);
+  int rc = make_tmap_2d(&tm_feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, featop, K2, (uint64_t)B_pad, ltc::BK, np, 2);
   if (rc != DPB_OK) return rc;
   ltc::KParams p{};
   p.V = h->V;
   p.V_pad = h->n_cols_pad;
   p.n_vt = h->n_cols_pad / ltc::TILE_V;
   p.ksteps_half = Kp / 16;
-  p.n_slabs = K2 / ltc::BK;
+  p.n_slabs = n_slabs;
   p.B = B;
-  p.n_groups = (int)(B_pad / ltc::NP);
+  p.n_groups = (int)((B + np - 1) / np);
   p.v_template = h->v_template;
   p.verts = verts;
-  const size_t fixed = (size_t)p.n_slabs * ltc::B_SLAB + (2 * ltc::MAX_STAGES + 6) * 8 + 16 + 1024;
+  const size_t fixed = (size_t)n_slabs * np * ltc::BK * 2 + bars;
   int stages = (int)((232448 - fixed) / ltc::A_SLAB);
   if (stages > ltc::MAX_STAGES) stages = ltc::MAX_STAGES;
   if (stages < 2) return fail(DPB_EUNSUPPORTED, "lbs tc: not enough shared memory for the operand ring");
   p.stages = stages;
   const size_t smem = fixed + (size_t)stages * ltc::A_SLAB;
-  DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.n_groups < h->sm_count ? p.n_groups : h->sm_count;
-  ltc::lbs_blend_tc_kernel<<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat);
+  if (np == 128) {
+    DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_blend_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ltc::lbs_blend_tc_kernel<128><<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat);
+  } else {
+    DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_blend_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ltc::lbs_blend_tc_kernel<64><<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat);
+  }
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }
