@@ -35,6 +35,53 @@ constexpr int NUM_THREADS = 384;   // 4 control warps + 8 epilogue warps (two pe
 constexpr int MAX_STAGES = 8;
 constexpr int PAD_POSES = 128;     // operand rows are padded to whole pose groups of either size
 
+constexpr int XP = 4;              // poses transposed per round through the per-warp staging buffer
+constexpr int XSTAGE = XP * 96;    // floats per warp: 32 vertices x (x,y,z) x XP poses
+
+// Lane l holds (x,y,z) of vertex v0+l for XP poses; memory wants, per pose, 96 consecutive floats.  Going through a
+// per-warp shared buffer turns 3 stride-12-byte stores (13 sectors each) into 3 fully coalesced 128-byte stores.
+__device__ __forceinline__ void warp_store_xyz(float* stage, const float (*xyz)[3], float* const* dst, int lane,
+                                               int n_floats, int n_poses) {
+#pragma unroll
+  for (int i = 0; i < XP; ++i) {
+    stage[i * 96 + 3 * lane + 0] = xyz[i][0];
+    stage[i * 96 + 3 * lane + 1] = xyz[i][1];
+    stage[i * 96 + 3 * lane + 2] = xyz[i][2];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < XP; ++i) {
+    if (i < n_poses) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int f = 32 * k + lane;
+        if (f < n_floats) dst[i][f] = stage[i * 96 + f];
+      }
+    }
+  }
+  __syncwarp();
+}
+// inverse: per pose 96 consecutive floats in memory -> (x,y,z) of this lane's vertex
+__device__ __forceinline__ void warp_load_xyz(float* stage, float (*xyz)[3], const float* const* src, int lane,
+                                              int n_floats, int n_poses) {
+#pragma unroll
+  for (int i = 0; i < XP; ++i) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int f = 32 * k + lane;
+      stage[i * 96 + f] = (i < n_poses && f < n_floats) ? src[i][f] : 0.f;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < XP; ++i) {
+    xyz[i][0] = stage[i * 96 + 3 * lane + 0];
+    xyz[i][1] = stage[i * 96 + 3 * lane + 1];
+    xyz[i][2] = stage[i * 96 + 3 * lane + 2];
+  }
+  __syncwarp();
+}
+
 struct KParams {
   int V, V_pad, n_vt;       // vertices, padded vertices, vertex tiles
   int ksteps_half;          // K16 steps of the hi (= lo) part: Kp / 16
@@ -46,9 +93,9 @@ struct KParams {
   float* verts;             // [B,V,3]
 };
 
-// One accumulation unit = (pose group, vertex tile, coordinate c): D_c[v, pose] over all K, N = NP poses per MMA.
-// NP = 128 when the group's operand fits shared memory (SMPL), 64 otherwise (SMPL-X): with N = 64 an MMA is only
-// 32 tensor cycles and the single issuing thread becomes the limiter, so the wider group is preferred.
+// One block = (pose group of NP poses, vertex tile): D_x | D_y | D_z [128 vertices x NP poses] in one TMEM buffer
+// (3*NP columns, double-buffered), so the epilogue has a vertex's three coordinates together and can write them
+// as contiguous 12-byte records (transposed per warp through shared memory into fully coalesced lines).
 template <int NP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUtensorMap tm_dirs,
@@ -68,6 +115,7 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
   const uint32_t bfull_bar = bar_base + 8u * (2 * MAX_STAGES + 4);
   const uint32_t bempty_bar = bar_base + 8u * (2 * MAX_STAGES + 5);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.n_slabs * B_SLAB + p.stages * A_SLAB + (2 * MAX_STAGES + 6) * 8);
+  float* xstage = reinterpret_cast<float*>(smem + p.n_slabs * B_SLAB + p.stages * A_SLAB + (2 * MAX_STAGES + 6) * 8 + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -83,7 +131,7 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
     ptx::mbar_init(bempty_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 256);
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -119,12 +167,12 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
         ptx::mbar_wait(bfull_bar, gph);
         gph ^= 1;
         ptx::tc_fence_after();
-        for (int vt = 0; vt < p.n_vt; ++vt)
+        for (int vt = 0; vt < p.n_vt; ++vt) {
+          const uint32_t buf = unit & 1;
+          ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
+          ptx::tc_fence_after();
           for (int c = 0; c < 3; ++c) {
-            const uint32_t buf = unit & 1;
-            ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + buf * NP;
+            const uint32_t taddr = tmem_base + buf * (3 * NP) + c * NP;
             uint32_t acc = 0;
             for (int i = 0; i < p.n_slabs; ++i) {
               ptx::mbar_wait(full_bar(stage), phase);
@@ -144,10 +192,11 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
               ptx::mma_commit(empty_bar(stage));
               if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
             }
-            ptx::mma_commit(tfull_bar(buf));
-            tph ^= 1u << buf;
-            ++unit;
           }
+          ptx::mma_commit(tfull_bar(buf));
+          tph ^= 1u << buf;
+          ++unit;
+        }
         ptx::mma_commit(bempty_bar);
       }
     }
@@ -156,46 +205,57 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
     const int hh = (warp - 4) >> 2;   // which half of the group's poses this warp stores
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const size_t pstride = (size_t)p.V * 3;
+    float* stage = xstage + (warp - 4) * XSTAGE;
     uint32_t unit = 0, tph = 0;
     for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
       const int64_t bb = (int64_t)grp * NP + hh * (NP / 2);
       for (int vt = 0; vt < p.n_vt; ++vt) {
-        const int v = vt * TILE_V + q * 32 + lane;
-        const bool vok = v < p.V;
-        for (int c = 0; c < 3; ++c) {
-          const float vtc = vok ? p.v_template[v * 3 + c] : 0.f;
-          const uint32_t buf = unit & 1;
-          ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
-          ptx::tc_fence_after();
-          uint32_t d[NP / 2];
-#pragma unroll
-          for (int k = 0; k < NP / 64; ++k)
-            ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * NP + hh * (NP / 2) + k * 32, d + k * 32);
+        const int v0 = vt * TILE_V + q * 32;          // first vertex of this warp's 32-vertex segment
+        const int v = v0 + lane;
+        const int n_floats = max(0, min(32, p.V - v0)) * 3;
+        float vt3[3] = {0.f, 0.f, 0.f};
+        if (v < p.V) { vt3[0] = p.v_template[v * 3]; vt3[1] = p.v_template[v * 3 + 1]; vt3[2] = p.v_template[v * 3 + 2]; }
+        const uint32_t buf = unit & 1;
+        ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int k = 0; k < NP / 64; ++k) {          // 32 poses per pass
+          uint32_t dx[32], dy[32], dz[32];
+          const uint32_t t0 = tmem_base + lane_addr + buf * (3 * NP) + hh * (NP / 2) + k * 32;
+          ptx::tmem_ld_32x32(t0, dx);
+          ptx::tmem_ld_32x32(t0 + NP, dy);
+          ptx::tmem_ld_32x32(t0 + 2 * NP, dz);
           ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
-          if (vok && bb < p.B) {
-            float* o = p.verts + ((size_t)bb * p.V + v) * 3 + c;
-            if (bb + NP / 2 <= p.B) {
-#pragma unroll
-              for (int i = 0; i < NP / 2; ++i, o += pstride) *o = __uint_as_float(d[i]) + vtc;
-            } else {
-#pragma unroll
-              for (int i = 0; i < NP / 2; ++i, o += pstride)
-                if (bb + i < p.B) *o = __uint_as_float(d[i]) + vtc;
-            }
+          if (k == NP / 64 - 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
           }
-          tph ^= 1u << buf;
-          ++unit;
+          const int64_t b32 = bb + k * 32;
+#pragma unroll
+          for (int i0 = 0; i0 < 32; i0 += XP) {
+            float xyz[XP][3];
+            float* dst[XP];
+#pragma unroll
+            for (int i = 0; i < XP; ++i) {
+              xyz[i][0] = __uint_as_float(dx[i0 + i]) + vt3[0];
+              xyz[i][1] = __uint_as_float(dy[i0 + i]) + vt3[1];
+              xyz[i][2] = __uint_as_float(dz[i0 + i]) + vt3[2];
+              dst[i] = p.verts + (size_t)(b32 + i0 + i) * pstride + (size_t)v0 * 3;
+            }
+            const int64_t left = p.B - (b32 + i0);
+            warp_store_xyz(stage, xyz, dst, lane, n_floats, left >= XP ? XP : (left > 0 ? (int)left : 0));
+          }
         }
+        tph ^= 1u << buf;
+        ++unit;
       }
     }
   }
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 256);
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -259,6 +319,7 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
   const uint32_t sfull = bar_base + 8u * (2 * SK_WSTAGES + 4);
   const uint32_t sempty = bar_base + 8u * (2 * SK_WSTAGES + 5);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + s_bytes + SK_WSTAGES * w_bytes + (2 * SK_WSTAGES + 6) * 8);
+  float* xstage = reinterpret_cast<float*>(smem + s_bytes + SK_WSTAGES * w_bytes + (2 * SK_WSTAGES + 6) * 8 + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -330,26 +391,27 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
+    const int h8 = (warp - 4) >> 2;     // warps 4-7: poses 0-7 of a chunk, warps 8-11: poses 8-15
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const size_t pstride = (size_t)p.V * 3;
+    float* stage = xstage + (warp - 4) * XSTAGE;
     uint32_t blk = 0, tph = 0;
     for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
       for (int vt = 0; vt < p.n_vt; ++vt) {
-        const int v = vt * TILE_V + q * 32 + lane;
-        const bool vok = v < p.V;
+        const int v0 = vt * TILE_V + q * 32;
+        const int n_floats = max(0, min(32, p.V - v0)) * 3;
         for (int c = 0; c < chunks; ++c) {
-          const int64_t b0 = (int64_t)grp * SK_GROUP + c * SK_POSES;
-          // this warp's 8 poses of the chunk (warps 4-7: poses 0-7, warps 8-11: poses 8-15); the blended
-          // vertices are requested before the TMEM wait so their latency hides behind it
-          const int h8 = (warp - 4) >> 2;
-          const int64_t bb = b0 + h8 * 8;
-          const bool full = vok && (bb + 8 <= p.B);
-          const size_t pstride = (size_t)p.V * 3;
-          float* o = p.verts + ((size_t)(vok && bb < p.B ? bb : 0) * p.V + (vok ? v : 0)) * 3;
+          const int64_t bb = (int64_t)grp * SK_GROUP + c * SK_POSES + h8 * 8;
+          // the blended vertices of this warp's 32 vertices x 8 poses: coalesced loads, transposed through the
+          // per-warp staging buffer, requested before the TMEM wait so their latency hides behind it
           float vp[8][3];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float* s = o + (size_t)((full || (vok && bb + i < p.B)) ? i : 0) * pstride;
-            vp[i][0] = s[0]; vp[i][1] = s[1]; vp[i][2] = s[2];
+          for (int i0 = 0; i0 < 8; i0 += XP) {
+            const float* src[XP];
+#pragma unroll
+            for (int i = 0; i < XP; ++i) src[i] = p.verts + (size_t)(bb + i0 + i) * pstride + (size_t)v0 * 3;
+            const int64_t left = p.B - (bb + i0);
+            warp_load_xyz(stage, vp + i0, src, lane, n_floats, left >= XP ? XP : (left > 0 ? (int)left : 0));
           }
           const uint32_t buf = blk & 1;
           ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
@@ -364,20 +426,25 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (full || (vok && bb + i < p.B)) {
-              const float* T = reinterpret_cast<const float*>(t) + i * 12;
-              const float x = vp[i][0], y = vp[i][1], z = vp[i][2];
+          for (int i0 = 0; i0 < 8; i0 += XP) {
+            float out[XP][3];
+            float* dst[XP];
+#pragma unroll
+            for (int i = 0; i < XP; ++i) {
+              const float* T = reinterpret_cast<const float*>(t) + (i0 + i) * 12;
+              const float x = vp[i0 + i][0], y = vp[i0 + i][1], z = vp[i0 + i][2];
               float tx = 0.f, ty = 0.f, tz = 0.f;
-              if (p.transl) {
-                const float* tr = p.transl + (bb + i) * 3;
+              if (p.transl && bb + i0 + i < p.B) {
+                const float* tr = p.transl + (bb + i0 + i) * 3;
                 tx = tr[0]; ty = tr[1]; tz = tr[2];
               }
-              float* w = o + (size_t)i * pstride;
-              w[0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
-              w[1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
-              w[2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
+              out[i][0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
+              out[i][1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
+              out[i][2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
+              dst[i] = p.verts + (size_t)(bb + i0 + i) * pstride + (size_t)v0 * 3;
             }
+            const int64_t left = p.B - (bb + i0);
+            warp_store_xyz(stage, out, dst, lane, n_floats, left >= XP ? XP : (left > 0 ? (int)left : 0));
           }
           tph ^= 1u << buf;
           ++blk;
@@ -481,7 +548,7 @@ size_t lbs_tc_ws_bytes(const dpb_lbs* h, int64_t B) {
 bool lbs_tc_skin_fits(const dpb_lbs* h) {
   const int n_slabs = 2 * h->jp / ltc::BK;
   const size_t smem = (size_t)(ltc::SK_GROUP / ltc::SK_POSES) * n_slabs * ltc::SK_N * ltc::BK * 2 +
-                      (size_t)ltc::SK_WSTAGES * n_slabs * ltc::A_SLAB + 2048;
+                      (size_t)ltc::SK_WSTAGES * n_slabs * ltc::A_SLAB + 8 * ltc::XSTAGE * 4 + 2048;
   return h->tc_ready && smem <= 232448;
 }
 
@@ -508,7 +575,8 @@ int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop,
   p.transl = h->J < Jp ? nullptr : transl;   // folded into the GEMM through the spare joint slot when there is one
   p.verts = verts;
   const size_t smem = (size_t)(ltc::SK_GROUP / ltc::SK_POSES) * p.n_slabs * ltc::SK_N * ltc::BK * 2 +
-                      (size_t)ltc::SK_WSTAGES * p.n_slabs * ltc::A_SLAB + (2 * ltc::SK_WSTAGES + 6) * 8 + 16 + 1024;
+                      (size_t)ltc::SK_WSTAGES * p.n_slabs * ltc::A_SLAB + (2 * ltc::SK_WSTAGES + 6) * 8 + 16 +
+                      8 * ltc::XSTAGE * 4 + 1024;
   if (smem > 232448) return fail(DPB_EUNSUPPORTED, "lbs tc skin: transform operand does not fit shared memory");
   DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.n_groups < h->sm_count ? p.n_groups : h->sm_count;
@@ -528,9 +596,8 @@ int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* feat
     DPB_CUDA_CHECK(cudaGetLastError());
   }
   const int n_slabs = K2 / ltc::BK;
-  const size_t bars = (2 * ltc::MAX_STAGES + 6) * 8 + 16 + 1024;
-  // 128-pose groups when their operand leaves room for >= 4 ring stages
-  const int np = ((size_t)n_slabs * 128 * ltc::BK * 2 + 4 * ltc::A_SLAB + bars <= 232448) ? 128 : 64;
+  const size_t bars = (2 * ltc::MAX_STAGES + 6) * 8 + 16 + 8 * ltc::XSTAGE * 4 + 1024;
+  const int np = 64;   // three coordinates x 64 poses x 2 buffers = 384 TMEM columns
   CUtensorMap tm_feat;
   int rc = make_tmap_2d(&tm_feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, featop, K2, (uint64_t)B_pad, ltc::BK, np, 2);
   if (rc != DPB_OK) return rc;
