@@ -391,27 +391,26 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int h8 = (warp - 4) >> 2;     // warps 4-7: poses 0-7 of a chunk, warps 8-11: poses 8-15
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const size_t pstride = (size_t)p.V * 3;
-    float* stage = xstage + (warp - 4) * XSTAGE;
     uint32_t blk = 0, tph = 0;
     for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
       for (int vt = 0; vt < p.n_vt; ++vt) {
-        const int v0 = vt * TILE_V + q * 32;
-        const int n_floats = max(0, min(32, p.V - v0)) * 3;
+        const int v = vt * TILE_V + q * 32 + lane;
+        const bool vok = v < p.V;
         for (int c = 0; c < chunks; ++c) {
-          const int64_t bb = (int64_t)grp * SK_GROUP + c * SK_POSES + h8 * 8;
-          // the blended vertices of this warp's 32 vertices x 8 poses: coalesced loads, transposed through the
-          // per-warp staging buffer, requested before the TMEM wait so their latency hides behind it
+          const int64_t b0 = (int64_t)grp * SK_GROUP + c * SK_POSES;
+          // this warp's 8 poses of the chunk (warps 4-7: poses 0-7, warps 8-11: poses 8-15); the blended
+          // vertices are requested before the TMEM wait so their latency hides behind it
+          const int h8 = (warp - 4) >> 2;
+          const int64_t bb = b0 + h8 * 8;
+          const bool full = vok && (bb + 8 <= p.B);
+          const size_t pstride = (size_t)p.V * 3;
+          float* o = p.verts + ((size_t)(vok && bb < p.B ? bb : 0) * p.V + (vok ? v : 0)) * 3;
           float vp[8][3];
 #pragma unroll
-          for (int i0 = 0; i0 < 8; i0 += XP) {
-            const float* src[XP];
-#pragma unroll
-            for (int i = 0; i < XP; ++i) src[i] = p.verts + (size_t)(bb + i0 + i) * pstride + (size_t)v0 * 3;
-            const int64_t left = p.B - (bb + i0);
-            warp_load_xyz(stage, vp + i0, src, lane, n_floats, left >= XP ? XP : (left > 0 ? (int)left : 0));
+          for (int i = 0; i < 8; ++i) {
+            const float* s = o + (size_t)((full || (vok && bb + i < p.B)) ? i : 0) * pstride;
+            vp[i][0] = s[0]; vp[i][1] = s[1]; vp[i][2] = s[2];
           }
           const uint32_t buf = blk & 1;
           ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
@@ -426,25 +425,20 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
 #pragma unroll
-          for (int i0 = 0; i0 < 8; i0 += XP) {
-            float out[XP][3];
-            float* dst[XP];
-#pragma unroll
-            for (int i = 0; i < XP; ++i) {
-              const float* T = reinterpret_cast<const float*>(t) + (i0 + i) * 12;
-              const float x = vp[i0 + i][0], y = vp[i0 + i][1], z = vp[i0 + i][2];
+          for (int i = 0; i < 8; ++i) {
+            if (full || (vok && bb + i < p.B)) {
+              const float* T = reinterpret_cast<const float*>(t) + i * 12;
+              const float x = vp[i][0], y = vp[i][1], z = vp[i][2];
               float tx = 0.f, ty = 0.f, tz = 0.f;
-              if (p.transl && bb + i0 + i < p.B) {
-                const float* tr = p.transl + (bb + i0 + i) * 3;
+              if (p.transl) {
+                const float* tr = p.transl + (bb + i) * 3;
                 tx = tr[0]; ty = tr[1]; tz = tr[2];
               }
-              out[i][0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
-              out[i][1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
-              out[i][2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
-              dst[i] = p.verts + (size_t)(bb + i0 + i) * pstride + (size_t)v0 * 3;
+              float* w = o + (size_t)i * pstride;
+              w[0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
+              w[1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
+              w[2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
             }
-            const int64_t left = p.B - (bb + i0);
-            warp_store_xyz(stage, out, dst, lane, n_floats, left >= XP ? XP : (left > 0 ? (int)left : 0));
           }
           tph ^= 1u << buf;
           ++blk;
