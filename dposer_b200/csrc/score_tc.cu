@@ -28,19 +28,22 @@ namespace tc {
 constexpr int TILE_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int CHUNK_N = 256;
-constexpr int STAGES = 3;
+constexpr bool TWO_SM = true;   // CTA pair: one tcgen05.mma.cta_group::2 (M = 256) per weight tile; each CTA keeps
+                                // its own 128 rows of A and HALF of the weight tile, so weight ingest per CTA halves
+constexpr int STAGES = TWO_SM ? 5 : 3;   // the operand ring is latency bound: utilisation ~ STAGES*512/(L+512), L ~ 2.2k cycles
 constexpr int NSUB = 1;      // row tiles in flight per CTA: one tile's epilogue overlaps the other tile's MMAs
 constexpr int CLUSTER = 2;   // CTAs (different row tiles) that share every weight tile through TMA multicast
 constexpr int A_BYTES = TILE_M * BLOCK_K * 2;   // 16 KB
-constexpr int B_BYTES = CHUNK_N * BLOCK_K * 2;  // 32 KB
+constexpr int B_BYTES = CHUNK_N * BLOCK_K * 2 / (TWO_SM ? 2 : 1);  // this CTA's share of the weight tile
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int POST_B_BYTES = DP * BLOCK_K * 2;  // 8 KB (N = 64)
+constexpr int POST_B_BYTES = DP * BLOCK_K * 2 / (TWO_SM ? 2 : 1);  // post_dense tile (N = 64)
 constexpr int XA_K = 192;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int PAR_BYTES = 3 * H * 4;
 constexpr int STG_BYTES = TILE_M * 128;          // one [128 rows x 64 fp16] SWIZZLE_128B box of outgoing activations
-constexpr int STG_TOTAL = 4 * STG_BYTES;         // 2 column halves (hf) x 2 buffers
+constexpr int STG_BUFS = TWO_SM ? 1 : 2;         // staging buffers per column half (shared memory is better spent on ring stages)
+constexpr int STG_TOTAL = 2 * STG_BUFS * STG_BYTES;
 constexpr int NUM_BARS = 2 * STAGES + 4 + NSUB * 5 + 8;  // full, empty, tfull[2], tempty[2], xa, act[4], sfull[2][2], sempty[2][2]
 constexpr int OFF_PAR = STAGES * STAGE_BYTES;
 constexpr int OFF_STG = OFF_PAR + PAR_BYTES;     // 1024-aligned: 3*49152 + 12288 = 159744
@@ -48,9 +51,11 @@ constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
 constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
 static_assert(OFF_STG % 1024 == 0, "staging boxes must be 1024-byte aligned for SWIZZLE_128B");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-constexpr uint32_t IDESC_F16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 0);
-constexpr uint32_t IDESC_BF16_256 = ptx::umma_idesc_f16(TILE_M, CHUNK_N, 1);
-constexpr uint32_t IDESC_F16_64 = ptx::umma_idesc_f16(TILE_M, DP, 0);
+constexpr int MMA_M = TWO_SM ? 2 * TILE_M : TILE_M;
+constexpr uint32_t IDESC_F16_256 = ptx::umma_idesc_f16(MMA_M, CHUNK_N, 0);
+constexpr uint32_t IDESC_BF16_256 = ptx::umma_idesc_f16(MMA_M, CHUNK_N, 1);
+constexpr uint32_t IDESC_F16_64 = ptx::umma_idesc_f16(MMA_M, DP, 0);
+static_assert(!TWO_SM || CLUSTER == 2, "cta_group::2 needs clusters of exactly two CTAs");
 
 struct KParams {
   int mode, n_steps, impute, noise_k, n_tiles;
@@ -251,12 +256,13 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 2);   // A producer + W producer (each arrive.expect_tx)
-      ptx::mbar_init(empty_bar(s), CLUSTER);  // tcgen05.commit of every CTA in the cluster (weights are shared)
+      // TWO_SM: the leader's barrier collects the A and W producers of BOTH CTAs; one multicast commit frees both
+      ptx::mbar_init(full_bar(s), TWO_SM ? 4 : 2);
+      ptx::mbar_init(empty_bar(s), TWO_SM ? 1 : CLUSTER);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tfull_bar(b), 1);   // tcgen05.commit
-      ptx::mbar_init(tempty_bar(b), 8);  // one lane of each epilogue warp
+      ptx::mbar_init(tempty_bar(b), TWO_SM ? 16 : 8);  // one lane of each epilogue warp (of both CTAs on the leader)
     }
     for (int sub = 0; sub < NSUB; ++sub) {
       ptx::mbar_init(xa_bar(sub), 8);
@@ -276,7 +282,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   if (warp == 2) {
     if (lane == 0) { ptx::prefetch_tmap(&tm_xa); ptx::prefetch_tmap(&tm_h); ptx::prefetch_tmap(&tm_t); }
     __syncwarp();
-    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+    if (TWO_SM) ptx::tmem_alloc_2sm(ptx::smem_u32(tmem_slot), 512);
+    else ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -307,8 +314,16 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
              for (int sub = 0; sub < NSUB; ++sub)
               for (int k = 0; k < nk; ++k) {
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1);  // every CTA of the cluster has consumed this stage
-                ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);  // whole tile: own part + the peers' multicasts
                 const int part_rows = (layer == 5 ? DP : CHUNK_N) / CLUSTER;
+                if (TWO_SM) {  // my half of the weight tile into MY shared memory, completion on the leader's barrier
+                  const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
+                  ptx::mbar_arrive_expect_tx_cluster(lbar, bytes);
+                  ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES + A_BYTES, tm, lbar, k * BLOCK_K,
+                                       chunk * CHUNK_N + crank * part_rows);
+                  if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                  continue;
+                }
+                ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);  // whole tile: own part + the peers' multicasts
                 const uint32_t dst = smem_base + stage * STAGE_BYTES + A_BYTES + crank * part_rows * (BLOCK_K * 2);
                 if (CLUSTER > 1)
                   ptx::tma_load_2d_mcast(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N + crank * part_rows,
@@ -321,7 +336,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
+    if (lane == 0 && (!TWO_SM || crank == 0)) {   // cta_group::2: the pair's leader issues for both CTAs
       uint32_t stage = 0, phase = 0, chunk_ctr = 0, tph = 0;
       for (int rnd = 0; rnd < rounds; ++rnd)
         for (int step = 0; step < p.n_steps; ++step)
@@ -342,12 +357,15 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 if (!(p.debug & 2))
 #pragma unroll
                 for (int kk = 0; kk < BLOCK_K / 16; ++kk)  // UMMA_K = 16: advance 32 B inside the swizzle row
-                  ptx::mma_f16_ss(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-                if (CLUSTER > 1) ptx::mma_commit_mcast(empty_bar(stage), CMASK);
+                  if (TWO_SM) ptx::mma_f16_ss_2sm(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                  else ptx::mma_f16_ss(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                if (TWO_SM) ptx::mma_commit_2sm_mcast(empty_bar(stage), CMASK);
+                else if (CLUSTER > 1) ptx::mma_commit_mcast(empty_bar(stage), CMASK);
                 else ptx::mma_commit(empty_bar(stage));
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
-              ptx::mma_commit(tfull_bar(buf));
+              if (TWO_SM) ptx::mma_commit_2sm_mcast(tfull_bar(buf), CMASK);
+              else ptx::mma_commit(tfull_bar(buf));
               tph ^= 1u << buf;
               ++chunk_ctr;
             }
@@ -372,9 +390,15 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 // layer's last chunks are still in the epilogue
                 if (layer > 0 && chunk == 0 && (k & 3) == 0) ptx::mbar_wait(act_bar(sub, k >> 2), aph);
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-                ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
-                ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), k * BLOCK_K,
-                                 slot_row0 + sub * TILE_M);
+                if (TWO_SM) {
+                  const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
+                  ptx::mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
+                  ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, k * BLOCK_K, slot_row0 + sub * TILE_M);
+                } else {
+                  ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
+                  ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), k * BLOCK_K,
+                                   slot_row0 + sub * TILE_M);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
              }
@@ -399,9 +423,9 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               const int chunk = cs / NSUB, sub = cs % NSUB;
               for (int gp = 0; gp < 2; ++gp)
                 for (int hf = 0; hf < 2; ++hf) {
-                  const uint32_t b = cnt[hf] & 1, ph = (cnt[hf] >> 1) & 1;
+                  const uint32_t b = cnt[hf] % STG_BUFS, ph = (cnt[hf] / STG_BUFS) & 1;
                   ptx::mbar_wait(sfull_bar(hf, b), ph);
-                  ptx::tma_store_2d(tm, stg_base + (hf * 2 + b) * STG_BYTES, chunk * CHUNK_N + hf * 128 + gp * 64,
+                  ptx::tma_store_2d(tm, stg_base + (hf * STG_BUFS + b) * STG_BYTES, chunk * CHUNK_N + hf * 128 + gp * 64,
                                     slot_row0 + sub * TILE_M);
                   ptx::tma_store_commit();
                   if (!last_released) {  // the previous store has finished READING its box: hand that box back
@@ -525,7 +549,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               if (gp == 1) {  // last TMEM read of this warp for the buffer: hand it back to the MMA warp
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+                if (lane == 0) {
+                  if (TWO_SM) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(buf), 0));
+                  else ptx::mbar_arrive(tempty_bar(buf));
+                }
               }
               uint4 o[8];
               if (p.debug & 1) {
@@ -537,9 +564,9 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               }
               // stage this row's 64 fp16 (128 B) in the SWIZZLE_128B box of my column half; the store warp
               // ships the box with one TMA store (full lines, asynchronous) -- no per-row global stores
-              const uint32_t sb = scnt & 1;
-              ptx::mbar_wait(sempty_bar(hf, sb), ((scnt >> 1) & 1) ^ 1);
-              const uint32_t rbase = stg_base + (hf * 2 + sb) * STG_BYTES + r_in * 128;
+              const uint32_t sb = scnt % STG_BUFS;
+              ptx::mbar_wait(sempty_bar(hf, sb), ((scnt / STG_BUFS) & 1) ^ 1);
+              const uint32_t rbase = stg_base + (hf * STG_BUFS + sb) * STG_BYTES + r_in * 128;
 #pragma unroll
               for (int j = 0; j < 8; ++j) st_shared_v4(rbase + ((j ^ (r_in & 7)) << 4), o[j]);
               ptx::fence_proxy_async_smem();
@@ -565,7 +592,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+          if (lane == 0) {
+                  if (TWO_SM) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(buf), 0));
+                  else ptx::mbar_arrive(tempty_bar(buf));
+                }
           tph ^= 1u << buf;
           ++chunk_ctr;
           float raw[32];
@@ -676,7 +706,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   if (CLUSTER > 1) ptx::cluster_sync();  // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (TWO_SM) ptx::tmem_dealloc_2sm(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
