@@ -27,6 +27,11 @@ sys.path.insert(0, ROOT)
 
 SCORE_FLOP_PER_ROW = 8646656          # 2*(63*1024 + 4*1024^2 + 1024*63), batch-uniform t
 LBS_BYTES_PER_POSE = 83560            # verts 6890*12 + joints 45*12 + inputs 85*4
+# DRAM traffic from the committed `ncu --set full` capture (profiles/r1_ncu_full_summary_final.md):
+#   fused sampler: 1.311 GB for 37 888 rows x 4 steps (mostly write-back of the L2-resident activation scratch)
+#   LBS (65 536 poses): blend 5.559 GB + skinning 10.898 GB (the blended vertices make one extra HBM round trip)
+SAMPLER_DRAM_BYTES_PER_ROW_STEP = 1.311e9 / (37888 * 4)
+LBS_DRAM_BYTES_PER_POSE = (5.559e9 + 10.898e9) / 65536
 N_SDE = 1000
 
 
@@ -295,13 +300,19 @@ def run_gpu_arm(args):
             ach = SCORE_FLOP_PER_ROW * B * args.sde_steps / (t_s * 1e-3) / 1e12
             roof = {'kernel': 'fused sampler (score net x N steps)', 'bound': 'tensor', 'achieved': ach,
                     'peak': peaks['tc_sustained'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tc_sustained'],
-                    'traffic': None, 'ms': t_s, 'peak_source': peaks['src'] + ' (bf16 sustained)'}
+                    'traffic': SAMPLER_DRAM_BYTES_PER_ROW_STEP * B * args.sde_steps,
+                    'traffic_note': 'DRAM bytes, scaled per row-step from the committed ncu capture', 'ms': t_s,
+                    'peak_source': peaks['src'] + ' (bf16 sustained)'}
         if wl in ('sample_lbs', 'lbs'):
             t_l = time_stage(lambda: bm(**lbs_res), reps=5)
             ach = LBS_BYTES_PER_POSE * B / (t_l * 1e-3) / 1e9
             roof_lbs = {'kernel': 'SMPL LBS forward', 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'],
-                        'unit': 'GB/s', 'frac': ach / peaks['hbm'], 'traffic': None, 'ms': t_l,
-                        'peak_source': peaks['src']}
+                        'unit': 'GB/s', 'frac': ach / peaks['hbm'], 'traffic': LBS_DRAM_BYTES_PER_POSE * B,
+                        'traffic_note': 'DRAM bytes, scaled per pose from the committed ncu capture (65536 poses)',
+                        'algorithmic_bytes': LBS_BYTES_PER_POSE * B, 'ms': t_l, 'peak_source': peaks['src']}
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     tc = engine != L.ENGINE_FP32 and B >= 64
@@ -309,7 +320,7 @@ def run_gpu_arm(args):
     if wl in ('sample_lbs', 'sample', 'completion'):
         launches += (1 + 1) if tc else (1 + args.sde_steps * 12)        # time table + fused / per-layer kernels
     if wl in ('sample_lbs', 'lbs'):
-        launches += 3                                                   # pose, vertex, gather kernels
+        launches += 6 if tc else 3          # pose, (featop, blend, skinop, skin | vertex), gather kernels
     h2d = xT_host.numel() * 4 + sum(v.numel() * 4 for v in lbs_host.values()) + \
         (0 if comp is None else sum(c.numel() * 4 for c in comp))
     d2h = sum(v.numel() * 4 for v in results_host.values())
@@ -328,7 +339,7 @@ def run_gpu_arm(args):
         line['roofline_lbs'] = roof_lbs
     if not args.no_cpu:
         line['cpu_baseline'] = cpu_reference(wl, budget_s=args.cpu_budget)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
