@@ -286,13 +286,15 @@ __global__ void lbs_featop_kernel(const float* __restrict__ betas, const float* 
 // (4 x 48 B of transform per (pose, vertex) through LDS); here the blend of transforms costs 6 MMAs per 2048 pairs.
 constexpr int SK_POSES = 16;               // poses per MMA (N = 192)
 constexpr int SK_N = SK_POSES * 12;
-constexpr int SK_GROUP = 64;               // poses whose transform operand stays resident (4 chunks)
+constexpr int SK_GROUP = 64;               // poses whose transform operand stays resident: 4 chunks of 16 when one
+                                           // K slab suffices (J <= 31), 2 chunks (32 poses) for SMPL-X's two slabs
 constexpr int SK_WSTAGES = 3;
 constexpr uint32_t SK_IDESC = ptx::umma_idesc_f16(TILE_V, SK_N, 0);
 
 struct SkinParams {
   int V, n_vt, jsteps;      // jsteps: K16 steps of the hi (= lo) part = Jp/16
   int n_slabs;              // 64-wide slabs of [hi | lo] = 2*Jp/64
+  int chunks;               // 16-pose chunks per resident pose group
   int64_t B;
   int n_groups;
   const float* transl;      // [B,3] or nullptr
@@ -305,7 +307,8 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = ptx::smem_u32(smem);
-  const int chunks = SK_GROUP / SK_POSES;
+  const int chunks = p.chunks;
+  const int group = chunks * SK_POSES;
   const uint32_t s_slab = SK_N * BK * 2;                           // 24 KB: one chunk, one 64-wide slab
   const uint32_t s_bytes = chunks * p.n_slabs * s_slab;            // resident transform operand of the pose group
   const uint32_t w_bytes = p.n_slabs * A_SLAB;                     // one vertex tile of weights
@@ -344,7 +347,7 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
         for (int c = 0; c < chunks; ++c)
           for (int i = 0; i < p.n_slabs; ++i)
             ptx::tma_load_2d(s_base + (c * p.n_slabs + i) * s_slab, &tm_s, sfull, i * BK,
-                             (grp * SK_GROUP + c * SK_POSES) * 12);
+                             (grp * group + c * SK_POSES) * 12);
         gph ^= 1;
         for (int vt = 0; vt < p.n_vt; ++vt) {
           ptx::mbar_wait(wempty(stage), phase ^ 1);
@@ -398,7 +401,7 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
         const int v = vt * TILE_V + q * 32 + lane;
         const bool vok = v < p.V;
         for (int c = 0; c < chunks; ++c) {
-          const int64_t b0 = (int64_t)grp * SK_GROUP + c * SK_POSES;
+          const int64_t b0 = (int64_t)grp * group + c * SK_POSES;
           // this warp's 8 poses of the chunk (warps 4-7: poses 0-7, warps 8-11: poses 8-15); the blended
           // vertices are requested before the TMEM wait so their latency hides behind it
           const int h8 = (warp - 4) >> 2;
@@ -541,16 +544,17 @@ size_t lbs_tc_ws_bytes(const dpb_lbs* h, int64_t B) {
 
 bool lbs_tc_skin_fits(const dpb_lbs* h) {
   const int n_slabs = 2 * h->jp / ltc::BK;
-  const size_t smem = (size_t)(ltc::SK_GROUP / ltc::SK_POSES) * n_slabs * ltc::SK_N * ltc::BK * 2 +
+  const int chunks = n_slabs == 1 ? 4 : 2;
+  const size_t smem = (size_t)chunks * n_slabs * ltc::SK_N * ltc::BK * 2 +
                       (size_t)ltc::SK_WSTAGES * n_slabs * ltc::A_SLAB + 8 * ltc::XSTAGE * 4 + 2048;
-  return h->tc_ready && smem <= 232448;
+  return h->tc_ready && h->J < h->jp && smem <= 232448;
 }
 
 // skins verts[B,V,3] (holding v_posed) in place with the per-pose transforms A[B,J,12]
 int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop, float* verts, int64_t B,
                 cudaStream_t st) {
   const int Jp = h->jp;
-  const int64_t B_pad = (B + ltc::SK_GROUP - 1) / ltc::SK_GROUP * ltc::SK_GROUP;
+  const int64_t B_pad = (B + ltc::SK_GROUP - 1) / ltc::SK_GROUP * ltc::SK_GROUP;   // operand rows (64 | 32 both divide)
   {
     const int64_t n = B_pad * 12 * Jp;
     ltc::lbs_skinop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, transl, h->J, Jp, skinop, B, B_pad);
@@ -565,10 +569,11 @@ int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop,
   p.jsteps = Jp / 16;
   p.n_slabs = 2 * Jp / ltc::BK;
   p.B = B;
-  p.n_groups = (int)(B_pad / ltc::SK_GROUP);
+  p.chunks = p.n_slabs == 1 ? 4 : 2;
+  p.n_groups = (int)(B_pad / (p.chunks * ltc::SK_POSES));
   p.transl = h->J < Jp ? nullptr : transl;   // folded into the GEMM through the spare joint slot when there is one
   p.verts = verts;
-  const size_t smem = (size_t)(ltc::SK_GROUP / ltc::SK_POSES) * p.n_slabs * ltc::SK_N * ltc::BK * 2 +
+  const size_t smem = (size_t)p.chunks * p.n_slabs * ltc::SK_N * ltc::BK * 2 +
                       (size_t)ltc::SK_WSTAGES * p.n_slabs * ltc::A_SLAB + (2 * ltc::SK_WSTAGES + 6) * 8 + 16 +
                       8 * ltc::XSTAGE * 4 + 1024;
   if (smem > 232448) return fail(DPB_EUNSUPPORTED, "lbs tc skin: transform operand does not fit shared memory");
