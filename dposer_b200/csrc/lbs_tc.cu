@@ -102,6 +102,9 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
                     const __grid_constant__ CUtensorMap tm_feat) {
   constexpr int B_SLAB = NP * BK * 2;
   constexpr uint32_t IDESC = ptx::umma_idesc_f16(TILE_V, NP, 0);
+  // NP = 64: two TMEM buffers (2 x 192 columns).  NP = 128: one buffer (384 columns) -- the epilogue is short
+  // (coalesced staged stores) and the N = 128 MMAs are long enough for the single issuing thread to keep up.
+  constexpr int NBUF = (2 * 3 * NP <= 512) ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -168,7 +171,7 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
         gph ^= 1;
         ptx::tc_fence_after();
         for (int vt = 0; vt < p.n_vt; ++vt) {
-          const uint32_t buf = unit & 1;
+          const uint32_t buf = unit % NBUF;
           ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
           ptx::tc_fence_after();
           for (int c = 0; c < 3; ++c) {
@@ -215,7 +218,7 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
         const int n_floats = max(0, min(32, p.V - v0)) * 3;
         float vt3[3] = {0.f, 0.f, 0.f};
         if (v < p.V) { vt3[0] = p.v_template[v * 3]; vt3[1] = p.v_template[v * 3 + 1]; vt3[2] = p.v_template[v * 3 + 2]; }
-        const uint32_t buf = unit & 1;
+        const uint32_t buf = unit % NBUF;
         ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
         ptx::tc_fence_after();
 #pragma unroll 1
@@ -596,7 +599,8 @@ int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   }
   const int n_slabs = K2 / ltc::BK;
   const size_t bars = (2 * ltc::MAX_STAGES + 6) * 8 + 16 + 8 * ltc::XSTAGE * 4 + 1024;
-  const int np = 64;   // three coordinates x 64 poses x 2 buffers = 384 TMEM columns
+  // 128-pose groups when the group's operand leaves room for >= 4 ring stages (SMPL), else 64 (SMPL-X)
+  const int np = ((size_t)n_slabs * 128 * ltc::BK * 2 + 4 * ltc::A_SLAB + bars <= 232448) ? 128 : 64;
   CUtensorMap tm_feat;
   int rc = make_tmap_2d(&tm_feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, featop, K2, (uint64_t)B_pad, ltc::BK, np, 2);
   if (rc != DPB_OK) return rc;
