@@ -141,66 +141,73 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
   const int half = p.ksteps_half;
 
+  // Warps 0 and 1 run their loops warp-wide; only the async instruction is issued by the elected lane
+  // (ptx::elect_one), so descriptors and coordinates stay in uniform registers.
   if (warp == 0) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tm_dirs);
       ptx::prefetch_tmap(&tm_feat);
-      uint32_t stage = 0, phase = 0, gph = 0;
-      for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-        ptx::mbar_wait(bempty_bar, gph ^ 1);  // previous group's MMAs are done with the resident operand
+    }
+    __syncwarp();
+    uint32_t stage = 0, phase = 0, gph = 0;
+    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+      ptx::mbar_wait(bempty_bar, gph ^ 1);  // previous group's MMAs are done with the resident operand
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(bfull_bar, (uint32_t)p.n_slabs * B_SLAB);
         for (int i = 0; i < p.n_slabs; ++i) ptx::tma_load_2d(b_base + i * B_SLAB, &tm_feat, bfull_bar, i * BK, grp * NP);
-        gph ^= 1;
-        for (int vt = 0; vt < p.n_vt; ++vt)
-          for (int c = 0; c < 3; ++c)
-            for (int i = 0; i < p.n_slabs; ++i) {
-              ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+      }
+      gph ^= 1;
+      for (int vt = 0; vt < p.n_vt; ++vt)
+        for (int c = 0; c < 3; ++c)
+          for (int i = 0; i < p.n_slabs; ++i) {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+            if (ptx::elect_one()) {
               ptx::mbar_arrive_expect_tx(full_bar(stage), A_SLAB);
               ptx::tma_load_2d(a_base + stage * A_SLAB, &tm_dirs, full_bar(stage), i * BK, c * p.V_pad + vt * TILE_V);
-              if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
             }
-      }
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, gph = 0, unit = 0, tph = 0;
-      const uint64_t adesc0 = ptx::umma_desc_sw128(a_base), bdesc0 = ptx::umma_desc_sw128(b_base);
-      auto bdesc = [&](int step) { return bdesc0 + (uint64_t)((step >> 2) * (B_SLAB >> 4) + 2 * (step & 3)); };
-      for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-        ptx::mbar_wait(bfull_bar, gph);
-        gph ^= 1;
+    uint32_t stage = 0, phase = 0, gph = 0, unit = 0, tph = 0;
+    const uint64_t adesc0 = ptx::umma_desc_sw128(a_base), bdesc0 = ptx::umma_desc_sw128(b_base);
+    auto bdesc = [&](int step) { return bdesc0 + (uint64_t)((step >> 2) * (B_SLAB >> 4) + 2 * (step & 3)); };
+    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+      ptx::mbar_wait(bfull_bar, gph);
+      gph ^= 1;
+      ptx::tc_fence_after();
+      for (int vt = 0; vt < p.n_vt; ++vt) {
+        const uint32_t buf = unit % NBUF;
+        ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
         ptx::tc_fence_after();
-        for (int vt = 0; vt < p.n_vt; ++vt) {
-          const uint32_t buf = unit % NBUF;
-          ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
-          ptx::tc_fence_after();
-          for (int c = 0; c < 3; ++c) {
-            const uint32_t taddr = tmem_base + buf * (3 * NP) + c * NP;
-            uint32_t acc = 0;
-            for (int i = 0; i < p.n_slabs; ++i) {
-              ptx::mbar_wait(full_bar(stage), phase);
-              ptx::tc_fence_after();
-              const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_SLAB >> 4));
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t taddr = tmem_base + buf * (3 * NP) + c * NP;
+          for (int i = 0; i < p.n_slabs; ++i) {
+            ptx::mbar_wait(full_bar(stage), phase);
+            ptx::tc_fence_after();
+            const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_SLAB >> 4));
+            if (ptx::elect_one()) {
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j) {
                 const int g = i * (BK / 16) + j;  // K16 step inside [hi | lo]
                 if (g < half) {  // basis_hi x (feat_hi + feat_lo)
-                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g), IDESC, acc);
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g), IDESC, g != 0 ? 1u : 0u);
                   ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(half + g), IDESC, 1u);
-                  acc = 1;
                 } else {         // basis_lo x feat_hi
                   ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g - half), IDESC, 1u);
                 }
               }
               ptx::mma_commit(empty_bar(stage));
-              if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+              if (c == 2 && i == p.n_slabs - 1) {
+                ptx::mma_commit(tfull_bar(buf));
+                if (vt == p.n_vt - 1) ptx::mma_commit(bempty_bar);
+              }
             }
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
-          ptx::mma_commit(tfull_bar(buf));
-          tph ^= 1u << buf;
-          ++unit;
         }
-        ptx::mma_commit(bempty_bar);
+        tph ^= 1u << buf;
+        ++unit;
       }
     }
   } else if (warp >= 4) {
@@ -341,58 +348,62 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, gph = 0;
-      for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-        ptx::mbar_wait(sempty, gph ^ 1);
+  if (warp == 0) {   // warp-wide loops, elected lane issues (see lbs_blend_tc_kernel)
+    uint32_t stage = 0, phase = 0, gph = 0;
+    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+      ptx::mbar_wait(sempty, gph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(sfull, s_bytes);
         for (int c = 0; c < chunks; ++c)
           for (int i = 0; i < p.n_slabs; ++i)
             ptx::tma_load_2d(s_base + (c * p.n_slabs + i) * s_slab, &tm_s, sfull, i * BK,
                              (grp * group + c * SK_POSES) * 12);
-        gph ^= 1;
-        for (int vt = 0; vt < p.n_vt; ++vt) {
-          ptx::mbar_wait(wempty(stage), phase ^ 1);
+      }
+      gph ^= 1;
+      for (int vt = 0; vt < p.n_vt; ++vt) {
+        ptx::mbar_wait(wempty(stage), phase ^ 1);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(wfull(stage), w_bytes);
           for (int i = 0; i < p.n_slabs; ++i)
             ptx::tma_load_2d(w_base + stage * w_bytes + i * A_SLAB, &tm_w, wfull(stage), i * BK, vt * TILE_V);
-          if (++stage == SK_WSTAGES) { stage = 0; phase ^= 1; }
         }
+        if (++stage == SK_WSTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, gph = 0, blk = 0, tph = 0;
-      const int js = p.jsteps;
-      for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-        ptx::mbar_wait(sfull, gph);
-        gph ^= 1;
-        for (int vt = 0; vt < p.n_vt; ++vt) {
-          ptx::mbar_wait(wfull(stage), phase);
+    uint32_t stage = 0, phase = 0, gph = 0, blk = 0, tph = 0;
+    const int js = p.jsteps;
+    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+      ptx::mbar_wait(sfull, gph);
+      gph ^= 1;
+      for (int vt = 0; vt < p.n_vt; ++vt) {
+        ptx::mbar_wait(wfull(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t wa = w_base + stage * w_bytes;
+        auto wdesc = [&](int step) { return ptx::umma_desc_sw128(wa + (step >> 2) * A_SLAB) + 2 * (step & 3); };
+        for (int c = 0; c < chunks; ++c) {
+          const uint32_t buf = blk & 1;
+          ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
           ptx::tc_fence_after();
-          const uint32_t wa = w_base + stage * w_bytes;
-          auto wdesc = [&](int step) { return ptx::umma_desc_sw128(wa + (step >> 2) * A_SLAB) + 2 * (step & 3); };
-          for (int c = 0; c < chunks; ++c) {
-            const uint32_t buf = blk & 1;
-            ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + buf * 256;
-            const uint32_t sa = s_base + c * p.n_slabs * s_slab;
-            auto sdesc = [&](int step) { return ptx::umma_desc_sw128(sa + (step >> 2) * s_slab) + 2 * (step & 3); };
+          const uint32_t taddr = tmem_base + buf * 256;
+          const uint32_t sa = s_base + c * p.n_slabs * s_slab;
+          auto sdesc = [&](int step) { return ptx::umma_desc_sw128(sa + (step >> 2) * s_slab) + 2 * (step & 3); };
+          if (ptx::elect_one()) {
             for (int g = 0; g < js; ++g) {   // w_hi x (A_hi + A_lo), then w_lo x A_hi
               ptx::mma_f16_ss(taddr, wdesc(g), sdesc(g), SK_IDESC, g ? 1u : 0u);
               ptx::mma_f16_ss(taddr, wdesc(g), sdesc(js + g), SK_IDESC, 1u);
               ptx::mma_f16_ss(taddr, wdesc(js + g), sdesc(g), SK_IDESC, 1u);
             }
             ptx::mma_commit(tfull_bar(buf));
-            tph ^= 1u << buf;
-            ++blk;
+            if (c == chunks - 1) {
+              ptx::mma_commit(wempty(stage));
+              if (vt == p.n_vt - 1) ptx::mma_commit(sempty);
+            }
           }
-          ptx::mma_commit(wempty(stage));
-          if (++stage == SK_WSTAGES) { stage = 0; phase ^= 1; }
+          tph ^= 1u << buf;
+          ++blk;
         }
-        ptx::mma_commit(sempty);
+        if (++stage == SK_WSTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {

@@ -83,6 +83,26 @@ __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One lane of a converged warp (deterministically the same lane for the same mask).  The single-thread roles run
+// their loops warp-wide and predicate only the async instruction with this: operands computed in uniform control
+// flow stay in uniform registers, while a loop nested under `if (lane == 0)` makes ptxas wrap every
+// UTCHMMA / UTMALDG in an ELECT / R2UR / BRA.U.ANY waterfall (measured: the issue loop, not the tensor pipe,
+// bounded both TC kernels).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\n@P1 mov.s32 %0, 1;\n}\n" : "+r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)

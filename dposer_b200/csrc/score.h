@@ -35,6 +35,7 @@ struct dpb_score {
   __nv_bfloat16* xa = nullptr;  // [slots*128, 192]  [x_hi | x_lo | x_hi]
   CUtensorMap tm_act_h, tm_act_t, tm_xa;  // box {64, 128}
   int tc_slots = 0;
+  int* tc_flags = nullptr;      // [slots] hand-off flags of the sampler's segment schedule (score_tc.cu: SegIter)
 };
 
 namespace dpb {

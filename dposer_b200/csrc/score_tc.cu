@@ -84,6 +84,45 @@ struct KParams {
   __half* act_h;
   __half* act_t;
   __nv_bfloat16* xa;
+  int* flags;   // one hand-off flag per CTA (zeroed before the launch), see SegIter
+};
+
+// ---- work distribution.  A "unit" is CLUSTER consecutive row tiles (one per CTA of a cluster) and a "chain" is
+// one unit's n_steps sampler steps, which must run in order.  The chains are laid end to end and cut into one
+// equal piece per cluster, so every cluster gets the same number of unit-steps (65536 rows on 148 SMs: 3.46
+// chains each instead of 4 rounds with a quarter-full last wave).  A chain cut between clusters w-1 and w is
+// run in two parts: cluster w starts its piece with the chain's FIRST steps, cluster w-1 ends its piece with
+// the chain's LAST steps (the state x travels through x_io, ordered by a release/acquire flag).  A piece is at
+// least one chain long, so part two never has to wait unless part one is late.
+struct Seg {
+  int unit, s0, s1;
+  bool publish;   // first part of a cut chain: set flags[this cluster] when done
+  bool acquire;   // second part of a cut chain: wait for flags[next cluster]
+};
+struct SegIter {
+  long long pos, end;
+  int S;
+  __device__ SegIter(int worker, int n_workers, int n_units, int S_) : S(S_) {
+    if (n_units <= n_workers) {
+      pos = (long long)min(worker, n_units) * S;
+      end = worker < n_units ? pos + S : pos;
+    } else {
+      const long long total = (long long)n_units * S;
+      pos = total * worker / n_workers;
+      end = total * (worker + 1) / n_workers;
+    }
+  }
+  __device__ bool next(Seg& g) {
+    if (pos >= end) return false;
+    const int unit = (int)(pos / S);
+    const int off = (int)(pos - (long long)unit * S);
+    const long long chain_end = (long long)(unit + 1) * S;
+    g.unit = unit; g.publish = false; g.acquire = false;
+    if (off > 0) { g.s0 = 0; g.s1 = S - off; g.publish = true; pos = chain_end; }
+    else if (chain_end > end) { g.s0 = S - (int)(end - pos); g.s1 = S; g.acquire = true; pos = end; }
+    else { g.s0 = 0; g.s1 = S; pos = chain_end; }
+    return true;
+  }
 };
 
 // L2-only load: the scratch is written by TMA stores (async proxy), which do not update this SM's L1
@@ -293,18 +332,18 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   const int slot_row0 = blockIdx.x * NSUB * TILE_M;  // this CTA's rows in the scratch buffers (NSUB slots)
   const uint32_t crank = CLUSTER > 1 ? ptx::cluster_ctarank() : 0;
   constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
-  // every CTA of a cluster runs the same number of rounds (ghost tiles beyond n_tiles keep feeding the shared
-  // weight pipeline; all their rows are >= B so nothing is written)
-  // a CTA works on NSUB row tiles at once: tiles NSUB*g .. NSUB*g+NSUB-1 of tile group g = blockIdx.x + rnd*gridDim.x
-  const int n_groups = (p.n_tiles + NSUB - 1) / NSUB;
-  const int rounds = (n_groups + (int)gridDim.x - 1) / (int)gridDim.x;
+  // both CTAs of a cluster walk the same segment list (SegIter); CTA `crank` owns tile unit*CLUSTER + crank
+  static_assert(NSUB == 1, "the segment schedule assumes one row tile per CTA");
+  const int worker = (int)blockIdx.x / CLUSTER, n_workers = (int)gridDim.x / CLUSTER;
+  const int n_units = (p.n_tiles + CLUSTER - 1) / CLUSTER;
+  Seg sg;
 
   if (warp == 0) {
     // ======================= weight producer =======================
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
-      for (int rnd = 0; rnd < rounds; ++rnd)
-        for (int step = 0; step < p.n_steps; ++step)
+      for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);)
+        for (int step = sg.s0; step < sg.s1; ++step)
           for (int layer = 0; layer < 6; ++layer) {
             const CUtensorMap* tm = layer == 0 ? &tm_pre : layer == 1 ? &tm_w0 : layer == 2 ? &tm_w1
                                   : layer == 3 ? &tm_w2 : layer == 4 ? &tm_w3 : &tm_post;
@@ -317,29 +356,33 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 const int part_rows = (layer == 5 ? DP : CHUNK_N) / CLUSTER;
                 if (TWO_SM) {  // my half of the weight tile into MY shared memory, completion on the leader's barrier
                   const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
-                  ptx::mbar_arrive_expect_tx_cluster(lbar, bytes);
-                  ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES + A_BYTES, tm, lbar, k * BLOCK_K,
-                                       chunk * CHUNK_N + crank * part_rows);
+                  if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx_cluster(lbar, bytes);
+                    ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES + A_BYTES, tm, lbar, k * BLOCK_K,
+                                         chunk * CHUNK_N + crank * part_rows);
+                  }
                   if (++stage == STAGES) { stage = 0; phase ^= 1; }
                   continue;
                 }
-                ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);  // whole tile: own part + the peers' multicasts
                 const uint32_t dst = smem_base + stage * STAGE_BYTES + A_BYTES + crank * part_rows * (BLOCK_K * 2);
-                if (CLUSTER > 1)
-                  ptx::tma_load_2d_mcast(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N + crank * part_rows,
-                                         CMASK);
-                else
-                  ptx::tma_load_2d(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N);
+                if (ptx::elect_one()) {
+                  ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);  // whole tile: own part + the peers' multicasts
+                  if (CLUSTER > 1)
+                    ptx::tma_load_2d_mcast(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N + crank * part_rows,
+                                           CMASK);
+                  else
+                    ptx::tma_load_2d(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
           }
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0 && (!TWO_SM || crank == 0)) {   // cta_group::2: the pair's leader issues for both CTAs
+    if (!TWO_SM || crank == 0) {   // cta_group::2: the pair's leader issues for both CTAs (warp-wide loop, elected lane issues)
       uint32_t stage = 0, phase = 0, chunk_ctr = 0, tph = 0;
-      for (int rnd = 0; rnd < rounds; ++rnd)
-        for (int step = 0; step < p.n_steps; ++step)
+      for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);)
+        for (int step = sg.s0; step < sg.s1; ++step)
           for (int layer = 0; layer < 6; ++layer) {
             const uint32_t idesc = layer == 0 ? IDESC_BF16_256 : layer == 5 ? IDESC_F16_64 : IDESC_F16_256;
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
@@ -354,18 +397,22 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
                 const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
                 const uint64_t bdesc = ptx::umma_desc_sw128(a_addr + A_BYTES);
-                if (!(p.debug & 2))
+                if (ptx::elect_one()) {
+                  if (!(p.debug & 2))
 #pragma unroll
-                for (int kk = 0; kk < BLOCK_K / 16; ++kk)  // UMMA_K = 16: advance 32 B inside the swizzle row
-                  if (TWO_SM) ptx::mma_f16_ss_2sm(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-                  else ptx::mma_f16_ss(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-                if (TWO_SM) ptx::mma_commit_2sm_mcast(empty_bar(stage), CMASK);
-                else if (CLUSTER > 1) ptx::mma_commit_mcast(empty_bar(stage), CMASK);
-                else ptx::mma_commit(empty_bar(stage));
+                  for (int kk = 0; kk < BLOCK_K / 16; ++kk)  // UMMA_K = 16: advance 32 B inside the swizzle row
+                    if (TWO_SM) ptx::mma_f16_ss_2sm(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                    else ptx::mma_f16_ss(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                  if (TWO_SM) ptx::mma_commit_2sm_mcast(empty_bar(stage), CMASK);
+                  else if (CLUSTER > 1) ptx::mma_commit_mcast(empty_bar(stage), CMASK);
+                  else ptx::mma_commit(empty_bar(stage));
+                  if (k == nk - 1) {   // the chunk's accumulator is complete once everything issued so far retires
+                    if (TWO_SM) ptx::mma_commit_2sm_mcast(tfull_bar(buf), CMASK);
+                    else ptx::mma_commit(tfull_bar(buf));
+                  }
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
-              if (TWO_SM) ptx::mma_commit_2sm_mcast(tfull_bar(buf), CMASK);
-              else ptx::mma_commit(tfull_bar(buf));
               tph ^= 1u << buf;
               ++chunk_ctr;
             }
@@ -373,10 +420,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     }
   } else if (warp == 2) {
     // ======================= activation producer =======================
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0, xph = 0, aph = 0;
-      for (int rnd = 0; rnd < rounds; ++rnd)
-        for (int step = 0; step < p.n_steps; ++step)
+      for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);)
+        for (int step = sg.s0; step < sg.s1; ++step)
           for (int layer = 0; layer < 6; ++layer) {
             // layer input: xa | H | T | H | T | H
             const CUtensorMap* tm = layer == 0 ? &tm_xa : (layer == 2 || layer == 4) ? &tm_t : &tm_h;
@@ -392,9 +439,11 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1);
                 if (TWO_SM) {
                   const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
-                  ptx::mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
-                  ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, k * BLOCK_K, slot_row0 + sub * TILE_M);
-                } else {
+                  if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
+                    ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, k * BLOCK_K, slot_row0 + sub * TILE_M);
+                  }
+                } else if (ptx::elect_one()) {
                   ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
                   ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), k * BLOCK_K,
                                    slot_row0 + sub * TILE_M);
@@ -411,35 +460,43 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     // Epilogue warps stage each [128 x 64] fp16 box in shared memory (swizzled); this warp turns boxes into
     // TMA stores (full 128-byte lines into the L2-resident scratch) and publishes a column chunk to the
     // activation producer once its stores have completed.
-    if (lane == 0) {
-      uint32_t cnt[2] = {0, 0};
+    // Bulk async-groups are tracked per thread: elect_one() names the same lane every time, so commit / wait
+    // pair up with the stores they follow.
+    {
+      uint32_t cnt0 = 0, cnt1 = 0;
       uint32_t last_bar = 0;      // sempty barrier of the most recent store that has not been handed back yet
       bool last_released = true;
-      for (int rnd = 0; rnd < rounds; ++rnd)
-        for (int step = 0; step < p.n_steps; ++step)
+      for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);)
+        for (int step = sg.s0; step < sg.s1; ++step)
           for (int layer = 0; layer < 5; ++layer) {
             const CUtensorMap* tm = (layer == 0 || layer == 2 || layer == 4) ? &tm_h : &tm_t;
             for (int cs = 0; cs < (H / CHUNK_N) * NSUB; ++cs) {
               const int chunk = cs / NSUB, sub = cs % NSUB;
               for (int gp = 0; gp < 2; ++gp)
+#pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-                  const uint32_t b = cnt[hf] % STG_BUFS, ph = (cnt[hf] / STG_BUFS) & 1;
+                  const uint32_t c = hf ? cnt1 : cnt0;
+                  const uint32_t b = c % STG_BUFS, ph = (c / STG_BUFS) & 1;
                   ptx::mbar_wait(sfull_bar(hf, b), ph);
-                  ptx::tma_store_2d(tm, stg_base + (hf * STG_BUFS + b) * STG_BYTES, chunk * CHUNK_N + hf * 128 + gp * 64,
-                                    slot_row0 + sub * TILE_M);
-                  ptx::tma_store_commit();
-                  if (!last_released) {  // the previous store has finished READING its box: hand that box back
-                    ptx::tma_store_wait_read<1>();
-                    ptx::mbar_arrive(last_bar);
+                  if (ptx::elect_one()) {
+                    ptx::tma_store_2d(tm, stg_base + (hf * STG_BUFS + b) * STG_BYTES,
+                                      chunk * CHUNK_N + hf * 128 + gp * 64, slot_row0 + sub * TILE_M);
+                    ptx::tma_store_commit();
+                    if (!last_released) {  // the previous store has finished READING its box: hand that box back
+                      ptx::tma_store_wait_read<1>();
+                      ptx::mbar_arrive(last_bar);
+                    }
                   }
                   last_bar = sempty_bar(hf, b);
                   last_released = false;
-                  ++cnt[hf];
+                  if (hf) ++cnt1; else ++cnt0;
                 }
-              ptx::tma_store_wait<0>();  // this chunk's stores are complete (visible to the TMA loads that follow)
-              ptx::mbar_arrive(last_bar);
+              if (ptx::elect_one()) {
+                ptx::tma_store_wait<0>();  // this chunk's stores are complete (visible to the TMA loads that follow)
+                ptx::mbar_arrive(last_bar);
+                ptx::mbar_arrive(act_bar(sub, chunk));
+              }
               last_released = true;
-              ptx::mbar_arrive(act_bar(sub, chunk));
             }
           }
     }
@@ -457,9 +514,16 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar);
     };
-    for (int rnd = 0; rnd < rounds; ++rnd) {
-      const long long tile0 = (long long)(blockIdx.x + rnd * (int)gridDim.x) * NSUB;
-      // ---------------- tile prologue: first-layer operand of step 0
+    for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);) {
+      const long long tile0 = (long long)sg.unit * CLUSTER + crank;
+      if (sg.acquire) {  // the chain's first steps ran on the next cluster: wait until its x_io rows are published
+        if (et == 0) {
+          const int* f = p.flags + (size_t)(worker + 1) * CLUSTER + crank;
+          while (ptx::ld_acquire_gpu(f) == 0) __nanosleep(200);
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);
+      }
+      // ---------------- tile prologue: first-layer operand of the segment's first step
 #pragma unroll 1
       for (int sub = 0; sub < NSUB; ++sub) {
         const long long row = (tile0 + sub) * TILE_M + r_in;
@@ -473,9 +537,9 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               int col = hf * 32 + i;
-              if (col < D) x[i] = p.x_io[row * D + col];
+              if (col < D) x[i] = __ldcg(p.x_io + row * D + col);
             }
-            if (p.impute) {  // imputation that follows the (none) corrector of step 0, sampling.py:459
+            if (p.impute && sg.s0 == 0) {  // imputation that follows the (none) corrector of step 0, sampling.py:459
               float zc[32];
               draw32(p.noise ? p.noise : nullptr, row, hf, p.seed, (uint32_t)p.step_offset, 0, zc);
               const float al = p.coef[3], sd = p.coef[4];
@@ -508,7 +572,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
         write_xa(xarow, hf, x);
         signal(xa_bar(sub));
       }
-      for (int step = 0; step < p.n_steps; ++step) {
+      for (int step = sg.s0; step < sg.s1; ++step) {
         // ---------------- hidden layers 0..4
         for (int layer = 0; layer < 5; ++layer) {
           ptx::named_bar_sync(1, EPI_THREADS);  // everyone is done with the previous layer's parameters
@@ -627,7 +691,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               for (int i = 0; i < 32; ++i) {
                 int col = hf * 32 + i;
                 if (col < D) {
-                  float xm = a * p.x_io[row * D + col] + b * raw[i];  // sampling.py:185-186 in affine form
+                  float xm = a * __ldcg(p.x_io + row * D + col) + b * raw[i];  // sampling.py:185-186 in affine form
                   x[i] = xm + c * zp[i];
                   if (last && p.x_mean) p.x_mean[row * D + col] = xm;
                 }
@@ -671,7 +735,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 if (col < D) p.x_io[row * D + col] = x[i];
               }
             }
-            if (!last) {
+            if (step + 1 < sg.s1) {  // (a segment that stops mid-chain leaves x in x_io for the cluster that continues)
               write_xa(xarow, hf, x);
               signal(xa_bar(sub));
             }
@@ -699,6 +763,11 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             if (lane == 0) atomicAdd(p.loss_out, acc * p.inv_div);
           }
         }
+      }
+      if (sg.publish) {  // first part of a cut chain: x_io rows of this tile are final for step s1
+        __threadfence();
+        ptx::named_bar_sync(1, EPI_THREADS);
+        if (et == 0) ptx::st_release_gpu(p.flags + (size_t)worker * CLUSTER + crank, 1);
       }
     }
   }
@@ -775,6 +844,8 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
   DPB_CUDA_CHECK(cudaMemset(h->act_h, 0, rows * H * sizeof(__half)));
   DPB_CUDA_CHECK(cudaMemset(h->act_t, 0, rows * H * sizeof(__half)));
   DPB_CUDA_CHECK(cudaMemset(h->xa, 0, rows * tc::XA_K * sizeof(__nv_bfloat16)));
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->tc_flags, sizeof(int) * h->tc_slots));
+  DPB_CUDA_CHECK(cudaMemset(h->tc_flags, 0, sizeof(int) * h->tc_slots));
   int rc = DPB_OK;
   for (int l = 0; l < 4 && rc == DPB_OK; ++l)
     rc = make_tmap_2d(&h->tm_w[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->w16[l], H, H, tc::BLOCK_K,
@@ -798,7 +869,7 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
 }
 
 void tc_release(dpb_score* h) {
-  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->act_t, h->xa};
+  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->act_t, h->xa, h->tc_flags};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   h->tc_ready = false;
@@ -822,6 +893,7 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   p.wgt = j.scale;  // prior loss: api.cu passes the weight through `scale`
   p.z = j.z; p.loss_out = j.loss_out; p.grad_out = j.grad_out; p.row_loss = j.row_loss;
   p.act_h = h->act_h; p.act_t = h->act_t; p.xa = h->xa;
+  p.flags = h->tc_flags;
   {
     const char* dbg = getenv("DPB_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
@@ -832,6 +904,7 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   int grid = (n_groups + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
   const int max_grid = (h->tc_slots / tc::NSUB) / tc::CLUSTER * tc::CLUSTER;
   if (grid > max_grid) grid = max_grid;
+  if (j.n_steps > 1) DPB_CUDA_CHECK(cudaMemsetAsync(h->tc_flags, 0, sizeof(int) * h->tc_slots, st));
   tc::score_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, h->tm_xa, h->tm_act_h, h->tm_act_t, h->tm_pre,
                                                                     h->tm_w[0], h->tm_w[1], h->tm_w[2], h->tm_w[3],
                                                                     h->tm_post);

@@ -107,3 +107,40 @@ def test_completion_keeps_observed_dims_statistics(gpu_model):
     last = traj[-1].cpu()
     sel = mask.bool()
     assert (last[sel] - obs[sel]).abs().max() < 5e-3
+
+
+@pytest.mark.parametrize('task', ['none', 'completion'])
+def test_sampler_balanced_schedule_matches_unsplit_run(gpu_model, task):
+    """More row tiles than SMs: the fused sampler cuts step chains between CTA pairs (score_tc.cu: SegIter) and
+    hands x over through x_io.  Rows are independent, so with injected noise the big run must equal, bit for bit,
+    the same rows sampled in slices small enough that no chain is cut."""
+    B, N, k = 40000, 6, (3 if task == 'completion' else 1)
+    gen = torch.Generator().manual_seed(77)
+    z0 = torch.randn(B, 63, generator=gen)
+    noise = torch.randn(N, k, B, 63, generator=gen).cuda()
+    kw = {}
+    if task == 'completion':
+        obs = torch.randn(B, 63, generator=gen) * 0.3
+        mask = (torch.rand(B, 63, generator=gen) < 0.5).float()
+        kw = dict(args=types.SimpleNamespace(task='completion'))
+    cfg = synthetic.default_config()
+    sde = sde_lib.subVPSDE(0.1, 20., N)
+    gpu_model.engine = L.ENGINE_TC
+    try:
+        def run(lo, hi):
+            fn = sampling.get_sampling_fn(cfg, sde, (hi - lo, 63), lambda x: x, 1e-3, device='cuda')
+            extra = dict(kw)
+            if task == 'completion':
+                extra.update(observation=obs[lo:hi], mask=mask[lo:hi])
+            traj, out = fn(gpu_model, z=z0[lo:hi], noise=noise[:, :, lo:hi].contiguous(), **extra)
+            return traj[-1], out
+        full_last, full_out = run(0, B)
+        step = 16384
+        for lo in range(0, B, step):
+            hi = min(B, lo + step)
+            last, out = run(lo, hi)
+            assert torch.equal(out, full_out[lo:hi]), (task, lo)
+            assert torch.equal(last, full_last[lo:hi]), (task, lo)
+    finally:
+        gpu_model.engine = L.ENGINE_AUTO
+    assert torch.isfinite(full_out).all()
