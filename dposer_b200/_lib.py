@@ -48,7 +48,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    # DPB_LIBRARY: developer knob, points at an instrumented build (build.py with DPB_BUILD_DEFINES)
+    return os.environ.get('DPB_LIBRARY') or _build.LIB
 
 
 def load():

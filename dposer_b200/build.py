@@ -32,13 +32,16 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(PKG, 'build')
-    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
+    # DPB_BUILD_DEFINES (timing experiments only): an instrumented copy next to the product library
+    defines = ['-D' + d for d in os.environ.get('DPB_BUILD_DEFINES', '').split(',') if d]
+    lib = LIB.replace('.so', '_prof.so') if defines else LIB
+    objdir = os.path.join(PKG, 'build_prof' if defines else 'build')
+    os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc, *NVCC_FLAGS, *defines, '-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -50,11 +53,11 @@ def build(force=False, verbose=False):
         if verbose and out:
             print(out)
         objs.append(obj)
-    cmd = [nvcc, '-shared', '-o', LIB, *objs]
+    cmd = [nvcc, '-shared', '-o', lib, *objs]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if out.returncode != 0:
         raise RuntimeError(f'link failed:\n{out.stdout}')
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':

@@ -92,6 +92,12 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Move registers between warpgroups (all 128 threads of the warpgroup execute it; counts are multiples of 8)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // One lane of a converged warp (deterministically the same lane for the same mask).  The single-thread roles run
 // their loops warp-wide and predicate only the async instruction with this: operands computed in uniform control
 // flow stay in uniform registers, while a loop nested under `if (lane == 0)` makes ptxas wrap every

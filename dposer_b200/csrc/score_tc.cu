@@ -48,7 +48,9 @@ constexpr int NUM_BARS = 2 * STAGES + 4 + NSUB * 5 + 8;  // full, empty, tfull[2
 constexpr int OFF_PAR = STAGES * STAGE_BYTES;
 constexpr int OFF_STG = OFF_PAR + PAR_BYTES;     // 1024-aligned: 3*49152 + 12288 = 159744
 constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
-constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;  // + alignment slack
+constexpr int OFF_POSTB = (OFF_BAR + NUM_BARS * 8 + 16 + 15) / 16 * 16;   // post_dense bias (64 floats)
+static_assert(OFF_POSTB % 16 == 0, "post_b is read with 128-bit loads");
+constexpr int SMEM_BYTES = OFF_POSTB + DP * 4 + 1024;  // + alignment slack
 static_assert(OFF_STG % 1024 == 0, "staging boxes must be 1024-byte aligned for SWIZZLE_128B");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr int MMA_M = TWO_SM ? 2 * TILE_M : TILE_M;
@@ -59,7 +61,9 @@ static_assert(!TWO_SM || CLUSTER == 2, "cta_group::2 needs clusters of exactly t
 
 struct KParams {
   int mode, n_steps, impute, noise_k, n_tiles;
-  int debug;  // timing experiments only (DPB_TC_DEBUG): 1 = skip hidden-layer epilogue math, 2 = skip MMAs
+  int debug;  // timing experiments only (DPB_TC_DEBUG): 1 = skip hidden-layer epilogue math, 2 = skip MMAs,
+              // 4 / 8 = skip the activation / weight TMA loads, 16 = skip the activation TMA stores,
+              // 64 = operand pipeline only (no epilogue, no activation dependencies; results are garbage)
   long long B;
   const float* x_in;
   float* x_io;
@@ -125,6 +129,27 @@ struct SegIter {
   }
 };
 
+// Wait-time accounting for timing experiments (build with DPB_BUILD_DEFINES=DPB_TC_PROFILE): every role sums
+// the cycles it spends in each kind of wait; tc_launch prints the per-role means after the kernel.
+#ifndef DPB_SILU_MODE
+#define DPB_SILU_MODE 0
+#endif
+#ifdef DPB_TC_PROFILE
+__device__ long long g_prof[256 * 12 * 5];
+#define PROF_DECL long long prof_acc[5] = {0, 0, 0, 0, 0}; const long long prof_t0 = clock64();
+#define PROF_WAIT(k, ...) do { const long long _t = clock64(); __VA_ARGS__; prof_acc[k] += clock64() - _t; } while (0)
+#define PROF_BEGIN(v) const long long v = clock64();
+#define PROF_END(k, v) prof_acc[k] += clock64() - v;
+#define PROF_FLUSH() do { if (lane == 0) { prof_acc[4] = clock64() - prof_t0; \
+    for (int _k = 0; _k < 5; ++_k) g_prof[((size_t)blockIdx.x * 12 + warp) * 5 + _k] = prof_acc[_k]; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_WAIT(k, ...) do { __VA_ARGS__; } while (0)
+#define PROF_BEGIN(v)
+#define PROF_END(k, v)
+#define PROF_FLUSH() do { } while (0)
+#endif
+
 // L2-only load: the scratch is written by TMA stores (async proxy), which do not update this SM's L1
 __device__ __forceinline__ uint4 ld_global_v4(const uint4* p) {
   uint4 r;
@@ -163,6 +188,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -172,6 +202,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // One thread, one row, one GroupNorm group (32 consecutive channels):  acc + time bias -> GroupNorm -> SiLU
 // (-> + residual) -> 32 fp16 values.  Reductions use four independent partial sums (short dependency chains);
 // the elementwise math is packed two channels per instruction.
+template <bool CLAMP>
 __device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* tb, const float* gm, const float* bt,
                                               bool residual, const uint4* res, uint4* out) {
   float2 v[16];
@@ -204,6 +235,29 @@ __device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* t
     const float4 b4 = *reinterpret_cast<const float4*>(bt + 2 * i);
     float2 y0 = fma2(v[i], mul2(r2, make_float2(g4.x, g4.y)), make_float2(b4.x, b4.y));
     float2 y1 = fma2(v[i + 1], mul2(r2, make_float2(g4.z, g4.w)), make_float2(b4.z, b4.w));
+#if DPB_SILU_MODE == 2
+    // SiLU: h + h tanh(h), h = y/2  (one MUFU per element)
+    const float2 hh0 = mul2(y0, make_float2(0.5f, 0.5f)), hh1 = mul2(y1, make_float2(0.5f, 0.5f));
+    y0 = fma2(hh0, make_float2(tanh_approx(hh0.x), tanh_approx(hh0.y)), hh0);
+    y1 = fma2(hh1, make_float2(tanh_approx(hh1.x), tanh_approx(hh1.y)), hh1);
+#elif DPB_SILU_MODE == 1
+    // SiLU: y / (1 + 2^(-y log2 e)); the four reciprocals share one MUFU.RCP:
+    // (da dc, db dd) -> P -> 1/P -> (1/(da dc), 1/(db dd)) -> x (dc, dd) = (1/da, 1/db), x (da, db) = (1/dc, 1/dd)
+    float2 e0 = mul2(y0, nl2e), e1 = mul2(y1, nl2e);
+    if (CLAMP) {  // keep the product of four denominators finite (2^31 each)
+      e0 = make_float2(fminf(e0.x, 30.f), fminf(e0.y, 30.f));
+      e1 = make_float2(fminf(e1.x, 30.f), fminf(e1.y, 30.f));
+    }
+    e0 = make_float2(ex2_approx(e0.x), ex2_approx(e0.y));
+    e1 = make_float2(ex2_approx(e1.x), ex2_approx(e1.y));
+    e0 = add2(e0, one);
+    e1 = add2(e1, one);
+    const float2 pp = mul2(e0, e1);
+    const float rP = rcp_approx(pp.x * pp.y);
+    const float2 rr = mul2(make_float2(rP, rP), make_float2(pp.y, pp.x));
+    y0 = mul2(y0, mul2(rr, e1));
+    y1 = mul2(y1, mul2(rr, e0));
+#else
     // SiLU: y / (1 + 2^(-y log2 e))
     float2 e0 = mul2(y0, nl2e), e1 = mul2(y1, nl2e);
     e0 = make_float2(ex2_approx(e0.x), ex2_approx(e0.y));
@@ -212,6 +266,7 @@ __device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* t
     e1 = add2(e1, one);
     y0 = mul2(y0, make_float2(rcp_approx(e0.x), rcp_approx(e0.y)));
     y1 = mul2(y1, make_float2(rcp_approx(e1.x), rcp_approx(e1.y)));
+#endif
     if (residual) {
       const uint32_t* rw = reinterpret_cast<const uint32_t*>(res);
       y0 = add2(y0, __half22float2(*reinterpret_cast<const __half2*>(&rw[i])));
@@ -291,6 +346,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   auto sfull_bar = [&](uint32_t hf, uint32_t b) { return bar_base + 8u * (2 * STAGES + 4 + NSUB * 5 + hf * 2 + b); };
   auto sempty_bar = [&](uint32_t hf, uint32_t b) { return bar_base + 8u * (2 * STAGES + 4 + NSUB * 5 + 4 + hf * 2 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NUM_BARS * 8);
+  float* postb = reinterpret_cast<float*>(smem + OFF_POSTB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -324,6 +380,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     if (TWO_SM) ptx::tmem_alloc_2sm(ptx::smem_u32(tmem_slot), 512);
     else ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   }
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + DP) postb[threadIdx.x - 128] = p.post_b[threadIdx.x - 128];
   ptx::tc_fence_before();
   __syncthreads();
   if (CLUSTER > 1) ptx::cluster_sync();  // peers' barriers are initialised before anyone multicasts / arrives remotely
@@ -333,11 +390,14 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   const uint32_t crank = CLUSTER > 1 ? ptx::cluster_ctarank() : 0;
   constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1);
   // both CTAs of a cluster walk the same segment list (SegIter); CTA `crank` owns tile unit*CLUSTER + crank
-  static_assert(NSUB == 1, "the segment schedule assumes one row tile per CTA");
   const int worker = (int)blockIdx.x / CLUSTER, n_workers = (int)gridDim.x / CLUSTER;
-  const int n_units = (p.n_tiles + CLUSTER - 1) / CLUSTER;
+  const int n_units = (p.n_tiles + CLUSTER * NSUB - 1) / (CLUSTER * NSUB);
   Seg sg;
+  PROF_DECL
 
+  // register budget: the four single-lane roles (warpgroup 0) give registers to the 256 epilogue threads
+  if (warp < 4) {
+  ptx::setmaxnreg_dec<56>();
   if (warp == 0) {
     // ======================= weight producer =======================
     {
@@ -352,14 +412,17 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             for (int chunk = 0; chunk < nc; ++chunk)
              for (int sub = 0; sub < NSUB; ++sub)
               for (int k = 0; k < nk; ++k) {
-                ptx::mbar_wait(empty_bar(stage), phase ^ 1);  // every CTA of the cluster has consumed this stage
+                PROF_WAIT(0, ptx::mbar_wait(empty_bar(stage), phase ^ 1));  // every CTA of the cluster has consumed this stage
                 const int part_rows = (layer == 5 ? DP : CHUNK_N) / CLUSTER;
                 if (TWO_SM) {  // my half of the weight tile into MY shared memory, completion on the leader's barrier
                   const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
                   if (ptx::elect_one()) {
-                    ptx::mbar_arrive_expect_tx_cluster(lbar, bytes);
-                    ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES + A_BYTES, tm, lbar, k * BLOCK_K,
-                                         chunk * CHUNK_N + crank * part_rows);
+                    if (p.debug & 8) ptx::mbar_arrive_cluster(lbar);
+                    else {
+                      ptx::mbar_arrive_expect_tx_cluster(lbar, bytes);
+                      ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES + A_BYTES, tm, lbar, k * BLOCK_K,
+                                           chunk * CHUNK_N + crank * part_rows);
+                    }
                   }
                   if (++stage == STAGES) { stage = 0; phase ^= 1; }
                   continue;
@@ -388,11 +451,11 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
             for (int cs = 0; cs < nc * NSUB; ++cs) {   // (chunk, sub) pairs; chunk_ctr & 1 == sub
               const uint32_t buf = chunk_ctr & 1;
-              ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
+              if (!(p.debug & 64)) PROF_WAIT(0, ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1));
               ptx::tc_fence_after();
               const uint32_t taddr = tmem_base + buf * CHUNK_N;
               for (int k = 0; k < nk; ++k) {
-                ptx::mbar_wait(full_bar(stage), phase);
+                PROF_WAIT(1, ptx::mbar_wait(full_bar(stage), phase));
                 ptx::tc_fence_after();
                 const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
                 const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
@@ -430,18 +493,21 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
             for (int chunk = 0; chunk < nc; ++chunk)
              for (int sub = 0; sub < NSUB; ++sub) {
-              if (layer == 0 && chunk == 0) ptx::mbar_wait(xa_bar(sub), xph);  // prologue / previous step's tail wrote x
+              if (layer == 0 && chunk == 0 && !(p.debug & 64)) PROF_WAIT(0, ptx::mbar_wait(xa_bar(sub), xph));  // prologue / previous step's tail wrote x
               for (int k = 0; k < nk; ++k) {
                 // K-slabs 4c..4c+3 of this layer's input are column chunk c of the previous layer's output:
                 // wait for exactly that chunk (first pass only), so the next layer starts while the previous
                 // layer's last chunks are still in the epilogue
-                if (layer > 0 && chunk == 0 && (k & 3) == 0) ptx::mbar_wait(act_bar(sub, k >> 2), aph);
-                ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+                if (layer > 0 && chunk == 0 && (k & 3) == 0 && !(p.debug & 64)) PROF_WAIT(1, ptx::mbar_wait(act_bar(sub, k >> 2), aph));
+                PROF_WAIT(2, ptx::mbar_wait(empty_bar(stage), phase ^ 1));
                 if (TWO_SM) {
                   const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
                   if (ptx::elect_one()) {
-                    ptx::mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
-                    ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, k * BLOCK_K, slot_row0 + sub * TILE_M);
+                    if (p.debug & 4) ptx::mbar_arrive_cluster(lbar);
+                    else {
+                      ptx::mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
+                      ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, k * BLOCK_K, slot_row0 + sub * TILE_M);
+                    }
                   }
                 } else if (ptx::elect_one()) {
                   ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
@@ -466,6 +532,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       uint32_t cnt0 = 0, cnt1 = 0;
       uint32_t last_bar = 0;      // sempty barrier of the most recent store that has not been handed back yet
       bool last_released = true;
+      if (!(p.debug & 64))
       for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);)
         for (int step = sg.s0; step < sg.s1; ++step)
           for (int layer = 0; layer < 5; ++layer) {
@@ -477,13 +544,14 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 for (int hf = 0; hf < 2; ++hf) {
                   const uint32_t c = hf ? cnt1 : cnt0;
                   const uint32_t b = c % STG_BUFS, ph = (c / STG_BUFS) & 1;
-                  ptx::mbar_wait(sfull_bar(hf, b), ph);
+                  PROF_WAIT(0, ptx::mbar_wait(sfull_bar(hf, b), ph));
                   if (ptx::elect_one()) {
+                    if (!(p.debug & 16))
                     ptx::tma_store_2d(tm, stg_base + (hf * STG_BUFS + b) * STG_BYTES,
                                       chunk * CHUNK_N + hf * 128 + gp * 64, slot_row0 + sub * TILE_M);
                     ptx::tma_store_commit();
                     if (!last_released) {  // the previous store has finished READING its box: hand that box back
-                      ptx::tma_store_wait_read<1>();
+                      PROF_WAIT(1, ptx::tma_store_wait_read<1>());
                       ptx::mbar_arrive(last_bar);
                     }
                   }
@@ -492,7 +560,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                   if (hf) ++cnt1; else ++cnt0;
                 }
               if (ptx::elect_one()) {
-                ptx::tma_store_wait<0>();  // this chunk's stores are complete (visible to the TMA loads that follow)
+                PROF_WAIT(2, ptx::tma_store_wait<0>());  // this chunk's stores are complete (visible to the TMA loads that follow)
                 ptx::mbar_arrive(last_bar);
                 ptx::mbar_arrive(act_bar(sub, chunk));
               }
@@ -500,8 +568,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             }
           }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ======================= epilogue =======================
+    ptx::setmaxnreg_inc<224>();
     const int q = warp & 3;          // TMEM lane quarter this warp may read
     const int hf = (warp - 4) >> 2;  // which half of the chunk's column groups
     const int et = threadIdx.x - 128;
@@ -514,8 +584,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar);
     };
+    float xs[NSUB][32];   // sampler state of this thread's (row, column half), carried in registers across the steps
+    if (!(p.debug & 64))
     for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);) {
-      const long long tile0 = (long long)sg.unit * CLUSTER + crank;
+      const long long tile0 = ((long long)sg.unit * CLUSTER + crank) * NSUB;
       if (sg.acquire) {  // the chain's first steps ran on the next cluster: wait until its x_io rows are published
         if (et == 0) {
           const int* f = p.flags + (size_t)(worker + 1) * CLUSTER + crank;
@@ -524,7 +596,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
         ptx::named_bar_sync(1, EPI_THREADS);
       }
       // ---------------- tile prologue: first-layer operand of the segment's first step
-#pragma unroll 1
+#pragma unroll
       for (int sub = 0; sub < NSUB; ++sub) {
         const long long row = (tile0 + sub) * TILE_M + r_in;
         const bool valid = row < p.B;
@@ -549,7 +621,6 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 if (col < D) {
                   float m = p.mask[row * D + col];
                   x[i] = x[i] * (1.0f - m) + (al * p.obs[row * D + col] + zc[i] * sd) * m;
-                  p.x_io[row * D + col] = x[i];
                 }
               }
             }
@@ -571,6 +642,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
         }
         write_xa(xarow, hf, x);
         signal(xa_bar(sub));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xs[sub][i] = x[i];
       }
       for (int step = sg.s0; step < sg.s1; ++step) {
         // ---------------- hidden layers 0..4
@@ -592,7 +665,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             const int chunk = cs / NSUB, sub = cs % NSUB;
             __half* drow = (to_h ? p.act_h : p.act_t) + (size_t)(slot_row0 + sub * TILE_M + r_in) * H;
             const uint32_t buf = chunk_ctr & 1;
-            ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+            PROF_WAIT(0, ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1));
             ptx::tc_fence_after();
             // two column groups per iteration: both TMEM loads and both residual loads are in flight before any
             // math, and the two independent instruction streams interleave (ILP for the 8-warp epilogue)
@@ -623,13 +696,13 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
               } else {
-                gn_silu_group(vr0, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o);
-                gn_silu_group(vr1, par + col0 + 32, par + H + col0 + 32, par + 2 * H + col0 + 32, residual, r1, o + 4);
+                PROF_WAIT(2, gn_silu_group<true>(vr0, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o);
+                gn_silu_group<true>(vr1, par + col0 + 32, par + H + col0 + 32, par + 2 * H + col0 + 32, residual, r1, o + 4));
               }
               // stage this row's 64 fp16 (128 B) in the SWIZZLE_128B box of my column half; the store warp
               // ships the box with one TMA store (full lines, asynchronous) -- no per-row global stores
               const uint32_t sb = scnt % STG_BUFS;
-              ptx::mbar_wait(sempty_bar(hf, sb), ((scnt / STG_BUFS) & 1) ^ 1);
+              PROF_WAIT(1, ptx::mbar_wait(sempty_bar(hf, sb), ((scnt / STG_BUFS) & 1) ^ 1));
               const uint32_t rbase = stg_base + (hf * STG_BUFS + sb) * STG_BYTES + r_in * 128;
 #pragma unroll
               for (int j = 0; j < 8; ++j) st_shared_v4(rbase + ((j ^ (r_in & 7)) << 4), o[j]);
@@ -643,13 +716,14 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           }
         }
         // ---------------- post_dense + mode-specific tail
-#pragma unroll 1
+#pragma unroll
         for (int sub = 0; sub < NSUB; ++sub) {
           const long long row = (tile0 + sub) * TILE_M + r_in;
           const bool valid = row < p.B;
           __nv_bfloat16* xarow = p.xa + (size_t)(slot_row0 + sub * TILE_M + r_in) * XA_K;
           const uint32_t buf = chunk_ctr & 1;
-          ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+          PROF_WAIT(0, ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1));
+          PROF_BEGIN(tail_t0)
           ptx::tc_fence_after();
           uint32_t vr[32];
           ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + hf * 32, vr);
@@ -664,7 +738,11 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           ++chunk_ctr;
           float raw[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) raw[i] = __uint_as_float(vr[i]) + __ldg(p.post_b + hf * 32 + i);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 pb = *reinterpret_cast<const float4*>(postb + hf * 32 + i);
+            raw[i] = __uint_as_float(vr[i]) + pb.x; raw[i + 1] = __uint_as_float(vr[i + 1]) + pb.y;
+            raw[i + 2] = __uint_as_float(vr[i + 2]) + pb.z; raw[i + 3] = __uint_as_float(vr[i + 3]) + pb.w;
+          }
           const bool last = (step + 1 == p.n_steps);
           if (p.mode == 0) {
             if (valid) {
@@ -691,7 +769,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               for (int i = 0; i < 32; ++i) {
                 int col = hf * 32 + i;
                 if (col < D) {
-                  float xm = a * __ldcg(p.x_io + row * D + col) + b * raw[i];  // sampling.py:185-186 in affine form
+                  float xm = a * xs[sub][i] + b * raw[i];  // sampling.py:185-186 in affine form
                   x[i] = xm + c * zp[i];
                   if (last && p.x_mean) p.x_mean[row * D + col] = xm;
                 }
@@ -729,12 +807,16 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                   }
                 }
               }
+              if (step + 1 == sg.s1) {  // end of the segment: the state leaves the registers
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                int col = hf * 32 + i;
-                if (col < D) p.x_io[row * D + col] = x[i];
+                for (int i = 0; i < 32; ++i) {
+                  int col = hf * 32 + i;
+                  if (col < D) p.x_io[row * D + col] = x[i];
+                }
               }
             }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xs[sub][i] = x[i];
             if (step + 1 < sg.s1) {  // (a segment that stops mid-chain leaves x in x_io for the cluster that continues)
               write_xa(xarow, hf, x);
               signal(xa_bar(sub));
@@ -762,6 +844,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) atomicAdd(p.loss_out, acc * p.inv_div);
           }
+          PROF_END(3, tail_t0)
         }
       }
       if (sg.publish) {  // first part of a cut chain: x_io rows of this tile are final for step s1
@@ -771,6 +854,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       }
     }
   }
+  PROF_FLUSH();
   __syncthreads();
   if (CLUSTER > 1) ptx::cluster_sync();  // no CTA leaves while a peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
@@ -909,6 +993,27 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
                                                                     h->tm_w[0], h->tm_w[1], h->tm_w[2], h->tm_w[3],
                                                                     h->tm_post);
   DPB_CUDA_CHECK(cudaGetLastError());
+#ifdef DPB_TC_PROFILE
+  {
+    cudaStreamSynchronize(st);
+    std::vector<long long> hp((size_t)grid * 12 * 5);
+    cudaMemcpyFromSymbol(hp.data(), tc::g_prof, hp.size() * sizeof(long long));
+    static const char* names[12] = {"W-producer", "MMA", "A-producer", "store", "epi", "epi", "epi", "epi", "epi", "epi", "epi", "epi"};
+    double acc[5][5] = {};
+    int cnt[5] = {};
+    for (int b = 0; b < grid; ++b)
+      for (int w = 0; w < 12; ++w) {
+        if (w == 1 && (b & 1)) continue;  // the MMA warp of the non-leader CTA is idle
+        const int r = w < 4 ? w : 4;
+        for (int k = 0; k < 5; ++k) acc[r][k] += (double)hp[((size_t)b * 12 + w) * 5 + k];
+        ++cnt[r];
+      }
+    for (int r = 0; r < 5; ++r)
+      fprintf(stderr, "[tc-prof] %-10s total %.0f  wait0 %.3f wait1 %.3f wait2 %.3f wait3 %.3f (fractions of total)\n",
+              names[r], acc[r][4] / cnt[r], acc[r][0] / acc[r][4], acc[r][1] / acc[r][4], acc[r][2] / acc[r][4],
+              acc[r][3] / acc[r][4]);
+  }
+#endif
   return DPB_OK;
 }
 

@@ -8,7 +8,7 @@ model = synthetic.make_score_model(42).cuda(); model.engine = L.ENGINE_TC
 cfg = synthetic.default_config()
 fn = sampling.get_sampling_fn(cfg, sde_lib.subVPSDE(0.1, 20., N), (B, 63), lambda x: x, 1e-3, device='cuda', return_trajs=False)
 z = torch.randn(B, 63)
-for dbg in ['0', '1', '2', '3']:
+for dbg in os.environ.get('PROF_DBG', '0,1,2,3').split(','):
     os.environ['DPB_TC_DEBUG'] = dbg
     for _ in range(2): fn(model, z=z)
     torch.cuda.synchronize()
