@@ -38,8 +38,12 @@ constexpr int B_BYTES = CHUNK_N * BLOCK_K * 2 / (TWO_SM ? 2 : 1);  // this CTA's
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int POST_B_BYTES = DP * BLOCK_K * 2 / (TWO_SM ? 2 : 1);  // post_dense tile (N = 64)
 constexpr int XA_K = 192;
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_THREADS = 256;
+constexpr int NUM_THREADS = 640;   // 4 single-lane role warps + 16 epilogue warps
+constexpr int EPI_THREADS = 512;
+constexpr int ROLE_REGS = 32;      // setmaxnreg: 640 threads start at 96 registers; the role warpgroup gives, the
+constexpr int EPI_REGS = 112;      // epilogue warpgroups take ((96 - 32) * 128 >= (112 - 96) * 512)
+constexpr int TCOLS = 16;          // pose columns per epilogue thread in the prologue / tail (64 / 4 warps per row quarter)
+static_assert(2 * H / 4 == EPI_THREADS, "parameter staging assumes one float4 of gamma|beta per epilogue thread");
 constexpr int PAR_BYTES = 3 * H * 4;
 constexpr int STG_BYTES = TILE_M * 128;          // one [128 rows x 64 fp16] SWIZZLE_128B box of outgoing activations
 constexpr int STG_BUFS = TWO_SM ? 1 : 2;         // staging buffers per column half (shared memory is better spent on ring stages)
@@ -131,17 +135,21 @@ struct SegIter {
 
 // Wait-time accounting for timing experiments (build with DPB_BUILD_DEFINES=DPB_TC_PROFILE): every role sums
 // the cycles it spends in each kind of wait; tc_launch prints the per-role means after the kernel.
+// SiLU evaluation in the epilogue.  2 (default): y sigmoid(y) = h + h tanh(h) with h = y/2 and MUFU.TANH
+// (tanh.approx.f32, documented relative error 2^-11, the rounding unit of the fp16 activations it feeds; the
+// measured end-to-end error is unchanged at 4.5e-4) -- one MUFU per element.  0: y / (1 + 2^(-y log2 e)) with
+// MUFU.EX2 + MUFU.RCP, two per element.
 #ifndef DPB_SILU_MODE
-#define DPB_SILU_MODE 0
+#define DPB_SILU_MODE 2
 #endif
 #ifdef DPB_TC_PROFILE
-__device__ long long g_prof[256 * 12 * 5];
+__device__ long long g_prof[256 * 20 * 5];
 #define PROF_DECL long long prof_acc[5] = {0, 0, 0, 0, 0}; const long long prof_t0 = clock64();
 #define PROF_WAIT(k, ...) do { const long long _t = clock64(); __VA_ARGS__; prof_acc[k] += clock64() - _t; } while (0)
 #define PROF_BEGIN(v) const long long v = clock64();
 #define PROF_END(k, v) prof_acc[k] += clock64() - v;
 #define PROF_FLUSH() do { if (lane == 0) { prof_acc[4] = clock64() - prof_t0; \
-    for (int _k = 0; _k < 5; ++_k) g_prof[((size_t)blockIdx.x * 12 + warp) * 5 + _k] = prof_acc[_k]; } } while (0)
+    for (int _k = 0; _k < 5; ++_k) g_prof[((size_t)blockIdx.x * 20 + warp) * 5 + _k] = prof_acc[_k]; } } while (0)
 #else
 #define PROF_DECL
 #define PROF_WAIT(k, ...) do { __VA_ARGS__; } while (0)
@@ -202,7 +210,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // One thread, one row, one GroupNorm group (32 consecutive channels):  acc + time bias -> GroupNorm -> SiLU
 // (-> + residual) -> 32 fp16 values.  Reductions use four independent partial sums (short dependency chains);
 // the elementwise math is packed two channels per instruction.
-template <bool CLAMP>
 __device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* tb, const float* gm, const float* bt,
                                               bool residual, const uint4* res, uint4* out) {
   float2 v[16];
@@ -225,9 +232,13 @@ __device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* t
   }
   const float2 qt = add2(add2(q[0], q[1]), add2(q[2], q[3]));
   const float rstd = rsqrtf((qt.x + qt.y) * (1.0f / GROUP) + GN_EPS);
+#if DPB_SILU_MODE == 2
+  const float2 r2 = make_float2(0.5f * rstd, 0.5f * rstd);   // h = y/2: the staged beta is already halved
+#else
   const float2 r2 = make_float2(rstd, rstd);
   const float2 nl2e = make_float2(-1.4426950408889634f, -1.4426950408889634f);
   const float2 one = make_float2(1.0f, 1.0f);
+#endif
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
@@ -236,27 +247,9 @@ __device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* t
     float2 y0 = fma2(v[i], mul2(r2, make_float2(g4.x, g4.y)), make_float2(b4.x, b4.y));
     float2 y1 = fma2(v[i + 1], mul2(r2, make_float2(g4.z, g4.w)), make_float2(b4.z, b4.w));
 #if DPB_SILU_MODE == 2
-    // SiLU: h + h tanh(h), h = y/2  (one MUFU per element)
-    const float2 hh0 = mul2(y0, make_float2(0.5f, 0.5f)), hh1 = mul2(y1, make_float2(0.5f, 0.5f));
-    y0 = fma2(hh0, make_float2(tanh_approx(hh0.x), tanh_approx(hh0.y)), hh0);
-    y1 = fma2(hh1, make_float2(tanh_approx(hh1.x), tanh_approx(hh1.y)), hh1);
-#elif DPB_SILU_MODE == 1
-    // SiLU: y / (1 + 2^(-y log2 e)); the four reciprocals share one MUFU.RCP:
-    // (da dc, db dd) -> P -> 1/P -> (1/(da dc), 1/(db dd)) -> x (dc, dd) = (1/da, 1/db), x (da, db) = (1/dc, 1/dd)
-    float2 e0 = mul2(y0, nl2e), e1 = mul2(y1, nl2e);
-    if (CLAMP) {  // keep the product of four denominators finite (2^31 each)
-      e0 = make_float2(fminf(e0.x, 30.f), fminf(e0.y, 30.f));
-      e1 = make_float2(fminf(e1.x, 30.f), fminf(e1.y, 30.f));
-    }
-    e0 = make_float2(ex2_approx(e0.x), ex2_approx(e0.y));
-    e1 = make_float2(ex2_approx(e1.x), ex2_approx(e1.y));
-    e0 = add2(e0, one);
-    e1 = add2(e1, one);
-    const float2 pp = mul2(e0, e1);
-    const float rP = rcp_approx(pp.x * pp.y);
-    const float2 rr = mul2(make_float2(rP, rP), make_float2(pp.y, pp.x));
-    y0 = mul2(y0, mul2(rr, e1));
-    y1 = mul2(y1, mul2(rr, e0));
+    // y0, y1 hold h = y/2 here: SiLU(y) = h + h tanh(h)
+    y0 = fma2(y0, make_float2(tanh_approx(y0.x), tanh_approx(y0.y)), y0);
+    y1 = fma2(y1, make_float2(tanh_approx(y1.x), tanh_approx(y1.y)), y1);
 #else
     // SiLU: y / (1 + 2^(-y log2 e))
     float2 e0 = mul2(y0, nl2e), e1 = mul2(y1, nl2e);
@@ -283,22 +276,22 @@ __device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* t
 __device__ __forceinline__ int layer_nk(int layer) { return layer == 0 ? XA_K / BLOCK_K : H / BLOCK_K; }
 __device__ __forceinline__ int layer_chunks(int layer) { return layer == 5 ? 1 : H / CHUNK_N; }
 
-// x[32] (fp32, columns hf*32..hf*32+31 of one row) -> [hi | lo | hi] bf16 segments of the xa row
-__device__ __forceinline__ void write_xa(__nv_bfloat16* row, int hf, const float* x) {
-  uint32_t hi[16], lo[16];
+// x[TCOLS] (fp32, columns c0..c0+TCOLS-1 of one row) -> [hi | lo | hi] bf16 segments of the xa row
+__device__ __forceinline__ void write_xa(__nv_bfloat16* row, int c0, const float* x) {
+  uint32_t hi[TCOLS / 2], lo[TCOLS / 2];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < TCOLS / 2; ++i) {
     __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
     __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
     __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
     hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
     lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
   }
-  uint4* p0 = reinterpret_cast<uint4*>(row + hf * 32);
-  uint4* p1 = reinterpret_cast<uint4*>(row + 64 + hf * 32);
-  uint4* p2 = reinterpret_cast<uint4*>(row + 128 + hf * 32);
+  uint4* p0 = reinterpret_cast<uint4*>(row + c0);
+  uint4* p1 = reinterpret_cast<uint4*>(row + 64 + c0);
+  uint4* p2 = reinterpret_cast<uint4*>(row + 128 + c0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < TCOLS / 8; ++i) {
     uint4 h = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
     uint4 l = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
     p0[i] = h;
@@ -307,18 +300,19 @@ __device__ __forceinline__ void write_xa(__nv_bfloat16* row, int hf, const float
   }
 }
 
-// Gaussian draws for this thread's 32 columns: caller-supplied plane or Philox (slot, step)
-__device__ __forceinline__ void draw32(const float* plane, long long row, int hf, unsigned long long seed,
-                                       uint32_t step, uint32_t slot, float* z) {
+// Gaussian draws for this thread's TCOLS columns: caller-supplied plane or Philox (slot, step); the Philox
+// addressing (row, step, slot, quad = column / 4) does not depend on how columns are split over threads
+__device__ __forceinline__ void draw_cols(const float* plane, long long row, int c0, unsigned long long seed,
+                                          uint32_t step, uint32_t slot, float* z) {
   if (plane) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      int col = hf * 32 + i;
+    for (int i = 0; i < TCOLS; ++i) {
+      int col = c0 + i;
       z[i] = col < D ? plane[row * D + col] : 0.f;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) normal4(seed, (uint64_t)row, step, slot, (uint32_t)(hf * 8 + j), z + 4 * j);
+    for (int j = 0; j < TCOLS / 4; ++j) normal4(seed, (uint64_t)row, step, slot, (uint32_t)(c0 / 4 + j), z + 4 * j);
   }
 }
 
@@ -357,15 +351,15 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tfull_bar(b), 1);   // tcgen05.commit
-      ptx::mbar_init(tempty_bar(b), TWO_SM ? 16 : 8);  // one lane of each epilogue warp (of both CTAs on the leader)
+      ptx::mbar_init(tempty_bar(b), TWO_SM ? 32 : 16);  // one lane of each epilogue warp (of both CTAs on the leader)
     }
     for (int sub = 0; sub < NSUB; ++sub) {
-      ptx::mbar_init(xa_bar(sub), 8);
+      ptx::mbar_init(xa_bar(sub), 16);
       for (int c = 0; c < 4; ++c) ptx::mbar_init(act_bar(sub, c), 1);  // the store warp, after the chunk's TMA stores completed
     }
     for (int hf = 0; hf < 2; ++hf)
       for (int b = 0; b < 2; ++b) {
-        ptx::mbar_init(sfull_bar(hf, b), 4);   // the four epilogue warps (row quarters) that fill one box
+        ptx::mbar_init(sfull_bar(hf, b), 8);   // the eight epilogue warps (row quarters x column groups) that fill one box
         ptx::mbar_init(sempty_bar(hf, b), 1);  // the store warp, once the TMA store has read the box
       }
     ptx::fence_barrier_init();
@@ -397,7 +391,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
 
   // register budget: the four single-lane roles (warpgroup 0) give registers to the 256 epilogue threads
   if (warp < 4) {
-  ptx::setmaxnreg_dec<56>();
+  ptx::setmaxnreg_dec<ROLE_REGS>();
   if (warp == 0) {
     // ======================= weight producer =======================
     {
@@ -570,12 +564,17 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     }
   }
   } else {
-    // ======================= epilogue =======================
-    ptx::setmaxnreg_inc<224>();
-    const int q = warp & 3;          // TMEM lane quarter this warp may read
-    const int hf = (warp - 4) >> 2;  // which half of the chunk's column groups
+    // ======================= epilogue (16 warps) =======================
+    // Warp (q, hf, sg2): TMEM lane quarter q (rows 32q..32q+31), column half hf of the chunk, and within each of the
+    // half's two 64-column boxes the 32-column GroupNorm group sg2.  Four warps per scheduler hide the MUFU / TMEM /
+    // shared-memory latencies of the per-row chains that two warps per scheduler left exposed.
+    ptx::setmaxnreg_inc<EPI_REGS>();
+    const int q = warp & 3;
+    const int hf = (warp - 4) >> 3;
+    const int sg2 = ((warp - 4) >> 2) & 1;
     const int et = threadIdx.x - 128;
     const int r_in = q * 32 + lane;
+    const int c0 = hf * 32 + sg2 * TCOLS;   // first of this thread's TCOLS pose columns (prologue / tail)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t chunk_ctr = 0, tph = 0, scnt = 0;
     auto signal = [&](uint32_t bar) {  // generic-proxy global writes -> visible to the TMA (async proxy) reads
@@ -584,7 +583,15 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar);
     };
-    float xs[NSUB][32];   // sampler state of this thread's (row, column half), carried in registers across the steps
+    auto tempty_arrive = [&](uint32_t buf) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (TWO_SM) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(buf), 0));
+        else ptx::mbar_arrive(tempty_bar(buf));
+      }
+    };
+    float xs[NSUB][TCOLS];   // sampler state of this thread's (row, TCOLS columns), carried in registers across the steps
     if (!(p.debug & 64))
     for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);) {
       const long long tile0 = ((long long)sg.unit * CLUSTER + crank) * NSUB;
@@ -601,23 +608,23 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
         const long long row = (tile0 + sub) * TILE_M + r_in;
         const bool valid = row < p.B;
         __nv_bfloat16* xarow = p.xa + (size_t)(slot_row0 + sub * TILE_M + r_in) * XA_K;
-        float x[32];
+        float x[TCOLS];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = 0.f;
+        for (int i = 0; i < TCOLS; ++i) x[i] = 0.f;
         if (valid) {
           if (p.mode == 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              int col = hf * 32 + i;
+            for (int i = 0; i < TCOLS; ++i) {
+              int col = c0 + i;
               if (col < D) x[i] = __ldcg(p.x_io + row * D + col);
             }
             if (p.impute && sg.s0 == 0) {  // imputation that follows the (none) corrector of step 0, sampling.py:459
-              float zc[32];
-              draw32(p.noise ? p.noise : nullptr, row, hf, p.seed, (uint32_t)p.step_offset, 0, zc);
+              float zc[TCOLS];
+              draw_cols(p.noise ? p.noise : nullptr, row, c0, p.seed, (uint32_t)p.step_offset, 0, zc);
               const float al = p.coef[3], sd = p.coef[4];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                int col = hf * 32 + i;
+              for (int i = 0; i < TCOLS; ++i) {
+                int col = c0 + i;
                 if (col < D) {
                   float m = p.mask[row * D + col];
                   x[i] = x[i] * (1.0f - m) + (al * p.obs[row * D + col] + zc[i] * sd) * m;
@@ -626,24 +633,24 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             }
           } else if (p.mode == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              int col = hf * 32 + i;
+            for (int i = 0; i < TCOLS; ++i) {
+              int col = c0 + i;
               if (col < D) x[i] = p.x_in[row * D + col];
             }
           } else {  // prior loss: x_t = alpha x0 + std z
-            float z[32];
-            draw32(p.z, row, hf, p.seed, (uint32_t)p.step_offset, 3, z);
+            float z[TCOLS];
+            draw_cols(p.z, row, c0, p.seed, (uint32_t)p.step_offset, 3, z);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              int col = hf * 32 + i;
+            for (int i = 0; i < TCOLS; ++i) {
+              int col = c0 + i;
               if (col < D) x[i] = p.alpha * p.x_in[row * D + col] + p.sd * z[i];
             }
           }
         }
-        write_xa(xarow, hf, x);
+        write_xa(xarow, c0, x);
         signal(xa_bar(sub));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) xs[sub][i] = x[i];
+        for (int i = 0; i < TCOLS; ++i) xs[sub][i] = x[i];
       }
       for (int step = sg.s0; step < sg.s1; ++step) {
         // ---------------- hidden layers 0..4
@@ -651,11 +658,14 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           ptx::named_bar_sync(1, EPI_THREADS);  // everyone is done with the previous layer's parameters
           {
             const float4* tb = reinterpret_cast<const float4*>(p.table + ((size_t)step * NL + layer) * H);
-            const float4* gm = reinterpret_cast<const float4*>(p.gn + (size_t)(layer * 2) * H);
-            const float4* bt = reinterpret_cast<const float4*>(p.gn + (size_t)(layer * 2 + 1) * H);
-            reinterpret_cast<float4*>(par)[et] = tb[et];
-            reinterpret_cast<float4*>(par + H)[et] = gm[et];
-            reinterpret_cast<float4*>(par + 2 * H)[et] = bt[et];
+            const float4* gn = reinterpret_cast<const float4*>(p.gn + (size_t)(layer * 2) * H);  // gamma | beta
+            float4* dst = reinterpret_cast<float4*>(par);
+            if (et < H / 4) dst[et] = tb[et];
+            float4 gb = gn[et];         // 2 * H / 4 == EPI_THREADS float4: threads 0..255 gamma, 256..511 beta
+#if DPB_SILU_MODE == 2
+            if (et >= H / 4) { gb.x *= 0.5f; gb.y *= 0.5f; gb.z *= 0.5f; gb.w *= 0.5f; }
+#endif
+            dst[H / 4 + et] = gb;
           }
           ptx::named_bar_sync(1, EPI_THREADS);
           const bool to_h = (layer == 0 || layer == 2 || layer == 4);
@@ -667,45 +677,34 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             const uint32_t buf = chunk_ctr & 1;
             PROF_WAIT(0, ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1));
             ptx::tc_fence_after();
-            // two column groups per iteration: both TMEM loads and both residual loads are in flight before any
-            // math, and the two independent instruction streams interleave (ILP for the 8-warp epilogue)
 #pragma unroll 1
             for (int gp = 0; gp < 2; ++gp) {
-              const int g0 = hf * 4 + gp * 2;
-              const int col0 = chunk * CHUNK_N + g0 * 32;
-              uint32_t vr0[32], vr1[32];
-              ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g0 * 32, vr0);
-              ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g0 * 32 + 32, vr1);
-              uint4 r0[4], r1[4];
+              const int g = hf * 4 + gp * 2 + sg2;           // my 32-column group of the chunk
+              const int col0 = chunk * CHUNK_N + g * 32;
+              uint32_t vr[32];
+              ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g * 32, vr);
+              uint4 r0[4];
               if (residual) {
                 const uint4* rp = reinterpret_cast<const uint4*>(drow + col0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { r0[i] = ld_global_v4(rp + i); r1[i] = ld_global_v4(rp + 4 + i); }
+                for (int i = 0; i < 4; ++i) r0[i] = ld_global_v4(rp + i);
               }
               ptx::tmem_ld_wait();
-              if (gp == 1) {  // last TMEM read of this warp for the buffer: hand it back to the MMA warp
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                  if (TWO_SM) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(buf), 0));
-                  else ptx::mbar_arrive(tempty_bar(buf));
-                }
-              }
-              uint4 o[8];
+              if (gp == 1) tempty_arrive(buf);  // last TMEM read of this warp for the buffer: hand it back to the MMA warp
+              uint4 o[4];
               if (p.debug & 1) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < 4; ++i) o[i] = make_uint4(0, 0, 0, 0);
               } else {
-                PROF_WAIT(2, gn_silu_group<true>(vr0, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o);
-                gn_silu_group<true>(vr1, par + col0 + 32, par + H + col0 + 32, par + 2 * H + col0 + 32, residual, r1, o + 4));
+                PROF_WAIT(2, gn_silu_group(vr, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o));
               }
-              // stage this row's 64 fp16 (128 B) in the SWIZZLE_128B box of my column half; the store warp
-              // ships the box with one TMA store (full lines, asynchronous) -- no per-row global stores
+              // stage this row's 32 fp16 (64 B, half of the 128-byte row) in the SWIZZLE_128B box (hf, gp); the
+              // store warp ships the box with one TMA store (full lines, asynchronous) -- no per-row global stores
               const uint32_t sb = scnt % STG_BUFS;
               PROF_WAIT(1, ptx::mbar_wait(sempty_bar(hf, sb), ((scnt / STG_BUFS) & 1) ^ 1));
               const uint32_t rbase = stg_base + (hf * STG_BUFS + sb) * STG_BYTES + r_in * 128;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) st_shared_v4(rbase + ((j ^ (r_in & 7)) << 4), o[j]);
+              for (int j = 0; j < 4; ++j) st_shared_v4(rbase + (((sg2 * 4 + j) ^ (r_in & 7)) << 4), o[j]);
               ptx::fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(sfull_bar(hf, sb));
@@ -725,21 +724,16 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           PROF_WAIT(0, ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1));
           PROF_BEGIN(tail_t0)
           ptx::tc_fence_after();
-          uint32_t vr[32];
-          ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + hf * 32, vr);
+          uint32_t vr[TCOLS];
+          ptx::tmem_ld_32x16(tmem_base + lane_addr + buf * CHUNK_N + c0, vr);
           ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-                  if (TWO_SM) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(buf), 0));
-                  else ptx::mbar_arrive(tempty_bar(buf));
-                }
+          tempty_arrive(buf);
           tph ^= 1u << buf;
           ++chunk_ctr;
-          float raw[32];
+          float raw[TCOLS];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 pb = *reinterpret_cast<const float4*>(postb + hf * 32 + i);
+          for (int i = 0; i < TCOLS; i += 4) {
+            const float4 pb = *reinterpret_cast<const float4*>(postb + c0 + i);
             raw[i] = __uint_as_float(vr[i]) + pb.x; raw[i + 1] = __uint_as_float(vr[i + 1]) + pb.y;
             raw[i + 2] = __uint_as_float(vr[i + 2]) + pb.z; raw[i + 3] = __uint_as_float(vr[i + 3]) + pb.w;
           }
@@ -748,26 +742,26 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             if (valid) {
               const float sc = p.row_scale ? p.row_scale[row] : p.scale;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                int col = hf * 32 + i;
+              for (int i = 0; i < TCOLS; ++i) {
+                int col = c0 + i;
                 if (col < D) p.out[row * D + col] = raw[i] * sc;
               }
             }
           } else if (p.mode == 1) {
-            float x[32];
+            float x[TCOLS];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = 0.f;
+            for (int i = 0; i < TCOLS; ++i) x[i] = 0.f;
             if (valid) {
               const float* cf = p.coef + (size_t)step * DPB_COEF_STRIDE;
               const float a = cf[0], b = cf[1], c = cf[2], al = cf[3], sd = cf[4];
               const uint32_t gstep = (uint32_t)(p.step_offset + (unsigned long long)step);
               const size_t plane = (size_t)p.B * D;
               const float* nz = p.noise ? p.noise + (size_t)step * p.noise_k * plane : nullptr;
-              float zp[32];
-              draw32(nz ? nz + (p.noise_k == 3 ? plane : 0) : nullptr, row, hf, p.seed, gstep, 1, zp);
+              float zp[TCOLS];
+              draw_cols(nz ? nz + (p.noise_k == 3 ? plane : 0) : nullptr, row, c0, p.seed, gstep, 1, zp);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                int col = hf * 32 + i;
+              for (int i = 0; i < TCOLS; ++i) {
+                int col = c0 + i;
                 if (col < D) {
                   float xm = a * xs[sub][i] + b * raw[i];  // sampling.py:185-186 in affine form
                   x[i] = xm + c * zp[i];
@@ -775,11 +769,11 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 }
               }
               if (p.impute) {
-                float zi[32];
-                draw32(nz ? nz + 2 * plane : nullptr, row, hf, p.seed, gstep, 2, zi);
+                float zi[TCOLS];
+                draw_cols(nz ? nz + 2 * plane : nullptr, row, c0, p.seed, gstep, 2, zi);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  int col = hf * 32 + i;
+                for (int i = 0; i < TCOLS; ++i) {
+                  int col = c0 + i;
                   if (col < D) {
                     float m = p.mask[row * D + col];
                     x[i] = x[i] * (1.0f - m) + (al * p.obs[row * D + col] + zi[i] * sd) * m;
@@ -788,19 +782,19 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               }
               if (p.traj) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  int col = hf * 32 + i;
+                for (int i = 0; i < TCOLS; ++i) {
+                  int col = c0 + i;
                   if (col < D) p.traj[((size_t)step * p.B + row) * D + col] = x[i];
                 }
               }
               if (!last && p.impute) {  // imputation in the corrector slot of the NEXT step precedes its score eval
-                float zc[32];
+                float zc[TCOLS];
                 const float* nz1 = p.noise ? p.noise + (size_t)(step + 1) * p.noise_k * plane : nullptr;
-                draw32(nz1, row, hf, p.seed, gstep + 1, 0, zc);
+                draw_cols(nz1, row, c0, p.seed, gstep + 1, 0, zc);
                 const float al1 = cf[DPB_COEF_STRIDE + 3], sd1 = cf[DPB_COEF_STRIDE + 4];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  int col = hf * 32 + i;
+                for (int i = 0; i < TCOLS; ++i) {
+                  int col = c0 + i;
                   if (col < D) {
                     float m = p.mask[row * D + col];
                     x[i] = x[i] * (1.0f - m) + (al1 * p.obs[row * D + col] + zc[i] * sd1) * m;
@@ -809,36 +803,38 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               }
               if (step + 1 == sg.s1) {  // end of the segment: the state leaves the registers
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  int col = hf * 32 + i;
+                for (int i = 0; i < TCOLS; ++i) {
+                  int col = c0 + i;
                   if (col < D) p.x_io[row * D + col] = x[i];
                 }
               }
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xs[sub][i] = x[i];
+            for (int i = 0; i < TCOLS; ++i) xs[sub][i] = x[i];
             if (step + 1 < sg.s1) {  // (a segment that stops mid-chain leaves x in x_io for the cluster that continues)
-              write_xa(xarow, hf, x);
+              write_xa(xarow, c0, x);
               signal(xa_bar(sub));
             }
           } else {  // prior loss
             float acc = 0.f;
             if (valid) {
-              float z[32];
-              draw32(p.z, row, hf, p.seed, (uint32_t)p.step_offset, 3, z);
+              float z[TCOLS];
+              draw_cols(p.z, row, c0, p.seed, (uint32_t)p.step_offset, 3, z);
+              float racc = 0.f;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                int col = hf * 32 + i;
+              for (int i = 0; i < TCOLS; ++i) {
+                int col = c0 + i;
                 if (col < D) {
                   float x0 = p.x_in[row * D + col];
                   float xt = p.alpha * x0 + p.sd * z[i];
                   float score = -raw[i] * p.inv_sigma_std;
                   float x0h = (xt + (p.sd * p.sd) * score) / p.alpha;
                   float d = x0 - x0h;
-                  acc = fmaf(p.wgt * d, d, acc);
+                  racc = fmaf(p.wgt * d, d, racc);
                   if (p.grad_out) p.grad_out[row * D + col] = 2.0f * p.wgt * d * p.inv_div;
                 }
               }
+              acc = racc;
               if (p.row_loss) atomicAdd(p.row_loss + row, acc);
             }
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -996,16 +992,16 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
 #ifdef DPB_TC_PROFILE
   {
     cudaStreamSynchronize(st);
-    std::vector<long long> hp((size_t)grid * 12 * 5);
+    std::vector<long long> hp((size_t)grid * 20 * 5);
     cudaMemcpyFromSymbol(hp.data(), tc::g_prof, hp.size() * sizeof(long long));
-    static const char* names[12] = {"W-producer", "MMA", "A-producer", "store", "epi", "epi", "epi", "epi", "epi", "epi", "epi", "epi"};
+    static const char* names[5] = {"W-producer", "MMA", "A-producer", "store", "epi"};
     double acc[5][5] = {};
     int cnt[5] = {};
     for (int b = 0; b < grid; ++b)
-      for (int w = 0; w < 12; ++w) {
+      for (int w = 0; w < 20; ++w) {
         if (w == 1 && (b & 1)) continue;  // the MMA warp of the non-leader CTA is idle
         const int r = w < 4 ? w : 4;
-        for (int k = 0; k < 5; ++k) acc[r][k] += (double)hp[((size_t)b * 12 + w) * 5 + k];
+        for (int k = 0; k < 5; ++k) acc[r][k] += (double)hp[((size_t)b * 20 + w) * 5 + k];
         ++cnt[r];
       }
     for (int r = 0; r < 5; ++r)
