@@ -30,7 +30,11 @@ constexpr int BLOCK_K = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int CHUNK_N = 256;
 constexpr bool TWO_SM = true;   // CTA pair: one tcgen05.mma.cta_group::2 (M = 256) per weight tile; each CTA keeps
                                 // its own 128 rows of A and HALF of the weight tile, so weight ingest per CTA halves
-constexpr int STAGES = TWO_SM ? 5 : 3;   // the operand ring is latency bound: utilisation ~ STAGES*512/(L+512), L ~ 2.2k cycles
+#ifdef DPB_TC_STAGES   // timing experiments: ring depth (with DPB_TC_TINY_STG the staging area shrinks so that six stages fit;
+constexpr int STAGES = DPB_TC_STAGES;   // only the operand-pipeline-only debug mode is meaningful then)
+#else
+constexpr int STAGES = TWO_SM ? 4 : 3;   // measured: the operand pipeline alone runs equally fast with 4, 5 or 6 stages
+#endif   // the operand ring is latency bound: utilisation ~ STAGES*512/(L+512), L ~ 2.2k cycles
 constexpr int NSUB = 1;      // row tiles in flight per CTA: one tile's epilogue overlaps the other tile's MMAs
 constexpr int CLUSTER = 2;   // CTAs (different row tiles) that share every weight tile through TMA multicast
 constexpr int A_BYTES = TILE_M * BLOCK_K * 2;   // 16 KB
@@ -46,8 +50,16 @@ constexpr int TCOLS = 16;          // pose columns per epilogue thread in the pr
 static_assert(2 * H / 4 == EPI_THREADS, "parameter staging assumes one float4 of gamma|beta per epilogue thread");
 constexpr int PAR_BYTES = 3 * H * 4;
 constexpr int STG_BYTES = TILE_M * 128;          // one [128 rows x 64 fp16] SWIZZLE_128B box of outgoing activations
-constexpr int STG_BUFS = TWO_SM ? 1 : 2;         // staging buffers per column half (shared memory is better spent on ring stages)
+constexpr int STG_BUFS = 2;                      // staging boxes per column half: box (hf, gp) of a chunk has its own buffer, so
+                                                 // the LAST chunk of a layer stays in shared memory and feeds the next layer's
+                                                 // first chunk directly (DIRECT_K0..), without the L2 round trip
+constexpr int DIRECT_K0 = H / BLOCK_K - CHUNK_N / BLOCK_K;   // first K slab that is a column box of the previous layer's last chunk
+static_assert(NSUB == 1 && STG_BUFS == 2 && CHUNK_N / BLOCK_K == 4, "the direct path assumes four boxes per chunk, one tile per CTA");
+#ifdef DPB_TC_TINY_STG
+constexpr int STG_TOTAL = 1024;
+#else
 constexpr int STG_TOTAL = 2 * STG_BUFS * STG_BYTES;
+#endif
 constexpr int NUM_BARS = 2 * STAGES + 4 + NSUB * 5 + 8;  // full, empty, tfull[2], tempty[2], xa, act[4], sfull[2][2], sempty[2][2]
 constexpr int OFF_PAR = STAGES * STAGE_BYTES;
 constexpr int OFF_STG = OFF_PAR + PAR_BYTES;     // 1024-aligned: 3*49152 + 12288 = 159744
@@ -67,7 +79,8 @@ struct KParams {
   int mode, n_steps, impute, noise_k, n_tiles;
   int debug;  // timing experiments only (DPB_TC_DEBUG): 1 = skip hidden-layer epilogue math, 2 = skip MMAs,
               // 4 / 8 = skip the activation / weight TMA loads, 16 = skip the activation TMA stores,
-              // 64 = operand pipeline only (no epilogue, no activation dependencies; results are garbage)
+              // 64 = operand pipeline only (no epilogue, no activation dependencies; results are garbage),
+              // 128 / 256 / 512 = skip the hidden layers' TMEM loads / staging stores / residual loads
   long long B;
   const float* x_in;
   float* x_io;
@@ -163,6 +176,11 @@ __device__ __forceinline__ uint4 ld_global_v4(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+}
+// 256-bit variant (one full 32-byte sector per lane: the residual rows are 2 KB apart, so every lane opens its own line)
+__device__ __forceinline__ void ld_global_v8(const uint4* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.cg.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -273,6 +291,9 @@ __device__ __forceinline__ void gn_silu_group(const uint32_t* vr, const float* t
   for (int i = 0; i < 4; ++i) out[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
 }
 
+// K-slab visited at loop position k: the boxes of the previous layer's last chunk are produced in the order
+// (hf0,gp0), (hf1,gp0), (hf0,gp1), (hf1,gp1) = slabs 12, 14, 13, 15, so positions 13 and 14 trade places
+__device__ __forceinline__ int kslab(int layer, int k) { return (layer > 0 && (k == 13 || k == 14)) ? 27 - k : k; }
 __device__ __forceinline__ int layer_nk(int layer) { return layer == 0 ? XA_K / BLOCK_K : H / BLOCK_K; }
 __device__ __forceinline__ int layer_chunks(int layer) { return layer == 5 ? 1 : H / CHUNK_N; }
 
@@ -414,7 +435,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                     if (p.debug & 8) ptx::mbar_arrive_cluster(lbar);
                     else {
                       ptx::mbar_arrive_expect_tx_cluster(lbar, bytes);
-                      ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES + A_BYTES, tm, lbar, k * BLOCK_K,
+                      ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES + A_BYTES, tm, lbar, kslab(layer, k) * BLOCK_K,
                                            chunk * CHUNK_N + crank * part_rows);
                     }
                   }
@@ -425,10 +446,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 if (ptx::elect_one()) {
                   ptx::mbar_arrive_expect_tx(full_bar(stage), bytes);  // whole tile: own part + the peers' multicasts
                   if (CLUSTER > 1)
-                    ptx::tma_load_2d_mcast(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N + crank * part_rows,
-                                           CMASK);
+                    ptx::tma_load_2d_mcast(dst, tm, full_bar(stage), kslab(layer, k) * BLOCK_K,
+                                           chunk * CHUNK_N + crank * part_rows, CMASK);
                   else
-                    ptx::tma_load_2d(dst, tm, full_bar(stage), k * BLOCK_K, chunk * CHUNK_N);
+                    ptx::tma_load_2d(dst, tm, full_bar(stage), kslab(layer, k) * BLOCK_K, chunk * CHUNK_N);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
@@ -451,9 +472,13 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               for (int k = 0; k < nk; ++k) {
                 PROF_WAIT(1, ptx::mbar_wait(full_bar(stage), phase));
                 ptx::tc_fence_after();
-                const uint32_t a_addr = smem_base + stage * STAGE_BYTES;
-                const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
-                const uint64_t bdesc = ptx::umma_desc_sw128(a_addr + A_BYTES);
+                const uint32_t s_addr = smem_base + stage * STAGE_BYTES;
+                const int ks = kslab(layer, k);
+                // first chunk of a layer: the last four K slabs are still in the staging boxes of the previous layer
+                const bool direct = layer > 0 && cs == 0 && ks >= DIRECT_K0 && !(p.debug & 64);
+                const uint64_t adesc = ptx::umma_desc_sw128(direct ? stg_base + (ks - DIRECT_K0) * STG_BYTES : s_addr);
+                const uint64_t bdesc = ptx::umma_desc_sw128(s_addr + A_BYTES);
+                PROF_BEGIN(issue_t0)
                 if (ptx::elect_one()) {
                   if (!(p.debug & 2))
 #pragma unroll
@@ -468,6 +493,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                     else ptx::mma_commit(tfull_bar(buf));
                   }
                 }
+                __syncwarp();
+                PROF_END(2, issue_t0)
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
               tph ^= 1u << buf;
@@ -490,23 +517,37 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               if (layer == 0 && chunk == 0 && !(p.debug & 64)) PROF_WAIT(0, ptx::mbar_wait(xa_bar(sub), xph));  // prologue / previous step's tail wrote x
               for (int k = 0; k < nk; ++k) {
                 // K-slabs 4c..4c+3 of this layer's input are column chunk c of the previous layer's output:
-                // wait for exactly that chunk (first pass only), so the next layer starts while the previous
-                // layer's last chunks are still in the epilogue
-                if (layer > 0 && chunk == 0 && (k & 3) == 0 && !(p.debug & 64)) PROF_WAIT(1, ptx::mbar_wait(act_bar(sub, k >> 2), aph));
+                // wait for exactly that chunk (first use only), so the next layer starts while the previous
+                // layer's last chunks are still in the epilogue.  The slabs of the LAST chunk are not loaded at
+                // all for this layer's first chunk: the MMA reads them from the staging boxes (box = slab - 12)
+                // as soon as the epilogue has filled them; the later chunks fetch them from the scratch.
+                const int ks = kslab(layer, k);
+                const bool direct = layer > 0 && chunk == 0 && ks >= DIRECT_K0 && !(p.debug & 64);
+                if (layer > 0 && !(p.debug & 64)) {
+                  if (direct) {
+                    const int kb = ks - DIRECT_K0;   // (hf, gp) = (kb >> 1, kb & 1); the last chunk's box phase is always odd
+                    PROF_WAIT(1, ptx::mbar_wait(sfull_bar(kb >> 1, kb & 1), 1));
+                  } else if ((chunk == 0 && (ks & 3) == 0) || (chunk == 1 && k == DIRECT_K0)) {
+                    PROF_WAIT(1, ptx::mbar_wait(act_bar(sub, ks >> 2), aph));
+                  }
+                }
                 PROF_WAIT(2, ptx::mbar_wait(empty_bar(stage), phase ^ 1));
                 if (TWO_SM) {
                   const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
                   if (ptx::elect_one()) {
-                    if (p.debug & 4) ptx::mbar_arrive_cluster(lbar);
+                    if ((p.debug & 4) || direct) ptx::mbar_arrive_cluster(lbar);
                     else {
                       ptx::mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
-                      ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, k * BLOCK_K, slot_row0 + sub * TILE_M);
+                      ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, ks * BLOCK_K, slot_row0 + sub * TILE_M);
                     }
                   }
                 } else if (ptx::elect_one()) {
-                  ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
-                  ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), k * BLOCK_K,
-                                   slot_row0 + sub * TILE_M);
+                  if (direct) ptx::mbar_arrive(full_bar(stage));
+                  else {
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), A_BYTES);
+                    ptx::tma_load_2d(smem_base + stage * STAGE_BYTES, tm, full_bar(stage), ks * BLOCK_K,
+                                     slot_row0 + sub * TILE_M);
+                  }
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
@@ -675,20 +716,31 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             const int chunk = cs / NSUB, sub = cs % NSUB;
             __half* drow = (to_h ? p.act_h : p.act_t) + (size_t)(slot_row0 + sub * TILE_M + r_in) * H;
             const uint32_t buf = chunk_ctr & 1;
+            // residual stream: this thread's 2 x 32 old values of the chunk are requested BEFORE the accumulator
+            // wait (they were stored two layers ago), so their L2 latency hides behind it
+            uint4 rres[2][4];
+            if (residual && !(p.debug & 512)) {
+#pragma unroll
+              for (int gp = 0; gp < 2; ++gp) {
+                const uint4* rp = reinterpret_cast<const uint4*>(drow + chunk * CHUNK_N + (hf * 4 + gp * 2 + sg2) * 32);
+                ld_global_v8(rp, rres[gp][0], rres[gp][1]);
+                ld_global_v8(rp + 2, rres[gp][2], rres[gp][3]);
+              }
+            }
             PROF_WAIT(0, ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1));
             ptx::tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int gp = 0; gp < 2; ++gp) {
               const int g = hf * 4 + gp * 2 + sg2;           // my 32-column group of the chunk
               const int col0 = chunk * CHUNK_N + g * 32;
               uint32_t vr[32];
-              ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g * 32, vr);
-              uint4 r0[4];
-              if (residual) {
-                const uint4* rp = reinterpret_cast<const uint4*>(drow + col0);
+              if (p.debug & 128) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) r0[i] = ld_global_v4(rp + i);
+                for (int i = 0; i < 32; ++i) vr[i] = 0;
+              } else {
+                ptx::tmem_ld_32x32(tmem_base + lane_addr + buf * CHUNK_N + g * 32, vr);
               }
+              const uint4* r0 = rres[gp];
               ptx::tmem_ld_wait();
               if (gp == 1) tempty_arrive(buf);  // last TMEM read of this warp for the buffer: hand it back to the MMA warp
               uint4 o[4];
@@ -704,7 +756,8 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
               PROF_WAIT(1, ptx::mbar_wait(sempty_bar(hf, sb), ((scnt / STG_BUFS) & 1) ^ 1));
               const uint32_t rbase = stg_base + (hf * STG_BUFS + sb) * STG_BYTES + r_in * 128;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) st_shared_v4(rbase + (((sg2 * 4 + j) ^ (r_in & 7)) << 4), o[j]);
+              for (int j = 0; j < 4; ++j)
+                if (!(p.debug & 256)) st_shared_v4(rbase + (((sg2 * 4 + j) ^ (r_in & 7)) << 4), o[j]);
               ptx::fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(sfull_bar(hf, sb));
