@@ -619,7 +619,9 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t chunk_ctr = 0, tph = 0, scnt = 0;
     auto signal = [&](uint32_t bar) {  // generic-proxy global writes -> visible to the TMA (async proxy) reads
+#ifndef DPB_TC_NO_THREADFENCE
       __threadfence();
+#endif
       ptx::fence_proxy_async_global();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar);
@@ -727,7 +729,11 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 ld_global_v8(rp + 2, rres[gp][2], rres[gp][3]);
               }
             }
+#ifdef DPB_TC_PROFILE_TAIL
+            ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+#else
             PROF_WAIT(0, ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1));
+#endif
             ptx::tc_fence_after();
 #pragma unroll
             for (int gp = 0; gp < 2; ++gp) {
@@ -748,12 +754,20 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = make_uint4(0, 0, 0, 0);
               } else {
+#ifdef DPB_TC_PROFILE_TAIL
+                gn_silu_group(vr, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o);
+#else
                 PROF_WAIT(2, gn_silu_group(vr, par + col0, par + H + col0, par + 2 * H + col0, residual, r0, o));
+#endif
               }
               // stage this row's 32 fp16 (64 B, half of the 128-byte row) in the SWIZZLE_128B box (hf, gp); the
               // store warp ships the box with one TMA store (full lines, asynchronous) -- no per-row global stores
               const uint32_t sb = scnt % STG_BUFS;
+#ifdef DPB_TC_PROFILE_TAIL
+              ptx::mbar_wait(sempty_bar(hf, sb), ((scnt / STG_BUFS) & 1) ^ 1);
+#else
               PROF_WAIT(1, ptx::mbar_wait(sempty_bar(hf, sb), ((scnt / STG_BUFS) & 1) ^ 1));
+#endif
               const uint32_t rbase = stg_base + (hf * STG_BUFS + sb) * STG_BYTES + r_in * 128;
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -774,13 +788,35 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
           const bool valid = row < p.B;
           __nv_bfloat16* xarow = p.xa + (size_t)(slot_row0 + sub * TILE_M + r_in) * XA_K;
           const uint32_t buf = chunk_ctr & 1;
-          PROF_WAIT(0, ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1));
+          // everything of the sampler update that does not depend on the network output is prepared BEFORE the
+          // accumulator wait: this step's coefficients and its Gaussian draws (Philox + Box-Muller)
+          const bool last = (step + 1 == p.n_steps);
+          const float* cf = p.coef + (size_t)step * DPB_COEF_STRIDE;
+          const uint32_t gstep = (uint32_t)(p.step_offset + (unsigned long long)step);
+          const size_t plane = (size_t)p.B * D;
+          float ca = 0.f, cb = 0.f, cc = 0.f, al = 0.f, sd = 0.f;
+          const float* nz = p.noise ? p.noise + (size_t)step * p.noise_k * plane : nullptr;
+          float zp[TCOLS];
+#pragma unroll
+          for (int i = 0; i < TCOLS; ++i) zp[i] = 0.f;
+          if (p.mode == 1 && valid) {
+            ca = cf[0]; cb = cf[1]; cc = cf[2]; al = cf[3]; sd = cf[4];
+            draw_cols(nz ? nz + (p.noise_k == 3 ? plane : 0) : nullptr, row, c0, p.seed, gstep, 1, zp);
+          }
+          if (p.mode == 1) {  // pin the draws above the wait (the compiler would otherwise sink them below it)
+#pragma unroll
+            for (int i = 0; i < TCOLS; ++i) asm volatile("" ::"f"(zp[i]));
+          }
+          ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
           PROF_BEGIN(tail_t0)
           ptx::tc_fence_after();
           uint32_t vr[TCOLS];
           ptx::tmem_ld_32x16(tmem_base + lane_addr + buf * CHUNK_N + c0, vr);
           ptx::tmem_ld_wait();
           tempty_arrive(buf);
+#ifdef DPB_TC_PROFILE_TAIL
+          prof_acc[0] += clock64() - tail_t0;
+#endif
           tph ^= 1u << buf;
           ++chunk_ctr;
           float raw[TCOLS];
@@ -790,7 +826,6 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             raw[i] = __uint_as_float(vr[i]) + pb.x; raw[i + 1] = __uint_as_float(vr[i + 1]) + pb.y;
             raw[i + 2] = __uint_as_float(vr[i + 2]) + pb.z; raw[i + 3] = __uint_as_float(vr[i + 3]) + pb.w;
           }
-          const bool last = (step + 1 == p.n_steps);
           if (p.mode == 0) {
             if (valid) {
               const float sc = p.row_scale ? p.row_scale[row] : p.scale;
@@ -805,19 +840,12 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
 #pragma unroll
             for (int i = 0; i < TCOLS; ++i) x[i] = 0.f;
             if (valid) {
-              const float* cf = p.coef + (size_t)step * DPB_COEF_STRIDE;
-              const float a = cf[0], b = cf[1], c = cf[2], al = cf[3], sd = cf[4];
-              const uint32_t gstep = (uint32_t)(p.step_offset + (unsigned long long)step);
-              const size_t plane = (size_t)p.B * D;
-              const float* nz = p.noise ? p.noise + (size_t)step * p.noise_k * plane : nullptr;
-              float zp[TCOLS];
-              draw_cols(nz ? nz + (p.noise_k == 3 ? plane : 0) : nullptr, row, c0, p.seed, gstep, 1, zp);
 #pragma unroll
               for (int i = 0; i < TCOLS; ++i) {
                 int col = c0 + i;
                 if (col < D) {
-                  float xm = a * xs[sub][i] + b * raw[i];  // sampling.py:185-186 in affine form
-                  x[i] = xm + c * zp[i];
+                  float xm = ca * xs[sub][i] + cb * raw[i];  // sampling.py:185-186 in affine form
+                  x[i] = xm + cc * zp[i];
                   if (last && p.x_mean) p.x_mean[row * D + col] = xm;
                 }
               }
@@ -865,8 +893,13 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
 #pragma unroll
             for (int i = 0; i < TCOLS; ++i) xs[sub][i] = x[i];
             if (step + 1 < sg.s1) {  // (a segment that stops mid-chain leaves x in x_io for the cluster that continues)
+#ifdef DPB_TC_PROFILE_TAIL
+              PROF_WAIT(2, write_xa(xarow, c0, x));
+              PROF_WAIT(1, signal(xa_bar(sub)));
+#else
               write_xa(xarow, c0, x);
               signal(xa_bar(sub));
+#endif
             }
           } else {  // prior loss
             float acc = 0.f;
