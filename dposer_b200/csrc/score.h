@@ -32,8 +32,7 @@ struct dpb_score {
   // TC scratch owned by the handle (sized by the grid, not by B): activations + x operand per CTA slot
   __half* act_h = nullptr;      // [slots*128, 1024] residual stream
   __half* act_t = nullptr;      // [slots*128, 1024] block intermediate
-  __nv_bfloat16* xa = nullptr;  // [slots*128, 192]  [x_hi | x_lo | x_hi]
-  CUtensorMap tm_act_h, tm_act_t, tm_xa;  // box {64, 128}
+  CUtensorMap tm_act_h, tm_act_t;  // box {64, 128}
   int tc_slots = 0;
   int* tc_flags = nullptr;      // [slots] hand-off flags of the sampler's segment schedule (score_tc.cu: SegIter)
 };

@@ -54,7 +54,7 @@ constexpr int STG_BUFS = 2;                      // staging boxes per column hal
                                                  // the LAST chunk of a layer stays in shared memory and feeds the next layer's
                                                  // first chunk directly (DIRECT_K0..), without the L2 round trip
 constexpr int DIRECT_K0 = H / BLOCK_K - CHUNK_N / BLOCK_K;   // first K slab that is a column box of the previous layer's last chunk
-static_assert(NSUB == 1 && STG_BUFS == 2 && CHUNK_N / BLOCK_K == 4, "the direct path assumes four boxes per chunk, one tile per CTA");
+static_assert(NSUB == 1 && STG_BUFS == 2 && CHUNK_N / BLOCK_K == 4 && STAGES >= 2, "the direct path assumes four boxes per chunk, one tile per CTA");
 #ifdef DPB_TC_TINY_STG
 constexpr int STG_TOTAL = 1024;
 #else
@@ -104,7 +104,6 @@ struct KParams {
   float* row_loss;
   __half* act_h;
   __half* act_t;
-  __nv_bfloat16* xa;
   int* flags;   // one hand-off flag per CTA (zeroed before the launch), see SegIter
 };
 
@@ -297,8 +296,11 @@ __device__ __forceinline__ int kslab(int layer, int k) { return (layer > 0 && (k
 __device__ __forceinline__ int layer_nk(int layer) { return layer == 0 ? XA_K / BLOCK_K : H / BLOCK_K; }
 __device__ __forceinline__ int layer_chunks(int layer) { return layer == 5 ? 1 : H / CHUNK_N; }
 
-// x[TCOLS] (fp32, columns c0..c0+TCOLS-1 of one row) -> [hi | lo | hi] bf16 segments of the xa row
-__device__ __forceinline__ void write_xa(__nv_bfloat16* row, int c0, const float* x) {
+// First-layer operand.  x[TCOLS] (fp32, columns c0..c0+TCOLS-1 of row r) -> bf16 hi and lo parts, written straight into
+// the A halves of ring stages 0 (hi) and 1 (lo) in the SWIZZLE_128B K-major layout the MMA reads ([128 rows x 64]:
+// row pitch 128 B, 16-byte chunk j of row r stored at chunk j ^ (r & 7)).  The first layer streams only weight tiles
+// through the ring, so the A halves are free while it runs; K slab 2 of [x_hi | x_lo | x_hi] reuses the hi tile.
+__device__ __forceinline__ void write_xa(uint32_t hi_base, uint32_t lo_base, int r, int c0, const float* x) {
   uint32_t hi[TCOLS / 2], lo[TCOLS / 2];
 #pragma unroll
   for (int i = 0; i < TCOLS / 2; ++i) {
@@ -308,16 +310,11 @@ __device__ __forceinline__ void write_xa(__nv_bfloat16* row, int c0, const float
     hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
     lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
   }
-  uint4* p0 = reinterpret_cast<uint4*>(row + c0);
-  uint4* p1 = reinterpret_cast<uint4*>(row + 64 + c0);
-  uint4* p2 = reinterpret_cast<uint4*>(row + 128 + c0);
 #pragma unroll
   for (int i = 0; i < TCOLS / 8; ++i) {
-    uint4 h = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-    uint4 l = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-    p0[i] = h;
-    p1[i] = l;
-    p2[i] = h;
+    const uint32_t off = (uint32_t)r * 128u + ((uint32_t)((c0 / 8 + i) ^ (r & 7)) << 4);
+    st_shared_v4(hi_base + off, make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]));
+    st_shared_v4(lo_base + off, make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]));
   }
 }
 
@@ -338,7 +335,7 @@ __device__ __forceinline__ void draw_cols(const float* plane, long long row, int
 }
 
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUtensorMap tm_xa,
+score_tc_kernel(const __grid_constant__ KParams p,
                 const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_t,
                 const __grid_constant__ CUtensorMap tm_pre, const __grid_constant__ CUtensorMap tm_w0,
                 const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
@@ -390,7 +387,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     ptx::prefetch_tmap(&tm_w2); ptx::prefetch_tmap(&tm_w3); ptx::prefetch_tmap(&tm_post);
   }
   if (warp == 2) {
-    if (lane == 0) { ptx::prefetch_tmap(&tm_xa); ptx::prefetch_tmap(&tm_h); ptx::prefetch_tmap(&tm_t); }
+    if (lane == 0) { ptx::prefetch_tmap(&tm_h); ptx::prefetch_tmap(&tm_t); }
     __syncwarp();
     if (TWO_SM) ptx::tmem_alloc_2sm(ptx::smem_u32(tmem_slot), 512);
     else ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
@@ -476,7 +473,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 const int ks = kslab(layer, k);
                 // first chunk of a layer: the last four K slabs are still in the staging boxes of the previous layer
                 const bool direct = layer > 0 && cs == 0 && ks >= DIRECT_K0 && !(p.debug & 64);
-                const uint64_t adesc = ptx::umma_desc_sw128(direct ? stg_base + (ks - DIRECT_K0) * STG_BYTES : s_addr);
+                // first layer: x_hi | x_lo | x_hi, written by the epilogue into the A halves of ring stages 0 / 1
+                const uint32_t a_addr = layer == 0 ? smem_base + (ks == 1 ? STAGE_BYTES : 0)
+                                      : direct ? stg_base + (ks - DIRECT_K0) * STG_BYTES : s_addr;
+                const uint64_t adesc = ptx::umma_desc_sw128(a_addr);
                 const uint64_t bdesc = ptx::umma_desc_sw128(s_addr + A_BYTES);
                 PROF_BEGIN(issue_t0)
                 if (ptx::elect_one()) {
@@ -505,14 +505,20 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
   } else if (warp == 2) {
     // ======================= activation producer =======================
     {
-      uint32_t stage = 0, phase = 0, xph = 0, aph = 0;
+      uint32_t stage = 0, phase = 0, xph = 0, aph = 0, cctr = 0;   // cctr: chunks so far (the MMA warp's chunk_ctr)
       for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);)
         for (int step = sg.s0; step < sg.s1; ++step)
           for (int layer = 0; layer < 6; ++layer) {
-            // layer input: xa | H | T | H | T | H
-            const CUtensorMap* tm = layer == 0 ? &tm_xa : (layer == 2 || layer == 4) ? &tm_t : &tm_h;
+            // layer input: x (shared memory, written by the epilogue) | H | T | H | T | H
+            const CUtensorMap* tm = (layer == 2 || layer == 4) ? &tm_t : &tm_h;
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
-            for (int chunk = 0; chunk < nc; ++chunk)
+            if (layer == 1 && !(p.debug & 64)) {
+              // the first layer's operand lives in the A halves of ring stages 0 / 1: no activation tile may land
+              // there before ALL first-layer MMAs have retired (= the accumulator of its last chunk is complete)
+              const uint32_t n = cctr - 1;
+              PROF_WAIT(1, ptx::mbar_wait(tfull_bar(n & 1), (n >> 1) & 1));
+            }
+            for (int chunk = 0; chunk < nc; ++chunk, ++cctr)
              for (int sub = 0; sub < NSUB; ++sub) {
               if (layer == 0 && chunk == 0 && !(p.debug & 64)) PROF_WAIT(0, ptx::mbar_wait(xa_bar(sub), xph));  // prologue / previous step's tail wrote x
               for (int k = 0; k < nk; ++k) {
@@ -522,9 +528,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
                 // all for this layer's first chunk: the MMA reads them from the staging boxes (box = slab - 12)
                 // as soon as the epilogue has filled them; the later chunks fetch them from the scratch.
                 const int ks = kslab(layer, k);
-                const bool direct = layer > 0 && chunk == 0 && ks >= DIRECT_K0 && !(p.debug & 64);
+                const bool boxed = layer > 0 && chunk == 0 && ks >= DIRECT_K0 && !(p.debug & 64);
+                const bool direct = boxed || layer == 0;   // nothing to load: the MMA reads shared memory the epilogue wrote
                 if (layer > 0 && !(p.debug & 64)) {
-                  if (direct) {
+                  if (boxed) {
                     const int kb = ks - DIRECT_K0;   // (hf, gp) = (kb >> 1, kb & 1); the last chunk's box phase is always odd
                     PROF_WAIT(1, ptx::mbar_wait(sfull_bar(kb >> 1, kb & 1), 1));
                   } else if ((chunk == 0 && (ks & 3) == 0) || (chunk == 1 && k == DIRECT_K0)) {
@@ -618,14 +625,12 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
     const int c0 = hf * 32 + sg2 * TCOLS;   // first of this thread's TCOLS pose columns (prologue / tail)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t chunk_ctr = 0, tph = 0, scnt = 0;
-    auto signal = [&](uint32_t bar) {  // generic-proxy global writes -> visible to the TMA (async proxy) reads
-#ifndef DPB_TC_NO_THREADFENCE
-      __threadfence();
-#endif
-      ptx::fence_proxy_async_global();
+    auto signal = [&](uint32_t bar) {  // generic-proxy shared-memory writes -> visible to the MMA (async proxy) reads
+      ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar);
     };
+    const uint32_t xa_hi = smem_base, xa_lo = smem_base + STAGE_BYTES;   // A halves of ring stages 0 and 1
     auto tempty_arrive = [&](uint32_t buf) {
       ptx::tc_fence_before();
       __syncwarp();
@@ -650,7 +655,6 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
       for (int sub = 0; sub < NSUB; ++sub) {
         const long long row = (tile0 + sub) * TILE_M + r_in;
         const bool valid = row < p.B;
-        __nv_bfloat16* xarow = p.xa + (size_t)(slot_row0 + sub * TILE_M + r_in) * XA_K;
         float x[TCOLS];
 #pragma unroll
         for (int i = 0; i < TCOLS; ++i) x[i] = 0.f;
@@ -690,7 +694,7 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             }
           }
         }
-        write_xa(xarow, c0, x);
+        write_xa(xa_hi, xa_lo, r_in, c0, x);
         signal(xa_bar(sub));
 #pragma unroll
         for (int i = 0; i < TCOLS; ++i) xs[sub][i] = x[i];
@@ -786,7 +790,6 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
         for (int sub = 0; sub < NSUB; ++sub) {
           const long long row = (tile0 + sub) * TILE_M + r_in;
           const bool valid = row < p.B;
-          __nv_bfloat16* xarow = p.xa + (size_t)(slot_row0 + sub * TILE_M + r_in) * XA_K;
           const uint32_t buf = chunk_ctr & 1;
           // everything of the sampler update that does not depend on the network output is prepared BEFORE the
           // accumulator wait: this step's coefficients and its Gaussian draws (Philox + Box-Muller)
@@ -894,10 +897,10 @@ score_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUten
             for (int i = 0; i < TCOLS; ++i) xs[sub][i] = x[i];
             if (step + 1 < sg.s1) {  // (a segment that stops mid-chain leaves x in x_io for the cluster that continues)
 #ifdef DPB_TC_PROFILE_TAIL
-              PROF_WAIT(2, write_xa(xarow, c0, x));
+              PROF_WAIT(2, write_xa(xa_hi, xa_lo, r_in, c0, x));
               PROF_WAIT(1, signal(xa_bar(sub)));
 #else
-              write_xa(xarow, c0, x);
+              write_xa(xa_hi, xa_lo, r_in, c0, x);
               signal(xa_bar(sub));
 #endif
             }
@@ -1006,10 +1009,8 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
   const size_t rows = (size_t)h->tc_slots * tc::TILE_M;
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_h, rows * H * sizeof(__half)));
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_t, rows * H * sizeof(__half)));
-  DPB_CUDA_CHECK(cudaMalloc((void**)&h->xa, rows * tc::XA_K * sizeof(__nv_bfloat16)));
   DPB_CUDA_CHECK(cudaMemset(h->act_h, 0, rows * H * sizeof(__half)));
   DPB_CUDA_CHECK(cudaMemset(h->act_t, 0, rows * H * sizeof(__half)));
-  DPB_CUDA_CHECK(cudaMemset(h->xa, 0, rows * tc::XA_K * sizeof(__nv_bfloat16)));
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->tc_flags, sizeof(int) * h->tc_slots));
   DPB_CUDA_CHECK(cudaMemset(h->tc_flags, 0, sizeof(int) * h->tc_slots));
   int rc = DPB_OK;
@@ -1025,8 +1026,6 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
     rc = make_tmap_2d(&h->tm_act_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->act_h, H, rows, tc::BLOCK_K, tc::TILE_M, 2);
   if (rc == DPB_OK)
     rc = make_tmap_2d(&h->tm_act_t, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->act_t, H, rows, tc::BLOCK_K, tc::TILE_M, 2);
-  if (rc == DPB_OK)
-    rc = make_tmap_2d(&h->tm_xa, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, h->xa, tc::XA_K, rows, tc::BLOCK_K, tc::TILE_M, 2);
   if (rc != DPB_OK) return rc;
   DPB_CUDA_CHECK(cudaFuncSetAttribute(tc::score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       tc::SMEM_BYTES));
@@ -1035,7 +1034,7 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
 }
 
 void tc_release(dpb_score* h) {
-  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->act_t, h->xa, h->tc_flags};
+  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->act_t, h->tc_flags};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   h->tc_ready = false;
@@ -1058,7 +1057,7 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   p.inv_div = j.divisor > 0.f ? 1.0f / j.divisor : 0.f;
   p.wgt = j.scale;  // prior loss: api.cu passes the weight through `scale`
   p.z = j.z; p.loss_out = j.loss_out; p.grad_out = j.grad_out; p.row_loss = j.row_loss;
-  p.act_h = h->act_h; p.act_t = h->act_t; p.xa = h->xa;
+  p.act_h = h->act_h; p.act_t = h->act_t;
   p.flags = h->tc_flags;
   {
     const char* dbg = getenv("DPB_TC_DEBUG");
@@ -1071,7 +1070,7 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   const int max_grid = (h->tc_slots / tc::NSUB) / tc::CLUSTER * tc::CLUSTER;
   if (grid > max_grid) grid = max_grid;
   if (j.n_steps > 1) DPB_CUDA_CHECK(cudaMemsetAsync(h->tc_flags, 0, sizeof(int) * h->tc_slots, st));
-  tc::score_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, h->tm_xa, h->tm_act_h, h->tm_act_t, h->tm_pre,
+  tc::score_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, h->tm_act_h, h->tm_act_t, h->tm_pre,
                                                                     h->tm_w[0], h->tm_w[1], h->tm_w[2], h->tm_w[3],
                                                                     h->tm_post);
   DPB_CUDA_CHECK(cudaGetLastError());
