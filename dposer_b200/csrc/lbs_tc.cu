@@ -348,6 +348,8 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  ptx::setmaxnreg_dec<56>();   // warpgroup 0 (producer, issuer, two idle warps) gives registers to the epilogue
   if (warp == 0) {   // warp-wide loops, elected lane issues (see lbs_blend_tc_kernel)
     uint32_t stage = 0, phase = 0, gph = 0;
     for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
@@ -406,61 +408,91 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
         if (++stage == SK_WSTAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    // Epilogue: warp (q, h8) applies the blended transforms of 8 poses to its 32 vertices, in place.  The blended
+    // vertices come from HBM (the blend kernel wrote 5.4 GB of them): each thread keeps the next PF blocks' 24 floats each
+    // in flight while it works on the current block, otherwise the loads are latency-bound (measured: the first
+    // FMUL after them held 28 % of the kernel's stall samples).
+    ptx::setmaxnreg_inc<224>();
     const int q = warp & 3;
+    const int h8 = (warp - 4) >> 2;   // warps 4-7: poses 0-7 of the chunk, warps 8-11: poses 8-15
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const size_t pstride = (size_t)p.V * 3;
     uint32_t blk = 0, tph = 0;
-    for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-      for (int vt = 0; vt < p.n_vt; ++vt) {
-        const int v = vt * TILE_V + q * 32 + lane;
-        const bool vok = v < p.V;
-        for (int c = 0; c < chunks; ++c) {
-          const int64_t b0 = (int64_t)grp * group + c * SK_POSES;
-          // this warp's 8 poses of the chunk (warps 4-7: poses 0-7, warps 8-11: poses 8-15); the blended
-          // vertices are requested before the TMEM wait so their latency hides behind it
-          const int h8 = (warp - 4) >> 2;
-          const int64_t bb = b0 + h8 * 8;
-          const bool full = vok && (bb + 8 <= p.B);
-          const size_t pstride = (size_t)p.V * 3;
-          float* o = p.verts + ((size_t)(vok && bb < p.B ? bb : 0) * p.V + (vok ? v : 0)) * 3;
-          float vp[8][3];
+    struct Blk { int grp, vt, c; };
+    auto advance = [&](Blk& b) {
+      if (++b.c == chunks) { b.c = 0; if (++b.vt == p.n_vt) { b.vt = 0; b.grp += (int)gridDim.x; } }
+    };
+    auto locate = [&](const Blk& b, bool& vok, int64_t& bb) -> float* {
+      const int v = b.vt * TILE_V + q * 32 + lane;
+      vok = v < p.V;
+      bb = ((int64_t)b.grp * group + b.c * SK_POSES) + h8 * 8;
+      return p.verts + ((size_t)(vok && bb < p.B ? bb : 0) * p.V + (vok ? v : 0)) * 3;
+    };
+    auto fetch = [&](const Blk& b, float (&vp)[8][3]) {
+      bool vok; int64_t bb;
+      const float* o = locate(b, vok, bb);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float* s = o + (size_t)((full || (vok && bb + i < p.B)) ? i : 0) * pstride;
-            vp[i][0] = s[0]; vp[i][1] = s[1]; vp[i][2] = s[2];
-          }
-          const uint32_t buf = blk & 1;
-          ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
-          ptx::tc_fence_after();
-          uint32_t t[96];
-          const uint32_t t0 = tmem_base + lane_addr + buf * 256 + h8 * 96;
-          ptx::tmem_ld_32x32(t0, t);
-          ptx::tmem_ld_32x32(t0 + 32, t + 32);
-          ptx::tmem_ld_32x32(t0 + 64, t + 64);
-          ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+      for (int i = 0; i < 8; ++i) {
+        const float* s = o + (size_t)((vok && bb + i < p.B) ? i : 0) * pstride;
+        vp[i][0] = s[0]; vp[i][1] = s[1]; vp[i][2] = s[2];
+      }
+    };
+    constexpr int PF = 2;                 // blocks in flight beyond the current one (3 measured no faster)
+    float vq[PF + 1][8][3];               // vq[0] = current block, vq[d] = d blocks ahead
+    Blk cur{(int)blockIdx.x, 0, 0};
+    Blk ahead = cur;                      // the block PF - 1 ahead of `cur` (fetched before the loop)
+    if (cur.grp < p.n_groups) fetch(cur, vq[0]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (full || (vok && bb + i < p.B)) {
-              const float* T = reinterpret_cast<const float*>(t) + i * 12;
-              const float x = vp[i][0], y = vp[i][1], z = vp[i][2];
-              float tx = 0.f, ty = 0.f, tz = 0.f;
-              if (p.transl) {
-                const float* tr = p.transl + (bb + i) * 3;
-                tx = tr[0]; ty = tr[1]; tz = tr[2];
-              }
-              float* w = o + (size_t)i * pstride;
-              w[0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
-              w[1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
-              w[2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
-            }
+    for (int d = 1; d < PF; ++d) {
+      advance(ahead);
+      if (ahead.grp < p.n_groups) fetch(ahead, vq[d]);
+    }
+    while (cur.grp < p.n_groups) {
+      advance(ahead);
+      if (ahead.grp < p.n_groups) fetch(ahead, vq[PF]);
+      float (&vp)[8][3] = vq[0];
+      bool vok; int64_t bb;
+      float* o = locate(cur, vok, bb);
+      const bool full = vok && (bb + 8 <= p.B);
+      const uint32_t buf = blk & 1;
+      ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
+      ptx::tc_fence_after();
+      uint32_t t[96];
+      const uint32_t t0 = tmem_base + lane_addr + buf * 256 + h8 * 96;
+      ptx::tmem_ld_32x32(t0, t);
+      ptx::tmem_ld_32x32(t0 + 32, t + 32);
+      ptx::tmem_ld_32x32(t0 + 64, t + 64);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (full || (vok && bb + i < p.B)) {
+          const float* T = reinterpret_cast<const float*>(t) + i * 12;
+          const float x = vp[i][0], y = vp[i][1], z = vp[i][2];
+          float tx = 0.f, ty = 0.f, tz = 0.f;
+          if (p.transl) {
+            const float* tr = p.transl + (bb + i) * 3;
+            tx = tr[0]; ty = tr[1]; tz = tr[2];
           }
-          tph ^= 1u << buf;
-          ++blk;
+          float* w = o + (size_t)i * pstride;
+          w[0] = T[0] * x + T[1] * y + T[2] * z + T[9] + tx;
+          w[1] = T[3] * x + T[4] * y + T[5] * z + T[10] + ty;
+          w[2] = T[6] * x + T[7] * y + T[8] * z + T[11] + tz;
         }
       }
+#pragma unroll
+      for (int d = 0; d < PF; ++d)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) vq[d][i][k] = vq[d + 1][i][k];
+      tph ^= 1u << buf;
+      ++blk;
+      advance(cur);
     }
   }
   __syncthreads();

@@ -73,6 +73,25 @@ def test_tc_engine_agrees_with_fp32_engine_on_device(gpu_model):
     assert rel_err(b, a) < 1e-3
 
 
+@pytest.mark.parametrize('B', [127, 129, 18944, 18945, 37889])
+def test_tc_engine_tile_and_wave_boundaries(gpu_model, B):
+    """Row counts around the 128-row tile and the one-tile-per-SM wave (148 x 128 = 18 944): ragged last tile,
+    ghost tile of an odd pair, more tile pairs than CTA pairs.  Every row must match the exact fp32 engine."""
+    gen = torch.Generator().manual_seed(B)
+    x = (torch.randn(B, 63, generator=gen) * 1.3).cuda()
+    lab = torch.full((B,), 250.25, device='cuda')
+    try:
+        gpu_model.engine = L.ENGINE_FP32
+        a = gpu_model(x, lab)
+        gpu_model.engine = L.ENGINE_TC
+        b = gpu_model(x, lab)
+    finally:
+        gpu_model.engine = L.ENGINE_AUTO
+    row = ((b - a).norm(dim=1) / a.norm(dim=1)).max()
+    assert float(row) < 1e-3, float(row)    # fp16 operands / fp32 accumulate: 1e-3 relative per row
+    assert torch.isfinite(b).all()
+
+
 def test_time_table_against_oracle(gpu_model, oracle_sd):
     """The hoisted time path: W_lt temb + b_lt + b_l for a few labels."""
     import torch.nn.functional as F
