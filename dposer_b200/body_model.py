@@ -73,6 +73,9 @@ class _LbsFn(torch.autograd.Function):
         L.check(L.load().dpb_lbs_forward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(t), L.ptr(verts), L.ptr(joints), B,
                                          core.engine, L.ptr(ws), ws.numel(), L.current_stream(dev)))
         ctx.core, ctx.need_verts, ctx.has_transl = core, need_verts, transl is not None
+        # an output the loss never touches arrives as None in backward (not as a [B,V,3] tensor of zeros): with no
+        # vertex gradient the backward runs over the <=174 vertices the extra joints read instead of all of them
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(b, p)
         ctx.ws = ws
         if verts is None:
@@ -88,13 +91,20 @@ class _LbsFn(torch.autograd.Function):
         h = core.handle(dev)
         gv = g_verts.contiguous().float() if (ctx.need_verts and g_verts is not None) else None
         gj = g_joints.contiguous().float() if g_joints is not None else None
+        if gv is None and gj is None:
+            return None, None, None, None, None
         g_pose = torch.empty_like(p)
         g_betas = torch.empty_like(b)
         g_transl = torch.empty(B, 3, dtype=torch.float32, device=dev) if ctx.has_transl else None
         ws = ctx.ws
+        scratch, n_scratch = None, 0
+        if gv is not None:   # full-vertex cotangents: scratch for the split (tensor-core + SGEMM) vertex pass
+            n_scratch = int(L.load().dpb_lbs_backward_scratch_bytes(h.ptr, B))
+            if n_scratch:
+                scratch = torch.empty(n_scratch, dtype=torch.uint8, device=dev)
         L.check(L.load().dpb_lbs_backward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(gv), L.ptr(gj), L.ptr(g_pose),
                                           L.ptr(g_betas), L.ptr(g_transl), B, core.engine, L.ptr(ws), ws.numel(),
-                                          L.current_stream(dev)))
+                                          L.ptr(scratch), n_scratch, L.current_stream(dev)))
         return g_betas, g_pose, g_transl, None, None
 
 

@@ -41,6 +41,9 @@ struct dpb_lbs {
   int jp = 0;                     // joints padded to 32
   __half* wop16 = nullptr;        // [V_pad, 2*jp] fp16 [hi | lo] skinning weights
   CUtensorMap tm_wop;
+  // backward: transposed-blend GEMM operand (lbs_bwd.cu)
+  int bw_np = 0, bw_kp = 0;       // (P+S) padded to 64, 3V padded to 16
+  float* dirs_pad = nullptr;      // [bw_np, bw_kp] fp32: rows 0..P-1 posedirs, rows P..P+S-1 shapedirs^T, zero padding
 };
 
 namespace dpb {
@@ -67,4 +70,6 @@ int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* feat
 int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop, float* verts, int64_t B,
                 cudaStream_t st);
 bool lbs_tc_skin_fits(const dpb_lbs* h);
+int lbs_bwd_prepare(dpb_lbs* h, const dpb_body_tensors* m);
+void lbs_bwd_release(dpb_lbs* h);
 }  // namespace dpb

@@ -138,3 +138,31 @@ def test_lbs_backward_vs_autograd_oracle(mt, B, use_verts):
         scale = ref.abs().max().clamp_min(1e-6)
         err = (got - ref).abs().max() / scale
         assert err < 2e-4, (k, float(err))
+
+
+@pytest.mark.parametrize('which', ['body_joints_only', 'verts_only'])
+def test_lbs_backward_with_an_unused_output(which):
+    """Full forward (vertices materialised) but the loss touches one output only, as motion denoising does with
+    Jtr[:, :22] (run/motion_denoising.py:236-262): the missing gradient must not be needed (it arrives as None and
+    the backward skips the all-vertex pass), and the result must match autograd through the oracle."""
+    mt, B = 'smplx', 7
+    m = synthetic.make_body_tensors(mt)
+    inp = synthetic.lbs_inputs(B, mt, seed=11)
+    g = torch.Generator().manual_seed(23)
+    V = m['v_template'].shape[0]
+    gv = torch.randn(B, V, 3, generator=g) / V
+    gj = torch.randn(B, 22, 3, generator=g)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    zeros = lambda n: torch.zeros(B, n)
+    pose = torch.cat([leaf['root_orient'], leaf['pose_body'], zeros(3), zeros(6), zeros(90)], 1)
+    shape = torch.cat([leaf['betas'], zeros(10)], 1)
+    v_ref, j_ref = lbs_ref.body_forward(m, shape, pose, leaf['trans'])
+    ((j_ref[:, :22] * gj).sum() if which == 'body_joints_only' else (v_ref * gv).sum()).backward()
+    bm = BodyModel(m, num_betas=10, batch_size=B, model_type=mt).cuda()
+    dl = {k: v.clone().cuda().requires_grad_(True) for k, v in inp.items()}
+    out = bm(**dl)
+    ((out.Jtr[:, :22] * gj.cuda()).sum() if which == 'body_joints_only' else (out.v * gv.cuda()).sum()).backward()
+    for k in inp:
+        ref, got = leaf[k].grad, dl[k].grad.cpu()
+        scale = ref.abs().max().clamp_min(1e-6)
+        assert (got - ref).abs().max() / scale < 2e-4, k
