@@ -104,7 +104,8 @@ def cpu_reference(workload, budget_s=20.0):
             done += steps
         dt = time.perf_counter() - t0
         t_pose += dt / done * N_SDE / rows
-        sample.append(f'pc_sampler {rows} rows x {done} of {N_SDE} steps, scaled x{N_SDE / done:.1f}')
+        sample.append(f'pc_sampler on {rows} rows: {done} Euler-Maruyama steps timed in runs of {steps}, '
+                      f'per-step time x {N_SDE} steps')
     if workload in ('sample_lbs', 'lbs'):
         m = synthetic.make_body_tensors('smpl')
         rows = 512
