@@ -213,52 +213,50 @@ __global__ void __launch_bounds__(BW_TV) lbs_skin_bwd_kernel(
   }
   if (threadIdx.x < BW_TP * 3) gtr_s[threadIdx.x] = 0.f;
   __syncthreads();
-  const int v = blockIdx.x * BW_TV + threadIdx.x;
-  if (v < V) {
+  // lane = (vertex, pose): the 8 poses of a vertex sit in adjacent lanes, so the shared-memory atomics of a warp go
+  // to 8 different [pose] slices (different banks) instead of 32 lanes hammering one joint's 12 floats
+  static_assert(BW_TP == 8 && BW_TV % 16 == 0, "lane mapping: 8 poses x 16 vertices per pass");
+  const int p = threadIdx.x & 7;
+  for (int it = 0; it < BW_TV / 16; ++it) {
+    const int v = blockIdx.x * BW_TV + it * 16 + (threadIdx.x >> 3);
+    if (v >= V || p >= np) continue;
+    const float* gv = g_verts + ((size_t)(b0 + p) * V + v) * 3;
+    float g[3] = {gv[0], gv[1], gv[2]};
     const int q = need_index ? need_index[v] : -1;
-    float w[8];
-    int jj[8];
-    const int nz = min(nnz, 8);
-    for (int n = 0; n < nz; ++n) {
-      w[n] = ell_w[(size_t)n * V + v];
-      jj[n] = ell_idx[(size_t)n * V + v];
+    if (q >= 0 && gextra) {
+      const float* ge = gextra + ((size_t)(b0 + p) * n_need + q) * 3;
+      g[0] += ge[0]; g[1] += ge[1]; g[2] += ge[2];
     }
-    for (int p = 0; p < np; ++p) {
-      const float* gv = g_verts + ((size_t)(b0 + p) * V + v) * 3;
-      float g[3] = {gv[0], gv[1], gv[2]};
-      if (q >= 0 && gextra) {
-        const float* ge = gextra + ((size_t)(b0 + p) * n_need + q) * 3;
-        g[0] += ge[0]; g[1] += ge[1]; g[2] += ge[2];
+    if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;   // gvp was zeroed
+    const float* xp = vposed + ((size_t)(b0 + p) * V + v) * 3;
+    const float x = xp[0], y = xp[1], z = xp[2];
+    float TR[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) TR[e] = 0.f;
+    for (int n = 0; n < nnz; ++n) {
+      const float w = ell_w[(size_t)n * V + v];
+      if (w == 0.f) continue;
+      const int j = ell_idx[(size_t)n * V + v];
+      const float* Ap = A_s + ((size_t)p * J + j) * 12;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) TR[e] = fmaf(w, Ap[e], TR[e]);
+      float* gp = gA_s + ((size_t)p * J + j) * 12;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float wg = w * g[i];
+        atomicAdd(gp + i * 3 + 0, wg * x);
+        atomicAdd(gp + i * 3 + 1, wg * y);
+        atomicAdd(gp + i * 3 + 2, wg * z);
+        atomicAdd(gp + 9 + i, wg);
       }
-      if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;   // gvp was zeroed
-      const float* xp = vposed + ((size_t)(b0 + p) * V + v) * 3;
-      const float x = xp[0], y = xp[1], z = xp[2];
-      float TR[9];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) TR[e] = 0.f;
-      for (int n = 0; n < nz; ++n) {
-        if (w[n] == 0.f) continue;
-        const float* Ap = A_s + ((size_t)p * J + jj[n]) * 12;
-#pragma unroll
-        for (int e = 0; e < 9; ++e) TR[e] = fmaf(w[n], Ap[e], TR[e]);
-        float* gp = gA_s + ((size_t)p * J + jj[n]) * 12;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float wg = w[n] * g[i];
-          atomicAdd(gp + i * 3 + 0, wg * x);
-          atomicAdd(gp + i * 3 + 1, wg * y);
-          atomicAdd(gp + i * 3 + 2, wg * z);
-          atomicAdd(gp + 9 + i, wg);
-        }
-      }
-      atomicAdd(gtr_s + p * 3 + 0, g[0]);
-      atomicAdd(gtr_s + p * 3 + 1, g[1]);
-      atomicAdd(gtr_s + p * 3 + 2, g[2]);
-      float* o = gvp + (size_t)(b0 + p) * Kp + (size_t)v * 3;   // g_vposed = T_R^T g
-      o[0] = TR[0] * g[0] + TR[3] * g[1] + TR[6] * g[2];
-      o[1] = TR[1] * g[0] + TR[4] * g[1] + TR[7] * g[2];
-      o[2] = TR[2] * g[0] + TR[5] * g[1] + TR[8] * g[2];
     }
+    atomicAdd(gtr_s + p * 3 + 0, g[0]);
+    atomicAdd(gtr_s + p * 3 + 1, g[1]);
+    atomicAdd(gtr_s + p * 3 + 2, g[2]);
+    float* o = gvp + (size_t)(b0 + p) * Kp + (size_t)v * 3;   // g_vposed = T_R^T g
+    o[0] = TR[0] * g[0] + TR[3] * g[1] + TR[6] * g[2];
+    o[1] = TR[1] * g[0] + TR[4] * g[1] + TR[7] * g[2];
+    o[2] = TR[2] * g[0] + TR[5] * g[1] + TR[8] * g[2];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < np * J * 12; i += BW_TV)
@@ -548,7 +546,7 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
   const bool full = g_verts != nullptr;
   const int n_verts = full ? h->V : h->n_need;
   const bool split = full && scratch && h->tc_ready && w.featop && h->dirs_pad &&
-                     scratch_bytes >= bwd_scratch_bytes(h, B) && h->nnz <= 8;
+                     scratch_bytes >= bwd_scratch_bytes(h, B);
   if (split) {
     uint8_t* sp = static_cast<uint8_t*>(scratch);
     float* vposed = reinterpret_cast<float*>(sp);
