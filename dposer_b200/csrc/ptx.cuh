@@ -98,6 +98,13 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS), no registers held while it is in flight
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // One lane of a converged warp (deterministically the same lane for the same mask).  The single-thread roles run
 // their loops warp-wide and predicate only the async instruction with this: operands computed in uniform control
 // flow stay in uniform registers, while a loop nested under `if (lane == 0)` makes ptxas wrap every

@@ -48,7 +48,7 @@ constexpr int ROLE_REGS = 32;      // setmaxnreg: 640 threads start at 96 regist
 constexpr int EPI_REGS = 112;      // epilogue warpgroups take ((96 - 32) * 128 >= (112 - 96) * 512)
 constexpr int TCOLS = 16;          // pose columns per epilogue thread in the prologue / tail (64 / 4 warps per row quarter)
 static_assert(2 * H / 4 == EPI_THREADS, "parameter staging assumes one float4 of gamma|beta per epilogue thread");
-constexpr int PAR_BYTES = 3 * H * 4;
+constexpr int PAR_BYTES = 2 * 3 * H * 4;   // [time bias | gamma | beta] x 1024 floats, double-buffered across layers
 constexpr int STG_BYTES = TILE_M * 128;          // one [128 rows x 64 fp16] SWIZZLE_128B box of outgoing activations
 constexpr int STG_BUFS = 2;                      // staging boxes per column half: box (hf, gp) of a chunk has its own buffer, so
                                                  // the LAST chunk of a layer stays in shared memory and feeds the next layer's
@@ -62,7 +62,7 @@ constexpr int STG_TOTAL = 2 * STG_BUFS * STG_BYTES;
 #endif
 constexpr int NUM_BARS = 2 * STAGES + 4 + NSUB * 5 + 8;  // full, empty, tfull[2], tempty[2], xa, act[4], sfull[2][2], sempty[2][2]
 constexpr int OFF_PAR = STAGES * STAGE_BYTES;
-constexpr int OFF_STG = OFF_PAR + PAR_BYTES;     // 1024-aligned: 3*49152 + 12288 = 159744
+constexpr int OFF_STG = OFF_PAR + PAR_BYTES;     // 1024-aligned
 constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
 constexpr int OFF_POSTB = (OFF_BAR + NUM_BARS * 8 + 16 + 15) / 16 * 16;   // post_dense bias (64 floats)
 static_assert(OFF_POSTB % 16 == 0, "post_b is read with 128-bit loads");
@@ -344,7 +344,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
   // 1024-byte alignment for SWIZZLE_128B; offset arithmetic on the __shared__ array keeps ld/st.shared
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = ptx::smem_u32(smem);
-  float* par = reinterpret_cast<float*>(smem + OFF_PAR);  // [tb | gamma | beta] x 1024
+  float* par_base = reinterpret_cast<float*>(smem + OFF_PAR);  // 2 x [tb | gamma | beta] x 1024
   const uint32_t stg_base = smem_base + OFF_STG;
   const uint32_t bar_base = smem_base + OFF_BAR;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
@@ -639,6 +639,16 @@ score_tc_kernel(const __grid_constant__ KParams p,
         else ptx::mbar_arrive(tempty_bar(buf));
       }
     };
+    uint32_t pcnt = 0;             // hidden layers processed so far (parameter buffer = pcnt & 1)
+    bool par_prefetched = false;
+    auto stage_par = [&](int step_, int layer_, uint32_t slot) {
+      const float4* tb = reinterpret_cast<const float4*>(p.table + ((size_t)step_ * NL + layer_) * H);
+      const float4* gn = reinterpret_cast<const float4*>(p.gn + (size_t)(layer_ * 2) * H);  // gamma | beta (pre-halved)
+      const uint32_t dst = ptx::smem_u32(par_base) + slot * (3 * H * 4);
+      if (et < H / 4) ptx::cp_async_16(dst + et * 16, tb + et);
+      ptx::cp_async_16(dst + (H / 4 + et) * 16, gn + et);   // 2 * H / 4 == EPI_THREADS float4
+      ptx::cp_async_commit();
+    };
     float xs[NSUB][TCOLS];   // sampler state of this thread's (row, TCOLS columns), carried in registers across the steps
     if (!(p.debug & 64))
     for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);) {
@@ -702,19 +712,17 @@ score_tc_kernel(const __grid_constant__ KParams p,
       for (int step = sg.s0; step < sg.s1; ++step) {
         // ---------------- hidden layers 0..4
         for (int layer = 0; layer < 5; ++layer) {
-          ptx::named_bar_sync(1, EPI_THREADS);  // everyone is done with the previous layer's parameters
-          {
-            const float4* tb = reinterpret_cast<const float4*>(p.table + ((size_t)step * NL + layer) * H);
-            const float4* gn = reinterpret_cast<const float4*>(p.gn + (size_t)(layer * 2) * H);  // gamma | beta
-            float4* dst = reinterpret_cast<float4*>(par);
-            if (et < H / 4) dst[et] = tb[et];
-            float4 gb = gn[et];         // 2 * H / 4 == EPI_THREADS float4: threads 0..255 gamma, 256..511 beta
-#if DPB_SILU_MODE == 2
-            if (et >= H / 4) { gb.x *= 0.5f; gb.y *= 0.5f; gb.z *= 0.5f; gb.w *= 0.5f; }
-#endif
-            dst[H / 4 + et] = gb;
-          }
-          ptx::named_bar_sync(1, EPI_THREADS);
+          // layer parameters (time bias of this step, gamma, beta/2) are double-buffered in shared memory: the next
+          // layer's set is copied with cp.async while this layer runs, so a layer boundary costs one barrier and no
+          // exposed global-memory latency
+          if (!par_prefetched) stage_par(step, layer, pcnt & 1);
+          ptx::cp_async_wait_all();
+          ptx::named_bar_sync(1, EPI_THREADS);  // all copies of this set have landed; everyone left the previous layer
+          par_prefetched = false;
+          if (layer < 4) { stage_par(step, layer + 1, (pcnt + 1) & 1); par_prefetched = true; }
+          else if (step + 1 < sg.s1) { stage_par(step + 1, 0, (pcnt + 1) & 1); par_prefetched = true; }
+          const float* par = par_base + (size_t)(pcnt & 1) * 3 * H;
+          ++pcnt;
           const bool to_h = (layer == 0 || layer == 2 || layer == 4);
           const bool residual = (layer == 2 || layer == 4);
 #pragma unroll 1
@@ -1011,6 +1019,16 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_t, rows * H * sizeof(__half)));
   DPB_CUDA_CHECK(cudaMemset(h->act_h, 0, rows * H * sizeof(__half)));
   DPB_CUDA_CHECK(cudaMemset(h->act_t, 0, rows * H * sizeof(__half)));
+  {  // gamma | beta of the five GroupNorms as the epilogue stages them (beta halved for the tanh-form SiLU)
+    std::vector<float> gn((size_t)NL * 2 * H);
+    DPB_CUDA_CHECK(cudaMemcpy(gn.data(), h->gn_packed, gn.size() * sizeof(float), cudaMemcpyDeviceToHost));
+#if DPB_SILU_MODE == 2
+    for (int l = 0; l < NL; ++l)
+      for (int c = 0; c < H; ++c) gn[((size_t)l * 2 + 1) * H + c] *= 0.5f;
+#endif
+    DPB_CUDA_CHECK(cudaMalloc((void**)&h->gn_tc, gn.size() * sizeof(float)));
+    DPB_CUDA_CHECK(cudaMemcpy(h->gn_tc, gn.data(), gn.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->tc_flags, sizeof(int) * h->tc_slots));
   DPB_CUDA_CHECK(cudaMemset(h->tc_flags, 0, sizeof(int) * h->tc_slots));
   int rc = DPB_OK;
@@ -1034,7 +1052,7 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
 }
 
 void tc_release(dpb_score* h) {
-  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->act_t, h->tc_flags};
+  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->act_t, h->tc_flags, h->gn_tc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   h->tc_ready = false;
@@ -1049,7 +1067,7 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   p.B = j.B;
   p.n_tiles = (int)((j.B + tc::TILE_M - 1) / tc::TILE_M);
   p.x_in = j.x_in; p.x_io = j.x_io; p.table = j.table; p.coef = j.coef;
-  p.gn = h->gn_packed; p.post_b = h->post_b;
+  p.gn = h->gn_tc; p.post_b = h->post_b;
   p.row_scale = j.row_scale; p.scale = j.scale; p.out = j.out;
   p.obs = j.obs; p.mask = j.mask; p.noise = j.noise;
   p.seed = j.seed; p.step_offset = j.step_offset; p.traj = j.traj; p.x_mean = j.x_mean;
