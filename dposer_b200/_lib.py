@@ -42,7 +42,7 @@ EXPORTS = ['dpb_version', 'dpb_last_error', 'dpb_device_info', 'dpb_score_create
            'dpb_score_time_table', 'dpb_score_workspace_bytes', 'dpb_score_forward', 'dpb_sampler_run',
            'dpb_langevin_norms', 'dpb_langevin_update', 'dpb_normal_fill', 'dpb_prior_loss', 'dpb_lbs_create',
            'dpb_lbs_destroy', 'dpb_lbs_num_joints_out', 'dpb_lbs_workspace_bytes', 'dpb_lbs_forward',
-           'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_apd_partial', 'dpb_mean_point_error']
+           'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_apd_partial', 'dpb_mean_point_error', 'dpb_fit_loss']
 
 _lib = None
 
@@ -88,6 +88,8 @@ def load():
     lib.dpb_lbs_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, vp, sz, vp, sz, vp]
     lib.dpb_lbs_backward_scratch_bytes.argtypes = [vp, i64]
     lib.dpb_lbs_backward_scratch_bytes.restype = sz
+    lib.dpb_fit_loss.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, f32, f32, f32, f32, vp, vp, vp,
+                                 vp, vp, i64, vp]
     lib.dpb_apd_partial.argtypes = [vp, i64, C.c_int, i64, i64, vp, vp]
     lib.dpb_mean_point_error.argtypes = [vp, vp, i64, C.c_int, vp, C.c_int, vp, vp]
     for name in EXPORTS:

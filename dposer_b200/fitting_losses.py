@@ -1,9 +1,13 @@
 """SMPLify fitting losses with the reference's names (lib/body_model/fitting_losses.py:6-136).
 
-Small per-joint arithmetic on [B,49,*] tensors, written with torch ops so autograd reaches the LBS
-kernel's backward (``dpb_lbs_backward``) and the prior kernel's closed-form gradient.  ``per_problem=True``
+On CUDA tensors ``body_fitting_loss`` runs as one fused kernel (``dpb_fit_loss``: projection, GMoF, angle and shape
+priors, loss and cotangents in a single pass) wrapped in an autograd.Function, so autograd still reaches the LBS
+kernel's backward (``dpb_lbs_backward``) and the prior kernel's closed-form gradient.  The torch-op versions of the
+reference's helpers are kept for host tensors, the camera loss and ``output='reprojection'``.  ``per_problem=True``
 reproduces the reference's B=1 normalisation for a batch of independent images (SURVEY App. B-6,B-10)."""
 import torch
+
+from . import _lib as L
 
 # constants.JOINT_IDS of the four torso joints used by the camera loss (lib/body_model/constants.py:89)
 OP_TORSO = [9, 12, 2, 5]        # OP RHip, OP LHip, OP RShoulder, OP LShoulder
@@ -35,6 +39,35 @@ def angle_prior(pose):
                      torch.tensor([1., -1., -1, -1.], device=pose.device)) ** 2
 
 
+class _FitLossFn(torch.autograd.Function):
+    """loss[b] = reprojection + angle prior + shape prior of sample b (fitting_losses.py:72-92 without the pose
+    prior, which the caller adds).  The kernel returns the cotangents with the loss; backward only scales them."""
+
+    @staticmethod
+    def forward(ctx, joints, body_pose, betas, joints_2d, conf, center, focal, sigma, w_angle, w_shape):
+        dev = joints.device
+        B, K = joints.shape[0], joints.shape[1]
+        f = lambda t: t.detach().to(torch.float32).contiguous()
+        j, p, b_, kp, c, ce = f(joints), f(body_pose), f(betas), f(joints_2d), f(conf), f(center)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        gj, gp, gb = torch.empty_like(j), torch.empty_like(p), torch.empty_like(b_)
+        L.check(L.load().dpb_fit_loss(L.ptr(j), L.ptr(kp), L.ptr(c), L.ptr(ce), L.ptr(p), p.shape[1], L.ptr(b_),
+                                      b_.shape[1], K, float(focal), float(sigma), float(w_angle), float(w_shape),
+                                      L.ptr(loss), None, L.ptr(gj), L.ptr(gp), L.ptr(gb), B, L.current_stream(dev)))
+        ctx.save_for_backward(gj, gp, gb)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        gj, gp, gb = ctx.saved_tensors
+        return gj * g[:, None, None], gp * g[:, None], gb * g[:, None], None, None, None, None, None, None, None
+
+
+def _fused_ok(model_joints, camera_center, output, verbose):
+    return (model_joints.is_cuda and output != 'reprojection' and not verbose and torch.is_tensor(camera_center)
+            and camera_center.dim() == 2)
+
+
 def body_fitting_loss(body_pose, betas, model_joints, camera_t, camera_center, joints_2d, joints_conf, pose_prior,
                       quan_t, focal_length=5000, sigma=100, pose_prior_weight=4.78, shape_prior_weight=5,
                       angle_prior_weight=15.2, output='mean', verbose=False, per_problem=False):
@@ -42,6 +75,14 @@ def body_fitting_loss(body_pose, betas, model_joints, camera_t, camera_center, j
     to the per-sample vector (:79,90).  With per_problem=True the result is the SUM of per-image losses (each
     image normalised as a batch of one), i.e. B independent reference problems solved at once."""
     batch_size = body_pose.shape[0]
+    if _fused_ok(model_joints, camera_center, output, verbose):
+        per_sample = _FitLossFn.apply(model_joints, body_pose, betas, joints_2d, joints_conf, camera_center,
+                                      focal_length, sigma, angle_prior_weight, shape_prior_weight)
+        prior = (pose_prior_weight ** 2) * pose_prior(body_pose, betas, quan_t) if pose_prior is not None else 0.0
+        if per_problem:
+            return per_sample.sum() + prior
+        total = per_sample + prior
+        return total.sum() if output == 'sum' else total.mean()
     rotation = torch.eye(3, device=body_pose.device).unsqueeze(0).expand(batch_size, -1, -1)
     projected = perspective_projection(model_joints, rotation, camera_t, focal_length, camera_center)
     reprojection_loss = (joints_conf ** 2) * gmof(projected - joints_2d, sigma).sum(dim=-1)

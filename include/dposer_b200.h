@@ -208,6 +208,21 @@ int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* full_pose, c
                      int flags, void* ws, size_t ws_bytes, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SMPLify body-fitting loss (replaces body_fitting_loss lib/body_model/fitting_losses.py:59-103 and the
+ * helpers it calls: perspective_projection :6-38, gmof :41-47, angle_prior :50-56), forward and cotangents
+ * in one pass.  All pointers DEVICE fp32.
+ *   joints [B,K,3] (camera translation already applied, as in the reference), joints_2d [B,K,2], conf [B,K],
+ *   center [B,2], body_pose [B,pose_dim] or NULL (no angle prior), betas [B,n_betas] or NULL (no shape prior)
+ *   loss [B] = sum_k conf^2 GMoF(proj - kp) + w_angle^2 sum exp(+-pose[..])^2 + w_shape^2 sum betas^2
+ *   reproj [B,K] or NULL (the per-joint reprojection term, output='reprojection')
+ *   g_joints [B,K,3], g_pose [B,pose_dim], g_betas [B,n_betas]: d loss[b] / d input, each may be NULL
+ * ---------------------------------------------------------------------------------------- */
+int dpb_fit_loss(const float* joints, const float* joints_2d, const float* conf, const float* center,
+                 const float* body_pose, int pose_dim, const float* betas, int n_betas, int n_joints,
+                 float focal, float sigma, float w_angle, float w_shape, float* loss, float* reproj,
+                 float* g_joints, float* g_pose, float* g_betas, int64_t B, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Metrics (replaces average_pairwise_distance lib/utils/metric.py:8-37 and the per-sample
  * reductions of Evaler.eval_bodys lib/dataset/AMASS.py:275-298)
  * ---------------------------------------------------------------------------------------- */

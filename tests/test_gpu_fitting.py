@@ -111,3 +111,45 @@ def test_smplify_steps_vs_oracle(gpu_model, oracle_sd):
     assert rel_err(betas.cpu() - init_betas, ref_betas - init_betas) < 5e-3
     assert rel_err(cam_t.cpu() - init_cam, ref_cam - init_cam) < 5e-3
     assert reproj.shape == (B, 49)
+
+
+@pytest.mark.parametrize('per_problem', [False, True])
+def test_fused_body_fitting_loss_vs_oracle(per_problem):
+    """dpb_fit_loss (projection + GMoF + angle / shape priors, loss and cotangents in one kernel) against the
+    oracle's restatement of fitting_losses.py:59-103, value and gradients w.r.t. joints, pose and betas."""
+    from dposer_b200 import fitting_losses as F
+    from oracle import fitting_ref as Fr
+    B, K = 37, 49
+    g = torch.Generator().manual_seed(3)
+    joints = torch.randn(B, K, 3, generator=g) * 0.4 + torch.tensor([0., 0., 25.])
+    kp = torch.randn(B, K, 2, generator=g) * 60 + 512
+    conf = torch.rand(B, K, generator=g)
+    conf[:, 30:] = 0
+    center = torch.full((B, 2), 512.) + torch.randn(B, 2, generator=g)
+    pose = torch.randn(B, 69, generator=g) * 0.3
+    betas = torch.randn(B, 10, generator=g)
+    prior_scalar = torch.tensor(0.731)
+
+    def run(fn, dev):
+        leaves = [t.clone().to(dev).requires_grad_(True) for t in (joints, pose, betas)]
+        return fn(*leaves), leaves
+
+    def oracle(j, p, b):
+        if not per_problem:
+            return Fr.body_fitting_loss(p, b, j, center, kp, conf, prior_scalar)
+        # B independent single-image problems (each normalised as a batch of one) + the shared prior term
+        zero = torch.tensor(0.)
+        per = [Fr.body_fitting_loss(p[i:i + 1], b[i:i + 1], j[i:i + 1], center[i:i + 1], kp[i:i + 1],
+                                    conf[i:i + 1], zero) for i in range(B)]
+        return torch.stack(per).sum() + (4.78 ** 2) * prior_scalar
+
+    ref, lr = run(oracle, 'cpu')
+    ref.backward()
+    got, lg = run(lambda j, p, b: F.body_fitting_loss(p, b, j, None, center.cuda(), kp.cuda(), conf.cuda(),
+                                                      lambda *_: prior_scalar.cuda(), 0, per_problem=per_problem),
+                  'cuda')
+    got.backward()
+    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+    for a, b_ in zip(lg, lr):
+        scale = b_.grad.abs().max().clamp_min(1e-12)
+        assert float((a.grad.cpu() - b_.grad).abs().max() / scale) < 1e-5
