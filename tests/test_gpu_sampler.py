@@ -144,3 +144,32 @@ def test_sampler_balanced_schedule_matches_unsplit_run(gpu_model, task):
     finally:
         gpu_model.engine = L.ENGINE_AUTO
     assert torch.isfinite(full_out).all()
+
+
+def test_ode_sampler_vs_oracle_rk45(gpu_model, oracle_sd):
+    """Probability-flow ODE sampler (sampling.py:471-542): scipy RK45 on the host drives the drift evaluated by the
+    GPU kernels; the same integrator driven by the oracle's drift is the reference.  The adaptive step control sees
+    slightly different drifts, so the end points agree to the integrator's own accuracy, not to rounding."""
+    from scipy import integrate
+    from oracle import score_ref as S
+    B = 16
+    gen = torch.Generator().manual_seed(21)
+    z0 = torch.randn(B, 63, generator=gen)
+    osde = S.SubVP(0.1, 20., 1000)
+
+    def rhs(t, xf):
+        x = torch.tensor(xf, dtype=torch.float32).reshape(B, 63)
+        d = S.reverse_drift(oracle_sd, osde, x, torch.ones(B) * float(t), probability_flow=True)[0]
+        return d.reshape(-1).numpy()
+
+    sol = integrate.solve_ivp(rhs, (1.0, 1e-3), z0.reshape(-1).numpy(), rtol=1e-5, atol=1e-5, method='RK45')
+    ref = torch.tensor(sol.y[:, -1], dtype=torch.float32).reshape(B, 63)
+    fn = sampling.get_ode_sampler(sde_lib.subVPSDE(0.1, 20., 1000), (B, 63), lambda x: x, eps=1e-3, device='cuda')
+    for engine, tol in [(L.ENGINE_FP32, 2e-3), (L.ENGINE_TC, 5e-3)]:
+        gpu_model.engine = engine
+        try:
+            nfe, x = fn(gpu_model, z=z0)
+        finally:
+            gpu_model.engine = L.ENGINE_AUTO
+        assert rel_err(x, ref) < tol, (engine, float(rel_err(x, ref)))
+        assert abs(nfe - sol.nfev) <= 0.25 * sol.nfev, (nfe, sol.nfev)
