@@ -173,3 +173,21 @@ def test_ode_sampler_vs_oracle_rk45(gpu_model, oracle_sd):
             gpu_model.engine = L.ENGINE_AUTO
         assert rel_err(x, ref) < tol, (engine, float(rel_err(x, ref)))
         assert abs(nfe - sol.nfev) <= 0.25 * sol.nfev, (nfe, sol.nfev)
+
+
+@pytest.mark.parametrize('engine,tol', [(L.ENGINE_FP32, 5e-5), (L.ENGINE_TC, 1e-3)])
+def test_vpsde_em_sampler_vs_reference_golden(gpu_model, engine, tol):
+    """Euler-Maruyama sampling under VPSDE (the fused kernel's affine step with VPSDE coefficients) against the real
+    reference with replayed draws."""
+    g = golden('sde_variants_golden.npz')
+    N, B = 8, 5
+    cfg = synthetic.default_config()
+    fn = sampling.get_sampling_fn(cfg, sde_lib.VPSDE(0.1, 20., N), (B, 63), lambda x: x, 1e-3, device='cuda')
+    noise = torch.tensor(g['vp_em_noise'])[:, None].cuda()
+    gpu_model.engine = engine
+    try:
+        traj, out = fn(gpu_model, z=torch.tensor(g['vp_em_z0']), noise=noise)
+    finally:
+        gpu_model.engine = L.ENGINE_AUTO
+    assert max_rel(out, g['vp_em_out']) < tol
+    assert max_rel(traj[-1], g['vp_em_last']) < tol

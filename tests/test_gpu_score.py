@@ -111,3 +111,20 @@ def test_empty_batch_and_bad_args(gpu_model):
     assert out.shape == (0, 63)
     with pytest.raises(RuntimeError):
         gpu_model(torch.zeros(2, 63), torch.ones(2))          # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize('engine', [L.ENGINE_FP32, L.ENGINE_TC])
+def test_score_fn_vpsde_vesde_vs_golden(gpu_model, engine):
+    """The other two SDEs of sde_lib.py (VPSDE :122-181, VESDE :234-291) through get_score_fn (utils.py:127-186),
+    against the real reference (tests/golden/make_golden_sde_variants.py)."""
+    g = golden('sde_variants_golden.npz')
+    x = torch.tensor(g['x']).cuda()
+    gpu_model.engine = engine
+    try:
+        for name, sde in [('vp', sde_lib.VPSDE(0.1, 20., 1000)), ('ve', sde_lib.VESDE(0.01, 50., 1000))]:
+            score_fn = mutils.get_score_fn(sde, gpu_model, train=False, continuous=True)
+            for tv in ['1.0', '0.5', '0.01']:
+                vt = torch.ones(7, device='cuda') * float(tv)
+                assert max_rel(score_fn(x, vt, None, None), g[f'{name}_score_{tv}']) < TOL[engine], (name, tv)
+    finally:
+        gpu_model.engine = L.ENGINE_AUTO
