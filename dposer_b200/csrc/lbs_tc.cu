@@ -18,6 +18,8 @@
 
 #include <vector>
 
+#include <cstdlib>
+
 #include "lbs.h"
 #include "ptx.cuh"
 
@@ -643,7 +645,8 @@ int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   const int n_slabs = K2 / ltc::BK;
   const size_t bars = (2 * ltc::MAX_STAGES + 6) * 8 + 16 + 8 * ltc::XSTAGE * 4 + 1024;
   // 128-pose groups when the group's operand leaves room for >= 4 ring stages (SMPL), else 64 (SMPL-X)
-  const int np = ((size_t)n_slabs * 128 * ltc::BK * 2 + 4 * ltc::A_SLAB + bars <= 232448) ? 128 : 64;
+  int np = ((size_t)n_slabs * 128 * ltc::BK * 2 + 4 * ltc::A_SLAB + bars <= 232448) ? 128 : 64;
+  if (const char* e = getenv("DPB_LBS_NP")) np = atoi(e) == 64 ? 64 : np;   // timing experiments only
   CUtensorMap tm_feat;
   int rc = make_tmap_2d(&tm_feat, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, featop, K2, (uint64_t)B_pad, ltc::BK, np, 2);
   if (rc != DPB_OK) return rc;

@@ -151,6 +151,14 @@ struct SegIter {
 // (tanh.approx.f32, documented relative error 2^-11, the rounding unit of the fp16 activations it feeds; the
 // measured end-to-end error is unchanged at 4.5e-4) -- one MUFU per element.  0: y / (1 + 2^(-y log2 e)) with
 // MUFU.EX2 + MUFU.RCP, two per element.
+// Timing-experiment knobs (KParams::debug, set from DPB_TC_DEBUG) exist only in instrumented builds
+// (DPB_BUILD_DEFINES=DPB_TC_PROFILE or DPB_TC_KNOBS); the product kernel compiles them out.
+#if defined(DPB_TC_PROFILE) || defined(DPB_TC_KNOBS)
+#define DBG(bit) ((p.debug & (bit)) != 0)
+#else
+#define DBG(bit) false
+#endif
+
 #ifndef DPB_SILU_MODE
 #define DPB_SILU_MODE 2
 #endif
@@ -429,7 +437,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
                 if (TWO_SM) {  // my half of the weight tile into MY shared memory, completion on the leader's barrier
                   const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
                   if (ptx::elect_one()) {
-                    if (p.debug & 8) ptx::mbar_arrive_cluster(lbar);
+                    if (DBG(8)) ptx::mbar_arrive_cluster(lbar);
                     else {
                       ptx::mbar_arrive_expect_tx_cluster(lbar, bytes);
                       ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES + A_BYTES, tm, lbar, kslab(layer, k) * BLOCK_K,
@@ -463,7 +471,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
             for (int cs = 0; cs < nc * NSUB; ++cs) {   // (chunk, sub) pairs; chunk_ctr & 1 == sub
               const uint32_t buf = chunk_ctr & 1;
-              if (!(p.debug & 64)) PROF_WAIT(0, ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1));
+              if (!DBG(64)) PROF_WAIT(0, ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1));
               ptx::tc_fence_after();
               const uint32_t taddr = tmem_base + buf * CHUNK_N;
               for (int k = 0; k < nk; ++k) {
@@ -472,7 +480,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
                 const uint32_t s_addr = smem_base + stage * STAGE_BYTES;
                 const int ks = kslab(layer, k);
                 // first chunk of a layer: the last four K slabs are still in the staging boxes of the previous layer
-                const bool direct = layer > 0 && cs == 0 && ks >= DIRECT_K0 && !(p.debug & 64);
+                const bool direct = layer > 0 && cs == 0 && ks >= DIRECT_K0 && !DBG(64);
                 // first layer: x_hi | x_lo | x_hi, written by the epilogue into the A halves of ring stages 0 / 1
                 const uint32_t a_addr = layer == 0 ? smem_base + (ks == 1 ? STAGE_BYTES : 0)
                                       : direct ? stg_base + (ks - DIRECT_K0) * STG_BYTES : s_addr;
@@ -480,7 +488,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
                 const uint64_t bdesc = ptx::umma_desc_sw128(s_addr + A_BYTES);
                 PROF_BEGIN(issue_t0)
                 if (ptx::elect_one()) {
-                  if (!(p.debug & 2))
+                  if (!DBG(2))
 #pragma unroll
                   for (int kk = 0; kk < BLOCK_K / 16; ++kk)  // UMMA_K = 16: advance 32 B inside the swizzle row
                     if (TWO_SM) ptx::mma_f16_ss_2sm(taddr, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
@@ -512,7 +520,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
             // layer input: x (shared memory, written by the epilogue) | H | T | H | T | H
             const CUtensorMap* tm = (layer == 2 || layer == 4) ? &tm_t : &tm_h;
             const int nk = layer_nk(layer), nc = layer_chunks(layer);
-            if (layer == 1 && !(p.debug & 64)) {
+            if (layer == 1 && !DBG(64)) {
               // the first layer's operand lives in the A halves of ring stages 0 / 1: no activation tile may land
               // there before ALL first-layer MMAs have retired (= the accumulator of its last chunk is complete)
               const uint32_t n = cctr - 1;
@@ -520,7 +528,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
             }
             for (int chunk = 0; chunk < nc; ++chunk, ++cctr)
              for (int sub = 0; sub < NSUB; ++sub) {
-              if (layer == 0 && chunk == 0 && !(p.debug & 64)) PROF_WAIT(0, ptx::mbar_wait(xa_bar(sub), xph));  // prologue / previous step's tail wrote x
+              if (layer == 0 && chunk == 0 && !DBG(64)) PROF_WAIT(0, ptx::mbar_wait(xa_bar(sub), xph));  // prologue / previous step's tail wrote x
               for (int k = 0; k < nk; ++k) {
                 // K-slabs 4c..4c+3 of this layer's input are column chunk c of the previous layer's output:
                 // wait for exactly that chunk (first use only), so the next layer starts while the previous
@@ -528,9 +536,9 @@ score_tc_kernel(const __grid_constant__ KParams p,
                 // all for this layer's first chunk: the MMA reads them from the staging boxes (box = slab - 12)
                 // as soon as the epilogue has filled them; the later chunks fetch them from the scratch.
                 const int ks = kslab(layer, k);
-                const bool boxed = layer > 0 && chunk == 0 && ks >= DIRECT_K0 && !(p.debug & 64);
+                const bool boxed = layer > 0 && chunk == 0 && ks >= DIRECT_K0 && !DBG(64);
                 const bool direct = boxed || layer == 0;   // nothing to load: the MMA reads shared memory the epilogue wrote
-                if (layer > 0 && !(p.debug & 64)) {
+                if (layer > 0 && !DBG(64)) {
                   if (boxed) {
                     const int kb = ks - DIRECT_K0;   // (hf, gp) = (kb >> 1, kb & 1); the last chunk's box phase is always odd
                     PROF_WAIT(1, ptx::mbar_wait(sfull_bar(kb >> 1, kb & 1), 1));
@@ -542,7 +550,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
                 if (TWO_SM) {
                   const uint32_t lbar = ptx::mapa(full_bar(stage), 0);
                   if (ptx::elect_one()) {
-                    if ((p.debug & 4) || direct) ptx::mbar_arrive_cluster(lbar);
+                    if (DBG(4) || direct) ptx::mbar_arrive_cluster(lbar);
                     else {
                       ptx::mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
                       ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, ks * BLOCK_K, slot_row0 + sub * TILE_M);
@@ -574,7 +582,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
       uint32_t cnt0 = 0, cnt1 = 0;
       uint32_t last_bar = 0;      // sempty barrier of the most recent store that has not been handed back yet
       bool last_released = true;
-      if (!(p.debug & 64))
+      if (!DBG(64))
       for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);)
         for (int step = sg.s0; step < sg.s1; ++step)
           for (int layer = 0; layer < 5; ++layer) {
@@ -588,7 +596,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
                   const uint32_t b = c % STG_BUFS, ph = (c / STG_BUFS) & 1;
                   PROF_WAIT(0, ptx::mbar_wait(sfull_bar(hf, b), ph));
                   if (ptx::elect_one()) {
-                    if (!(p.debug & 16))
+                    if (!DBG(16))
                     ptx::tma_store_2d(tm, stg_base + (hf * STG_BUFS + b) * STG_BYTES,
                                       chunk * CHUNK_N + hf * 128 + gp * 64, slot_row0 + sub * TILE_M);
                     ptx::tma_store_commit();
@@ -650,7 +658,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
       ptx::cp_async_commit();
     };
     float xs[NSUB][TCOLS];   // sampler state of this thread's (row, TCOLS columns), carried in registers across the steps
-    if (!(p.debug & 64))
+    if (!DBG(64))
     for (SegIter it(worker, n_workers, n_units, p.n_steps); it.next(sg);) {
       const long long tile0 = ((long long)sg.unit * CLUSTER + crank) * NSUB;
       if (sg.acquire) {  // the chain's first steps ran on the next cluster: wait until its x_io rows are published
@@ -733,7 +741,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
             // residual stream: this thread's 2 x 32 old values of the chunk are requested BEFORE the accumulator
             // wait (they were stored two layers ago), so their L2 latency hides behind it
             uint4 rres[2][4];
-            if (residual && !(p.debug & 512)) {
+            if (residual && !DBG(512)) {
 #pragma unroll
               for (int gp = 0; gp < 2; ++gp) {
                 const uint4* rp = reinterpret_cast<const uint4*>(drow + chunk * CHUNK_N + (hf * 4 + gp * 2 + sg2) * 32);
@@ -752,7 +760,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
               const int g = hf * 4 + gp * 2 + sg2;           // my 32-column group of the chunk
               const int col0 = chunk * CHUNK_N + g * 32;
               uint32_t vr[32];
-              if (p.debug & 128) {
+              if (DBG(128)) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) vr[i] = 0;
               } else {
@@ -762,7 +770,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
               ptx::tmem_ld_wait();
               if (gp == 1) tempty_arrive(buf);  // last TMEM read of this warp for the buffer: hand it back to the MMA warp
               uint4 o[4];
-              if (p.debug & 1) {
+              if (DBG(1)) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) o[i] = make_uint4(0, 0, 0, 0);
               } else {
@@ -783,7 +791,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
               const uint32_t rbase = stg_base + (hf * STG_BUFS + sb) * STG_BYTES + r_in * 128;
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                if (!(p.debug & 256)) st_shared_v4(rbase + (((sg2 * 4 + j) ^ (r_in & 7)) << 4), o[j]);
+                if (!DBG(256)) st_shared_v4(rbase + (((sg2 * 4 + j) ^ (r_in & 7)) << 4), o[j]);
               ptx::fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) ptx::mbar_arrive(sfull_bar(hf, sb));
@@ -1077,10 +1085,12 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   p.z = j.z; p.loss_out = j.loss_out; p.grad_out = j.grad_out; p.row_loss = j.row_loss;
   p.act_h = h->act_h; p.act_t = h->act_t;
   p.flags = h->tc_flags;
+#if defined(DPB_TC_PROFILE) || defined(DPB_TC_KNOBS)
   {
     const char* dbg = getenv("DPB_TC_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+#endif
   if (j.mode == 2 && j.row_loss) DPB_CUDA_CHECK(cudaMemsetAsync(j.row_loss, 0, sizeof(float) * j.B, st));
   // grid: a multiple of the cluster size, at most one CTA per scratch slot
   const int n_groups = (p.n_tiles + tc::NSUB - 1) / tc::NSUB;

@@ -1,4 +1,9 @@
-"""Timing experiment for the fused sampler kernel (run under gpurun): DPB_TC_DEBUG variants."""
+"""Timing experiment for the fused sampler kernel (run under gpurun): DPB_TC_DEBUG variants.
+
+The knobs exist only in an instrumented build of the library:
+    DPB_BUILD_DEFINES=DPB_TC_KNOBS python -c "from dposer_b200 import build; build.build(force=True)"   # or DPB_TC_PROFILE
+    DPB_LIBRARY=$PWD/dposer_b200/lib/libdposer_b200_prof.so PROF_DBG=0,1,64 python scripts/tc_experiment.py
+"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
