@@ -4,6 +4,8 @@
 //
 // Follows smplx==0.1.28 lbs()/SMPL.forward/SMPLX.forward as called by the reference at
 // lib/body_model/body_model.py:75-88 and lib/body_model/smpl.py:67-78.
+#include <cstdlib>
+
 #include "lbs.h"
 
 #include <algorithm>
@@ -490,6 +492,12 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
     if (!compact && engine == DPB_LBS_ENGINE_TC && !use_tc)
       return fail(DPB_EUNSUPPORTED, "dpb_lbs_forward: tensor-core engine unavailable");
     if (use_tc) {
+      static const bool fused_off = getenv("DPB_LBS_FUSED") && atoi(getenv("DPB_LBS_FUSED")) == 0;   // A/B timing only
+      if (!fused_off && w.skinop && lbs_tc_fused_fits(h)) {
+        // blend + skinning in one tcgen05 kernel: the blended vertices stay in TMEM
+        int rc = lbs_tc_fused(h, betas, w.feat, w.featop, w.A, transl, w.skinop, verts, B, st);
+        if (rc != DPB_OK) return rc;
+      } else {
       // blend on tcgen05 (writes v_posed into verts), then skin in place with the transforms from the pose kernel
       int rc = lbs_tc_blend(h, betas, w.feat, w.featop, verts, B, st);
       if (rc != DPB_OK) return rc;
@@ -505,6 +513,7 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
                                                     h->posedirs, h->ell_idx, h->ell_w, nullptr, n_verts, h->V, h->J,
                                                     0, 0, h->nnz, verts, verts, B);
       DPB_CUDA_CHECK(cudaGetLastError());
+      }
       }
     } else {
       size_t smem = ((size_t)h->P * LBS_TP + (size_t)h->S * LBS_TP + (size_t)LBS_TP * h->J * 12 + LBS_TP * 3) * 4;

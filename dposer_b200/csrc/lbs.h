@@ -70,6 +70,9 @@ int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* feat
 int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop, float* verts, int64_t B,
                 cudaStream_t st);
 bool lbs_tc_skin_fits(const dpb_lbs* h);
+bool lbs_tc_fused_fits(const dpb_lbs* h);
+int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* featop, const float* A, const float* transl,
+                 __half* skinop, float* verts, int64_t B, cudaStream_t st);
 int lbs_bwd_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_bwd_release(dpb_lbs* h);
 }  // namespace dpb
