@@ -536,17 +536,20 @@ __global__ void lbs_skinop_kernel(const float* __restrict__ A, const float* __re
 //   warp 0  TMA: blend operand (per unit), basis slabs (ring);  warp 3  TMA: skin weights (per tile), transform chunks
 //   warp 1  MMA issuer;  warp 2  TMEM allocator;  warps 4-11 epilogue (warp set h = (warp - 4) >> 2)
 // HBM traffic is the output only (5.4 GB for 65 536 SMPL poses instead of 16.4 GB through the two-kernel path).
-constexpr int FU_NP = 128;                 // poses per group
+constexpr int FU_NP = 96;                  // poses per group: D_x | D_y | D_z take 288 TMEM columns, three 64-column
+                                           // T buffers the rest; the group's blend operand (84 KB) leaves room for a
+                                           // 6-stage basis ring (the blend phase is bound by slab ingest, not by MMAs)
 constexpr int FU_CP = 5;                   // poses per skinning chunk (N = 60 -> 64)
-constexpr int FU_NCHUNK = (FU_NP + FU_CP - 1) / FU_CP;   // 26
-constexpr int FU_ASTAGES = 3;
+constexpr int FU_NCHUNK = (FU_NP + FU_CP - 1) / FU_CP;   // 20 (even: chunk parity = warp set across tiles)
+constexpr int FU_NT = 3;                   // T buffers (ring over chunks)
+constexpr int FU_ASTAGES = 6;
 constexpr int FU_SSTAGES = 3;
 constexpr int FU_S_BYTES = 64 * BK * 2;    // one transform chunk: 64 rows x 64 k fp16
 constexpr int FU_B_SLAB = FU_NP * BK * 2;
-constexpr int FU_XSTAGE = FU_CP * 96;      // floats per warp: 5 poses x 32 vertices x (x,y,z)
 constexpr uint32_t FU_IDESC_BLEND = ptx::umma_idesc_f16(TILE_V, FU_NP, 0);
 constexpr uint32_t FU_IDESC_SKIN = ptx::umma_idesc_f16(TILE_V, 64, 0);
-constexpr int FU_NBARS = 2 * FU_ASTAGES + 2 * FU_SSTAGES + 10;
+constexpr int FU_NBARS = 2 * FU_ASTAGES + 2 * FU_SSTAGES + 6 + 2 * FU_NT;
+static_assert(FU_NCHUNK % 2 == 0 && 3 * FU_NP + FU_NT * 64 <= 512 && FU_B_SLAB % 1024 == 0, "fused LBS TMEM / SMEM layout");
 
 struct FusedParams {
   int V, V_pad, n_vt, vsplit;
@@ -558,6 +561,10 @@ struct FusedParams {
   float* verts;
 };
 
+// HALF = K16 steps of the hi part of the blend K, NSLABS = 64-wide slabs of [hi | lo], JS = K16 steps of the hi part of
+// the skinning K: compile-time so that the issuer's loops unroll and every descriptor is base + constant (with
+// run-time geometry the single issuing thread spent ~100 cycles of address arithmetic per 48-cycle MMA).
+template <int HALF, int NSLABS, int JS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CUtensorMap tm_dirs,
                     const __grid_constant__ CUtensorMap tm_feat, const __grid_constant__ CUtensorMap tm_w,
@@ -578,10 +585,9 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
   const uint32_t bfull = bar2, bempty = bar2 + 8, wfull = bar2 + 16, wempty = bar2 + 24, dfull = bar2 + 32,
                  dempty = bar2 + 40;
   auto tfull = [&](uint32_t b) { return bar2 + 48 + 8u * b; };
-  auto tempty = [&](uint32_t b) { return bar2 + 64 + 8u * b; };
+  auto tempty = [&](uint32_t b) { return bar2 + 48 + 8u * (FU_NT + b); };
   const size_t off_bar = (size_t)p.n_slabs * FU_B_SLAB + FU_ASTAGES * A_SLAB + A_SLAB + FU_SSTAGES * FU_S_BYTES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bar + FU_NBARS * 8);
-  float* xstage = reinterpret_cast<float*>(smem + off_bar + FU_NBARS * 8 + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -590,7 +596,7 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
     ptx::mbar_init(bfull, 1); ptx::mbar_init(bempty, 1);
     ptx::mbar_init(wfull, 1); ptx::mbar_init(wempty, 1);
     ptx::mbar_init(dfull, 1); ptx::mbar_init(dempty, 8);
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull(b), 1); ptx::mbar_init(tempty(b), 4); }
+    for (int b = 0; b < FU_NT; ++b) { ptx::mbar_init(tfull(b), 1); ptx::mbar_init(tempty(b), 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
@@ -652,11 +658,9 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
     }
   } else if (warp == 1) {
     // ---- MMA issuer
-    uint32_t astage = 0, aphase = 0, sstage = 0, sphase = 0, uph = 0, wph = 0, dph = 0, tph = 0;
+    uint32_t astage = 0, aphase = 0, sstage = 0, sphase = 0, uph = 0, wph = 0, dph = 0, cc = 0;   // cc: chunks so far
     const uint64_t adesc0 = ptx::umma_desc_sw128(a_base), bdesc0 = ptx::umma_desc_sw128(b_base);
     const uint64_t wdesc0 = ptx::umma_desc_sw128(w_base);
-    auto bdesc = [&](int step) { return bdesc0 + (uint64_t)((step >> 2) * (FU_B_SLAB >> 4) + 2 * (step & 3)); };
-    const int half = p.ksteps_half, js = p.jsteps;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int part = u % p.vsplit;
       const int vt0 = part * tiles_per_part, vt1 = min(p.n_vt, vt0 + tiles_per_part);
@@ -667,25 +671,31 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
         ptx::mbar_wait(dempty, dph ^ 1);   // the previous tile's epilogue has read all of D
         dph ^= 1;
         ptx::tc_fence_after();
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {
           const uint32_t taddr = tmem_base + c * FU_NP;
-          for (int i = 0; i < p.n_slabs; ++i) {
+#pragma unroll
+          for (int i = 0; i < NSLABS; ++i) {
             ptx::mbar_wait(afull(astage), aphase);
             ptx::tc_fence_after();
             const uint64_t adesc = adesc0 + (uint64_t)(astage * (A_SLAB >> 4));
             if (ptx::elect_one()) {
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j) {
-                const int g = i * (BK / 16) + j;
-                if (g < half) {
-                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g), FU_IDESC_BLEND, g != 0 ? 1u : 0u);
-                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(half + g), FU_IDESC_BLEND, 1u);
+                constexpr int SL = FU_B_SLAB >> 4;
+                const int g = i * (BK / 16) + j;   // compile-time after unrolling
+                if (g < HALF) {
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc0 + (uint64_t)((g >> 2) * SL + 2 * (g & 3)), FU_IDESC_BLEND,
+                                  g != 0 ? 1u : 0u);
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j,
+                                  bdesc0 + (uint64_t)(((HALF + g) >> 2) * SL + 2 * ((HALF + g) & 3)), FU_IDESC_BLEND, 1u);
                 } else {
-                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g - half), FU_IDESC_BLEND, 1u);
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j,
+                                  bdesc0 + (uint64_t)(((g - HALF) >> 2) * SL + 2 * ((g - HALF) & 3)), FU_IDESC_BLEND, 1u);
                 }
               }
               ptx::mma_commit(aempty(astage));
-              if (c == 2 && i == p.n_slabs - 1) ptx::mma_commit(dfull);
+              if (c == 2 && i == NSLABS - 1) ptx::mma_commit(dfull);
             }
             if (++astage == FU_ASTAGES) { astage = 0; aphase ^= 1; }
           }
@@ -693,18 +703,19 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
         ptx::mbar_wait(wfull, wph);
         wph ^= 1;
         ptx::tc_fence_after();
-        for (int c = 0; c < FU_NCHUNK; ++c) {
-          const uint32_t buf = c & 1;
-          ptx::mbar_wait(tempty(buf), ((tph >> buf) & 1) ^ 1);
+        for (int c = 0; c < FU_NCHUNK; ++c, ++cc) {
+          const uint32_t buf = cc % FU_NT;
+          ptx::mbar_wait(tempty(buf), ((cc / FU_NT) & 1) ^ 1);
           ptx::mbar_wait(sfull(sstage), sphase);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + 3 * FU_NP + buf * 64;
           const uint64_t sdesc0 = ptx::umma_desc_sw128(s_base + sstage * FU_S_BYTES);
           if (ptx::elect_one()) {
-            for (int g = 0; g < js; ++g) {   // w_hi x (A_hi + A_lo), then w_lo x A_hi
+#pragma unroll
+            for (int g = 0; g < JS; ++g) {   // w_hi x (A_hi + A_lo), then w_lo x A_hi
               ptx::mma_f16_ss(taddr, wdesc0 + 2 * g, sdesc0 + 2 * g, FU_IDESC_SKIN, g ? 1u : 0u);
-              ptx::mma_f16_ss(taddr, wdesc0 + 2 * g, sdesc0 + 2 * (js + g), FU_IDESC_SKIN, 1u);
-              ptx::mma_f16_ss(taddr, wdesc0 + 2 * (js + g), sdesc0 + 2 * g, FU_IDESC_SKIN, 1u);
+              ptx::mma_f16_ss(taddr, wdesc0 + 2 * g, sdesc0 + 2 * (JS + g), FU_IDESC_SKIN, 1u);
+              ptx::mma_f16_ss(taddr, wdesc0 + 2 * (JS + g), sdesc0 + 2 * g, FU_IDESC_SKIN, 1u);
             }
             ptx::mma_commit(sempty(sstage));
             ptx::mma_commit(tfull(buf));
@@ -713,7 +724,6 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
               if (vt == vt1 - 1) ptx::mma_commit(bempty);
             }
           }
-          tph ^= 1u << buf;
           if (++sstage == FU_SSTAGES) { sstage = 0; sphase ^= 1; }
         }
       }
@@ -724,8 +734,7 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
     const int h = (warp - 4) >> 2;     // warp set = T buffer = chunk parity
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const size_t pstride = (size_t)p.V * 3;
-    float* stage = xstage + (warp - 4) * FU_XSTAGE;
-    uint32_t dph = 0, tph = 0;
+    uint32_t dph = 0, cc0 = 0;         // cc0: chunk counter at the start of the tile (the MMA warp's cc)
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int grp = u / p.vsplit, part = u % p.vsplit;
       const int vt0 = part * tiles_per_part, vt1 = min(p.n_vt, vt0 + tiles_per_part);
@@ -740,47 +749,23 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
         ptx::tc_fence_after();
 #pragma unroll 1
         for (int c = h; c < FU_NCHUNK; c += 2) {
-          ptx::mbar_wait(tfull(h), tph);
-          tph ^= 1;
+          const uint32_t cc = cc0 + c, buf = cc % FU_NT;
+          ptx::mbar_wait(tfull(buf), (cc / FU_NT) & 1);
           ptx::tc_fence_after();
           uint32_t t[64], dx[8], dy[8], dz[8];
           const uint32_t d0 = tmem_base + lane_addr + c * FU_CP;
-          ptx::tmem_ld_32x64(tmem_base + lane_addr + 3 * FU_NP + h * 64, t);
+          ptx::tmem_ld_32x64(tmem_base + lane_addr + 3 * FU_NP + buf * 64, t);
           ptx::tmem_ld_32x8(d0, dx);
           ptx::tmem_ld_32x8(d0 + FU_NP, dy);
           ptx::tmem_ld_32x8(d0 + 2 * FU_NP, dz);
           ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tempty(h));
+          if (lane == 0) ptx::mbar_arrive(tempty(buf));
           const int64_t b0 = (int64_t)grp * FU_NP + c * FU_CP;
           int n_ok = FU_NP - c * FU_CP;                       // poses of this chunk inside the group ...
           if (n_ok > FU_CP) n_ok = FU_CP;
           if (b0 + n_ok > p.B) n_ok = (int)max((int64_t)0, p.B - b0);   // ... and inside the batch
-#ifdef DPB_LBS_FUSED_STAGED
-#pragma unroll
-          for (int i = 0; i < FU_CP; ++i) {
-            const float* T = reinterpret_cast<const float*>(t) + i * 12;
-            const float x = __uint_as_float(dx[i]) + vt3[0], y = __uint_as_float(dy[i]) + vt3[1],
-                        z = __uint_as_float(dz[i]) + vt3[2];
-            stage[i * 96 + 3 * lane + 0] = T[0] * x + T[1] * y + T[2] * z + T[9];
-            stage[i * 96 + 3 * lane + 1] = T[3] * x + T[4] * y + T[5] * z + T[10];
-            stage[i * 96 + 3 * lane + 2] = T[6] * x + T[7] * y + T[8] * z + T[11];
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < FU_CP; ++i) {
-            if (i < n_ok) {
-              float* dst = p.verts + (size_t)(b0 + i) * pstride + (size_t)v0 * 3;
-#pragma unroll
-              for (int k = 0; k < 3; ++k) {
-                const int f = 32 * k + lane;
-                if (f < n_floats) dst[f] = stage[i * 96 + f];
-              }
-            }
-          }
-          __syncwarp();
-#else
           // each lane stores its vertex's 12 bytes; the warp's 32 records are one contiguous 384-byte run
           if (v < p.V) {
             float* dst = p.verts + (size_t)b0 * pstride + (size_t)v * 3;
@@ -797,8 +782,8 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
               }
             }
           }
-#endif
         }
+        cc0 += FU_NCHUNK;
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(dempty);
@@ -924,9 +909,10 @@ int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop,
 
 bool lbs_tc_fused_fits(const dpb_lbs* h) {
   if (!h->tc_ready || h->J >= h->jp || 2 * h->jp != ltc::BK) return false;   // one [hi | lo] slab incl. the transl slot
+  if (h->kext != 448) return false;   // the kernel is instantiated for SMPL's blend K (10 + 207 -> 224, hi | lo)
   const int n_slabs = h->kext / ltc::BK;
   const size_t smem = (size_t)n_slabs * ltc::FU_B_SLAB + (ltc::FU_ASTAGES + 1) * ltc::A_SLAB +
-                      ltc::FU_SSTAGES * ltc::FU_S_BYTES + ltc::FU_NBARS * 8 + 16 + 8 * ltc::FU_XSTAGE * 4 + 1024;
+                      ltc::FU_SSTAGES * ltc::FU_S_BYTES + ltc::FU_NBARS * 8 + 16 + 1024;
   return smem <= 232448;
 }
 
@@ -951,7 +937,7 @@ int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   p.V = h->V;
   p.V_pad = h->n_cols_pad;
   p.n_vt = h->n_cols_pad / ltc::TILE_V;
-  p.vsplit = 2;
+  p.vsplit = 3;
   p.ksteps_half = Kp / 16;
   p.n_slabs = K2 / ltc::BK;
   p.jsteps = Jp / 16;
@@ -960,10 +946,11 @@ int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   p.v_template = h->v_template;
   p.verts = verts;
   const size_t smem = (size_t)p.n_slabs * ltc::FU_B_SLAB + (ltc::FU_ASTAGES + 1) * ltc::A_SLAB +
-                      ltc::FU_SSTAGES * ltc::FU_S_BYTES + ltc::FU_NBARS * 8 + 16 + 8 * ltc::FU_XSTAGE * 4 + 1024;
-  DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                      ltc::FU_SSTAGES * ltc::FU_S_BYTES + ltc::FU_NBARS * 8 + 16 + 1024;
+  auto kern = ltc::lbs_fused_tc_kernel<14, 7, 2>;   // SMPL: K16 steps 224/16, slabs 448/64, joints 32/16
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = p.n_units < h->sm_count ? p.n_units : h->sm_count;
-  ltc::lbs_fused_tc_kernel<<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat, h->tm_wop, tm_s);
+  kern<<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat, h->tm_wop, tm_s);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }
