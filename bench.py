@@ -28,10 +28,10 @@ sys.path.insert(0, ROOT)
 SCORE_FLOP_PER_ROW = 8646656          # 2*(63*1024 + 4*1024^2 + 1024*63), batch-uniform t
 LBS_BYTES_PER_POSE = 83560            # verts 6890*12 + joints 45*12 + inputs 85*4
 # DRAM traffic from the committed `ncu --set full` capture (profiles/r1_ncu_full_summary_final.md):
-#   fused sampler: 1.084 GB for 37 888 rows x 4 steps (mostly write-back of the L2-resident activation scratch)
-#   LBS (65 536 poses): blend 5.516 GB + skinning 10.897 GB (the blended vertices make one extra HBM round trip)
-SAMPLER_DRAM_BYTES_PER_ROW_STEP = 1.084e9 / (37888 * 4)
-LBS_DRAM_BYTES_PER_POSE = (5.516e9 + 10.897e9) / 65536
+#   fused sampler: 1.201 GB for 37 888 rows x 4 steps (mostly write-back of the L2-resident activation scratch)
+#   LBS (65 536 poses): fused blend + skinning kernel 5.369 GB written + 0.450 GB read (the output plus operand refills)
+SAMPLER_DRAM_BYTES_PER_ROW_STEP = 1.201e9 / (37888 * 4)
+LBS_DRAM_BYTES_PER_POSE = (5.369e9 + 0.450e9) / 65536
 N_SDE = 1000
 
 
