@@ -98,7 +98,9 @@ struct KParams {
 // One block = (pose group of NP poses, vertex tile): D_x | D_y | D_z [128 vertices x NP poses] in one TMEM buffer
 // (3*NP columns, double-buffered), so the epilogue has a vertex's three coordinates together and can write them
 // as contiguous 12-byte records (transposed per warp through shared memory into fully coalesced lines).
-template <int NP>
+// HALF / NSLABS: the blend K geometry at compile time (K16 steps of the hi part, 64-wide slabs of [hi | lo]) so that the
+// issuer's slab loop unrolls and every operand descriptor is base + constant; 0 = take them from KParams.
+template <int NP, int HALF = 0, int NSLABS = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ CUtensorMap tm_dirs,
                     const __grid_constant__ CUtensorMap tm_feat) {
@@ -182,9 +184,12 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
         const uint32_t buf = unit % NBUF;
         ptx::mbar_wait(tempty_bar(buf), ((tph >> buf) & 1) ^ 1);
         ptx::tc_fence_after();
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {
           const uint32_t taddr = tmem_base + buf * (3 * NP) + c * NP;
-          for (int i = 0; i < p.n_slabs; ++i) {
+          const int n_slabs = NSLABS ? NSLABS : p.n_slabs;
+          const int khalf = HALF ? HALF : p.ksteps_half;
+          auto slab = [&](int i) {
             ptx::mbar_wait(full_bar(stage), phase);
             ptx::tc_fence_after();
             const uint64_t adesc = adesc0 + (uint64_t)(stage * (A_SLAB >> 4));
@@ -192,20 +197,26 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
 #pragma unroll
               for (int j = 0; j < BK / 16; ++j) {
                 const int g = i * (BK / 16) + j;  // K16 step inside [hi | lo]
-                if (g < half) {  // basis_hi x (feat_hi + feat_lo)
+                if (g < khalf) {  // basis_hi x (feat_hi + feat_lo)
                   ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g), IDESC, g != 0 ? 1u : 0u);
-                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(half + g), IDESC, 1u);
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(khalf + g), IDESC, 1u);
                 } else {         // basis_lo x feat_hi
-                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g - half), IDESC, 1u);
+                  ptx::mma_f16_ss(taddr, adesc + 2 * j, bdesc(g - khalf), IDESC, 1u);
                 }
               }
               ptx::mma_commit(empty_bar(stage));
-              if (c == 2 && i == p.n_slabs - 1) {
+              if (c == 2 && i == n_slabs - 1) {
                 ptx::mma_commit(tfull_bar(buf));
                 if (vt == p.n_vt - 1) ptx::mma_commit(bempty_bar);
               }
             }
             if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+          };
+          if (NSLABS) {
+#pragma unroll
+            for (int i = 0; i < NSLABS; ++i) slab(i);
+          } else {
+            for (int i = 0; i < n_slabs; ++i) slab(i);
           }
         }
         tph ^= 1u << buf;
@@ -990,13 +1001,13 @@ int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   p.stages = stages;
   const size_t smem = fixed + (size_t)stages * ltc::A_SLAB;
   const int grid = p.n_groups < h->sm_count ? p.n_groups : h->sm_count;
-  if (np == 128) {
-    DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_blend_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ltc::lbs_blend_tc_kernel<128><<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat);
-  } else {
-    DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_blend_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ltc::lbs_blend_tc_kernel<64><<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat);
-  }
+  // instantiations with compile-time K geometry for the two body models, run-time geometry otherwise
+  void (*kern)(ltc::KParams, CUtensorMap, CUtensorMap) = nullptr;
+  if (np == 128) kern = (K2 == 448) ? ltc::lbs_blend_tc_kernel<128, 14, 7> : ltc::lbs_blend_tc_kernel<128>;
+  else kern = (K2 == 1024) ? ltc::lbs_blend_tc_kernel<64, 32, 16>
+            : (K2 == 448) ? ltc::lbs_blend_tc_kernel<64, 14, 7> : ltc::lbs_blend_tc_kernel<64>;
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }
