@@ -547,13 +547,14 @@ __global__ void lbs_skinop_kernel(const float* __restrict__ A, const float* __re
 //   warp 0  TMA: blend operand (per unit), basis slabs (ring);  warp 3  TMA: skin weights (per tile), transform chunks
 //   warp 1  MMA issuer;  warp 2  TMEM allocator;  warps 4-11 epilogue (warp set h = (warp - 4) >> 2)
 // HBM traffic is the output only (5.4 GB for 65 536 SMPL poses instead of 16.4 GB through the two-kernel path).
-constexpr int FU_NP = 96;                  // poses per group: D_x | D_y | D_z take 288 TMEM columns, three 64-column
-                                           // T buffers the rest; the group's blend operand (84 KB) leaves room for a
-                                           // 6-stage basis ring (the blend phase is bound by slab ingest, not by MMAs)
+constexpr int FU_NP = 128;                 // poses per group: D_x | D_y | D_z take 384 TMEM columns, two 64-column T
+                                           // buffers the rest.  Measured: 96 poses / three T buffers / 6-stage ring 3.44 ms,
+                                           // 128 poses / two T buffers / 4-stage ring 3.30 ms (an M = 128 MMA costs about
+                                           // 32 + N/4 cycles of operand fetch, so the blend is cheapest per pose at N = 128)
 constexpr int FU_CP = 5;                   // poses per skinning chunk (N = 60 -> 64)
-constexpr int FU_NCHUNK = (FU_NP + FU_CP - 1) / FU_CP;   // 20 (even: chunk parity = warp set across tiles)
-constexpr int FU_NT = 3;                   // T buffers (ring over chunks)
-constexpr int FU_ASTAGES = 6;
+constexpr int FU_NCHUNK = (FU_NP + FU_CP - 1) / FU_CP;   // 26 (even: chunk parity = warp set across tiles)
+constexpr int FU_NT = 2;                   // T buffers (ring over chunks)
+constexpr int FU_ASTAGES = 4;
 constexpr int FU_SSTAGES = 3;
 constexpr int FU_S_BYTES = 64 * BK * 2;    // one transform chunk: 64 rows x 64 k fp16
 constexpr int FU_B_SLAB = FU_NP * BK * 2;
@@ -948,7 +949,7 @@ int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   p.V = h->V;
   p.V_pad = h->n_cols_pad;
   p.n_vt = h->n_cols_pad / ltc::TILE_V;
-  p.vsplit = 3;
+  p.vsplit = 2;
   p.ksteps_half = Kp / 16;
   p.n_slabs = K2 / ltc::BK;
   p.jsteps = Jp / 16;
