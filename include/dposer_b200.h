@@ -15,7 +15,9 @@
  *     scratch comes from the caller through (ws, ws_bytes), sized by the *_workspace_bytes query.
  *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*;
  *     torch.cuda.current_stream().cuda_stream); no entry point synchronises the host.
- *   - handles are immutable after creation and may be used from any host thread.
+ *   - model tensors in a handle are immutable after creation and a handle may be used from any host thread;
+ *     a score handle also owns the tensor-core engine's per-SM activation scratch, so calls on ONE score
+ *     handle must be ordered (same stream, or serialised by events) -- use one handle per concurrent stream.
  *   - there is no CPU fallback: on a machine without a B200-class GPU every compute entry
  *     point fails with DPB_ECUDA.
  */
