@@ -166,3 +166,20 @@ def test_lbs_backward_with_an_unused_output(which):
         ref, got = leaf[k].grad, dl[k].grad.cpu()
         scale = ref.abs().max().clamp_min(1e-6)
         assert (got - ref).abs().max() / scale < 2e-4, k
+
+
+def test_lbs_fused_kernel_group_boundary_without_translation():
+    """tcgen05 engine (fused blend + skinning kernel for SMPL) at a pose count one past a 128-pose group and with no
+    translation: the spare joint slot that carries transl must then contribute nothing."""
+    m = synthetic.make_body_tensors('smpl')
+    B = 129
+    inp = synthetic.lbs_inputs(B, 'smpl', seed=13)
+    inp.pop('trans')
+    pose, shape = synthetic.full_pose_from(inp, 'smpl')
+    v_ref, j_ref = lbs_ref.body_forward(m, shape, pose, None)
+    bm = BodyModel(m, num_betas=10, batch_size=B, model_type='smpl').cuda()
+    bm.core.engine = 2
+    with torch.no_grad():
+        out = bm(**{k: v.cuda() for k, v in inp.items()})
+    assert (out.v.cpu() - v_ref).abs().max() < TOL_M
+    assert (out.Jtr.cpu() - j_ref).abs().max() < TOL_M
