@@ -58,11 +58,25 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
     const float* __restrict__ j_template, const float* __restrict__ j_shapedirs,
     const int32_t* __restrict__ parents, const int32_t* __restrict__ depth, int J, int S, int max_depth,
     float* __restrict__ A_out, float* __restrict__ G_out, float* __restrict__ feat_out,
-    float* __restrict__ jrest_out, float* __restrict__ joints_out, int n_out, int64_t B) {
+    float* __restrict__ jrest_out, float* __restrict__ joints_out, int n_out, int64_t B,
+    __half* __restrict__ featop, int Kp, __half* __restrict__ skinop, int Jp) {
+  // featop / skinop (optional): the tcgen05 engine's fp16 [hi | lo] operands, written here instead of by two more
+  // passes over feat and A (lbs_tc.cu: lbs_featop_kernel / lbs_skinop_kernel define the layout)
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= B) return;  // warp-uniform
   const int P = (J - 1) * 9;
+  auto put_split = [](__half* row, int k, int half_width, float x) {
+    const __half hi = __float2half_rn(x);
+    row[k] = hi;
+    row[half_width + k] = __float2half_rn(x - __half2float(hi));
+  };
+  if (featop) {   // [beta | feat | 0] of this pose; the feat part is written with the rotations below
+    __half* frow = featop + (size_t)b * 2 * Kp;
+    for (int k = lane; k < Kp; k += 32)
+      if (k < S) put_split(frow, k, Kp, betas[b * S + k]);
+      else if (k >= S + P) put_split(frow, k, Kp, 0.f);
+  }
   float M[SLOTS][12], G[SLOTS][12], jr[SLOTS][3];
   int par[SLOTS], dep[SLOTS];
 #pragma unroll
@@ -88,7 +102,11 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
       if (j > 0) {
 #pragma unroll
         for (int e = 0; e < 9; ++e)
-          feat_out[b * P + (j - 1) * 9 + e] = M[s][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+        {
+          const float f = M[s][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+          feat_out[b * P + (j - 1) * 9 + e] = f;
+          if (featop) put_split(featop + (size_t)b * 2 * Kp, S + (j - 1) * 9 + e, Kp, f);
+        }
       }
     }
   }
@@ -136,6 +154,12 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int j = lane + 32 * s;
+    if (skinop && j >= J && j < Jp) {   // the spare joint slot J carries the translation (weight 1), the rest is padding
+      const float t3[3] = {tx, ty, tz};
+#pragma unroll
+      for (int e = 0; e < 12; ++e)
+        put_split(skinop + ((size_t)b * 12 + e) * 2 * Jp, j, Jp, (j == J && e >= 9) ? t3[e - 9] : 0.f);
+    }
     if (j >= J) continue;
     float* Ao = A_out + (b * J + j) * 12;
     float* Go = G_out + (b * J + j) * 12;
@@ -146,6 +170,10 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       Ao[9 + i] = G[s][9 + i] - (G[s][i * 3 + 0] * jr[s][0] + G[s][i * 3 + 1] * jr[s][1] + G[s][i * 3 + 2] * jr[s][2]);
+    if (skinop) {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) put_split(skinop + ((size_t)b * 12 + e) * 2 * Jp, j, Jp, Ao[e]);
+    }
     float* jo = joints_out + (b * n_out + j) * 3;
     jo[0] = G[s][9] + tx;
     jo[1] = G[s][10] + ty;
@@ -473,29 +501,41 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
   const bool compact = (verts == nullptr);
   LbsWs w;
   if (!lbs_carve(h, B, compact, ws, ws_bytes, &w)) return fail(DPB_ENOMEM, "dpb_lbs_forward: workspace too small");
+  const int engine = flags & DPB_ENGINE_MASK;
+  const int n_verts = compact ? h->n_need : h->V;
+  float* vout = compact ? w.compact : verts;
+  const bool use_tc = n_verts > 0 && !compact && h->tc_ready && w.featop &&
+                      (engine == DPB_LBS_ENGINE_TC || (engine == DPB_ENGINE_AUTO && B >= 64));
+  static const bool fused_off = getenv("DPB_LBS_FUSED") && atoi(getenv("DPB_LBS_FUSED")) == 0;   // A/B timing only
+  const bool use_fused = use_tc && !fused_off && w.skinop && lbs_tc_fused_fits(h);
+  // the fused kernel's operands come straight out of the pose kernel (pad rows of the last pose group are zeroed)
+  __half* fop = use_fused ? w.featop : nullptr;
+  __half* sop = use_fused ? w.skinop : nullptr;
+  if (use_fused) {
+    const int64_t B_pad = (B + 127) / 128 * 128;
+    if (B_pad > B) {
+      DPB_CUDA_CHECK(cudaMemsetAsync(w.featop + (size_t)B * h->kext, 0, (size_t)(B_pad - B) * h->kext * sizeof(__half), st));
+      DPB_CUDA_CHECK(cudaMemsetAsync(w.skinop + (size_t)B * 12 * 2 * h->jp, 0,
+                                     (size_t)(B_pad - B) * 12 * 2 * h->jp * sizeof(__half), st));
+    }
+  }
   const unsigned pose_grid = (unsigned)((B + 3) / 4);
   if (h->J > 32)
     lbs_pose_kernel<2><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirs, h->parents,
                                                    h->depth, h->J, h->S, h->max_depth, w.A, w.G, w.feat, w.jrest,
-                                                   joints, h->n_out, B);
+                                                   joints, h->n_out, B, fop, h->kext / 2, sop, h->jp);
   else
     lbs_pose_kernel<1><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirs, h->parents,
                                                    h->depth, h->J, h->S, h->max_depth, w.A, w.G, w.feat, w.jrest,
-                                                   joints, h->n_out, B);
+                                                   joints, h->n_out, B, fop, h->kext / 2, sop, h->jp);
   DPB_CUDA_CHECK(cudaGetLastError());
-  const int engine = flags & DPB_ENGINE_MASK;
-  const int n_verts = compact ? h->n_need : h->V;
-  float* vout = compact ? w.compact : verts;
   if (n_verts > 0) {
-    const bool use_tc = !compact && h->tc_ready && w.featop &&
-                        (engine == DPB_LBS_ENGINE_TC || (engine == DPB_ENGINE_AUTO && B >= 64));
     if (!compact && engine == DPB_LBS_ENGINE_TC && !use_tc)
       return fail(DPB_EUNSUPPORTED, "dpb_lbs_forward: tensor-core engine unavailable");
     if (use_tc) {
-      static const bool fused_off = getenv("DPB_LBS_FUSED") && atoi(getenv("DPB_LBS_FUSED")) == 0;   // A/B timing only
-      if (!fused_off && w.skinop && lbs_tc_fused_fits(h)) {
+      if (use_fused) {
         // blend + skinning in one tcgen05 kernel: the blended vertices stay in TMEM
-        int rc = lbs_tc_fused(h, betas, w.feat, w.featop, w.A, transl, w.skinop, verts, B, st);
+        int rc = lbs_tc_fused(h, nullptr, nullptr, w.featop, nullptr, nullptr, w.skinop, verts, B, st);
         if (rc != DPB_OK) return rc;
       } else {
       // blend on tcgen05 (writes v_posed into verts), then skin in place with the transforms from the pose kernel

@@ -933,7 +933,7 @@ int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* feat
                  __half* skinop, float* verts, int64_t B, cudaStream_t st) {
   const int K2 = h->kext, Kp = K2 / 2, Jp = h->jp;
   const int64_t B_pad = (B + ltc::PAD_POSES - 1) / ltc::PAD_POSES * ltc::PAD_POSES;
-  {
+  if (feat && A) {   // operands not already written by the pose kernel
     const int64_t n = B_pad * Kp;
     ltc::lbs_featop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(betas, feat, h->S, h->P, Kp, featop, B, B_pad);
     const int64_t n2 = B_pad * 12 * Jp;
