@@ -149,7 +149,7 @@ def test_fused_body_fitting_loss_vs_oracle(per_problem):
                                                       lambda *_: prior_scalar.cuda(), 0, per_problem=per_problem),
                   'cuda')
     got.backward()
-    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert abs(float(got.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
     for a, b_ in zip(lg, lr):
         scale = b_.grad.abs().max().clamp_min(1e-12)
         assert float((a.grad.cpu() - b_.grad).abs().max() / scale) < 1e-5
