@@ -1,6 +1,6 @@
 """GPU diagnostic: error of both engines vs the oracle per t / batch (run under gpurun)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import torch
 from dposer_b200 import _lib as L, synthetic, sde_lib, utils as mutils
 from oracle import score_ref as S
