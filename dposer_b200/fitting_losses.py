@@ -3,7 +3,8 @@
 On CUDA tensors ``body_fitting_loss`` runs as one fused kernel (``dpb_fit_loss``: projection, GMoF, angle and shape
 priors, loss and cotangents in a single pass) wrapped in an autograd.Function, so autograd still reaches the LBS
 kernel's backward (``dpb_lbs_backward``) and the prior kernel's closed-form gradient.  The torch-op versions of the
-reference's helpers are kept for host tensors, the camera loss and ``output='reprojection'``.  ``per_problem=True``
+reference's helpers serve the camera loss (8 torso joints) and ``output='reprojection'`` on device tensors; host
+tensors are refused like everywhere else in the package (no CPU fallback).  ``per_problem=True``
 reproduces the reference's B=1 normalisation for a batch of independent images (SURVEY App. B-6,B-10)."""
 import torch
 
@@ -75,6 +76,7 @@ def body_fitting_loss(body_pose, betas, model_joints, camera_t, camera_center, j
     to the per-sample vector (:79,90).  With per_problem=True the result is the SUM of per-image losses (each
     image normalised as a batch of one), i.e. B independent reference problems solved at once."""
     batch_size = body_pose.shape[0]
+    L.require_cuda(model_joints, 'model_joints')   # no CPU fallback: the joints come from the LBS kernels
     if _fused_ok(model_joints, camera_center, output, verbose):
         per_sample = _FitLossFn.apply(model_joints, body_pose, betas, joints_2d, joints_conf, camera_center,
                                       focal_length, sigma, angle_prior_weight, shape_prior_weight)
@@ -103,6 +105,7 @@ def camera_fitting_loss(model_joints, camera_t, camera_t_est, camera_center, joi
                         focal_length=5000, depth_loss_weight=100):
     """fitting_losses.py:106-136."""
     batch_size = model_joints.shape[0]
+    L.require_cuda(model_joints, 'model_joints')
     rotation = torch.eye(3, device=model_joints.device).unsqueeze(0).expand(batch_size, -1, -1)
     projected = perspective_projection(model_joints, rotation, camera_t, focal_length, camera_center)
     err_op = (joints_2d[:, OP_TORSO] - projected[:, OP_TORSO]) ** 2
