@@ -183,3 +183,27 @@ def test_lbs_fused_kernel_group_boundary_without_translation():
         out = bm(**{k: v.cuda() for k, v in inp.items()})
     assert (out.v.cpu() - v_ref).abs().max() < TOL_M
     assert (out.Jtr.cpu() - j_ref).abs().max() < TOL_M
+
+
+def test_lbs_backward_split_path_across_tile_boundaries():
+    """Vertex cotangents at a batch that crosses the split backward's tiles (8-pose skinning groups, 64-row GEMM tiles,
+    128-pose operand padding): gradients must still match autograd through the oracle."""
+    mt, B = 'smpl', 70
+    m = synthetic.make_body_tensors(mt)
+    inp = synthetic.lbs_inputs(B, mt, seed=29)
+    g = torch.Generator().manual_seed(31)
+    V = m['v_template'].shape[0]
+    gv = torch.randn(B, V, 3, generator=g) / V
+    gj = torch.randn(B, 45, 3, generator=g)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    pose = torch.cat([leaf['root_orient'], leaf['pose_body']], 1)
+    v_ref, j_ref = lbs_ref.body_forward(m, leaf['betas'], pose, leaf['trans'])
+    ((v_ref * gv).sum() + (j_ref * gj).sum()).backward()
+    bm = BodyModel(m, num_betas=10, batch_size=B, model_type=mt).cuda()
+    dl = {k: v.clone().cuda().requires_grad_(True) for k, v in inp.items()}
+    out = bm(**dl)
+    ((out.v * gv.cuda()).sum() + (out.Jtr * gj.cuda()).sum()).backward()
+    for k in inp:
+        ref, got = leaf[k].grad, dl[k].grad.cpu()
+        scale = ref.abs().max().clamp_min(1e-6)
+        assert (got - ref).abs().max() / scale < 2e-4, k
