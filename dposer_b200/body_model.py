@@ -207,6 +207,9 @@ def load_body_tensors(path, model_type, num_betas=10, num_expressions=10):
         faces = np.asarray(d['f'], np.int64)
         out['lmk_faces'] = torch.tensor(faces[np.asarray(d['lmk_faces_idx'], np.int64)].astype(np.int32))
         out['lmk_bary'] = torch.tensor(np.asarray(d['lmk_bary_coords'], np.float32))
+    if 'hands_meanl' in d and 'hands_meanr' in d:
+        out['hands_mean'] = torch.tensor(np.concatenate([np.asarray(d['hands_meanl'], np.float32).reshape(-1),
+                                                         np.asarray(d['hands_meanr'], np.float32).reshape(-1)]))
     return out
 
 
@@ -311,10 +314,12 @@ SMPLOutput = Struct
 
 class SMPLX(nn.Module):
     """lib/body_model/smpl.py:49-78: SMPL-X layer whose joints are re-indexed to the 49 SMPLify joints.
-    Hands stay at a constant pose (smplx default use_pca / flat_hand_mean=False -> constant mean hand pose,
-    passed here as ``hand_mean`` [90] or zeros), jaw / eyes / expression are zero."""
+    The reference constructs ``smplx.SMPLX(model_path, **kw)`` with the smplx defaults (use_pca=True with zero PCA
+    coefficients, flat_hand_mean=False), so ``full_pose`` = cat(orient, body, jaw, eyes, hands) + pose_mean carries the
+    model file's constant NON-ZERO mean hand pose (``hands_meanl`` | ``hands_meanr``); jaw / eyes / expression are
+    zero.  ``hand_mean`` [90] overrides it; ``flat_hand_mean=True`` gives zeros (what ``BodyModel`` uses)."""
 
-    def __init__(self, model_path, batch_size=1, hand_mean=None, **kwargs):
+    def __init__(self, model_path, batch_size=1, hand_mean=None, flat_hand_mean=False, **kwargs):
         super().__init__()
         tensors = model_path if isinstance(model_path, dict) else load_body_tensors(model_path, 'smplx')
         self.core = LbsCore(tensors)
@@ -324,7 +329,10 @@ class SMPLX(nn.Module):
         self.register_buffer('mean_poses', rot6d_to_axis_angle(torch.tensor(mean['pose'], dtype=torch.float32))
                              .reshape(-1))                                        # [72]
         self.register_buffer('mean_shape', torch.tensor(mean['shape'], dtype=torch.float32))
-        self.register_buffer('hand_mean', torch.zeros(90) if hand_mean is None else hand_mean.float())
+        if hand_mean is None:
+            hm = tensors.get('hands_mean')
+            hand_mean = torch.zeros(90) if (flat_hand_mean or hm is None) else torch.as_tensor(hm)
+        self.register_buffer('hand_mean', hand_mean.detach().float().reshape(90).clone())
         faces = tensors.get('faces')
         self.faces = None if faces is None else faces.numpy()
         self.joint_map = torch.tensor(JOINT_MAP_49, dtype=torch.long)

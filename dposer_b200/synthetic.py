@@ -89,6 +89,10 @@ def make_body_tensors(model_type='smpl', seed=None, nnz=4, reg_nnz=32):
     if model_type == 'smplx':
         out['lmk_faces'] = torch.randint(0, V, (51, 3), generator=g).to(torch.int32)
         out['lmk_bary'] = dirichlet(51, 3)
+        # smplx model files carry hands_meanl / hands_meanr (45 each); lib/body_model/smpl.py's SMPLX runs with the
+        # smplx defaults (flat_hand_mean=False) so this constant NON-ZERO hand pose is part of every forward.
+        # Separate generator: the tensors above stay bit-identical to the round-1 recipe.
+        out['hands_mean'] = 0.2 * torch.randn(90, generator=torch.Generator().manual_seed(seed + 1000))
     return out
 
 

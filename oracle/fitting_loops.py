@@ -1,7 +1,14 @@
-"""Oracle: CPU restatement of the two fitting loops (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
+"""Oracle: CPU restatement of the three task loops (TEST INFRASTRUCTURE ONLY, see oracle/__init__.py).
 
-  motion_denoise  run/motion_denoising.py:199-300 (one or several independent sequences)
-  smplify         run/smplify.py:168-281          (per-image normalisation, B independent images)
+  completion_optimize  run/completion.py:167-207       (DPoserComp.optimize)
+  motion_denoise       run/motion_denoising.py:199-300 (one or several independent sequences)
+  smplify              run/smplify.py:168-281          (per-image normalisation, B independent images)
+
+PINNED: tests/golden/make_golden_loops.py runs the REAL reference classes (run.completion.DPoserComp.optimize,
+run.motion_denoising.MotionDenoise.optimize, run.smplify.SMPLify.__call__, imported from /root/reference with
+the SURVEY Appendix C shims; body model = a BodyModel-compatible object over oracle/lbs_ref.py because smplx is
+absent) with the Gaussian draws replayed, asserts these functions reproduce them, and stores the fixtures in
+tests/golden/loops_golden.npz; tests/test_oracle_golden.py re-checks that on every CPU run.
 
 torch autograd differentiates the oracle LBS (oracle/lbs_ref.py); the prior term detaches x0_hat exactly as the
 reference does.  Every Gaussian draw is injected so the GPU path can be compared step for step.
@@ -28,6 +35,28 @@ def _smplx_pose(body_pose, global_orient=None, hand=None):
     go = torch.zeros(B, 3) if global_orient is None else global_orient
     hd = torch.zeros(B, 90) if hand is None else hand
     return torch.cat([go, body_pose, torch.zeros(B, 9), hd], dim=1)
+
+
+def completion_optimize(sd, observation, mask, z_list, sde_N=1000, lr=0.1, sample_trun=5.0, iterations=2,
+                        steps_per_iter=100):
+    """DPoserComp.optimize, time strategy '3' (run/completion.py:167-207).  The reference passes quan_t into the
+    `weighted` slot (:196, SURVEY B-3): the loss is weighted whenever quan_t != 0.  mean over B*63 (:147)."""
+    sde = score_ref.SubVP(0.1, 20., sde_N)
+    ts = torch.linspace(1.0, 1e-3, sde_N)
+    total = iterations * steps_per_iter
+    x = observation.clone().requires_grad_(True)
+    opt = torch.optim.Adam([x], lr, betas=(0.9, 0.999))
+    for it in range(iterations):
+        for i in range(steps_per_iter):
+            step = it * steps_per_iter + i
+            opt.zero_grad()
+            quan_t = sde_N - math.floor(torch.tensor(total - step - 1) * (sde_N / (sample_trun * total))) - 2
+            l_prior = _prior_term(sd, sde, x, ts[quan_t], z_list[step], bool(quan_t), float(x.numel()))
+            l_data = torch.mean((x * mask - observation * mask) ** 2)
+            tot = 100. * l_data / (1 + it) + 0.1 * l_prior * (it + 1)
+            tot.backward()
+            opt.step()
+    return (observation * mask + x * (1.0 - mask)).detach()
 
 
 def motion_denoise(sd, model, joints3d, init_pose, mean, std, z_list, seq_len, sde_N=500, iterations=1,
@@ -61,8 +90,10 @@ def motion_denoise(sd, model, joints3d, init_pose, mean, std, z_list, seq_len, s
 
 
 def smplify(sd, model, joint_map, init_pose, init_betas, init_cam_t, center, kp2d, mean, std, z_list, num_iters=2,
-            sde_N=500, focal=5000., step_size=1e-2, ign_joints=(1, 9, 12, 27, 28)):
-    """Returns (pose[B,66], betas, cam_t) after num_iters camera steps + 5*num_iters body steps."""
+            sde_N=500, focal=5000., step_size=1e-2, ign_joints=(1, 9, 12, 27, 28), hand_mean=None):
+    """Returns (pose[B,66], betas, cam_t) after num_iters camera steps + 5*num_iters body steps.
+    hand_mean [90]: the constant hand pose of lib/body_model/smpl.py's SMPLX (smplx defaults: flat_hand_mean=False)."""
+    hand = None if hand_mean is None else hand_mean[None].expand(init_pose.shape[0], -1)
     sde = score_ref.SubVP(0.1, 20., sde_N)
     ts = torch.linspace(1.0, 1e-3, sde_N)
     B = init_pose.shape[0]
@@ -74,7 +105,7 @@ def smplify(sd, model, joint_map, init_pose, init_betas, init_cam_t, center, kp2
 
     def joints(bt, bp, go, tr):
         shape = torch.cat([bt, torch.zeros(B, model['shapedirs'].shape[2] - bt.shape[1])], 1)
-        _, j = lbs_ref.body_forward(model, shape, _smplx_pose(bp, go), tr)
+        _, j = lbs_ref.body_forward(model, shape, _smplx_pose(bp, go, hand), tr)
         return j[:, joint_map]
     opt = torch.optim.Adam([glob, cam_t], lr=step_size, betas=(0.9, 0.999))
     for _ in range(num_iters):

@@ -12,6 +12,9 @@ batch_rigid_transform) and of ``SMPL.forward`` / ``SMPLX.forward`` / ``VertexJoi
 lib/body_model/body_model.py:68-112 and lib/body_model/smpl.py:67-78.  Weak pins available
 from the reference: 22-joint parents (lib/body_model/utils.py:180-205), 49-entry joint map
 (lib/body_model/smpl.py:53-65), SMPL-X vertex count 10475 (smplx_vert_segmentation.json).
+Second opinion: oracle/lbs_np64.py is an independent float64 formulation (no homogeneous matrices); the CPU suite
+checks that the two agree to fp32 round-off and that both satisfy the zero-pose / rigid-root / translation /
+single-joint invariants (tests/test_oracle_golden.py).
 """
 import torch
 

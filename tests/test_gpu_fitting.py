@@ -5,7 +5,7 @@ import types
 import pytest
 import torch
 
-from conftest import rel_err
+from conftest import golden, rel_err
 from dposer_b200 import _lib as L
 from dposer_b200 import fitting, prior, sde_lib, synthetic
 from dposer_b200.body_model import BodyModel, SMPLX
@@ -111,6 +111,65 @@ def test_smplify_steps_vs_oracle(gpu_model, oracle_sd):
     assert rel_err(betas.cpu() - init_betas, ref_betas - init_betas) < 5e-3
     assert rel_err(cam_t.cpu() - init_cam, ref_cam - init_cam) < 5e-3
     assert reproj.shape == (B, 49)
+
+
+@pytest.mark.parametrize('engine,tol', [(L.ENGINE_FP32, 2e-3), (L.ENGINE_TC, 5e-3)])
+def test_motion_denoise_vs_reference_golden(gpu_model, engine, tol):
+    """MotionDenoise.optimize against the REAL run/motion_denoising.py:199-300 (loops_golden.npz: two sequences,
+    2 x 3 Adam steps, the reference's own draws replayed; LBS = the restatement on both sides)."""
+    g = golden('loops_golden.npz')
+    t = lambda k: torch.tensor(g[k])         # noqa: E731
+    seq_len, n_seq, iters, spi = g['md_geom'].tolist()
+    rows = seq_len * n_seq
+    m = synthetic.make_body_tensors('smplx')
+    norm = Posenormalizer(None, device='cuda', normalize=True, min_max=False, rot_rep='axis')
+    bm = BodyModel(m, num_betas=10, batch_size=rows, model_type='smplx').cuda()
+    gpu_model.engine = engine
+    try:
+        md = fitting.MotionDenoise(synthetic.default_config(), types.SimpleNamespace(device='cuda'), gpu_model, bm,
+                                   sde_lib.subVPSDE(0.1, 20., 1000), norm, sde_N=500, batch_size=rows,
+                                   seq_len=seq_len)
+        md.poses = t('md_init').cuda()
+        _InjectZ(md, list(t('md_z')))
+        res = md.optimize(t('md_noisy').cuda(), gt_poses=t('md_gt').cuda(), time_strategy='3', sample_trun=4.0,
+                          iterations=iters, steps_per_iter=spi)
+    finally:
+        gpu_model.engine = L.ENGINE_AUTO
+    init = t('md_init')
+    assert rel_err(res['pose_body'].cpu() - init, t('md_smooth') - init) < tol
+    assert rel_err(res['MPJPE'], g['md_MPJPE']) < tol and rel_err(res['MPVPE'], g['md_MPVPE']) < tol
+    assert rel_err(res['init_MPJPE'], g['md_init_MPJPE']) < 1e-4
+
+
+@pytest.mark.parametrize('engine,tol', [(L.ENGINE_FP32, 2e-3), (L.ENGINE_TC, 5e-3)])
+def test_smplify_vs_reference_golden(gpu_model, engine, tol):
+    """SMPLify.__call__ against the REAL run/smplify.py:168-281 run image by image (B=1, as the reference requires):
+    2 camera + 10 body Adam steps, hands at the model's non-zero mean pose (smplx defaults)."""
+    g = golden('loops_golden.npz')
+    t = lambda k: torch.tensor(g[k])         # noqa: E731
+    (iters,) = g['sf_iters'].tolist()
+    m = synthetic.make_body_tensors('smplx')
+    B = g['sf_init_pose'].shape[0]
+    norm = Posenormalizer(None, device='cuda', normalize=True, min_max=False, rot_rep='axis')
+    smpl = SMPLX(m, batch_size=B).cuda()
+    args = types.SimpleNamespace(device='cuda', sde_N=500, time_strategy='3')
+    gpu_model.engine = engine
+    try:
+        pp = prior.DPoser(batch_size=B, args=args, model=gpu_model, sde=sde_lib.subVPSDE(0.1, 20., 1000),
+                          normalizer=norm)
+        _InjectZ(pp, list(t('sf_z')))
+        fit = fitting.SMPLify(smpl, step_size=1e-2, batch_size=B, num_iters=iters, focal_length=5000., args=args,
+                              pose_prior=pp)
+        kp2d = t('sf_kp2d').cuda()
+        pose, betas, cam_t, reproj = fit(t('sf_init_pose').cuda(), t('sf_init_betas').cuda(), t('sf_init_cam').cuda(),
+                                         t('sf_center').cuda(), kp2d)
+    finally:
+        gpu_model.engine = L.ENGINE_AUTO
+    assert float(kp2d[:, 9, 2].abs().max()) == 0.            # B-13: ignored joints zeroed in the caller's tensor
+    assert rel_err(pose.cpu() - t('sf_init_pose'), t('sf_pose') - t('sf_init_pose')) < tol
+    assert rel_err(betas.cpu() - t('sf_init_betas'), t('sf_betas') - t('sf_init_betas')) < tol
+    assert rel_err(cam_t.cpu() - t('sf_init_cam'), t('sf_cam') - t('sf_init_cam')) < tol
+    assert rel_err(reproj.cpu(), t('sf_reproj')) < tol
 
 
 @pytest.mark.parametrize('per_problem', [False, True])

@@ -1,5 +1,7 @@
 """CPU: the oracle must reproduce every golden vector produced by the REAL reference
 (tests/golden/make_golden.py).  This is what pins the oracle (prompt section 3)."""
+import os
+
 import numpy as np
 import torch
 
@@ -139,3 +141,110 @@ def test_lbs_oracle_invariants():
     expect = torch.einsum('bij,bvj->bvi', R, v_shaped - jrest[:, :1]) + jrest[:, :1]
     assert (v2 - expect).abs().max() < 2e-6
     assert j.shape == (B, 45, 3)
+
+
+def test_task_loops_match_reference(oracle_sd):
+    """oracle/fitting_loops.py against the REAL DPoserComp.optimize / MotionDenoise.optimize / SMPLify.__call__
+    (tests/golden/make_golden_loops.py; reference draws replayed)."""
+    from conftest import rel_err
+    from dposer_b200 import synthetic
+    from dposer_b200.body_model import JOINT_MAP_49
+    from oracle import fitting_loops
+    g = golden('loops_golden.npz')
+    t = lambda k: torch.tensor(g[k])         # noqa: E731
+    stats = np.load(os.path.join(os.path.dirname(synthetic.__file__), 'data', 'amass_stats.npz'))
+    mean, std = torch.tensor(stats['mean_poses']), torch.tensor(stats['std_poses'])
+    # completion
+    iters, spi = g['comp_iters'].tolist()
+    obs = t('comp_obs')
+    out = fitting_loops.completion_optimize(oracle_sd, obs, t('comp_mask'), list(t('comp_z')), iterations=iters,
+                                            steps_per_iter=spi)
+    assert rel_err(out - obs, t('comp_out') - obs) < 1e-5
+    # motion denoising: two sequences in one batch == two separate reference runs
+    m = synthetic.make_body_tensors('smplx')
+    seq_len, n_seq, iters, spi = g['md_geom'].tolist()
+    init = t('md_init')
+    pose = fitting_loops.motion_denoise(oracle_sd, m, t('md_noisy'), init, mean, std, list(t('md_z')), seq_len,
+                                        sde_N=500, iterations=iters, steps_per_iter=spi, sample_trun=4.0)
+    assert rel_err(pose - init, t('md_final') - init) < 2e-4
+    # SMPLify: three images in one batch == three B=1 reference runs; hands at the model's non-zero mean pose
+    (iters,) = g['sf_iters'].tolist()
+    ip, ib, ic = t('sf_init_pose'), t('sf_init_betas'), t('sf_init_cam')
+    pose, betas, cam = fitting_loops.smplify(oracle_sd, m, torch.tensor(JOINT_MAP_49), ip, ib, ic, t('sf_center'),
+                                             t('sf_kp2d'), mean, std, list(t('sf_z')), num_iters=iters, sde_N=500,
+                                             hand_mean=m['hands_mean'])
+    assert rel_err(pose - ip, t('sf_pose') - ip) < 2e-4
+    assert rel_err(betas - ib, t('sf_betas') - ib) < 2e-4
+    assert rel_err(cam - ic, t('sf_cam') - ic) < 2e-4
+    # the hand pose matters: with flat hands the same loop lands elsewhere (guards the SMPLX default semantics)
+    pose0, _, _ = fitting_loops.smplify(oracle_sd, m, torch.tensor(JOINT_MAP_49), ip, ib, ic, t('sf_center'),
+                                        t('sf_kp2d'), mean, std, list(t('sf_z')), num_iters=iters, sde_N=500)
+    assert rel_err(pose0 - ip, t('sf_pose') - ip) > 1e-3
+
+
+def test_lbs_two_independent_restatements_agree():
+    """LBS parity is unpinned (smplx absent).  The torch-fp32 restatement (smplx structure: 4x4 matrices) and an
+    independent float64 formulation (world rotations + posed joints, no homogeneous matrices) must agree to fp32
+    round-off on SMPL and SMPL-X with every input exercised (hands, jaw, eyes, expression, translation)."""
+    from dposer_b200 import synthetic
+    from oracle import lbs_np64, lbs_ref
+    for mt, tol in [('smpl', 2e-6), ('smplx', 2e-6)]:
+        m = synthetic.make_body_tensors(mt)
+        B = 4
+        g = torch.Generator().manual_seed(5)
+        J = m['J_regressor'].shape[0]
+        pose = 0.4 * torch.randn(B, J * 3, generator=g)
+        shape = torch.randn(B, m['shapedirs'].shape[2], generator=g)
+        tr = torch.randn(B, 3, generator=g)
+        v, j = lbs_ref.body_forward(m, shape, pose, tr)
+        v64, j64 = lbs_np64.body_forward(m, shape, pose, tr)
+        assert np.abs(v.numpy() - v64).max() < tol and np.abs(j.numpy() - j64).max() < tol
+        assert j.shape[1] == J + 21 + (51 if mt == 'smplx' else 0)
+        # invariants on BOTH: translation equivariance; a single non-root joint rotation leaves every vertex that
+        # has no weight on that joint's subtree untouched
+        v0, _ = lbs_np64.body_forward(m, shape, pose)
+        assert np.abs(v64 - (v0 + tr.numpy()[:, None])).max() < 1e-12
+        pose1 = torch.zeros(B, J * 3)
+        jj = 18                                                  # left elbow: subtree = {18, 20, (hand joints)}
+        pose1[:, jj * 3:jj * 3 + 3] = torch.randn(B, 3, generator=g)
+        parents = m['parents']
+        sub = {jj}
+        for k in range(jj + 1, J):
+            if parents[k] in sub:
+                sub.add(k)
+        untouched = (m['lbs_weights'][:, sorted(sub)].sum(1) == 0).numpy()
+        zero = torch.zeros(B, J * 3)
+        for fwd in (lambda p: lbs_ref.body_forward(m, shape, p)[0].numpy(),
+                    lambda p: lbs_np64.body_forward(m, shape, p)[0]):
+            a, b = fwd(pose1), fwd(zero)
+            # posedirs move every vertex by the (R-I) feature of joint jj: remove that linear term first
+            feat = (lbs_ref.batch_rodrigues(pose1[:, jj * 3:jj * 3 + 3]) - torch.eye(3)).reshape(B, 9).numpy()
+            off = (feat @ m['posedirs'][(jj - 1) * 9:jj * 9].numpy().astype(np.float64)).reshape(B, -1, 3)
+            assert np.abs((a - off)[:, untouched] - b[:, untouched]).max() < 2e-6
+            assert np.abs(a[:, ~untouched] - b[:, ~untouched]).max() > 1e-3
+
+
+def test_load_body_tensors_smplx_layout(tmp_path):
+    """load_body_tensors on a file written in the smplx .npz layout (posedirs [V,3,P], shapedirs with 300 shape +
+    expression components, kintree_table, f, weights, lmk_*, hands_mean*) gives back the tensors LbsCore expects."""
+    from dposer_b200 import synthetic
+    from dposer_b200.body_model import load_body_tensors
+    m = synthetic.make_body_tensors('smplx')
+    V, J = 10475, 55
+    sd = np.zeros((V, 3, 310), np.float32)
+    sd[:, :, :10] = m['shapedirs'][:, :, :10].numpy()
+    sd[:, :, 300:310] = m['shapedirs'][:, :, 10:].numpy()
+    faces = m['faces'].numpy()
+    lmk_idx = np.arange(51) * 7
+    faces[lmk_idx] = m['lmk_faces'].numpy()
+    kt = np.stack([np.array([2 ** 32 - 1] + m['parents'][1:], np.int64), np.arange(J)])
+    path = str(tmp_path / 'SMPLX_SYNTH.npz')
+    np.savez(path, v_template=m['v_template'].numpy(), shapedirs=sd,
+             posedirs=m['posedirs'].numpy().T.reshape(V, 3, -1), J_regressor=m['J_regressor'].numpy(),
+             weights=m['lbs_weights'].numpy(), kintree_table=kt, f=faces, lmk_faces_idx=lmk_idx,
+             lmk_bary_coords=m['lmk_bary'].numpy(), hands_meanl=m['hands_mean'][:45].numpy(),
+             hands_meanr=m['hands_mean'][45:].numpy())
+    t = load_body_tensors(path, 'smplx')
+    for k in ['v_template', 'shapedirs', 'posedirs', 'J_regressor', 'lbs_weights', 'lmk_bary', 'hands_mean']:
+        assert torch.equal(t[k], m[k]), k
+    assert t['parents'] == m['parents'] and torch.equal(t['lmk_faces'], m['lmk_faces'])
