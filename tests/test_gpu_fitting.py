@@ -79,8 +79,9 @@ def test_smplify_steps_vs_oracle(gpu_model, oracle_sd):
     cam = torch.stack([0.2 * torch.randn(B, generator=g), 0.2 * torch.randn(B, generator=g),
                        20 + 20 * torch.rand(B, generator=g)], 1)
     betas_gt = torch.randn(B, 10, generator=g)
+    hm = m['hands_mean'][None].expand(B, -1)        # SMPLX runs with the model's constant mean hand pose
     _, j = lbs_ref.body_forward(m, torch.cat([betas_gt, torch.zeros(B, 10)], 1),
-                                torch.cat([gt_glob, gt_body, torch.zeros(B, 99)], 1), cam)
+                                torch.cat([gt_glob, gt_body, torch.zeros(B, 9), hm], 1), cam)
     j = j[:, jm]
     center = torch.full((B, 2), 512.)
     from oracle import fitting_ref as Fr
@@ -94,7 +95,7 @@ def test_smplify_steps_vs_oracle(gpu_model, oracle_sd):
     z_list = [torch.randn(B, 63, generator=g) for _ in range(5 * iters + 1)]
     ref_pose, ref_betas, ref_cam = fitting_loops.smplify(oracle_sd, m, jm, init_pose, init_betas, init_cam, center,
                                                          kp2d.clone(), norm.mean_poses.cpu(), norm.std_poses.cpu(),
-                                                         z_list, num_iters=iters, sde_N=500)
+                                                         z_list, num_iters=iters, sde_N=500, hand_mean=m['hands_mean'])
     args = types.SimpleNamespace(device='cuda', sde_N=500, time_strategy='3')
     gpu_model.engine = L.ENGINE_FP32
     try:

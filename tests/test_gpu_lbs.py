@@ -92,7 +92,8 @@ def test_smplify_wrapper_joints():
     smpl = SMPLX(m, batch_size=B).cuda()
     with torch.no_grad():
         out = smpl(betas=betas.cuda(), body_pose=body.cuda(), global_orient=glob.cuda(), transl=transl.cuda())
-    full = torch.cat([glob, body, torch.zeros(B, 99)], 1)
+    # smplx defaults in lib/body_model/smpl.py: hands at the model's constant NON-ZERO mean pose
+    full = torch.cat([glob, body, torch.zeros(B, 9), m['hands_mean'][None].expand(B, -1)], 1)
     _, j_ref = lbs_ref.body_forward(m, torch.cat([betas, torch.zeros(B, 10)], 1), full, transl)
     assert out.joints.shape == (B, 49, 3)
     assert (out.joints.cpu() - j_ref[:, smpl.joint_map]).abs().max() < TOL_M
