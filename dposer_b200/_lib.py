@@ -88,7 +88,7 @@ def load():
     lib.dpb_lbs_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, vp, sz, vp, sz, vp]
     lib.dpb_lbs_backward_scratch_bytes.argtypes = [vp, i64]
     lib.dpb_lbs_backward_scratch_bytes.restype = sz
-    lib.dpb_fit_loss.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, f32, f32, f32, f32, vp, vp, vp,
+    lib.dpb_fit_loss.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, f32, f32, f32, f32, vp, vp, vp,
                                  vp, vp, i64, vp]
     lib.dpb_apd_partial.argtypes = [vp, i64, C.c_int, i64, i64, vp, vp]
     lib.dpb_mean_point_error.argtypes = [vp, vp, i64, C.c_int, vp, C.c_int, vp, vp]

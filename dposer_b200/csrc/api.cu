@@ -70,7 +70,7 @@ extern "C" int dpb_score_create(dpb_score_t** out, const dpb_score_weights* w, i
   int rc = dpb_device_info(device, &sm, &maj, &mnr);
   if (rc != DPB_OK) return rc;
   if (maj != 10) return fail(DPB_ECUDA, "dpb_score_create: device is not sm_100 (B200) class");
-  DPB_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard guard(device);
   dpb_score* h = new dpb_score();
   h->device = device;
   h->sm_count = sm;
@@ -113,7 +113,7 @@ extern "C" int dpb_score_create(dpb_score_t** out, const dpb_score_weights* w, i
 
 extern "C" int dpb_score_destroy(dpb_score_t* h) {
   if (!h) return DPB_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   tc_release(h);
   std::vector<void*> ptrs = {h->pre_w, h->post_w, h->post_b, h->temb_w, h->temb_b, h->emb_freqs, h->gn_packed};
   for (int i = 0; i < 4; ++i) ptrs.push_back(h->blk_w[i]);
@@ -128,6 +128,7 @@ extern "C" int dpb_score_destroy(dpb_score_t* h) {
 
 extern "C" int dpb_score_time_table(dpb_score_t* h, const float* labels, int n, float* table, void* stream) {
   if (!h || !labels || !table || n < 0) return fail(DPB_EINVAL, "dpb_score_time_table: bad argument");
+  DeviceGuard guard(h->device);
   return simt_time_table(h, labels, n, table, (cudaStream_t)stream);
 }
 
@@ -162,6 +163,7 @@ extern "C" int dpb_score_forward(dpb_score_t* h, const float* x, const float* ta
                                  const float* row_scale, float scale, float* out, int64_t B, int flags, void* ws,
                                  size_t ws_bytes, void* stream) {
   if (!h) return fail(DPB_EINVAL, "dpb_score_forward: null handle");
+  DeviceGuard guard(h->device);
   DPB_REQUIRE(x && table && out, "dpb_score_forward: x, table and out are required");
   if (B <= 0) return DPB_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -186,6 +188,7 @@ extern "C" int dpb_sampler_run(dpb_score_t* h, float* x_io, const dpb_step_table
                                float* traj, float* x_mean, int64_t B, int flags, void* ws, size_t ws_bytes,
                                void* stream) {
   if (!h || !tbl) return fail(DPB_EINVAL, "dpb_sampler_run: null handle or tables");
+  DeviceGuard guard(h->device);
   DPB_REQUIRE(x_io && tbl->coef && tbl->time_table && tbl->n_steps >= 0, "dpb_sampler_run: bad tables / x_io");
   const int impute = (flags & DPB_SAMPLER_IMPUTE) ? 1 : 0;
   const bool given = (flags & DPB_SAMPLER_NOISE_GIVEN) != 0;
@@ -227,6 +230,7 @@ extern "C" int dpb_prior_loss(dpb_score_t* h, const float* x0, const float* tabl
                               uint64_t step, float* loss_out, float* grad_out, float* row_loss, int64_t B, int flags,
                               void* ws, size_t ws_bytes, void* stream) {
   if (!h) return fail(DPB_EINVAL, "dpb_prior_loss: null handle");
+  DeviceGuard guard(h->device);
   DPB_REQUIRE(x0 && table && loss_out, "dpb_prior_loss: x0, table and loss_out are required");
   DPB_REQUIRE(divisor > 0.f && alpha > 0.f, "dpb_prior_loss: divisor and alpha must be positive");
   if (B <= 0) return DPB_OK;

@@ -28,6 +28,36 @@ int fail(int code, const std::string& msg);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Makes `device` current for the duration of an entry point and restores the caller's device afterwards
+// (torch tracks its own current device; the library must not change it behind torch's back).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+// device that owns a device pointer (entry points without a handle); -1 if it cannot be determined
+static inline int device_of(const void* p) {
+  cudaPointerAttributes a;
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return -1;
+  }
+  return a.device;
+}
+struct PtrDeviceGuard : DeviceGuard {
+  static int pick(const void* p) {
+    int d = device_of(p), cur = 0;
+    if (d < 0) { cudaGetDevice(&cur); return cur; }
+    return d;
+  }
+  explicit PtrDeviceGuard(const void* p) : DeviceGuard(pick(p)) {}
+};
+
 // carve sub-buffers out of the caller's workspace (256-byte aligned)
 struct WsCarver {
   char* base;

@@ -12,13 +12,14 @@ namespace dpb {
 __global__ void __launch_bounds__(256) fit_loss_kernel(
     const float* __restrict__ joints, const float* __restrict__ kp2d, const float* __restrict__ conf,
     const float* __restrict__ center, const float* __restrict__ pose, int pose_dim, const float* __restrict__ betas,
-    int n_betas, int K, float focal, float sigma, float w_angle, float w_shape, float* __restrict__ loss,
+    int n_betas, int K, const float* __restrict__ focal_b, float focal, float sigma, float w_angle, float w_shape, float* __restrict__ loss,
     float* __restrict__ reproj, float* __restrict__ g_joints, float* __restrict__ g_pose,
     float* __restrict__ g_betas, int64_t B) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
   const float cx = center[b * 2], cy = center[b * 2 + 1];
+  if (focal_b) focal = focal_b[b];   // K[:,0,0] = K[:,1,1] = focal_length accepts a per-image tensor (fitting_losses.py:24-26)
   const float s2 = sigma * sigma;
   float acc = 0.f;
   for (int k = lane; k < K; k += 32) {
@@ -74,14 +75,16 @@ using namespace dpb;
 
 extern "C" int dpb_fit_loss(const float* joints, const float* joints_2d, const float* conf, const float* center,
                             const float* body_pose, int pose_dim, const float* betas, int n_betas, int n_joints,
-                            float focal, float sigma, float w_angle, float w_shape, float* loss, float* reproj,
+                            const float* focal_b, float focal, float sigma, float w_angle, float w_shape, float* loss,
+                            float* reproj,
                             float* g_joints, float* g_pose, float* g_betas, int64_t B, void* stream) {
   DPB_REQUIRE(joints && joints_2d && conf && center && loss, "dpb_fit_loss: joints, joints_2d, conf, center, loss are required");
   DPB_REQUIRE(n_joints > 0 && pose_dim >= 0 && n_betas >= 0, "dpb_fit_loss: bad sizes");
   DPB_REQUIRE(!body_pose || pose_dim > 55, "dpb_fit_loss: the angle prior reads body_pose[:, 52] and [:, 55]");
   if (B <= 0) return DPB_OK;
+  PtrDeviceGuard guard(joints);
   fit_loss_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      joints, joints_2d, conf, center, body_pose, pose_dim, betas, n_betas, n_joints, focal, sigma, w_angle, w_shape,
+      joints, joints_2d, conf, center, body_pose, pose_dim, betas, n_betas, n_joints, focal_b, focal, sigma, w_angle, w_shape,
       loss, reproj, g_joints, g_pose, g_betas, B);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;

@@ -383,7 +383,7 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
     DPB_REQUIRE(m->extra_vids[i] >= 0 && m->extra_vids[i] < m->V, "dpb_lbs_create: extra vertex id out of range");
   for (int i = 0; i < m->n_lmk * 3; ++i)
     DPB_REQUIRE(m->lmk_faces[i] >= 0 && m->lmk_faces[i] < m->V, "dpb_lbs_create: landmark vertex id out of range");
-  DPB_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard guard(device);
   dpb_lbs* h = new dpb_lbs();
   h->device = device;
   cudaDeviceProp prop;
@@ -472,7 +472,7 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
 
 extern "C" int dpb_lbs_destroy(dpb_lbs_t* h) {
   if (!h) return DPB_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   lbs_tc_release(h);
   lbs_bwd_release(h);
   void* ptrs[] = {h->v_template, h->shapedirs, h->posedirs, h->j_template, h->j_shapedirs, h->parents, h->depth,
@@ -495,6 +495,7 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
                                float* verts, float* joints, int64_t B, int flags, void* ws, size_t ws_bytes,
                                void* stream) {
   if (!h) return fail(DPB_EINVAL, "dpb_lbs_forward: null handle");
+  DeviceGuard guard(h->device);
   DPB_REQUIRE(betas && full_pose && joints, "dpb_lbs_forward: betas, full_pose and joints are required");
   if (B <= 0) return DPB_OK;
   cudaStream_t st = (cudaStream_t)stream;

@@ -523,6 +523,7 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
                                 void* stream) {
   (void)flags;
   if (!h) return fail(DPB_EINVAL, "dpb_lbs_backward: null handle");
+  DeviceGuard guard(h->device);
   DPB_REQUIRE(betas && full_pose, "dpb_lbs_backward: betas and full_pose are required");
   DPB_REQUIRE(g_verts || g_joints, "dpb_lbs_backward: need g_verts and/or g_joints");
   if (B <= 0) return DPB_OK;

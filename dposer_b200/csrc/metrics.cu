@@ -4,28 +4,32 @@
 
 namespace dpb {
 
-// grid (ceil(B/128), nrows); block i handles row row0+blockIdx.y against 128 columns j
-__global__ void __launch_bounds__(128) apd_kernel(const float* __restrict__ joints, int64_t B, int nj, int64_t row0,
-                                                  float* __restrict__ out) {
+// One block per row i: threads stride over all columns j, block-reduce in a fixed order, one store per row.
+// No atomics: row_sums[i - row0] is deterministic, and the caller adds the rows in double precision (a single fp32
+// accumulator over B^2 pair distances loses digits for B well above 10^4).
+__global__ void __launch_bounds__(256) apd_kernel(const float* __restrict__ joints, int64_t B, int nj, int64_t row0,
+                                                  float* __restrict__ row_sums) {
   extern __shared__ float ji[];  // [nj*3] joints of row i
-  const int64_t i = row0 + blockIdx.y;
-  for (int k = threadIdx.x; k < nj * 3; k += 128) ji[k] = joints[i * nj * 3 + k];
+  const int64_t i = row0 + blockIdx.x;
+  for (int k = threadIdx.x; k < nj * 3; k += 256) ji[k] = joints[i * nj * 3 + k];
   __syncthreads();
-  const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  float d = 0.f;
-  if (j < B && j != i) {
+  float acc = 0.f;
+  for (int64_t j = threadIdx.x; j < B; j += 256) {
+    if (j == i) continue;
     const float* jj = joints + j * nj * 3;
+    float d = 0.f;
     for (int k = 0; k < nj; ++k) {
       float dx = ji[k * 3] - jj[k * 3], dy = ji[k * 3 + 1] - jj[k * 3 + 1], dz = ji[k * 3 + 2] - jj[k * 3 + 2];
       d += sqrtf(dx * dx + dy * dy + dz * dz);
     }
-    d /= (float)nj;
+    acc += d / (float)nj;
   }
-  for (int s = 16; s > 0; s >>= 1) d += __shfl_xor_sync(0xffffffffu, d, s);
-  __shared__ float part[4];
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = d;
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(out, (part[0] + part[1]) + (part[2] + part[3]));
+  if (threadIdx.x == 0)
+    row_sums[blockIdx.x] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
 }
 
 // one warp per sample
@@ -50,16 +54,14 @@ __global__ void __launch_bounds__(256) point_error_kernel(const float* __restric
 
 }  // namespace dpb
 
-extern "C" int dpb_apd_partial(const float* joints, int64_t B, int n_joints, int64_t row0, int64_t nrows, float* out,
-                               void* stream) {
-  if (!joints || !out || B <= 0 || n_joints <= 0 || row0 < 0 || nrows < 0 || row0 + nrows > B)
+extern "C" int dpb_apd_partial(const float* joints, int64_t B, int n_joints, int64_t row0, int64_t nrows,
+                               float* row_sums, void* stream) {
+  if (!joints || !row_sums || B <= 0 || n_joints <= 0 || row0 < 0 || nrows < 0 || row0 + nrows > B)
     return dpb::fail(DPB_EINVAL, "dpb_apd_partial: bad argument");
   if (nrows == 0) return DPB_OK;
-  for (int64_t r = 0; r < nrows; r += 65535) {
-    dim3 grid((unsigned)((B + 127) / 128), (unsigned)std::min<int64_t>(65535, nrows - r));
-    dpb::apd_kernel<<<grid, 128, n_joints * 3 * sizeof(float), (cudaStream_t)stream>>>(joints, B, n_joints, row0 + r,
-                                                                                      out);
-  }
+  dpb::PtrDeviceGuard guard(joints);
+  dpb::apd_kernel<<<(unsigned)nrows, 256, n_joints * 3 * sizeof(float), (cudaStream_t)stream>>>(joints, B, n_joints,
+                                                                                              row0, row_sums);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }
@@ -68,6 +70,7 @@ extern "C" int dpb_mean_point_error(const float* a, const float* c, int64_t B, i
                                     int n_idx, float* out, void* stream) {
   if (!a || !c || !out || B <= 0 || n_points <= 0 || (idx && n_idx <= 0))
     return dpb::fail(DPB_EINVAL, "dpb_mean_point_error: bad argument");
+  dpb::PtrDeviceGuard guard(a);
   dpb::point_error_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a, c, B, n_points, idx, n_idx,
                                                                                     out);
   DPB_CUDA_CHECK(cudaGetLastError());

@@ -257,6 +257,7 @@ int launch_prior_loss(const float* x0, const float* xt, const float* raw, float 
 // ------------------------------------------------------------------ C ABI (stateless helpers)
 extern "C" int dpb_langevin_norms(const float* grad, const float* noise, float* sums, int64_t B, void* stream) {
   if (!grad || !noise || !sums || B <= 0) return dpb::fail(DPB_EINVAL, "dpb_langevin_norms: bad argument");
+  dpb::PtrDeviceGuard guard(grad);
   dpb::langevin_norms_kernel<<<dpb::blocks_for(B, 8), 256, 0, (cudaStream_t)stream>>>(grad, noise, sums, B);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
@@ -265,6 +266,7 @@ extern "C" int dpb_langevin_norms(const float* grad, const float* noise, float* 
 extern "C" int dpb_langevin_update(float* x_io, float* x_mean, const float* grad, const float* noise,
                                    const float* sums, float snr, float alpha, int64_t B, void* stream) {
   if (!x_io || !grad || !noise || !sums || B <= 0) return dpb::fail(DPB_EINVAL, "dpb_langevin_update: bad argument");
+  dpb::PtrDeviceGuard guard(x_io);
   dpb::langevin_update_kernel<<<dpb::blocks_for(B * dpb::D, 256), 256, 0, (cudaStream_t)stream>>>(
       x_io, x_mean, grad, noise, sums, snr, alpha, B);
   DPB_CUDA_CHECK(cudaGetLastError());
@@ -273,6 +275,7 @@ extern "C" int dpb_langevin_update(float* x_io, float* x_mean, const float* grad
 
 extern "C" int dpb_normal_fill(float* out, int64_t B, uint64_t seed, uint64_t step, int slot, void* stream) {
   if (!out || B <= 0) return dpb::fail(DPB_EINVAL, "dpb_normal_fill: bad argument");
+  dpb::PtrDeviceGuard guard(out);
   dpb::normal_fill_kernel<<<dpb::blocks_for(B * 16, 256), 256, 0, (cudaStream_t)stream>>>(out, B, seed,
                                                                                          (uint32_t)step, (uint32_t)slot);
   DPB_CUDA_CHECK(cudaGetLastError());

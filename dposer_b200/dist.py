@@ -36,18 +36,29 @@ def my_shard(total, units=1):
     return s * units, n * units
 
 
-def all_gather_rows(local, total):
-    """Concatenate ragged row shards from all ranks in rank order -> [total, ...] on every rank."""
+def all_gather_rows(local, total, out=None):
+    """Concatenate ragged row shards from all ranks in rank order -> [total, ...] on every rank.
+
+    One ``all_gather_into_tensor`` on a preallocated [world, pad, ...] buffer (no Python list of per-rank tensors);
+    when the shards are equal (total % world == 0) the gathered buffer IS the result, otherwise the at-most-one-row
+    padding per rank is cut away.  ``out`` ([world*pad, ...]) may be passed to reuse the buffer across calls."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world = dist.get_world_size()
     counts = [shard_range(total, world, r)[1] for r in range(world)]
     pad = max(counts)
-    buf = local.new_zeros((pad,) + tuple(local.shape[1:]))
-    buf[:local.shape[0]] = local
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf)
-    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+    tail = tuple(local.shape[1:])
+    if out is None:
+        out = local.new_empty((world * pad,) + tail)
+    if local.shape[0] == pad:
+        src = local.contiguous()
+    else:
+        src = local.new_zeros((pad,) + tail)
+        src[:local.shape[0]] = local
+    dist.all_gather_into_tensor(out, src)
+    if total % world == 0:
+        return out
+    return torch.cat([out[r * pad:r * pad + c] for r, c in enumerate(counts)], dim=0)
 
 
 def all_reduce_sum(t):

@@ -52,8 +52,17 @@ class _FitLossFn(torch.autograd.Function):
         j, p, b_, kp, c, ce = f(joints), f(body_pose), f(betas), f(joints_2d), f(conf), f(center)
         loss = torch.empty(B, dtype=torch.float32, device=dev)
         gj, gp, gb = torch.empty_like(j), torch.empty_like(p), torch.empty_like(b_)
+        # focal: python number, or a [B] tensor of per-image focal lengths (run/fitting.py passes batch['focal_length'])
+        focal_b, focal_s = None, 0.0
+        if torch.is_tensor(focal) and focal.numel() > 1:
+            focal_b = focal.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            if focal_b.numel() != B:
+                raise ValueError(f'focal_length has {focal_b.numel()} entries for a batch of {B}')
+        else:
+            focal_s = float(focal)        # a 1-element tensor costs one device read here: pass a float in loops
         L.check(L.load().dpb_fit_loss(L.ptr(j), L.ptr(kp), L.ptr(c), L.ptr(ce), L.ptr(p), p.shape[1], L.ptr(b_),
-                                      b_.shape[1], K, float(focal), float(sigma), float(w_angle), float(w_shape),
+                                      b_.shape[1], K, L.ptr(focal_b), focal_s, float(sigma), float(w_angle),
+                                      float(w_shape),
                                       L.ptr(loss), None, L.ptr(gj), L.ptr(gp), L.ptr(gb), B, L.current_stream(dev)))
         ctx.save_for_backward(gj, gp, gb)
         return loss

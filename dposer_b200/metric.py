@@ -1,6 +1,6 @@
 """Metrics of the hot path as device reductions (reference lib/utils/metric.py:8-37 and
-lib/dataset/AMASS.py:263-324).  ``average_pairwise_distance`` shards its row block across
-ranks when a process group is initialised (result all-reduced), otherwise runs on one GPU."""
+lib/dataset/AMASS.py:263-324).  ``average_pairwise_distance`` runs on one GPU unless the caller opts into
+sharding with an explicit ``group=`` (then every rank of the group must call it)."""
 import numpy as np
 import torch
 
@@ -9,18 +9,25 @@ from .misc import BodyPartIndices, shard_range
 
 
 def average_pairwise_distance(joints3d, group=None):
-    """APD = mean over ordered pairs (i != j) of mean-over-joints L2 distance (metric.py:8-37)."""
-    import torch.distributed as dist
+    """APD = mean over ordered pairs (i != j) of mean-over-joints L2 distance (metric.py:8-37).
+
+    Single-process by default, like the reference (which calls it on one rank only).  Sharding is OPT-IN: pass
+    ``group=`` (a process group, or ``torch.distributed.group.WORLD``) and call it on EVERY rank of that group with
+    the same ``joints3d``; each rank then reduces its contiguous row block and the partial sums are all-reduced."""
     L.require_cuda(joints3d, 'joints3d')
     j = joints3d.detach().to(torch.float32).contiguous()
     B, nj = j.shape[0], j.shape[1]
-    out = torch.zeros(1, dtype=torch.float32, device=j.device)
-    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_initialized() else (1, 0)
+    world, rank = 1, 0
+    if group is not None:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
     row0, nrows = shard_range(B, world, rank)
-    L.check(L.load().dpb_apd_partial(L.ptr(j), B, nj, row0, nrows, L.ptr(out), L.current_stream(j.device)))
+    rows = torch.empty(max(nrows, 1), dtype=torch.float32, device=j.device)
+    L.check(L.load().dpb_apd_partial(L.ptr(j), B, nj, row0, nrows, L.ptr(rows), L.current_stream(j.device)))
+    out = rows[:nrows].double().sum().reshape(1)          # per-row fp32 sums, added in double
     if world > 1:
         dist.all_reduce(out, group=group)
-    return (out / (B * (B - 1)))[0]
+    return (out / (B * (B - 1)))[0].float()
 
 
 def mean_point_error_mm(a, b, idx=None):

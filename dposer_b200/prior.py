@@ -57,6 +57,11 @@ class _PriorBase:
         self._tables = {}
 
     def _table(self, t, label):
+        # the tables are built from the handle's weights: a weight reload / device move gives a new handle
+        # (ScoreModelFC.handle()), and every cached table is dropped with the old one
+        h = self.model.handle()
+        if getattr(self, '_tables_handle', None) is not h:
+            self._tables, self._tables_handle = {}, h
         key = float(t)
         tb = self._tables.get(key)
         if tb is None:

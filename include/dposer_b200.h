@@ -215,23 +215,26 @@ int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* full_pose, c
  * in one pass.  All pointers DEVICE fp32.
  *   joints [B,K,3] (camera translation already applied, as in the reference), joints_2d [B,K,2], conf [B,K],
  *   center [B,2], body_pose [B,pose_dim] or NULL (no angle prior), betas [B,n_betas] or NULL (no shape prior)
+ *   focal_b [B] per-image focal lengths or NULL (then the scalar `focal` is used for every image; the reference
+ *   assigns K[:,0,0] = focal_length, fitting_losses.py:24-26, so both a float and a [B] tensor are valid there)
  *   loss [B] = sum_k conf^2 GMoF(proj - kp) + w_angle^2 sum exp(+-pose[..])^2 + w_shape^2 sum betas^2
  *   reproj [B,K] or NULL (the per-joint reprojection term, output='reprojection')
  *   g_joints [B,K,3], g_pose [B,pose_dim], g_betas [B,n_betas]: d loss[b] / d input, each may be NULL
  * ---------------------------------------------------------------------------------------- */
 int dpb_fit_loss(const float* joints, const float* joints_2d, const float* conf, const float* center,
                  const float* body_pose, int pose_dim, const float* betas, int n_betas, int n_joints,
-                 float focal, float sigma, float w_angle, float w_shape, float* loss, float* reproj,
-                 float* g_joints, float* g_pose, float* g_betas, int64_t B, void* stream);
+                 const float* focal_b, float focal, float sigma, float w_angle, float w_shape, float* loss,
+                 float* reproj, float* g_joints, float* g_pose, float* g_betas, int64_t B, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Metrics (replaces average_pairwise_distance lib/utils/metric.py:8-37 and the per-sample
  * reductions of Evaler.eval_bodys lib/dataset/AMASS.py:275-298)
  * ---------------------------------------------------------------------------------------- */
-/* sum over i in [row0,row0+nrows), j in [0,B), j != i of mean_k ||joints[i,k]-joints[j,k]|| ;
- * out DEVICE fp32[1] is ACCUMULATED into (zero it first; divide by B(B-1) afterwards). */
+/* row_sums[i - row0] = sum over j in [0,B), j != i of mean_k ||joints[i,k]-joints[j,k]||  for i in [row0,row0+nrows).
+ * row_sums DEVICE fp32[nrows] (overwritten; no atomics, deterministic).  APD = sum(row_sums over all rows) / (B(B-1));
+ * the caller adds the rows in double precision. */
 int dpb_apd_partial(const float* joints, int64_t B, int n_joints, int64_t row0, int64_t nrows,
-                    float* out, void* stream);
+                    float* row_sums, void* stream);
 /* out[b] = 1000 * mean_{k in idx} ||a[b,idx[k]] - c[b,idx[k]]||  (idx DEVICE int32[n_idx] or NULL = all) */
 int dpb_mean_point_error(const float* a, const float* c, int64_t B, int n_points, const int32_t* idx,
                          int n_idx, float* out, void* stream);
