@@ -12,6 +12,7 @@ from . import build as _build
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TC = 0, 1, 2
 SAMPLER_IMPUTE, SAMPLER_NOISE_GIVEN = 1 << 4, 1 << 5
+LBS_CONST_TAIL = 1 << 4
 COEF_STRIDE = 8
 POSE_DIM, HIDDEN, EMBED, NUM_DENSE = 63, 1024, 512, 5
 
@@ -41,7 +42,7 @@ class BodyTensors(C.Structure):
 EXPORTS = ['dpb_version', 'dpb_last_error', 'dpb_device_info', 'dpb_score_create', 'dpb_score_destroy',
            'dpb_score_time_table', 'dpb_score_workspace_bytes', 'dpb_score_forward', 'dpb_sampler_run',
            'dpb_langevin_norms', 'dpb_langevin_update', 'dpb_normal_fill', 'dpb_prior_loss', 'dpb_lbs_create',
-           'dpb_lbs_destroy', 'dpb_lbs_num_joints_out', 'dpb_lbs_workspace_bytes', 'dpb_lbs_forward',
+           'dpb_lbs_destroy', 'dpb_lbs_set_const_tail', 'dpb_lbs_num_joints_out', 'dpb_lbs_workspace_bytes', 'dpb_lbs_forward',
            'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_apd_partial', 'dpb_mean_point_error', 'dpb_fit_loss']
 
 _lib = None
@@ -81,6 +82,7 @@ def load():
                                    vp, sz, vp]
     lib.dpb_lbs_create.argtypes = [C.POINTER(vp), C.POINTER(BodyTensors), C.c_int]
     lib.dpb_lbs_destroy.argtypes = [vp]
+    lib.dpb_lbs_set_const_tail.argtypes = [vp, C.c_int, _f32p]
     lib.dpb_lbs_num_joints_out.argtypes = [vp]
     lib.dpb_lbs_workspace_bytes.argtypes = [vp, i64, C.c_int]
     lib.dpb_lbs_workspace_bytes.restype = sz

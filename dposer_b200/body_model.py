@@ -60,7 +60,7 @@ class _LbsFn(torch.autograd.Function):
     extra joints / landmarks read (SMPLify only uses joints, run/smplify.py:243-256)."""
 
     @staticmethod
-    def forward(ctx, betas, full_pose, transl, core, need_verts):
+    def forward(ctx, betas, full_pose, transl, core, need_verts, const_tail=False):
         h = core.handle(betas.device)
         B = betas.shape[0]
         dev = betas.device
@@ -70,8 +70,9 @@ class _LbsFn(torch.autograd.Function):
         verts = torch.empty(B, core.V, 3, dtype=torch.float32, device=dev) if need_verts else None
         joints = torch.empty(B, core.n_out, 3, dtype=torch.float32, device=dev)
         ws = core.workspace(B, dev)
+        flags = core.engine | (L.LBS_CONST_TAIL if (const_tail and core.tail is not None) else 0)
         L.check(L.load().dpb_lbs_forward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(t), L.ptr(verts), L.ptr(joints), B,
-                                         core.engine, L.ptr(ws), ws.numel(), L.current_stream(dev)))
+                                         flags, L.ptr(ws), ws.numel(), L.current_stream(dev)))
         ctx.core, ctx.need_verts, ctx.has_transl = core, need_verts, transl is not None
         # an output the loss never touches arrives as None in backward (not as a [B,V,3] tensor of zeros): with no
         # vertex gradient the backward runs over the <=174 vertices the extra joints read instead of all of them
@@ -92,7 +93,7 @@ class _LbsFn(torch.autograd.Function):
         gv = g_verts.contiguous().float() if (ctx.need_verts and g_verts is not None) else None
         gj = g_joints.contiguous().float() if g_joints is not None else None
         if gv is None and gj is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         g_pose = torch.empty_like(p)
         g_betas = torch.empty_like(b)
         g_transl = torch.empty(B, 3, dtype=torch.float32, device=dev) if ctx.has_transl else None
@@ -105,7 +106,7 @@ class _LbsFn(torch.autograd.Function):
         L.check(L.load().dpb_lbs_backward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(gv), L.ptr(gj), L.ptr(g_pose),
                                           L.ptr(g_betas), L.ptr(g_transl), B, core.engine, L.ptr(ws), ws.numel(),
                                           L.ptr(scratch), n_scratch, L.current_stream(dev)))
-        return g_betas, g_pose, g_transl, None, None
+        return g_betas, g_pose, g_transl, None, None, None
 
 
 class LbsCore:
@@ -125,6 +126,22 @@ class LbsCore:
         self.engine = L.ENGINE_AUTO       # tcgen05 blend for batches >= 64, fp32 blend otherwise (ENGINE_FP32 forces exact)
         self._handles = {}
         self._ws = {}
+        self.tail = None                  # (n_var, [ (J-n_var)*3 ] axis-angle) declared with set_const_tail
+
+    def set_const_tail(self, n_var, tail_pose):
+        """Joints n_var..J-1 always carry ``tail_pose`` (hands / jaw / eyes at their default or mean pose): their
+        pose-blend features are constants, folded into the template by ``dpb_lbs_set_const_tail``; calls that pass
+        ``const_tail=True`` then run the blend with K = S + 9(n_var-1) instead of S + 9(J-1)."""
+        tail = torch.as_tensor(tail_pose, dtype=torch.float32).detach().cpu().reshape(-1).contiguous()
+        assert tail.numel() == (self.J - n_var) * 3
+        self.tail = (int(n_var), tail)
+        for h in self._handles.values():
+            self._declare_tail(h)
+
+    def _declare_tail(self, h):
+        n_var, tail = self.tail
+        a, p = L.host_f32(tail)
+        L.check(L.load().dpb_lbs_set_const_tail(h.ptr, n_var, p), 'dpb_lbs_set_const_tail')
 
     def handle(self, device):
         device = torch.device(device)
@@ -160,6 +177,8 @@ class LbsCore:
         L.check(L.load().dpb_lbs_create(C.byref(out), C.byref(m), key), 'dpb_lbs_create')
         h = _LbsHandle(out, device)
         self._handles[key] = h
+        if self.tail is not None:
+            self._declare_tail(h)
         return h
 
     def workspace(self, B, device):
@@ -174,8 +193,8 @@ class LbsCore:
             self._ws = {key: ws}
         return ws
 
-    def __call__(self, betas, full_pose, transl=None, need_verts=True):
-        return _LbsFn.apply(betas, full_pose, transl, self, need_verts)
+    def __call__(self, betas, full_pose, transl=None, need_verts=True, const_tail=False):
+        return _LbsFn.apply(betas, full_pose, transl, self, need_verts, const_tail)
 
 
 def load_body_tensors(path, model_type, num_betas=10, num_expressions=10):
@@ -239,6 +258,10 @@ class BodyModel(nn.Module):
         faces = tensors.get('faces')
         self.register_buffer('faces_tensor', faces if faces is not None else torch.zeros(0, 3, dtype=torch.long))
         self.register_buffer('_dev', torch.zeros(1))
+        if model_type in ('smplh', 'smplx'):
+            # hands / jaw / eyes default to zero parameters (smplx, flat_hand_mean=True): a constant tail after
+            # the 22 body joints whenever the caller omits them (every hot-path call of the reference does)
+            self.core.set_const_tail(22, torch.zeros((self.core.J - 22) * 3))
 
     def _default(self, val, width):
         """smplx creates zero nn.Parameters [batch_size, width] for omitted inputs."""
@@ -275,7 +298,8 @@ class BodyModel(nn.Module):
             expr = self._default(expression, self.num_expressions)
             shape = torch.cat([betas_, expr if expr.shape[0] == B else expr.expand(B, -1)], dim=1)
         # smplx applies transl when given OR when the default (zero) parameter exists -> identical result
-        verts, joints = self.core(shape, full_pose, trans, need_verts)
+        const_tail = pose_hand is None and pose_jaw is None and pose_eye is None
+        verts, joints = self.core(shape, full_pose, trans, need_verts, const_tail)
         out = {'v': verts if need_verts else None, 'f': self.faces_tensor, 'betas': betas_, 'Jtr': joints,
                'body_joints': joints[:22],           # reference slices the BATCH dim here (body_model.py:95)
                'pose_body': body_pose, 'full_pose': full_pose}
@@ -333,6 +357,8 @@ class SMPLX(nn.Module):
             hm = tensors.get('hands_mean')
             hand_mean = torch.zeros(90) if (flat_hand_mean or hm is None) else torch.as_tensor(hm)
         self.register_buffer('hand_mean', hand_mean.detach().float().reshape(90).clone())
+        # jaw / eyes zero and hands at the constant mean pose in EVERY call: fold their pose blend into the template
+        self.core.set_const_tail(22, torch.cat([torch.zeros(9), self.hand_mean.detach().cpu()]))
         faces = tensors.get('faces')
         self.faces = None if faces is None else faces.numpy()
         self.joint_map = torch.tensor(JOINT_MAP_49, dtype=torch.long)
@@ -348,7 +374,7 @@ class SMPLX(nn.Module):
         full_pose = torch.cat([global_orient, body_pose, z(9), self.hand_mean[None].expand(B, -1)], dim=1)
         S = self.core.S
         shape = torch.cat([betas, z(S - betas.shape[1])], dim=1) if S > betas.shape[1] else betas
-        verts, joints = self.core(shape, full_pose, transl, need_verts)
+        verts, joints = self.core(shape, full_pose, transl, need_verts, True)
         joints = joints[:, self.joint_map.to(dev), :]
         return SMPLOutput(vertices=verts if need_verts else None, global_orient=global_orient, body_pose=body_pose,
                           joints=joints, betas=betas, full_pose=full_pose)

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
     const int32_t* __restrict__ parents, const int32_t* __restrict__ depth, int J, int S, int max_depth,
     float* __restrict__ A_out, float* __restrict__ G_out, float* __restrict__ feat_out,
     float* __restrict__ jrest_out, float* __restrict__ joints_out, int n_out, int64_t B,
-    __half* __restrict__ featop, int Kp, __half* __restrict__ skinop, int Jp) {
+    __half* __restrict__ featop, int Kp, int p_feat, __half* __restrict__ skinop, int Jp) {
   // featop / skinop (optional): the tcgen05 engine's fp16 [hi | lo] operands, written here instead of by two more
   // passes over feat and A (lbs_tc.cu: lbs_featop_kernel / lbs_skinop_kernel define the layout)
   const int lane = threadIdx.x & 31;
@@ -71,11 +71,11 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
     row[k] = hi;
     row[half_width + k] = __float2half_rn(x - __half2float(hi));
   };
-  if (featop) {   // [beta | feat | 0] of this pose; the feat part is written with the rotations below
-    __half* frow = featop + (size_t)b * 2 * Kp;
+  if (featop) {   // [beta | feat (p_feat of them: the variant's varying joints) | 1 (template slot) | 0] of this pose;
+    __half* frow = featop + (size_t)b * 2 * Kp;   // the feat part is written with the rotations below
     for (int k = lane; k < Kp; k += 32)
       if (k < S) put_split(frow, k, Kp, betas[b * S + k]);
-      else if (k >= S + P) put_split(frow, k, Kp, 0.f);
+      else if (k >= S + p_feat) put_split(frow, k, Kp, k == S + p_feat ? 1.0f : 0.f);
   }
   float M[SLOTS][12], G[SLOTS][12], jr[SLOTS][3];
   int par[SLOTS], dep[SLOTS];
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
         {
           const float f = M[s][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
           feat_out[b * P + (j - 1) * 9 + e] = f;
-          if (featop) put_split(featop + (size_t)b * 2 * Kp, S + (j - 1) * 9 + e, Kp, f);
+          if (featop && (j - 1) * 9 + e < p_feat) put_split(featop + (size_t)b * 2 * Kp, S + (j - 1) * 9 + e, Kp, f);
         }
       }
     }
@@ -485,6 +485,13 @@ extern "C" int dpb_lbs_destroy(dpb_lbs_t* h) {
 
 extern "C" int dpb_lbs_num_joints_out(dpb_lbs_t* h) { return h ? h->n_out : DPB_EINVAL; }
 
+extern "C" int dpb_lbs_set_const_tail(dpb_lbs_t* h, int n_var, const float* tail_pose) {
+  if (!h) return fail(DPB_EINVAL, "dpb_lbs_set_const_tail: null handle");
+  DPB_REQUIRE(n_var >= 1 && n_var < h->J && tail_pose, "dpb_lbs_set_const_tail: need 1 <= n_var < J and a tail pose");
+  DeviceGuard guard(h->device);
+  return lbs_tc_make_tail(h, n_var, tail_pose);
+}
+
 extern "C" size_t dpb_lbs_workspace_bytes(dpb_lbs_t* h, int64_t B, int flags) {
   (void)flags;
   if (!h || B <= 0) return 0;
@@ -507,15 +514,20 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
   float* vout = compact ? w.compact : verts;
   const bool use_tc = n_verts > 0 && !compact && h->tc_ready && w.featop &&
                       (engine == DPB_LBS_ENGINE_TC || (engine == DPB_ENGINE_AUTO && B >= 64));
-  static const bool fused_off = getenv("DPB_LBS_FUSED") && atoi(getenv("DPB_LBS_FUSED")) == 0;   // A/B timing only
-  const bool use_fused = use_tc && !fused_off && w.skinop && lbs_tc_fused_fits(h);
+  const int fused_sel = getenv("DPB_LBS_FUSED") ? atoi(getenv("DPB_LBS_FUSED")) : 2;   // A/B timing only: 0 two kernels, 1 first fused kernel, 2 CTA-pair kernel
+  // const-tail calls (DPB_LBS_CONST_TAIL) read the pruned basis; everything else the full one
+  const bool want_tail = (flags & DPB_LBS_CONST_TAIL) != 0;
+  if (want_tail) DPB_REQUIRE(h->tailv.n_var > 0 || !h->tc_ready, "dpb_lbs_forward: DPB_LBS_CONST_TAIL without dpb_lbs_set_const_tail");
+  const LbsVariant var = (want_tail && h->tailv.dirs16) ? h->tailv : lbs_full_variant(h);
+  const bool use_fused2 = use_tc && fused_sel == 2 && w.skinop && lbs_fused2_fits(h, var);
+  const bool use_fused = use_fused2 || (use_tc && fused_sel != 0 && w.skinop && var.n_var == h->J && lbs_tc_fused_fits(h));
   // the fused kernel's operands come straight out of the pose kernel (pad rows of the last pose group are zeroed)
   __half* fop = use_fused ? w.featop : nullptr;
   __half* sop = use_fused ? w.skinop : nullptr;
   if (use_fused) {
     const int64_t B_pad = (B + 127) / 128 * 128;
     if (B_pad > B) {
-      DPB_CUDA_CHECK(cudaMemsetAsync(w.featop + (size_t)B * h->kext, 0, (size_t)(B_pad - B) * h->kext * sizeof(__half), st));
+      DPB_CUDA_CHECK(cudaMemsetAsync(w.featop + (size_t)B * var.kext, 0, (size_t)(B_pad - B) * var.kext * sizeof(__half), st));
       DPB_CUDA_CHECK(cudaMemsetAsync(w.skinop + (size_t)B * 12 * 2 * h->jp, 0,
                                      (size_t)(B_pad - B) * 12 * 2 * h->jp * sizeof(__half), st));
     }
@@ -524,18 +536,21 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
   if (h->J > 32)
     lbs_pose_kernel<2><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirs, h->parents,
                                                    h->depth, h->J, h->S, h->max_depth, w.A, w.G, w.feat, w.jrest,
-                                                   joints, h->n_out, B, fop, h->kext / 2, sop, h->jp);
+                                                   joints, h->n_out, B, fop, var.kext / 2, var.p_feat, sop, h->jp);
   else
     lbs_pose_kernel<1><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirs, h->parents,
                                                    h->depth, h->J, h->S, h->max_depth, w.A, w.G, w.feat, w.jrest,
-                                                   joints, h->n_out, B, fop, h->kext / 2, sop, h->jp);
+                                                   joints, h->n_out, B, fop, var.kext / 2, var.p_feat, sop, h->jp);
   DPB_CUDA_CHECK(cudaGetLastError());
   if (n_verts > 0) {
     if (!compact && engine == DPB_LBS_ENGINE_TC && !use_tc)
       return fail(DPB_EUNSUPPORTED, "dpb_lbs_forward: tensor-core engine unavailable");
     if (use_tc) {
-      if (use_fused) {
-        // blend + skinning in one tcgen05 kernel: the blended vertices stay in TMEM
+      if (use_fused2) {
+        // blend + skinning in one tcgen05 kernel on CTA pairs: the blended vertices stay in TMEM
+        int rc = lbs_fused2(h, var, w.featop, w.skinop, verts, B, st);
+        if (rc != DPB_OK) return rc;
+      } else if (use_fused) {
         int rc = lbs_tc_fused(h, nullptr, nullptr, w.featop, nullptr, nullptr, w.skinop, verts, B, st);
         if (rc != DPB_OK) return rc;
       } else {

@@ -6,6 +6,17 @@
 
 #include "common.cuh"
 
+// A blend basis as the tcgen05 engine reads it: row (c*V_pad + v) = [shape dirs | pose dirs of joints 1..n_var-1 |
+// template] as fp16 [hi | lo].  The FULL variant has n_var = J; a CONST-TAIL variant folds the (constant) pose-blend
+// contribution of joints n_var..J-1 into the template slot, so K shrinks from S + 9(J-1) + 1 to S + 9(n_var-1) + 1.
+struct LbsVariant {
+  int n_var = 0;            // joints whose rotation varies per pose
+  int p_feat = 0;           // pose features in the blend K: 9 * (n_var - 1)
+  int kext = 0;             // [hi | lo] width, multiple of 64
+  __half* dirs16 = nullptr; // [3*V_pad, kext]
+  CUtensorMap tm_dirs;      // box {64, 128}
+};
+
 struct dpb_lbs {
   int device = 0;
   int sm_count = 0;
@@ -41,6 +52,7 @@ struct dpb_lbs {
   int jp = 0;                     // joints padded to 32
   __half* wop16 = nullptr;        // [V_pad, 2*jp] fp16 [hi | lo] skinning weights
   CUtensorMap tm_wop;
+  LbsVariant tailv;               // const-tail variant (dpb_lbs_set_const_tail), dirs16 == nullptr until declared
   // backward: transposed-blend GEMM operand (lbs_bwd.cu)
   int bw_np = 0, bw_kp = 0;       // (P+S) padded to 64, 3V padded to 16
   float* dirs_pad = nullptr;      // [bw_np, bw_kp] fp32: rows 0..P-1 posedirs, rows P..P+S-1 shapedirs^T, zero padding
@@ -73,6 +85,15 @@ bool lbs_tc_skin_fits(const dpb_lbs* h);
 bool lbs_tc_fused_fits(const dpb_lbs* h);
 int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* featop, const float* A, const float* transl,
                  __half* skinop, float* verts, int64_t B, cudaStream_t st);
+inline LbsVariant lbs_full_variant(const dpb_lbs* h) {
+  LbsVariant v;
+  v.n_var = h->J; v.p_feat = h->P; v.kext = h->kext; v.dirs16 = h->dirs16; v.tm_dirs = h->tm_dirs;
+  return v;
+}
+int lbs_tc_make_tail(dpb_lbs* h, int n_var, const float* tail_pose);
+bool lbs_fused2_fits(const dpb_lbs* h, const LbsVariant& v);
+int lbs_fused2(dpb_lbs* h, const LbsVariant& v, __half* featop, __half* skinop, float* verts, int64_t B,
+               cudaStream_t st);
 int lbs_bwd_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_bwd_release(dpb_lbs* h);
 }  // namespace dpb

@@ -18,6 +18,7 @@
 
 #include <vector>
 
+#include <cmath>
 #include <cstdlib>
 
 #include "lbs.h"
@@ -236,8 +237,8 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
         const int v0 = vt * TILE_V + q * 32;          // first vertex of this warp's 32-vertex segment
         const int v = v0 + lane;
         const int n_floats = max(0, min(32, p.V - v0)) * 3;
-        float vt3[3] = {0.f, 0.f, 0.f};
-        if (v < p.V) { vt3[0] = p.v_template[v * 3]; vt3[1] = p.v_template[v * 3 + 1]; vt3[2] = p.v_template[v * 3 + 2]; }
+        float vt3[3] = {0.f, 0.f, 0.f};   // v_template rides in the GEMM (K slot S+P, feature 1): nothing to add here
+        if (p.v_template && v < p.V) { vt3[0] = p.v_template[v * 3]; vt3[1] = p.v_template[v * 3 + 1]; vt3[2] = p.v_template[v * 3 + 2]; }
         const uint32_t buf = unit % NBUF;
         ptx::mbar_wait(tfull_bar(buf), (tph >> buf) & 1);
         ptx::tc_fence_after();
@@ -293,6 +294,7 @@ __global__ void lbs_featop_kernel(const float* __restrict__ betas, const float* 
   if (b < B) {
     if (k < S) x = betas[b * S + k];
     else if (k < S + P) x = feat[b * P + (k - S)];
+    else if (k == S + P) x = 1.0f;      // the template slot
   }
   const __half hi = __float2half_rn(x);
   const __half lo = __float2half_rn(x - __half2float(hi));
@@ -754,8 +756,8 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
         const int v0 = vt * TILE_V + q * 32;
         const int v = v0 + lane;
         const int n_floats = max(0, min(32, p.V - v0)) * 3;
-        float vt3[3] = {0.f, 0.f, 0.f};
-        if (v < p.V) { vt3[0] = p.v_template[v * 3]; vt3[1] = p.v_template[v * 3 + 1]; vt3[2] = p.v_template[v * 3 + 2]; }
+        float vt3[3] = {0.f, 0.f, 0.f};   // v_template rides in the GEMM (K slot S+P, feature 1)
+        if (p.v_template && v < p.V) { vt3[0] = p.v_template[v * 3]; vt3[1] = p.v_template[v * 3 + 1]; vt3[2] = p.v_template[v * 3 + 2]; }
         ptx::mbar_wait(dfull, dph);
         dph ^= 1;
         ptx::tc_fence_after();
@@ -814,7 +816,7 @@ lbs_fused_tc_kernel(const __grid_constant__ FusedParams p, const __grid_constant
 int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   h->tc_ready = false;
   const int V = h->V, S = h->S, P = h->P;
-  const int Kp = (S + P + 31) / 32 * 32;   // hi (= lo) width: multiple of 32 so that [hi | lo] is whole 64-wide slabs
+  const int Kp = (S + P + 1 + 31) / 32 * 32;   // hi (= lo) width incl. the template slot: multiple of 32 so that [hi | lo] is whole 64-wide slabs
   const int K2 = 2 * Kp;
   const int V_pad = (V + ltc::TILE_V - 1) / ltc::TILE_V * ltc::TILE_V;
   const int n_slabs = K2 / ltc::BK;
@@ -830,6 +832,12 @@ int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
         const __half hi = __float2half_rn(x);
         row[k] = hi;
         row[Kp + k] = __float2half_rn(x - __half2float(hi));
+      }
+      {   // template slot (the pose operand carries a 1 there)
+        const float x = m->v_template[(size_t)v * 3 + c];
+        const __half hi = __float2half_rn(x);
+        row[S + P] = hi;
+        row[Kp + S + P] = __float2half_rn(x - __half2float(hi));
       }
     }
   DPB_CUDA_CHECK(cudaMalloc((void**)&h->dirs16, basis.size() * sizeof(__half)));
@@ -861,7 +869,65 @@ int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   return DPB_OK;
 }
 
+// Const-tail variant: joints n_var..J-1 always carry `tail_pose` (HOST [(J-n_var)*3]); their pose-blend contribution
+// posedirs[tail features]^T . (R(tail) - I) is a constant per vertex and moves into the template slot.
+int lbs_tc_make_tail(dpb_lbs* h, int n_var, const float* tail_pose) {
+  const int V = h->V, S = h->S, P = h->P, J = h->J, V_pad = h->n_cols_pad;
+  if (h->tailv.dirs16) { cudaFree(h->tailv.dirs16); h->tailv = LbsVariant(); }
+  if (!h->tc_ready) return DPB_OK;
+  const int Pf = 9 * (n_var - 1);
+  const int Kp = (S + Pf + 1 + 31) / 32 * 32, K2 = 2 * Kp;
+  std::vector<float> sd((size_t)V * 3 * S), pd((size_t)P * V * 3), vt((size_t)V * 3);
+  DPB_CUDA_CHECK(cudaMemcpy(sd.data(), h->shapedirs, sd.size() * 4, cudaMemcpyDeviceToHost));
+  DPB_CUDA_CHECK(cudaMemcpy(pd.data(), h->posedirs, pd.size() * 4, cudaMemcpyDeviceToHost));
+  DPB_CUDA_CHECK(cudaMemcpy(vt.data(), h->v_template, vt.size() * 4, cudaMemcpyDeviceToHost));
+  // (R - I) of the tail joints with smplx's Rodrigues (angle = ||r + 1e-8||), in double
+  std::vector<double> tf((size_t)(J - n_var) * 9);
+  for (int j = n_var; j < J; ++j) {
+    const float* r = tail_pose + (size_t)(j - n_var) * 3;
+    const double bx = (double)r[0] + 1e-8, by = (double)r[1] + 1e-8, bz = (double)r[2] + 1e-8;
+    const double ang = std::sqrt(bx * bx + by * by + bz * bz);
+    const double x = r[0] / ang, y = r[1] / ang, z = r[2] / ang, s = std::sin(ang), oc = 1.0 - std::cos(ang);
+    const double R[9] = {1 + oc * (-(z * z) - y * y), s * -z + oc * x * y, s * y + oc * x * z,
+                         s * z + oc * x * y, 1 + oc * (-(z * z) - x * x), s * -x + oc * y * z,
+                         s * -y + oc * x * z, s * x + oc * y * z, 1 + oc * (-(y * y) - x * x)};
+    for (int e = 0; e < 9; ++e) tf[(size_t)(j - n_var) * 9 + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0 : 0.0);
+  }
+  std::vector<double> tmpl((size_t)V * 3);
+  for (size_t i = 0; i < tmpl.size(); ++i) tmpl[i] = vt[i];
+  for (int k = Pf; k < P; ++k) {
+    const double f = tf[(size_t)(k - Pf)];
+    if (f == 0.0) continue;
+    const float* row = pd.data() + (size_t)k * V * 3;
+    for (size_t i = 0; i < tmpl.size(); ++i) tmpl[i] += f * row[i];
+  }
+  std::vector<__half> basis((size_t)3 * V_pad * K2, __float2half_rn(0.f));
+  auto put = [&](__half* row, int k, float x) {
+    const __half hi = __float2half_rn(x);
+    row[k] = hi;
+    row[Kp + k] = __float2half_rn(x - __half2float(hi));
+  };
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < V; ++v) {
+      __half* row = basis.data() + ((size_t)c * V_pad + v) * K2;
+      for (int k = 0; k < S; ++k) put(row, k, sd[((size_t)v * 3 + c) * S + k]);
+      for (int k = 0; k < Pf; ++k) put(row, S + k, pd[(size_t)k * V * 3 + (size_t)v * 3 + c]);
+      put(row, S + Pf, (float)tmpl[(size_t)v * 3 + c]);
+    }
+  LbsVariant t;
+  t.n_var = n_var; t.p_feat = Pf; t.kext = K2;
+  DPB_CUDA_CHECK(cudaMalloc((void**)&t.dirs16, basis.size() * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMemcpy(t.dirs16, basis.data(), basis.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  int rc = make_tmap_2d(&t.tm_dirs, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, t.dirs16, K2, (uint64_t)3 * V_pad, ltc::BK,
+                        ltc::TILE_V, 2);
+  if (rc != DPB_OK) { cudaFree(t.dirs16); return rc; }
+  h->tailv = t;
+  return DPB_OK;
+}
+
 void lbs_tc_release(dpb_lbs* h) {
+  if (h->tailv.dirs16) cudaFree(h->tailv.dirs16);
+  h->tailv = LbsVariant();
   if (h->dirs16) cudaFree(h->dirs16);
   if (h->wop16) cudaFree(h->wop16);
   h->dirs16 = nullptr;
@@ -955,7 +1021,7 @@ int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   p.jsteps = Jp / 16;
   p.B = B;
   p.n_units = (int)((B + ltc::FU_NP - 1) / ltc::FU_NP) * p.vsplit;
-  p.v_template = h->v_template;
+  p.v_template = nullptr;   // folded into the GEMM
   p.verts = verts;
   const size_t smem = (size_t)p.n_slabs * ltc::FU_B_SLAB + (ltc::FU_ASTAGES + 1) * ltc::A_SLAB +
                       ltc::FU_SSTAGES * ltc::FU_S_BYTES + ltc::FU_NBARS * 8 + 16 + 1024;
@@ -993,7 +1059,7 @@ int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   p.n_slabs = n_slabs;
   p.B = B;
   p.n_groups = (int)((B + np - 1) / np);
-  p.v_template = h->v_template;
+  p.v_template = nullptr;   // folded into the GEMM
   p.verts = verts;
   const size_t fixed = (size_t)n_slabs * np * ltc::BK * 2 + bars;
   int stages = (int)((232448 - fixed) / ltc::A_SLAB);

@@ -185,7 +185,17 @@ typedef struct {
 #define DPB_LBS_ENGINE_FP32 1 /* fp32 FFMA pose-blend (exact) */
 #define DPB_LBS_ENGINE_TC 2   /* tcgen05 pose-blend, fp16 hi/lo-split operands, fp32 accumulate */
 
+#define DPB_LBS_CONST_TAIL (1 << 4) /* dpb_lbs_forward flag: full_pose[:, n_var*3:] equals the declared constant tail */
+
 int dpb_lbs_create(dpb_lbs_t** h, const dpb_body_tensors* m, int device);
+/* Declare that joints n_var..J-1 always carry the same rotation (SMPL-X through lib/body_model/body_model.py with
+ * pose_hand / pose_jaw / pose_eye omitted: zeros; through lib/body_model/smpl.py: the model's constant mean hand pose,
+ * jaw and eyes zero).  Their pose-blend features (R - I) are then constants: the library folds
+ * posedirs[tail]^T . feat(tail) into the template and the blend's K shrinks from S + 9(J-1) to S + 9(n_var-1)
+ * (SMPL-X: 506 -> 209).  tail_pose HOST [(J - n_var)*3] axis-angle.  Afterwards dpb_lbs_forward calls that pass
+ * DPB_LBS_CONST_TAIL promise full_pose[:, n_var*3:] == tail_pose in every row (the kinematic chain still reads
+ * full_pose); calls without the flag are unaffected. */
+int dpb_lbs_set_const_tail(dpb_lbs_t* h, int n_var, const float* tail_pose);
 int dpb_lbs_destroy(dpb_lbs_t* h);
 int dpb_lbs_num_joints_out(dpb_lbs_t* h); /* J + n_extra + n_lmk */
 size_t dpb_lbs_workspace_bytes(dpb_lbs_t* h, int64_t B, int flags);

@@ -169,6 +169,51 @@ def test_lbs_backward_with_an_unused_output(which):
         assert (got - ref).abs().max() / scale < 2e-4, k
 
 
+@pytest.mark.parametrize('B', [97, 193, 1000])
+@pytest.mark.parametrize('staged', ['1', '0'])
+def test_lbs_pair_kernel_group_boundaries(B, staged, monkeypatch):
+    """CTA-pair fused kernel (lbs_fused2_kernel): pose counts one past / straddling 96-pose groups, both store paths
+    (staged full-line stores / direct stride-12 stores), SMPL and SMPL-X (const tail folded into the template)."""
+    monkeypatch.setenv('DPB_LBS_STAGED', staged)
+    for mt in ('smpl', 'smplx'):
+        m = synthetic.make_body_tensors(mt)
+        inp = synthetic.lbs_inputs(B, mt, seed=17)
+        v_ref, j_ref = _oracle(m, inp, mt)
+        bm = BodyModel(m, num_betas=10, batch_size=B, model_type=mt).cuda()
+        bm.core.engine = 2
+        with torch.no_grad():
+            out = bm(**{k: v.cuda() for k, v in inp.items()})
+        assert (out.v.cpu() - v_ref).abs().max() < TOL_M, mt
+        assert (out.Jtr.cpu() - j_ref).abs().max() < TOL_M, mt
+
+
+def test_smplx_posed_hands_take_the_full_basis_and_const_tail_matches():
+    """(1) explicit hand / jaw / eye poses: the const-tail shortcut must NOT be taken (full 486-feature blend);
+    (2) SMPLX wrapper (hands at the non-zero mean pose, folded into the template) with vertices, vs the oracle."""
+    m = synthetic.make_body_tensors('smplx')
+    B = 130
+    g = torch.Generator().manual_seed(23)
+    inp = synthetic.lbs_inputs(B, 'smplx', seed=19)
+    hand, jaw, eye = (0.3 * torch.randn(B, n, generator=g) for n in (90, 3, 6))
+    pose = torch.cat([inp['root_orient'], inp['pose_body'], jaw, eye, hand], 1)
+    shape = torch.cat([inp['betas'], torch.zeros(B, 10)], 1)
+    v_ref, j_ref = lbs_ref.body_forward(m, shape, pose, inp['trans'])
+    bm = BodyModel(m, num_betas=10, batch_size=B, model_type='smplx').cuda()
+    bm.core.engine = 2
+    with torch.no_grad():
+        out = bm(pose_hand=hand.cuda(), pose_jaw=jaw.cuda(), pose_eye=eye.cuda(), **{k: v.cuda() for k, v in inp.items()})
+    assert (out.v.cpu() - v_ref).abs().max() < TOL_M and (out.Jtr.cpu() - j_ref).abs().max() < TOL_M
+    smpl = SMPLX(m, batch_size=B).cuda()
+    smpl.core.engine = 2
+    with torch.no_grad():
+        o2 = smpl(betas=inp['betas'].cuda(), body_pose=inp['pose_body'].cuda(), global_orient=inp['root_orient'].cuda(),
+                  transl=inp['trans'].cuda(), need_verts=True)
+    full = torch.cat([inp['root_orient'], inp['pose_body'], torch.zeros(B, 9), m['hands_mean'][None].expand(B, -1)], 1)
+    v2, j2 = lbs_ref.body_forward(m, shape, full, inp['trans'])
+    assert (o2.vertices.cpu() - v2).abs().max() < TOL_M
+    assert (o2.joints.cpu() - j2[:, smpl.joint_map]).abs().max() < TOL_M
+
+
 def test_lbs_fused_kernel_group_boundary_without_translation():
     """tcgen05 engine (fused blend + skinning kernel for SMPL) at a pose count one past a 128-pose group and with no
     translation: the spare joint slot that carries transl must then contribute nothing."""
