@@ -12,7 +12,7 @@ from . import build as _build
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TC = 0, 1, 2
 SAMPLER_IMPUTE, SAMPLER_NOISE_GIVEN = 1 << 4, 1 << 5
-LBS_CONST_TAIL = 1 << 4
+LBS_CONST_TAIL, LBS_NO_SAVE = 1 << 4, 1 << 5
 COEF_STRIDE = 8
 POSE_DIM, HIDDEN, EMBED, NUM_DENSE = 63, 1024, 512, 5
 

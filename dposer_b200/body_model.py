@@ -71,6 +71,8 @@ class _LbsFn(torch.autograd.Function):
         joints = torch.empty(B, core.n_out, 3, dtype=torch.float32, device=dev)
         ws = core.workspace(B, dev)
         flags = core.engine | (L.LBS_CONST_TAIL if (const_tail and core.tail is not None) else 0)
+        if not (betas.requires_grad or full_pose.requires_grad or (transl is not None and transl.requires_grad)):
+            flags |= L.LBS_NO_SAVE      # no backward will follow: skip the per-pose fp32 side outputs
         L.check(L.load().dpb_lbs_forward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(t), L.ptr(verts), L.ptr(joints), B,
                                          flags, L.ptr(ws), ws.numel(), L.current_stream(dev)))
         ctx.core, ctx.need_verts, ctx.has_transl = core, need_verts, transl is not None

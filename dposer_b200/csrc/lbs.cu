@@ -64,15 +64,21 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
   // passes over feat and A (lbs_tc.cu: lbs_featop_kernel / lbs_skinop_kernel define the layout)
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  // The fp16 operand rows are assembled in shared memory (2-byte scattered writes) and leave as 16-byte vectors:
+  // written straight to global they were ~60 two-byte stores per lane and the kernel took 0.28 ms per 65 536 poses.
+  __shared__ __align__(16) __half stage_f[4][1024];       // [hi | lo] blend operand row (2 * Kp <= 1024)
+  __shared__ __align__(16) __half stage_s[4][12 * 128];   // 12 transform rows x [hi | lo] (2 * Jp <= 128)
   if (b >= B) return;  // warp-uniform
   const int P = (J - 1) * 9;
+  __half* fs = stage_f[threadIdx.x >> 5];
+  __half* ss = stage_s[threadIdx.x >> 5];
   auto put_split = [](__half* row, int k, int half_width, float x) {
     const __half hi = __float2half_rn(x);
     row[k] = hi;
     row[half_width + k] = __float2half_rn(x - __half2float(hi));
   };
   if (featop) {   // [beta | feat (p_feat of them: the variant's varying joints) | 1 (template slot) | 0] of this pose;
-    __half* frow = featop + (size_t)b * 2 * Kp;   // the feat part is written with the rotations below
+    __half* frow = fs;                            // the feat part is written with the rotations below
     for (int k = lane; k < Kp; k += 32)
       if (k < S) put_split(frow, k, Kp, betas[b * S + k]);
       else if (k >= S + p_feat) put_split(frow, k, Kp, k == S + p_feat ? 1.0f : 0.f);
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
         float acc = j_template[j * 3 + c];
         for (int k = 0; k < S; ++k) acc = fmaf(j_shapedirs[(j * 3 + c) * S + k], betas[b * S + k], acc);
         jr[s][c] = acc;
-        jrest_out[(b * J + j) * 3 + c] = acc;
+        if (jrest_out) jrest_out[(b * J + j) * 3 + c] = acc;
       }
       rodrigues(pose + (b * J + j) * 3, M[s]);
       if (j > 0) {
@@ -104,8 +110,8 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
         for (int e = 0; e < 9; ++e)
         {
           const float f = M[s][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
-          feat_out[b * P + (j - 1) * 9 + e] = f;
-          if (featop && (j - 1) * 9 + e < p_feat) put_split(featop + (size_t)b * 2 * Kp, S + (j - 1) * 9 + e, Kp, f);
+          if (feat_out) feat_out[b * P + (j - 1) * 9 + e] = f;
+          if (featop && (j - 1) * 9 + e < p_feat) put_split(fs, S + (j - 1) * 9 + e, Kp, f);
         }
       }
     }
@@ -158,26 +164,41 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
       const float t3[3] = {tx, ty, tz};
 #pragma unroll
       for (int e = 0; e < 12; ++e)
-        put_split(skinop + ((size_t)b * 12 + e) * 2 * Jp, j, Jp, (j == J && e >= 9) ? t3[e - 9] : 0.f);
+        put_split(ss + e * 2 * Jp, j, Jp, (j == J && e >= 9) ? t3[e - 9] : 0.f);
     }
     if (j >= J) continue;
-    float* Ao = A_out + (b * J + j) * 12;
-    float* Go = G_out + (b * J + j) * 12;
-#pragma unroll
-    for (int e = 0; e < 12; ++e) Go[e] = G[s][e];
+    float Ao[12];
 #pragma unroll
     for (int e = 0; e < 9; ++e) Ao[e] = G[s][e];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       Ao[9 + i] = G[s][9 + i] - (G[s][i * 3 + 0] * jr[s][0] + G[s][i * 3 + 1] * jr[s][1] + G[s][i * 3 + 2] * jr[s][2]);
+    if (A_out) {   // fp32 copies for the backward pass / the fp32 vertex kernel (skipped on forward-only fused calls)
+      float* Ag = A_out + (b * J + j) * 12;
+      float* Go = G_out + (b * J + j) * 12;
+#pragma unroll
+      for (int e = 0; e < 12; ++e) { Go[e] = G[s][e]; Ag[e] = Ao[e]; }
+    }
     if (skinop) {
 #pragma unroll
-      for (int e = 0; e < 12; ++e) put_split(skinop + ((size_t)b * 12 + e) * 2 * Jp, j, Jp, Ao[e]);
+      for (int e = 0; e < 12; ++e) put_split(ss + e * 2 * Jp, j, Jp, Ao[e]);
     }
     float* jo = joints_out + (b * n_out + j) * 3;
     jo[0] = G[s][9] + tx;
     jo[1] = G[s][10] + ty;
     jo[2] = G[s][11] + tz;
+  }
+  // shared-memory operand rows -> global, 16 bytes per lane per step
+  if (featop || skinop) __syncwarp();
+  if (featop) {
+    const uint4* src = reinterpret_cast<const uint4*>(fs);
+    uint4* dst = reinterpret_cast<uint4*>(featop + (size_t)b * 2 * Kp);
+    for (int i = lane; i < Kp / 4; i += 32) dst[i] = src[i];          // 2*Kp halves = Kp/4 vectors
+  }
+  if (skinop) {
+    const uint4* src = reinterpret_cast<const uint4*>(ss);
+    uint4* dst = reinterpret_cast<uint4*>(skinop + (size_t)b * 12 * 2 * Jp);
+    for (int i = lane; i < 3 * Jp; i += 32) dst[i] = src[i];          // 12 rows x 2*Jp halves = 3*Jp vectors
   }
 }
 
@@ -532,14 +553,20 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
                                      (size_t)(B_pad - B) * 12 * 2 * h->jp * sizeof(__half), st));
     }
   }
+  // forward-only fused calls (DPB_LBS_NO_SAVE): nothing downstream reads the fp32 transforms / features
+  const bool no_save = (flags & DPB_LBS_NO_SAVE) && use_fused2;
+  float* A_o = no_save ? nullptr : w.A;
+  float* G_o = no_save ? nullptr : w.G;
+  float* feat_o = no_save ? nullptr : w.feat;
+  float* jrest_o = no_save ? nullptr : w.jrest;
   const unsigned pose_grid = (unsigned)((B + 3) / 4);
   if (h->J > 32)
     lbs_pose_kernel<2><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirs, h->parents,
-                                                   h->depth, h->J, h->S, h->max_depth, w.A, w.G, w.feat, w.jrest,
+                                                   h->depth, h->J, h->S, h->max_depth, A_o, G_o, feat_o, jrest_o,
                                                    joints, h->n_out, B, fop, var.kext / 2, var.p_feat, sop, h->jp);
   else
     lbs_pose_kernel<1><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirs, h->parents,
-                                                   h->depth, h->J, h->S, h->max_depth, w.A, w.G, w.feat, w.jrest,
+                                                   h->depth, h->J, h->S, h->max_depth, A_o, G_o, feat_o, jrest_o,
                                                    joints, h->n_out, B, fop, var.kext / 2, var.p_feat, sop, h->jp);
   DPB_CUDA_CHECK(cudaGetLastError());
   if (n_verts > 0) {

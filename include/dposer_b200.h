@@ -186,6 +186,8 @@ typedef struct {
 #define DPB_LBS_ENGINE_TC 2   /* tcgen05 pose-blend, fp16 hi/lo-split operands, fp32 accumulate */
 
 #define DPB_LBS_CONST_TAIL (1 << 4) /* dpb_lbs_forward flag: full_pose[:, n_var*3:] equals the declared constant tail */
+#define DPB_LBS_NO_SAVE (1 << 5)    /* dpb_lbs_forward flag: forward only -- `ws` will NOT be handed to dpb_lbs_backward,
+                                       so the per-pose fp32 transforms / features need not be stored */
 
 int dpb_lbs_create(dpb_lbs_t** h, const dpb_body_tensors* m, int device);
 /* Declare that joints n_var..J-1 always carry the same rotation (SMPL-X through lib/body_model/body_model.py with
