@@ -43,7 +43,9 @@ EXPORTS = ['dpb_version', 'dpb_last_error', 'dpb_device_info', 'dpb_score_create
            'dpb_score_time_table', 'dpb_score_workspace_bytes', 'dpb_score_forward', 'dpb_sampler_run',
            'dpb_langevin_norms', 'dpb_langevin_update', 'dpb_normal_fill', 'dpb_prior_loss', 'dpb_lbs_create',
            'dpb_lbs_destroy', 'dpb_lbs_set_const_tail', 'dpb_lbs_num_joints_out', 'dpb_lbs_workspace_bytes', 'dpb_lbs_forward',
-           'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_apd_partial', 'dpb_mean_point_error', 'dpb_fit_loss']
+           'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_apd_partial', 'dpb_mean_point_error', 'dpb_fit_loss',
+           'dpb_motion_loss', 'dpb_camera_fit_loss', 'dpb_adam_step', 'dpb_affine_cols', 'dpb_joint_map_gather',
+           'dpb_joint_map_scatter', 'dpb_masked_mse_grad']
 
 _lib = None
 
@@ -93,6 +95,14 @@ def load():
     lib.dpb_fit_loss.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, f32, f32, f32, f32, vp, vp, vp,
                                  vp, vp, i64, vp]
     lib.dpb_apd_partial.argtypes = [vp, i64, C.c_int, i64, i64, vp, vp]
+    lib.dpb_motion_loss.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp, vp, vp]
+    lib.dpb_camera_fit_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, f32, f32, C.c_int, vp, vp, vp, i64, vp]
+    lib.dpb_adam_step.argtypes = [vp, i64, vp, vp, vp, i64, f32, vp, i64, f32, vp, vp, i64, f32, i64, C.c_int, f32, f32,
+                                  f32, f32, C.c_int, vp]
+    lib.dpb_masked_mse_grad.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.dpb_affine_cols.argtypes = [vp, i64, vp, vp, vp, i64, C.c_int, C.c_int, vp]
+    lib.dpb_joint_map_gather.argtypes = [vp, C.c_int, vp, C.c_int, vp, i64, vp]
+    lib.dpb_joint_map_scatter.argtypes = [vp, C.c_int, vp, C.c_int, vp, i64, vp]
     lib.dpb_mean_point_error.argtypes = [vp, vp, i64, C.c_int, vp, C.c_int, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)

@@ -130,18 +130,23 @@ class DPoserComp(_PriorBase):
         return torch.stack([weight_dict[k](loss_dict[k], it) for k in loss_dict]).sum()
 
     def optimize(self, observation, mask, time_strategy='3', lr=0.1, sample_trun=5.0, sample_time=900,
-                 iterations=2, steps_per_iter=100):
-        """run/completion.py:167-207: Adam on the pose with data + DPoser losses."""
+                 iterations=2, steps_per_iter=100, z_list=None, graphs=False):
+        """run/completion.py:167-207: Adam on the pose with data + DPoser losses.  Per step three kernels: prior loss
+        with its closed-form gradient, the masked-MSE cotangent, fused Adam (no framework op, no autograd).
+        ``z_list`` (parity mode): the Gaussian draw of every step; ``graphs``: capture / replay every step as a CUDA graph."""
+        from . import steps as S
+        L.require_cuda(observation, 'observation')
+        dev = observation.device
         total_steps = iterations * steps_per_iter
-        opti_variable = observation.clone().detach()
-        opti_variable.requires_grad = True
-        optimizer = torch.optim.Adam([opti_variable], lr, betas=(0.9, 0.999))
-        weight_dict = self.get_loss_weights()
+        obs = observation.detach().to(torch.float32).contiguous()
+        msk = mask.detach().to(torch.float32).expand_as(obs).contiguous()
+        x = obs.clone()
+        rows = x.shape[0]
         timesteps = mutils.timestep_grid(self.sde, 1e-3)           # host copy: no per-step device read
+        sched = []
         for it in range(iterations):
             for i in range(steps_per_iter):
                 step = it * steps_per_iter + i
-                optimizer.zero_grad()
                 if time_strategy == '1':
                     quan_t = int(torch.randint(self.sde.N, [1]))
                 elif time_strategy == '2':
@@ -151,13 +156,32 @@ class DPoserComp(_PriorBase):
                         torch.tensor(total_steps - step - 1) * (self.sde.N / (sample_trun * total_steps))) - 2
                 else:
                     raise NotImplementedError('unsupported time sampling strategy')
-                t = float(timesteps[quan_t])
-                # the reference passes quan_t into `weighted` (run/completion.py:196): weighted iff quan_t != 0
-                loss_dict = {'dposer': self.loss(opti_variable, t, quan_t),
-                             'data': self.data_loss(opti_variable * mask, observation * mask)}
-                self.backward_step(loss_dict, weight_dict, it).backward()
-                optimizer.step()
-        return (observation * mask + opti_variable * (1.0 - mask)).detach()
+                sched.append((it, quan_t, float(timesteps[quan_t])))
+        pri = S.PriorStep(self.model, self.sde, self.continuous, rows, dev)
+        pri.schedule([t for _, _, t in sched])
+        g_data = torch.empty_like(x)
+        zbuf = torch.empty_like(x) if z_list is not None else None
+        opt = S.Adam(x, 0, 63, lr)
+        wd = self.get_loss_weights()
+        seed = mutils.host_seed() if z_list is None else 0
+        sg = S.StepGraphs(graphs and z_list is None)
+        lib = L.load()
+
+        def one_step(k):
+            it, quan_t, _ = sched[k]
+            z = None
+            if z_list is not None:
+                zbuf.copy_(z_list[k].to(dev))
+                z = zbuf
+            # the reference passes quan_t into `weighted` (run/completion.py:196): weighted iff quan_t != 0
+            pri(x, k, bool(quan_t), float(x.numel()), z=z, seed=seed, step=k)
+            L.check(lib.dpb_masked_mse_grad(L.ptr(x), L.ptr(obs), L.ptr(msk), L.ptr(g_data), x.numel(),
+                                            L.current_stream(dev)))
+            opt.step(g_data, 0, 63, wd['data'](1.0, it), g2=pri.grad, off2=0, ld2=63, s2=wd['dposer'](1.0, it))
+
+        for k in range(total_steps):
+            sg.run(k, lambda k=k: one_step(k))
+        return obs * msk + x * (1.0 - msk)
 
 
 class MotionPrior(_PriorBase):

@@ -239,6 +239,45 @@ int dpb_fit_loss(const float* joints, const float* joints_2d, const float* conf,
                  float* reproj, float* g_joints, float* g_pose, float* g_betas, int64_t B, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fitting-loop steps on the device: everything an Adam step of the reference's task loops does besides the LBS
+ * and the prior (run/motion_denoising.py:226-268, run/smplify.py:208-260, run/completion.py:178-203), so that no
+ * framework op runs inside a step and a whole step can be captured in one CUDA graph.  All pointers DEVICE fp32.
+ * ---------------------------------------------------------------------------------------- */
+/* Motion-denoising terms for rows = n_seq * seq_len frames (each sequence an independent problem):
+ *   temporal  w_temp * mean_{t < seq_len-1, v} ||verts[t,v] - verts[t+1,v]||   (motion_denoising.py:256-257; rows of
+ *             different sequences are never differenced)
+ *   data      w_data * mean_{t, j < n_data} ||joints[t,j] - target[t,j]||, dropped for a sequence whose term is not
+ *             > 0 (the reference's NaN guard `if data_term > 0`, :262, as a per-sequence device predicate)
+ * Writes the cotangents g_verts [rows,V,3] and g_joints [rows,n_out,3] (zero beyond n_data) of the weighted sum.
+ * seq_terms [n_seq,2] (optional, reporting): unweighted temporal and data term of each sequence. */
+int dpb_motion_loss(const float* verts, const float* joints, const float* target, int64_t rows, int seq_len, int V,
+                    int n_out, int n_data, float w_temp, float w_data, float* g_verts, float* g_joints,
+                    float* seq_terms, void* stream);
+/* camera_fitting_loss (lib/body_model/fitting_losses.py:106-136): loss [B] = reprojection of the four torso joints
+ * (OpenPose slots when all four are confident, else the GT slots) + depth_weight^2 (t_z - t_z,est)^2, with the
+ * cotangents g_joints [B,K,3] and g_cam_t [B,3] (either may be NULL).  focal_b [B] or NULL as in dpb_fit_loss. */
+int dpb_camera_fit_loss(const float* joints, const float* joints_2d, const float* conf, const float* center,
+                        const float* cam_t, const float* cam_t_est, const float* focal_b, float focal,
+                        float depth_weight, int n_joints, float* loss, float* g_joints, float* g_cam_t, int64_t B,
+                        void* stream);
+/* torch.optim.Adam step `step` (1-based; amsgrad off, no weight decay) on a strided [rows, cols] parameter view with
+ * state m, v [rows*cols]:  grad = s1 g1 + s2 col_scale2[c] g2 + s3 g3  (g2, col_scale2, g3 may be NULL). */
+int dpb_adam_step(float* param, int64_t ld_p, float* m, float* v, const float* g1, int64_t ld1, float s1,
+                  const float* g2, int64_t ld2, float s2, const float* col_scale2, const float* g3, int64_t ld3,
+                  float s3, int64_t rows, int cols, float lr, float beta1, float beta2, float eps, int step,
+                  void* stream);
+/* grad = d/dx mean((x*mask - obs*mask)^2) = 2 mask^2 (x - obs) / n   (the data term of run/completion.py:197) */
+int dpb_masked_mse_grad(const float* x, const float* obs, const float* mask, float* grad, int64_t n, void* stream);
+/* Posenormalizer z-score (lib/dataset/AMASS.py:187-259): out = (x - mean) / std per column, or x * std + mean (inverse) */
+int dpb_affine_cols(const float* x, int64_t ldx, const float* mean, const float* std, float* out, int64_t rows,
+                    int cols, int inverse, void* stream);
+/* joints[:, joint_map] (lib/body_model/smpl.py:70) and its adjoint (g_in is overwritten; repeated map entries add) */
+int dpb_joint_map_gather(const float* joints, int n_in, const int32_t* map, int n_map, float* out, int64_t B,
+                         void* stream);
+int dpb_joint_map_scatter(const float* g_out, int n_map, const int32_t* map, int n_in, float* g_in, int64_t B,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Metrics (replaces average_pairwise_distance lib/utils/metric.py:8-37 and the per-sample
  * reductions of Evaler.eval_bodys lib/dataset/AMASS.py:275-298)
  * ---------------------------------------------------------------------------------------- */

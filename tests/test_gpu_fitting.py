@@ -15,19 +15,6 @@ from oracle import fitting_loops, lbs_ref
 pytestmark = pytest.mark.gpu
 
 
-class _InjectZ:
-    """Feeds a fixed list of Gaussian draws to the prior loss (parity mode)."""
-
-    def __init__(self, obj, z_list):
-        self.z, self.k, self.orig = z_list, 0, obj._fused_loss
-        obj._fused_loss = self
-
-    def __call__(self, x_0, t, weighted, divisor, z=None):
-        z = self.z[self.k].to(x_0.device)
-        self.k += 1
-        return self.orig(x_0, t, weighted, divisor, z)
-
-
 @pytest.mark.parametrize('engine,tol', [(L.ENGINE_FP32, 2e-3), (L.ENGINE_TC, 5e-3)])
 def test_motion_denoise_steps_vs_oracle(gpu_model, oracle_sd, engine, tol):
     m = synthetic.make_body_tensors('smplx')
@@ -50,10 +37,9 @@ def test_motion_denoise_steps_vs_oracle(gpu_model, oracle_sd, engine, tol):
         md = fitting.MotionDenoise(cfg, args, gpu_model, bm, sde_lib.subVPSDE(0.1, 20., 1000), norm, sde_N=500,
                                    batch_size=rows, seq_len=seq_len)
         md.poses = init.cuda()
-        _InjectZ(md, z_list)
         # smoothing off for the comparison: take the raw optimised pose through a 1-frame window trick
         res = md.optimize(noisy.cuda(), gt_poses=gt.cuda(), time_strategy='3', sample_trun=4.0, iterations=1,
-                          steps_per_iter=steps)
+                          steps_per_iter=steps, z_list=z_list)
     finally:
         gpu_model.engine = L.ENGINE_AUTO
     from oracle import fitting_ref as Fr
@@ -101,11 +87,10 @@ def test_smplify_steps_vs_oracle(gpu_model, oracle_sd):
     try:
         pp = prior.DPoser(batch_size=B, args=args, model=gpu_model, sde=sde_lib.subVPSDE(0.1, 20., 1000),
                           normalizer=norm)
-        _InjectZ(pp, z_list)
         fit = fitting.SMPLify(smpl, step_size=1e-2, batch_size=B, num_iters=iters, focal_length=5000., args=args,
                               pose_prior=pp)
         pose, betas, cam_t, reproj = fit(init_pose.cuda(), init_betas.cuda(), init_cam.cuda(), center.cuda(),
-                                         kp2d.clone().cuda())
+                                         kp2d.clone().cuda(), z_list=z_list)
     finally:
         gpu_model.engine = L.ENGINE_AUTO
     assert rel_err(pose.cpu() - init_pose, ref_pose - init_pose) < 5e-3
@@ -131,9 +116,8 @@ def test_motion_denoise_vs_reference_golden(gpu_model, engine, tol):
                                    sde_lib.subVPSDE(0.1, 20., 1000), norm, sde_N=500, batch_size=rows,
                                    seq_len=seq_len)
         md.poses = t('md_init').cuda()
-        _InjectZ(md, list(t('md_z')))
         res = md.optimize(t('md_noisy').cuda(), gt_poses=t('md_gt').cuda(), time_strategy='3', sample_trun=4.0,
-                          iterations=iters, steps_per_iter=spi)
+                          iterations=iters, steps_per_iter=spi, z_list=list(t('md_z')))
     finally:
         gpu_model.engine = L.ENGINE_AUTO
     init = t('md_init')
@@ -158,12 +142,11 @@ def test_smplify_vs_reference_golden(gpu_model, engine, tol):
     try:
         pp = prior.DPoser(batch_size=B, args=args, model=gpu_model, sde=sde_lib.subVPSDE(0.1, 20., 1000),
                           normalizer=norm)
-        _InjectZ(pp, list(t('sf_z')))
         fit = fitting.SMPLify(smpl, step_size=1e-2, batch_size=B, num_iters=iters, focal_length=5000., args=args,
                               pose_prior=pp)
         kp2d = t('sf_kp2d').cuda()
         pose, betas, cam_t, reproj = fit(t('sf_init_pose').cuda(), t('sf_init_betas').cuda(), t('sf_init_cam').cuda(),
-                                         t('sf_center').cuda(), kp2d)
+                                         t('sf_center').cuda(), kp2d, z_list=list(t('sf_z')))
     finally:
         gpu_model.engine = L.ENGINE_AUTO
     assert float(kp2d[:, 9, 2].abs().max()) == 0.            # B-13: ignored joints zeroed in the caller's tensor

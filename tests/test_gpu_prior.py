@@ -67,18 +67,12 @@ def test_completion_optimize_vs_reference_golden(gpu_model, engine, tol):
     g = golden('loops_golden.npz')
     iters, spi = g['comp_iters'].tolist()
     obs, mask = torch.tensor(g['comp_obs']).cuda(), torch.tensor(g['comp_mask']).cuda()
-    zs, k = list(torch.tensor(g['comp_z'])), [0]
+    zs = list(torch.tensor(g['comp_z']))
     gpu_model.engine = engine
     try:
         comp = prior.DPoserComp(gpu_model, sde_lib.subVPSDE(0.1, 20., 1000), True, batch_size=obs.shape[0])
-        orig = comp._fused_loss
-
-        def inject(x_0, t, weighted, divisor, z=None):
-            k[0] += 1
-            return orig(x_0, t, weighted, divisor, zs[k[0] - 1].cuda())
-        comp._fused_loss = inject
         out = comp.optimize(obs, mask, time_strategy='3', lr=0.1, sample_trun=5.0, iterations=iters,
-                            steps_per_iter=spi)
+                            steps_per_iter=spi, z_list=zs)
     finally:
         gpu_model.engine = L.ENGINE_AUTO
     ref = torch.tensor(g['comp_out'])
