@@ -535,12 +535,15 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
   float* vout = compact ? w.compact : verts;
   const bool use_tc = n_verts > 0 && !compact && h->tc_ready && w.featop &&
                       (engine == DPB_LBS_ENGINE_TC || (engine == DPB_ENGINE_AUTO && B >= 64));
-  const int fused_sel = getenv("DPB_LBS_FUSED") ? atoi(getenv("DPB_LBS_FUSED")) : 2;   // A/B timing only: 0 two kernels, 1 first fused kernel, 2 CTA-pair kernel
+  const int fused_sel = getenv("DPB_LBS_FUSED") ? atoi(getenv("DPB_LBS_FUSED")) : 3;   // A/B timing only: 0 two kernels, 1 first fused kernel, 2 / 3 CTA-pair kernels
   // const-tail calls (DPB_LBS_CONST_TAIL) read the pruned basis; everything else the full one
   const bool want_tail = (flags & DPB_LBS_CONST_TAIL) != 0;
   if (want_tail) DPB_REQUIRE(h->tailv.n_var > 0 || !h->tc_ready, "dpb_lbs_forward: DPB_LBS_CONST_TAIL without dpb_lbs_set_const_tail");
   const LbsVariant var = (want_tail && h->tailv.dirs16) ? h->tailv : lbs_full_variant(h);
-  const bool use_fused2 = use_tc && fused_sel == 2 && w.skinop && lbs_fused2_fits(h, var);
+  // measured (profiles/r2_lbs_fused3_experiments.md): the 128-pose-group kernel wins for SMPL-sized joint counts (one
+  // skinning K slab), the 96-pose-group kernel for SMPL-X (two slabs: its three T buffers hide the longer chunks)
+  const bool use_fused3 = use_tc && fused_sel == 3 && w.skinop && h->jp == 32 && lbs_fused3_fits(h, var);
+  const bool use_fused2 = use_fused3 || (use_tc && fused_sel >= 2 && w.skinop && lbs_fused2_fits(h, var));
   const bool use_fused = use_fused2 || (use_tc && fused_sel != 0 && w.skinop && var.n_var == h->J && lbs_tc_fused_fits(h));
   // the fused kernel's operands come straight out of the pose kernel (pad rows of the last pose group are zeroed)
   __half* fop = use_fused ? w.featop : nullptr;
@@ -575,7 +578,8 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
     if (use_tc) {
       if (use_fused2) {
         // blend + skinning in one tcgen05 kernel on CTA pairs: the blended vertices stay in TMEM
-        int rc = lbs_fused2(h, var, w.featop, w.skinop, verts, B, st);
+        int rc = use_fused3 ? lbs_fused3(h, var, w.featop, w.skinop, verts, B, st)
+                            : lbs_fused2(h, var, w.featop, w.skinop, verts, B, st);
         if (rc != DPB_OK) return rc;
       } else if (use_fused) {
         int rc = lbs_tc_fused(h, nullptr, nullptr, w.featop, nullptr, nullptr, w.skinop, verts, B, st);

@@ -94,6 +94,9 @@ int lbs_tc_make_tail(dpb_lbs* h, int n_var, const float* tail_pose);
 bool lbs_fused2_fits(const dpb_lbs* h, const LbsVariant& v);
 int lbs_fused2(dpb_lbs* h, const LbsVariant& v, __half* featop, __half* skinop, float* verts, int64_t B,
                cudaStream_t st);
+bool lbs_fused3_fits(const dpb_lbs* h, const LbsVariant& v);
+int lbs_fused3(dpb_lbs* h, const LbsVariant& v, __half* featop, __half* skinop, float* verts, int64_t B,
+               cudaStream_t st);
 int lbs_bwd_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_bwd_release(dpb_lbs* h);
 }  // namespace dpb

@@ -227,6 +227,13 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* v) {
                : "r"(taddr)
                : "memory");
 }
+// 32 lanes x 4 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
 // 32 lanes x 64 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
