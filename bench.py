@@ -10,7 +10,15 @@ One "step" = one pass of the hot path over one batch of synthetic input resident
   lbs:     configs[1] alone (SMPL LBS forward, B = 65536).
   sample:  the sampler alone.     completion: configs[2] (imputation sampler, 40960 rows).
 Prints ONE JSON line (rank 0).  Multi-GPU: rows are independent, every rank processes its own B rows
-(weak scaling, no data-path collective); timing is barrier + CUDA events, max over ranks.
+(weak scaling, no data-path collective in `value`); timing is barrier + CUDA events, max over ranks.  The end-to-end
+leg (`e2e`) at N > 1 also runs the collectives the reference's evaluation uses (run/completion.py:300-305,
+lib/utils/metric.py:8-37): all-gather of the generated poses and the rank-sharded APD with its all-reduce.
+
+Keys beyond the contract:
+  roofline          the fused sampler kernel against the measured sustained bf16 peak, with `roofline.lbs` = the LBS
+                    forward against the measured HBM copy bandwidth (and against its three-product tensor floor)
+  configs           (N = 1) every BASELINE.json config measured at its stated size, or the largest batch of independent
+                    problems that is one pass of the path (stated), each with the CPU port's figure
 """
 import argparse
 import json
@@ -32,6 +40,9 @@ LBS_BYTES_PER_POSE = 83560            # verts 6890*12 + joints 45*1
 #   LBS (65 536 poses): fused blend + skinning kernel 5.369 GB written + 0.450 GB read (the output plus operand refills)
 SAMPLER_DRAM_BYTES_PER_ROW_STEP = 1.201e9 / (37888 * 4)
 LBS_DRAM_BYTES_PER_POSE = (5.369e9 + 0.450e9) / 65536
+# tensor floor of the LBS forward at three fp16 products: (63 blend + 38.4 skinning) tensor-pipe cycles per (pose,
+# 128-vertex tile), 54 tiles, 148 SMs, 1.92 GHz (LBS design)
+LBS_TENSOR_FLOOR_MS = 65536 * 54 * 101.4 / 148 / 1.92e9 * 1e3
 N_SDE = 1000
 
 
@@ -77,35 +88,88 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU reference arm
+def _reference_sampler(workload, rows):
+    """The UNMODIFIED reference sampler (oracle/_ref, staged by oracle/make_ref.py from /root/reference) with the
+    synthetic weights recipe, or None when the staged modules are absent."""
+    from dposer_b200 import synthetic
+    from oracle import make_ref
+    mods = make_ref.import_reference()
+    if mods is None:
+        return None
+    model_m, sde_m, _, sampling_m = mods
+    cfg = synthetic.default_config()
+    cfg.device = torch.device('cpu')
+    torch.manual_seed(42)
+    model = model_m.ScoreModelFC(cfg, n_poses=21, pose_dim=3, hidden_dim=1024, embed_dim=512, n_blocks=2)
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.GroupNorm):
+            with torch.no_grad():
+                mod.weight.copy_(torch.rand(1024) + 0.5)
+                mod.bias.copy_(torch.randn(1024) * 0.1)
+    model.eval()
+    sde = sde_m.subVPSDE(beta_min=0.1, beta_max=20., N=N_SDE)
+    fn = sampling_m.get_pc_sampler(sde, (rows, 63), sampling_m.EulerMaruyamaPredictor, sampling_m.NoneCorrector,
+                                   lambda x: x, 0.16, n_steps=1, probability_flow=False, continuous=True, denoise=True,
+                                   eps=1e-3, device='cpu')
+    return model, fn
+
+
 def cpu_reference(workload, budget_s=20.0):
-    """The reference algorithm on the host cores (oracle port: torch-CPU restatement pinned bit-exactly to the
-    real reference by tests/golden).  Bounded sample, linear in rows and steps (all rows independent)."""
+    """The reference algorithm on the host cores.  Sampler: the reference's own `get_pc_sampler` from oracle/_ref when it
+    is staged (kind "reference"), else the oracle port (pinned bit-exactly to it by tests/golden).  LBS: always the port
+    (third-party smplx is absent).  Bounded sample, linear in rows (all rows independent)."""
+    import types
     from dposer_b200 import synthetic
     from oracle import lbs_ref, score_ref
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     t_pose = 0.0
     sample = []
+    kind = 'port'
     if workload in ('sample_lbs', 'sample', 'completion'):
-        sd = score_ref.make_state_dict(42)
-        sde = score_ref.SubVP(0.1, 20., N_SDE)
-        rows, steps = 512, 8
+        rows = 256
         gen = torch.Generator().manual_seed(1234)
         x = torch.randn(rows, 63, generator=gen)
         kw = {}
         if workload == 'completion':
             _, mask, obs = synthetic.completion_inputs(n_partial=rows, hypotheses=1)
-            kw = dict(observation=obs, mask=mask, task='completion')
-        score_ref.pc_sample(sd, sde, x, 1e-3, n_run=1, **kw)                       # warm-up
-        t0 = time.perf_counter()
-        done = 0
-        while time.perf_counter() - t0 < budget_s * 0.6:
-            score_ref.pc_sample(sd, sde, x, 1e-3, n_run=steps, **kw)
-            done += steps
-        dt = time.perf_counter() - t0
-        t_pose += dt / done * N_SDE / rows
-        sample.append(f'pc_sampler on {rows} rows: {done} Euler-Maruyama steps timed in runs of {steps}, '
-                      f'per-step time x {N_SDE} steps')
+            kw = dict(observation=obs, mask=mask)
+        ref = _reference_sampler(workload, rows)
+        if ref is not None:
+            kind = 'reference'
+            model, fn = ref
+            # the stock pc_sampler, all of its steps from `start`: the 'denoise' task is the reference's own way to
+            # enter the loop late (sampling.py:451-453); completion keeps its imputation and runs all N steps
+            k_steps = max(20, min(N_SDE, int(budget_s * 0.6 / 0.012)))
+            if workload == 'completion':
+                k_steps, a = N_SDE, types.SimpleNamespace(task='completion')
+                t0 = time.perf_counter()
+                fn(model, z=x, args=a, **kw)
+            else:
+                a = types.SimpleNamespace(task='denoise')
+                fn(model, z=x, start_step=N_SDE - 3, args=a)                   # warm-up
+                t0 = time.perf_counter()
+                fn(model, z=x, start_step=N_SDE - k_steps, args=a)
+            dt = time.perf_counter() - t0
+            t_pose += dt / k_steps * N_SDE / rows
+            sample.append(f'reference get_pc_sampler (oracle/_ref, unmodified) on {rows} rows: {k_steps} of {N_SDE} '
+                          f'Euler-Maruyama steps in {dt:.1f} s, per-step time x {N_SDE}')
+        else:
+            sd = score_ref.make_state_dict(42)
+            sde = score_ref.SubVP(0.1, 20., N_SDE)
+            steps = 8
+            if workload == 'completion':
+                kw['task'] = 'completion'
+            score_ref.pc_sample(sd, sde, x, 1e-3, n_run=1, **kw)                       # warm-up
+            t0 = time.perf_counter()
+            done = 0
+            while time.perf_counter() - t0 < budget_s * 0.6:
+                score_ref.pc_sample(sd, sde, x, 1e-3, n_run=steps, **kw)
+                done += steps
+            dt = time.perf_counter() - t0
+            t_pose += dt / done * N_SDE / rows
+            sample.append(f'oracle port pc_sampler on {rows} rows: {done} Euler-Maruyama steps timed in runs of {steps}, '
+                          f'per-step time x {N_SDE} steps')
     if workload in ('sample_lbs', 'lbs'):
         m = synthetic.make_body_tensors('smpl')
         rows = 512
@@ -118,8 +182,9 @@ def cpu_reference(workload, budget_s=20.0):
             lbs_ref.body_forward(m, shape, pose, inp['trans'], chunk=256)
             done += rows
         t_pose += (time.perf_counter() - t0) / done
-        sample.append(f'SMPL LBS {done} poses in chunks of 256')
-    return dict(value=1.0 / t_pose, unit='poses/s', cores=cores, kind='port', sample='; '.join(sample))
+        sample.append(f'SMPL LBS (oracle port of smplx lbs(); smplx itself is not installable here) {done} poses in '
+                      'chunks of 256')
+    return dict(value=1.0 / t_pose, unit='poses/s', cores=cores, kind=kind, sample='; '.join(sample))
 
 
 def run_reference_arm(args):
@@ -165,10 +230,202 @@ def workload_config(args, B):
             'weights': 'random-init ScoreModelFC (seed 42), synthetic SMPL tensors (seed 7)'}
 
 
+def _ev_time(f, flush, reps=3):
+    """best-of-`reps` CUDA-event time (ms) of f() with the L2 flushed before every run"""
+    f()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        f()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def bench_configs(args, dev, model, peaks, flush, cpu_per_row_step):
+    """Every BASELINE.json config at its stated size (or one batch of independent problems, stated) on ONE GPU."""
+    import types
+    from dposer_b200 import _lib as L
+    from dposer_b200 import fitting, prior, sampling, sde_lib, synthetic
+    from dposer_b200.body_model import BodyModel, SMPLX
+    from dposer_b200.misc import Posenormalizer
+    out = {}
+    cfg = synthetic.default_config()
+    norm = Posenormalizer(None, device=dev, normalize=True, min_max=False, rot_rep='axis')
+    sde = sde_lib.subVPSDE(0.1, 20., N_SDE)
+
+    def cpu_sampler(evals_per_step=1):
+        if cpu_per_row_step is None:
+            return None
+        return {'value': 1.0 / (cpu_per_row_step * N_SDE * evals_per_step), 'unit': 'poses/s',
+                'note': 'CPU arm of this run (cpu_baseline), per row and score evaluation'}
+
+    with torch.no_grad():
+        # ---- configs[0] literal: 500 poses, EM predictor (run/demo.py:127-136) and EM + Langevin (--metrics, :137-145)
+        B = 500
+        z = torch.randn(B, 63, generator=torch.Generator().manual_seed(5)).to(dev)
+        fn = sampling.get_sampling_fn(cfg, sde, (B, 63), lambda x: x, 1e-3, device=dev, return_trajs=False)
+        ms = _ev_time(lambda: fn(model, z=z), flush)
+        tf = SCORE_FLOP_PER_ROW * B * N_SDE / (ms * 1e-3) / 1e12
+        out['c1_generation_500_em'] = {
+            'workload': 'configs[0] literal: 500 poses, subVP reverse SDE, N=1000, EM predictor', 'rows': B, 'ms': ms,
+            'value': B / (ms * 1e-3), 'unit': 'poses/s', 'ms_per_sde_step': ms / N_SDE,
+            'roofline': {'bound': 'latency (4 row tiles on 148 SMs)', 'achieved': tf, 'unit': 'TFLOP/s',
+                         'frac_of_tensor_peak': tf / peaks['tc_sustained']}, 'cpu': cpu_sampler()}
+        cfg_l = synthetic.default_config()
+        cfg_l.sampling.corrector = 'langevin'
+        fn_l = sampling.get_sampling_fn(cfg_l, sde, (B, 63), lambda x: x, 1e-3, device=dev, return_trajs=False)
+        ms = _ev_time(lambda: fn_l(model, z=z), flush, reps=2)
+        out['c1_generation_500_pc'] = {
+            'workload': 'configs[0] --metrics variant: EM predictor + Langevin corrector (snr 0.16), 2 score '
+                        'evaluations per step', 'rows': B, 'ms': ms, 'value': B / (ms * 1e-3), 'unit': 'poses/s',
+            'ms_per_sde_step': ms / N_SDE, 'cpu': cpu_sampler(2)}
+
+        # ---- configs[2]: completion by imputation sampler, 10 hypotheses x 4096 partial poses
+        B = 40960
+        _, mask, obs = synthetic.completion_inputs(n_partial=B // 10, hypotheses=10, seed=21)
+        mask, obs = mask.to(dev), obs.to(dev)
+        z = torch.randn(B, 63, generator=torch.Generator().manual_seed(6)).to(dev)
+        fn_c = sampling.get_sampling_fn(cfg, sde, (B, 63), lambda x: x, 1e-3, device=dev, return_trajs=False)
+        targs = types.SimpleNamespace(task='completion')
+        ms = _ev_time(lambda: fn_c(model, z=z, observation=obs, mask=mask, args=targs), flush, reps=2)
+        tf = SCORE_FLOP_PER_ROW * B * N_SDE / (ms * 1e-3) / 1e12
+        out['c3_completion'] = {
+            'workload': 'configs[2]: 10 hypotheses x 4096 partial poses (legs masked), imputation sampler, N=1000',
+            'rows': B, 'ms': ms, 'value': B / (ms * 1e-3), 'unit': 'poses/s',
+            'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peaks['tc_sustained'], 'unit': 'TFLOP/s',
+                         'frac': tf / peaks['tc_sustained']}, 'cpu': cpu_sampler()}
+        del mask, obs, z
+
+    # ---- configs[3]: motion denoising, SMPL-X, 3 x 60 Adam steps (run/motion_denoising.py:332), batches of sequences
+    n_seq, Lf = args.c4_sequences, 60
+    rows = n_seq * Lf
+    mx = synthetic.make_body_tensors('smplx')
+    bm = BodyModel(mx, num_betas=10, batch_size=rows, model_type='smplx').to(dev)
+    ges, _ = synthetic.gesture_sequences()
+    gt = ges[:Lf].repeat(n_seq, 1).to(dev)
+    with torch.no_grad():
+        jn = bm(pose_body=gt, need_verts=False).Jtr[:, :22] + 0.04 * torch.randn(rows, 22, 3, device=dev)
+    md = fitting.MotionDenoise(cfg, types.SimpleNamespace(device=dev), model, bm, sde_lib.subVPSDE(0.1, 20., N_SDE), norm,
+                               sde_N=500, batch_size=rows, seq_len=Lf)
+    kw = dict(time_strategy='3', sample_trun=4.0, sample_time=490, iterations=3, steps_per_iter=60, graphs=True)
+    md.optimize(jn, **kw)                      # first batch: allocates, captures the 180 step graphs
+    torch.cuda.synchronize()
+    md.poses = torch.randn(rows, 63, device=dev) * 0.01
+    flush.fill_(1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = md.optimize(jn, gt_poses=None, **kw)   # a further batch of sequences: graph replays only
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out['c4_motion_denoise'] = {
+        'workload': f'configs[3]: DPoser prior + temporal vertex term + joint data term, SMPL-X (10475 verts), Adam 3 x 60 '
+                    f'steps; ONE batch of {n_seq} independent 60-frame sequences (the config\'s 8192 sequences are '
+                    f'{8192 // n_seq} such batches replaying the same captured step graphs)',
+        'sequences': n_seq, 'frames': rows, 'adam_steps': 180, 'seconds': dt, 'value': rows / dt, 'unit': 'frames/s',
+        'ms_per_adam_step': dt * 1e3 / 180, 'seconds_for_8192_sequences': dt * 8192 / n_seq,
+        'finite': bool(torch.isfinite(res['pose_body']).all())}
+    del md, bm, jn, gt, res
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: SMPLify, SMPL-X joints, 100 camera + 5 x 100 body Adam steps (run/fitting.py:117), per-GPU shard
+    B = args.c5_images
+    smpl = SMPLX(mx, batch_size=B).to(dev)
+    g = torch.Generator().manual_seed(41)
+    body = synthetic.toy_poses().repeat((B + 499) // 500, 1)[:B]
+    glob = torch.tensor([3.14159, 0., 0.]) + 0.2 * torch.randn(B, 3, generator=g)
+    cam = torch.stack([0.2 * torch.randn(B, generator=g), 0.2 * torch.randn(B, generator=g),
+                       20 + 20 * torch.rand(B, generator=g)], 1)
+    betas = torch.randn(B, 10, generator=g)
+    with torch.no_grad():
+        j = smpl(betas=betas.to(dev), body_pose=body.to(dev), global_orient=glob.to(dev), transl=cam.to(dev)).joints
+        center = torch.full((B, 2), 512., device=dev)
+        kp = torch.stack([5000 * j[..., 0] / j[..., 2] + 512, 5000 * j[..., 1] / j[..., 2] + 512], -1) + \
+            2 * torch.randn(B, 49, 2, device=dev)
+        conf = 0.3 + 0.7 * torch.rand(B, 49, device=dev)
+        conf[:, 25:] = 0
+        kp2d = torch.cat([kp, conf[..., None]], -1)
+    sargs = types.SimpleNamespace(device=dev, sde_N=500, time_strategy='3')
+    pp = prior.DPoser(batch_size=B, args=sargs, model=model, sde=sde_lib.subVPSDE(0.1, 20., N_SDE), normalizer=norm)
+    init_pose = torch.cat([glob + 0.1, smpl.mean_poses[3:66].cpu()[None].repeat(B, 1)], 1).to(dev)
+    init_betas = smpl.mean_shape[None].repeat(B, 1).to(dev)
+    init_cam = (cam + torch.tensor([0.1, -0.1, 2.0])).to(dev)
+    warm = fitting.SMPLify(smpl, step_size=1e-2, batch_size=B, num_iters=2, focal_length=5000., args=sargs, pose_prior=pp)
+    warm(init_pose, init_betas, init_cam, center, kp2d.clone())
+    fit = fitting.SMPLify(smpl, step_size=1e-2, batch_size=B, num_iters=100, focal_length=5000., args=sargs, pose_prior=pp)
+    flush.fill_(1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pose, _, _, reproj = fit(init_pose, init_betas, init_cam, center, kp2d.clone())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out['c5_smplify'] = {
+        'workload': f'configs[4]: DPoser prior + SMPL-X joints (joints-only LBS, 55 + 89 outputs) + 2D reprojection, 100 '
+                    f'camera + 5 x 100 body Adam steps, {B} independent images on one GPU (1M images = 8 such shards)',
+        'images': B, 'adam_steps': 600, 'seconds': dt, 'value': B / dt, 'unit': 'poses/s',
+        'ms_per_adam_step': dt * 1e3 / 600, 'finite': bool(torch.isfinite(pose).all() and torch.isfinite(reproj).all())}
+    return out
+
+
+def cpu_task_loops(budget_s=12.0):
+    """configs[3] / configs[4] on the host cores: the oracle loops (pinned to the real run/motion_denoising.py and
+    run/smplify.py by tests/golden/loops_golden.npz) on one sequence / four images, a few Adam steps, scaled to the
+    full step count (every step costs the same)."""
+    from dposer_b200 import synthetic
+    from dposer_b200.body_model import JOINT_MAP_49
+    from dposer_b200.misc import Posenormalizer
+    from oracle import fitting_loops, fitting_ref, lbs_ref, score_ref
+    torch.set_num_threads(os.cpu_count())
+    sd = score_ref.make_state_dict(42)
+    m = synthetic.make_body_tensors('smplx')
+    norm = Posenormalizer(None, device='cpu', normalize=True, min_max=False, rot_rep='axis')
+    mean, std = norm.mean_poses.cpu(), norm.std_poses.cpu()
+    g = torch.Generator().manual_seed(3)
+    res = {}
+    Lf, steps = 60, 2
+    ges, _ = synthetic.gesture_sequences()
+    gt = ges[:Lf]
+    _, jg = lbs_ref.body_forward(m, torch.zeros(Lf, 20), torch.cat([torch.zeros(Lf, 3), gt, torch.zeros(Lf, 99)], 1))
+    noisy = jg[:, :22] + 0.04 * torch.randn(Lf, 22, 3, generator=g)
+    zl = [torch.randn(Lf, 63, generator=g) for _ in range(steps)]
+    t0 = time.perf_counter()
+    fitting_loops.motion_denoise(sd, m, noisy, 0.01 * torch.randn(Lf, 63, generator=g), mean, std, zl, Lf, sde_N=500,
+                                 iterations=1, steps_per_iter=steps, sample_trun=4.0)
+    dt = (time.perf_counter() - t0) / steps
+    res['c4_motion_denoise'] = {'value': Lf / (dt * 180), 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                'sample': f'one 60-frame sequence, {steps} of 180 Adam steps, {dt:.2f} s per step'}
+    B, iters = 4, 1
+    jm = torch.tensor(JOINT_MAP_49)
+    body = synthetic.toy_poses()[:B]
+    glob = torch.tensor([3.14159, 0., 0.]) + 0.2 * torch.randn(B, 3, generator=g)
+    cam = torch.stack([0.2 * torch.randn(B, generator=g), 0.2 * torch.randn(B, generator=g), 20 + 20 * torch.rand(B, generator=g)], 1)
+    hm = m['hands_mean'][None].expand(B, -1)
+    _, j = lbs_ref.body_forward(m, torch.zeros(B, 20), torch.cat([glob, body, torch.zeros(B, 9), hm], 1), cam)
+    center = torch.full((B, 2), 512.)
+    kp = fitting_ref.perspective_projection(j[:, jm], 5000., center)
+    conf = torch.ones(B, 49)
+    conf[:, 25:] = 0
+    kp2d = torch.cat([kp, conf[..., None]], -1)
+    zl = [torch.randn(B, 63, generator=g) for _ in range(5 * iters + 1)]
+    init_pose = torch.cat([glob + 0.1, body], 1)
+    t0 = time.perf_counter()
+    fitting_loops.smplify(sd, m, jm, init_pose, torch.zeros(B, 10), cam + torch.tensor([0.1, -0.1, 2.0]), center, kp2d,
+                          mean, std, zl, num_iters=iters, sde_N=500, hand_mean=m['hands_mean'])
+    dt = (time.perf_counter() - t0) / (6 * iters)
+    res['c5_smplify'] = {'value': B / (dt * 600), 'unit': 'poses/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': f'{B} images, {6 * iters} of 600 Adam steps, {dt:.2f} s per step'}
+    return res
+
+
 def run_gpu_arm(args):
     from dposer_b200 import _lib as L
     from dposer_b200 import dist as D
-    from dposer_b200 import sampling, sde_lib, synthetic
+    from dposer_b200 import metric, sampling, sde_lib, steps, synthetic
     from dposer_b200.body_model import BodyModel
     from dposer_b200.misc import Posenormalizer
     import types
@@ -186,6 +443,7 @@ def run_gpu_arm(args):
     cfg = synthetic.default_config()
     sde = sde_lib.subVPSDE(0.1, 20., args.sde_steps)
     norm = Posenormalizer(None, device=dev, normalize=True, min_max=False, rot_rep='axis')
+    mean, std = norm.mean_poses.to(dev).float().contiguous(), norm.std_poses.to(dev).float().contiguous()
     body = synthetic.make_body_tensors('smpl')
     bm = BodyModel(body, batch_size=B, model_type='smpl').to(dev)
     fn = sampling.get_sampling_fn(cfg, sde, (B, 63), lambda x: x, 1e-3, device=dev, return_trajs=False)
@@ -200,6 +458,9 @@ def run_gpu_arm(args):
         comp = (obs.pin_memory(), mask.pin_memory())
     task_args = types.SimpleNamespace(task='completion') if wl == 'completion' else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pose69 = torch.zeros(B, 69, dtype=torch.float32, device=dev)     # body pose | two zero hand joints (SMPL)
+    n_apd = 512                                                      # rows per rank that enter the APD (reference: 500)
+    gathered = torch.empty(world * B, 63, dtype=torch.float32, device=dev) if world > 1 else None
 
     def to_dev(d):
         return {k: v.to(dev, non_blocking=True) for k, v in d.items()}
@@ -214,11 +475,10 @@ def run_gpu_arm(args):
             _, x0 = fn(model, z=xT, **kw)
             res['poses'] = x0
         if wl == 'sample_lbs':
-            # random-init weights drive |x| to ~1e4: squash to a plausible angle range so the
-            # LBS input is well-conditioned; the squash is outside the measured kernels' arithmetic
-            pose = torch.cat([norm.offline_denormalize(torch.tanh(res['poses'] * 1e-4)),
-                              torch.zeros(B, 6, device=dev)], dim=1)
-            out = bm(root_orient=lbs_in['root_orient'], pose_body=pose, betas=lbs_in['betas'], trans=lbs_in['trans'])
+            # de-normalise (run/demo.py:148) in one native kernel.  Random-init weights drive |x| to ~1e4 (SURVEY App.
+            # B-1): tanh(1e-4 x) first, so that the LBS input is a plausible angle range (stated in config)
+            steps.affine_cols(res['poses'], 0, 63, mean, std, pose69, inverse=True, out_ld=69, cols=63, squash=1e-4)
+            out = bm(root_orient=lbs_in['root_orient'], pose_body=pose69, betas=lbs_in['betas'], trans=lbs_in['trans'])
             res['joints'], res['verts'] = out.Jtr, out.v
         elif wl == 'lbs':
             out = bm(**lbs_in)
@@ -226,6 +486,20 @@ def run_gpu_arm(args):
         return res
 
     results_host = {}
+    apd_check = {}
+
+    def collectives(res):
+        """what the reference's evaluation does with the generated poses across ranks (run/completion.py:300-305,
+        lib/utils/metric.py:8-37): gather them on every rank, APD over the gathered joints with rank-sharded rows"""
+        if world == 1 or 'poses' not in res:
+            return
+        allp = D.all_gather_rows(res['poses'], world * B, out=gathered)
+        sub = allp.view(world, B, 63)[:, :n_apd].reshape(world * n_apd, 21, 3)
+        apd = metric.average_pairwise_distance(sub, group=torch.distributed.group.WORLD)
+        res['apd'] = apd
+        if 'ref' not in apd_check:          # once: the N-rank APD equals the 1-rank APD of the same gathered rows
+            apd_check['ref'] = float(metric.average_pairwise_distance(sub))
+            apd_check['sharded'] = float(apd)
 
     def step(e2e):
         if e2e:
@@ -236,8 +510,10 @@ def run_gpu_arm(args):
             xT, lbs_in, comp_dev = xT_res, lbs_res, comp_res
         with torch.no_grad():
             res = hot_path(xT, lbs_in, comp_dev)
+            if e2e:
+                collectives(res)
         if e2e:
-            for k in ('poses', 'joints'):
+            for k in ('poses', 'joints', 'apd'):
                 if k in res:
                     if k not in results_host:
                         results_host[k] = torch.empty(res[k].shape, dtype=res[k].dtype).pin_memory()
@@ -280,39 +556,34 @@ def run_gpu_arm(args):
     clk = clocks.stop() if rank == 0 else None
 
     # per-kernel timing of the two stages for the roofline (same stream, CUDA events, inputs resident)
-    def time_stage(f, reps=3):
-        f()
-        torch.cuda.synchronize()
-        best = 1e30
-        for _ in range(reps):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            f()
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        return best
-
     roof, roof_lbs = None, None
     with torch.no_grad():
         if wl in ('sample_lbs', 'sample', 'completion'):
             kw = {} if comp_res is None else dict(observation=comp_res[0], mask=comp_res[1], args=task_args)
-            t_s = time_stage(lambda: fn(model, z=xT_res, **kw), reps=2)
+            t_s = _ev_time(lambda: fn(model, z=xT_res, **kw), flush, reps=2)
             ach = SCORE_FLOP_PER_ROW * B * args.sde_steps / (t_s * 1e-3) / 1e12
-            roof = {'kernel': 'fused sampler (score net x N steps)', 'bound': 'tensor', 'achieved': ach,
+            roof = {'kernel': 'tc::score_tc_kernel: fused sampler (score net x N steps)', 'bound': 'tensor', 'achieved': ach,
                     'peak': peaks['tc_sustained'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tc_sustained'],
                     'traffic': SAMPLER_DRAM_BYTES_PER_ROW_STEP * B * args.sde_steps,
                     'traffic_note': 'DRAM bytes, scaled per row-step from the committed ncu capture', 'ms': t_s,
                     'peak_source': peaks['src'] + ' (bf16 sustained)'}
         if wl in ('sample_lbs', 'lbs'):
-            t_l = time_stage(lambda: bm(**lbs_res), reps=5)
+            t_l = _ev_time(lambda: bm(**lbs_res), flush, reps=5)
             ach = LBS_BYTES_PER_POSE * B / (t_l * 1e-3) / 1e9
-            roof_lbs = {'kernel': 'SMPL LBS forward', 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'],
+            roof_lbs = {'kernel': 'lbs_pose_kernel + lt3::lbs_fused3_kernel + lbs_gather_kernel: SMPL LBS forward',
+                        'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'],
                         'unit': 'GB/s', 'frac': ach / peaks['hbm'], 'traffic': LBS_DRAM_BYTES_PER_POSE * B,
                         'traffic_note': 'DRAM bytes, scaled per pose from the committed ncu capture (65536 poses)',
-                        'algorithmic_bytes': LBS_BYTES_PER_POSE * B, 'ms': t_l, 'peak_source': peaks['src']}
+                        'algorithmic_bytes': LBS_BYTES_PER_POSE * B, 'ms': t_l, 'peak_source': peaks['src'],
+                        'tensor_floor_ms': LBS_TENSOR_FLOOR_MS * B / 65536,
+                        'frac_of_tensor_floor': LBS_TENSOR_FLOOR_MS * B / 65536 / t_l,
+                        'tensor_floor_note': 'three fp16 products (hi.hi + hi.lo + lo.hi) for 1e-5 m: 101 tensor-pipe '
+                                             'cycles per (pose, 128-vertex tile) at 1.92 GHz on 148 SMs'}
+    configs = None
+    if world == 1 and args.configs != 'none' and wl == 'sample_lbs':
+        del bm, pose69, xT_res, lbs_res
+        torch.cuda.empty_cache()
+        configs = True
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -322,8 +593,10 @@ def run_gpu_arm(args):
     launches = 0
     if wl in ('sample_lbs', 'sample', 'completion'):
         launches += (1 + 1) if tc else (1 + args.sde_steps * 12)        # time table + fused / per-layer kernels
+    if wl == 'sample_lbs':
+        launches += 1                       # de-normalise
     if wl in ('sample_lbs', 'lbs'):
-        launches += 6 if tc else 3          # pose, (featop, blend, skinop, skin | vertex), gather kernels
+        launches += 3 if tc else 3          # pose, fused blend + skinning (or vertex), joint gather kernels
     h2d = xT_host.numel() * 4 + sum(v.numel() * 4 for v in lbs_host.values()) + \
         (0 if comp is None else sum(c.numel() * 4 for c in comp))
     d2h = sum(v.numel() * 4 for v in results_host.values())
@@ -335,13 +608,41 @@ def run_gpu_arm(args):
             'data': 'synthetic', 'config': workload_config(args, B), 'clocks': clk,
             'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': 'poses/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e,
-                    'note': 'pinned host inputs -> device, hot path, generated poses + joints -> pinned host'},
-            'gpu_launches': launches * args.steps,
-            'roofline': roof if roof is not None else roof_lbs}
+                    'note': 'pinned host inputs -> device, hot path, generated poses + joints -> pinned host'
+                            + ('; plus NCCL all-gather of the poses and the rank-sharded APD all-reduce' if world > 1 else '')},
+            'gpu_launches': launches * args.steps}
+    if world > 1 and apd_check:
+        line['e2e']['collectives'] = {'all_gather_bytes_per_rank': B * 63 * 4, 'apd_rows': world * n_apd,
+                                      'apd_sharded': apd_check['sharded'], 'apd_single_rank': apd_check['ref'],
+                                      'rel_diff': abs(apd_check['sharded'] - apd_check['ref']) / max(abs(apd_check['ref']), 1e-30)}
+    rf = roof if roof is not None else roof_lbs
     if roof is not None and roof_lbs is not None:
-        line['roofline_lbs'] = roof_lbs
+        rf = dict(roof)
+        rf['lbs'] = roof_lbs
+    line['roofline'] = rf
+    cpu_per_row_step = None
     if not args.no_cpu:
         line['cpu_baseline'] = cpu_reference(wl, budget_s=args.cpu_budget)
+    if configs:
+        if not args.no_cpu:
+            try:
+                t0 = time.perf_counter()
+                cs = cpu_reference('sample', budget_s=6.0)
+                cpu_per_row_step = 1.0 / (cs['value'] * N_SDE)
+            except Exception:
+                cpu_per_row_step = None
+        cfgs = bench_configs(args, dev, model, peaks, flush, cpu_per_row_step)
+        if roof_lbs is not None:
+            cfgs['c2_lbs'] = {'workload': 'configs[1]: SMPL LBS forward only, 65536 poses', 'rows': B, 'ms': roof_lbs['ms'],
+                              'value': B / (roof_lbs['ms'] * 1e-3), 'unit': 'poses/s',
+                              'roofline': {k: roof_lbs[k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'frac_of_tensor_floor')}}
+        if not args.no_cpu:
+            try:
+                for k, v in cpu_task_loops().items():
+                    cfgs[k]['cpu'] = v
+            except Exception as e:       # the CPU figures are reported baselines: never lose the GPU line over them
+                cfgs['cpu_task_loops_error'] = repr(e)[:200]
+        line['configs'] = cfgs
     print(json.dumps(line), flush=True)
 
 
@@ -357,6 +658,9 @@ def main():
     ap.add_argument('--engine', default='auto', choices=['auto', 'tc', 'fp32'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--cpu-budget', type=float, default=20.0)
+    ap.add_argument('--configs', default='all', choices=['all', 'none'], help='N=1: also measure every BASELINE config')
+    ap.add_argument('--c4-sequences', type=int, default=256, help='sequences per batch of the motion-denoising config')
+    ap.add_argument('--c5-images', type=int, default=131072, help='images on this GPU for the SMPLify config')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -100,7 +100,7 @@ def load():
     lib.dpb_adam_step.argtypes = [vp, i64, vp, vp, vp, i64, f32, vp, i64, f32, vp, vp, i64, f32, i64, C.c_int, f32, f32,
                                   f32, f32, C.c_int, vp]
     lib.dpb_masked_mse_grad.argtypes = [vp, vp, vp, vp, i64, vp]
-    lib.dpb_affine_cols.argtypes = [vp, i64, vp, vp, vp, i64, C.c_int, C.c_int, vp]
+    lib.dpb_affine_cols.argtypes = [vp, i64, vp, vp, vp, i64, i64, C.c_int, C.c_int, f32, vp]
     lib.dpb_joint_map_gather.argtypes = [vp, C.c_int, vp, C.c_int, vp, i64, vp]
     lib.dpb_joint_map_scatter.argtypes = [vp, C.c_int, vp, C.c_int, vp, i64, vp]
     lib.dpb_mean_point_error.argtypes = [vp, vp, i64, C.c_int, vp, C.c_int, vp, vp]

@@ -160,14 +160,15 @@ __global__ void adam_kernel(float* __restrict__ param, int64_t ld_p, float* __re
 }
 
 __global__ void affine_cols_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ mean,
-                                   const float* __restrict__ sd, float* __restrict__ out, int64_t rows, int cols,
-                                   int inverse) {
+                                   const float* __restrict__ sd, float* __restrict__ out, int64_t ldo, int64_t rows,
+                                   int cols, int inverse, float squash) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int64_t r = i / cols;
   const int c = (int)(i % cols);
-  const float xv = x[r * ldx + c];
-  out[i] = inverse ? xv * sd[c] + mean[c] : (xv - mean[c]) / sd[c];
+  float xv = x[r * ldx + c];
+  if (squash > 0.f) xv = tanhf(xv * squash);
+  out[r * ldo + c] = inverse ? xv * sd[c] + mean[c] : (xv - mean[c]) / sd[c];
 }
 
 // cotangent of mean((x*m - o*m)^2) (nn.MSELoss 'mean' on masked tensors, run/completion.py:197): 2 m^2 (x - o) / n
@@ -256,12 +257,12 @@ extern "C" int dpb_adam_step(float* param, int64_t ld_p, float* m, float* v, con
 }
 
 extern "C" int dpb_affine_cols(const float* x, int64_t ldx, const float* mean, const float* sd, float* out,
-                               int64_t rows, int cols, int inverse, void* stream) {
-  DPB_REQUIRE(x && mean && sd && out && cols > 0, "dpb_affine_cols: bad argument");
+                               int64_t ldo, int64_t rows, int cols, int inverse, float squash, void* stream) {
+  DPB_REQUIRE(x && mean && sd && out && cols > 0 && ldo >= cols, "dpb_affine_cols: bad argument");
   if (rows <= 0) return DPB_OK;
   PtrDeviceGuard guard(x);
   const int64_t n = rows * cols;
-  affine_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean, sd, out, rows, cols, inverse);
+  affine_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, mean, sd, out, ldo, rows, cols, inverse, squash);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }

@@ -1,6 +1,7 @@
 // Internal layout of the LBS handle (not part of the C ABI).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <vector>
 
@@ -56,6 +57,11 @@ struct dpb_lbs {
   // backward: transposed-blend GEMM operand (lbs_bwd.cu)
   int bw_np = 0, bw_kp = 0;       // (P+S) padded to 64, 3V padded to 16
   float* dirs_pad = nullptr;      // [bw_np, bw_kp] fp32: rows 0..P-1 posedirs, rows P..P+S-1 shapedirs^T, zero padding
+  // backward: the same operand for the tcgen05 transposed blend (lbs_bwd_tc.cu)
+  bool bt_ready = false;
+  int bt_rp = 0, bt_kp = 0;       // 3V padded to 64; feature rows padded to 256 / 512
+  __half* basisT16 = nullptr;     // [bt_kp, 2*bt_rp] fp16 [hi | lo]
+  CUtensorMap tm_bT;
 };
 
 namespace dpb {
@@ -97,6 +103,10 @@ int lbs_fused2(dpb_lbs* h, const LbsVariant& v, __half* featop, __half* skinop, 
 bool lbs_fused3_fits(const dpb_lbs* h, const LbsVariant& v);
 int lbs_fused3(dpb_lbs* h, const LbsVariant& v, __half* featop, __half* skinop, float* verts, int64_t B,
                cudaStream_t st);
+int lbs_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m);
+void lbs_bwd_tc_release(dpb_lbs* h);
+int lbs_blendT_splits(const dpb_lbs* h, int64_t B);
+int lbs_blendT_tc(dpb_lbs* h, const __half* gvp16, float* cpart, float* gfeat, float* gbeta, int64_t B, cudaStream_t st);
 int lbs_bwd_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_bwd_release(dpb_lbs* h);
 }  // namespace dpb

@@ -16,6 +16,8 @@
 //
 // This is the adjoint of lbs.cu (smplx 0.1.28 lbs(); reference call sites lib/body_model/body_model.py:75-88,
 // run/motion_denoising.py:255-268, run/smplify.py:243-258 where autograd differentiates the smplx ops).
+#include <cstdlib>
+
 #include "lbs.h"
 
 namespace dpb {
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(BW_TV) lbs_skin_bwd_kernel(
     const float* __restrict__ A, const float* __restrict__ vposed, const int32_t* __restrict__ ell_idx,
     const float* __restrict__ ell_w, const int32_t* __restrict__ need_index, int n_need, int V, int J, int S, int nnz,
     const float* __restrict__ g_verts, const float* __restrict__ gextra, float* __restrict__ gA,
-    float* __restrict__ gvp, int Kp, float* __restrict__ gbt, int64_t B) {
+    float* __restrict__ gvp, int Kp, __half* __restrict__ gvp16, int Rp, float* __restrict__ gbt, int64_t B) {
   extern __shared__ float smem[];
   float* A_s = smem;                                 // [TP][J][12]
   float* gA_s = A_s + (size_t)BW_TP * J * 12;        // [TP][J][12]
@@ -253,10 +255,20 @@ __global__ void __launch_bounds__(BW_TV) lbs_skin_bwd_kernel(
     atomicAdd(gtr_s + p * 3 + 0, g[0]);
     atomicAdd(gtr_s + p * 3 + 1, g[1]);
     atomicAdd(gtr_s + p * 3 + 2, g[2]);
-    float* o = gvp + (size_t)(b0 + p) * Kp + (size_t)v * 3;   // g_vposed = T_R^T g
-    o[0] = TR[0] * g[0] + TR[3] * g[1] + TR[6] * g[2];
-    o[1] = TR[1] * g[0] + TR[4] * g[1] + TR[7] * g[2];
-    o[2] = TR[2] * g[0] + TR[5] * g[1] + TR[8] * g[2];
+    const float o0 = TR[0] * g[0] + TR[3] * g[1] + TR[6] * g[2];   // g_vposed = T_R^T g
+    const float o1 = TR[1] * g[0] + TR[4] * g[1] + TR[7] * g[2];
+    const float o2 = TR[2] * g[0] + TR[5] * g[1] + TR[8] * g[2];
+    if (gvp16) {   // operand of the tcgen05 transposed blend: fp16 [hi | lo] halves of a [B, 2*Rp] row
+      __half* oh = gvp16 + (size_t)(b0 + p) * 2 * Rp + (size_t)v * 3;
+      const __half h0 = __float2half_rn(o0), h1 = __float2half_rn(o1), h2 = __float2half_rn(o2);
+      oh[0] = h0; oh[1] = h1; oh[2] = h2;
+      oh[Rp + 0] = __float2half_rn(o0 - __half2float(h0));
+      oh[Rp + 1] = __float2half_rn(o1 - __half2float(h1));
+      oh[Rp + 2] = __float2half_rn(o2 - __half2float(h2));
+    } else {
+      float* o = gvp + (size_t)(b0 + p) * Kp + (size_t)v * 3;
+      o[0] = o0; o[1] = o1; o[2] = o2;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < np * J * 12; i += BW_TV)
@@ -503,9 +515,15 @@ void lbs_bwd_release(dpb_lbs* h) {
   h->dirs_pad = nullptr;
 }
 
+// vposed | g_vposed (fp32 [B, bw_kp] or fp16 [B, 2*bt_rp]) | GEMM output (fp32 [B, bw_np] or [splits, B, bt_kp])
+static size_t bwd_gvp_bytes(const dpb_lbs* h, int64_t B) {
+  const size_t a = (size_t)B * h->bw_kp * 4, b = h->bt_ready ? (size_t)B * 2 * h->bt_rp * 2 : 0;
+  return align_up(a > b ? a : b, 256);
+}
 static size_t bwd_scratch_bytes(const dpb_lbs* h, int64_t B) {
-  return align_up((size_t)B * h->V * 3 * 4, 256) + align_up((size_t)B * h->bw_kp * 4, 256) +
-         align_up((size_t)B * h->bw_np * 4, 256);
+  const size_t a = (size_t)B * h->bw_np * 4;
+  const size_t b = h->bt_ready ? (size_t)lbs_blendT_splits(h, B) * B * h->bt_kp * 4 : 0;
+  return align_up((size_t)B * h->V * 3 * 4, 256) + bwd_gvp_bytes(h, B) + align_up(a > b ? a : b, 256);
 }
 
 }  // namespace dpb
@@ -552,11 +570,14 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
     uint8_t* sp = static_cast<uint8_t*>(scratch);
     float* vposed = reinterpret_cast<float*>(sp);
     float* gvp = reinterpret_cast<float*>(sp + align_up((size_t)B * h->V * 3 * 4, 256));
-    float* gout = reinterpret_cast<float*>(sp + align_up((size_t)B * h->V * 3 * 4, 256) +
-                                           align_up((size_t)B * h->bw_kp * 4, 256));
+    float* gout = reinterpret_cast<float*>(sp + align_up((size_t)B * h->V * 3 * 4, 256) + bwd_gvp_bytes(h, B));
+    // the transposed blend on tcgen05 (fp16 [hi | lo] operand) unless DPB_LBS_BWD_SGEMM=1 asks for the fp32 SGEMM (A/B)
+    const bool tcT = h->bt_ready && !(getenv("DPB_LBS_BWD_SGEMM") && atoi(getenv("DPB_LBS_BWD_SGEMM")));
+    __half* gvp16 = tcT ? reinterpret_cast<__half*>(gvp) : nullptr;
     int rc = lbs_tc_blend(h, betas, w.feat, w.featop, vposed, B, st);
     if (rc != DPB_OK) return rc;
-    DPB_CUDA_CHECK(cudaMemsetAsync(gvp, 0, (size_t)B * h->bw_kp * 4, st));
+    if (tcT) DPB_CUDA_CHECK(cudaMemsetAsync(gvp16, 0, (size_t)B * 2 * h->bt_rp * 2, st));
+    else DPB_CUDA_CHECK(cudaMemsetAsync(gvp, 0, (size_t)B * h->bw_kp * 4, st));
     const size_t smem = ((size_t)2 * BW_TP * J * 12 + BW_TP * 3) * 4;
     DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_skin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((h->V + BW_TV - 1) / BW_TV, (unsigned)((B + BW_TP - 1) / BW_TP));
@@ -564,12 +585,18 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
     lbs_skin_bwd_kernel<<<grid, BW_TV, smem, st>>>(w.A, vposed, h->ell_idx, h->ell_w,
                                                    have_extra ? h->need_index : nullptr, h->n_need, h->V, J, S, h->nnz,
                                                    g_verts, have_extra ? w.gextra : nullptr, w.gA, gvp, h->bw_kp,
-                                                   w.gbeta, B);
-    dim3 ggrid(h->bw_np / 64, (unsigned)((B + 63) / 64));
-    bwd_gemm_kernel<<<ggrid, 256, 0, st>>>(gvp, h->dirs_pad, gout, B, h->bw_np, h->bw_kp);
-    const int64_t n = B * (P + S);
-    bwd_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gout, h->bw_np, P, S, w.gfeat, w.gbeta, B);
+                                                   gvp16, h->bt_rp, w.gbeta, B);
     DPB_CUDA_CHECK(cudaGetLastError());
+    if (tcT) {
+      rc = lbs_blendT_tc(h, gvp16, gout, w.gfeat, w.gbeta, B, st);
+      if (rc != DPB_OK) return rc;
+    } else {
+      dim3 ggrid(h->bw_np / 64, (unsigned)((B + 63) / 64));
+      bwd_gemm_kernel<<<ggrid, 256, 0, st>>>(gvp, h->dirs_pad, gout, B, h->bw_np, h->bw_kp);
+      const int64_t n = B * (P + S);
+      bwd_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gout, h->bw_np, P, S, w.gfeat, w.gbeta, B);
+      DPB_CUDA_CHECK(cudaGetLastError());
+    }
   } else if (full || have_extra) {
     size_t smem = ((size_t)P * BW_TP + (size_t)S * BW_TP + 2 * (size_t)BW_TP * J * 12 + (size_t)BW_TP * 3 * BW_TV +
                    BW_TP * 3) * 4;

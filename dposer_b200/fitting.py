@@ -81,8 +81,9 @@ class MotionDenoise(MotionPrior):
                  z=f(rows, 63), lbs=S.LbsStep(core, rows, dev, need_verts=True),
                  prior=S.PriorStep(self.model, self.sde, self.continuous, rows, dev),
                  mean=self.Normalizer.mean_poses.to(dev).float().contiguous(),
-                 std=self.Normalizer.std_poses.to(dev).float().contiguous(), graphs=None)
+                 std=self.Normalizer.std_poses.to(dev).float().contiguous(), graphs=None, sched_key=None, seed=0)
         b['inv_std'] = (1.0 / b['std']).contiguous()
+        b['opt'] = S.Adam(b['full_pose'], 3, 63, 0.03)
         self._bufs = b
         return b
 
@@ -119,11 +120,17 @@ class MotionDenoise(MotionPrior):
                 step = it * steps_per_iter + i
                 qt = _quan_t(time_strategy, self.sde.N, total_steps, step, sample_trun, sample_time, 2)
                 sched.append((it, float(timesteps[qt])))
-        pri.schedule([t for _, t in sched])
-        opt = S.Adam(b['full_pose'], 3, 63, 0.03)
+        # the schedule's tables, the optimiser state and the captured step graphs live with the buffers: a further batch
+        # of sequences with the same (deterministic) schedule replays the graphs of the first one
+        key = None if time_strategy == '1' else (time_strategy, sample_trun, sample_time, iterations, steps_per_iter,
+                                                 bool(graphs and z_list is None), self.dposer_weight)
+        if key is None or b['sched_key'] != key:
+            pri.schedule([t for _, t in sched])
+            b['sched_key'], b['seed'] = key, (mutils.host_seed() if z_list is None else 0)
+            b['graphs'] = S.StepGraphs(graphs and z_list is None)
+        opt, seed, sg = b['opt'], b['seed'], b['graphs']
+        opt.reset()
         wd = self.get_loss_weights()
-        seed = mutils.host_seed() if z_list is None else 0
-        sg = S.StepGraphs(graphs and z_list is None)
 
         def one_step(k):
             it = sched[k][0]

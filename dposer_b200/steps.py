@@ -28,6 +28,12 @@ class Adam:
         self.v = torch.zeros_like(self.m)
         self.t = 0
 
+    def reset(self):
+        """Fresh optimiser state on the same buffers (a new batch of problems; captured graphs stay valid)."""
+        self.m.zero_()
+        self.v.zero_()
+        self.t = 0
+
     def step(self, g1, off1, ld1, s1=1.0, g2=None, off2=0, ld2=0, s2=0.0, col_scale2=None, g3=None, off3=0, ld3=0,
              s3=0.0):
         self.t += 1
@@ -100,9 +106,12 @@ class LbsStep:
                                           L.current_stream(self.dev)))
 
 
-def affine_cols(x, off, ld, mean, std, out, inverse=False):
-    L.check(L.load().dpb_affine_cols(_p(x, off), ld, L.ptr(mean), L.ptr(std), L.ptr(out), out.shape[0], out.shape[1],
-                                     int(inverse), L.current_stream(out.device)))
+def affine_cols(x, off, ld, mean, std, out, inverse=False, out_off=0, out_ld=None, cols=None, squash=0.0):
+    """out[:, out_off:out_off+cols] = (x[:, off:off+cols] - mean) / std   (or the inverse map; see dpb_affine_cols)."""
+    cols = out.shape[1] if cols is None else cols
+    L.check(L.load().dpb_affine_cols(_p(x, off), ld, L.ptr(mean), L.ptr(std), _p(out, out_off),
+                                     out.shape[1] if out_ld is None else out_ld, out.shape[0], cols, int(inverse),
+                                     float(squash), L.current_stream(out.device)))
 
 
 def motion_loss(lbs, target, seq_len, n_data, w_temp, w_data, seq_terms=None):

@@ -268,9 +268,11 @@ int dpb_adam_step(float* param, int64_t ld_p, float* m, float* v, const float* g
                   void* stream);
 /* grad = d/dx mean((x*mask - obs*mask)^2) = 2 mask^2 (x - obs) / n   (the data term of run/completion.py:197) */
 int dpb_masked_mse_grad(const float* x, const float* obs, const float* mask, float* grad, int64_t n, void* stream);
-/* Posenormalizer z-score (lib/dataset/AMASS.py:187-259): out = (x - mean) / std per column, or x * std + mean (inverse) */
-int dpb_affine_cols(const float* x, int64_t ldx, const float* mean, const float* std, float* out, int64_t rows,
-                    int cols, int inverse, void* stream);
+/* Posenormalizer z-score (lib/dataset/AMASS.py:187-259): out = (x - mean) / std per column, or x * std + mean (inverse),
+ * on strided views (row strides ldx, ldo).  squash > 0 first maps x -> tanh(squash * x): benchmarks with random-init
+ * score weights use it to bring the sampler's output into a plausible angle range before the body model. */
+int dpb_affine_cols(const float* x, int64_t ldx, const float* mean, const float* std, float* out, int64_t ldo,
+                    int64_t rows, int cols, int inverse, float squash, void* stream);
 /* joints[:, joint_map] (lib/body_model/smpl.py:70) and its adjoint (g_in is overwritten; repeated map entries add) */
 int dpb_joint_map_gather(const float* joints, int n_in, const int32_t* map, int n_map, float* out, int64_t B,
                          void* stream);
