@@ -487,6 +487,7 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
   if (rc == DPB_OK) rc = lbs_tc_prepare(h, m);
   if (rc == DPB_OK) rc = lbs_bwd_prepare(h, m);
   if (rc == DPB_OK && h->tc_ready) rc = lbs_bwd_tc_prepare(h, m);
+  if (rc == DPB_OK && h->bt_ready) rc = lbs_skin_bwd_tc_prepare(h, m);
   if (rc != DPB_OK) { dpb_lbs_destroy(h); return rc; }
   *out = h;
   return DPB_OK;
@@ -498,6 +499,7 @@ extern "C" int dpb_lbs_destroy(dpb_lbs_t* h) {
   lbs_tc_release(h);
   lbs_bwd_release(h);
   lbs_bwd_tc_release(h);
+  lbs_skin_bwd_tc_release(h);
   void* ptrs[] = {h->v_template, h->shapedirs, h->posedirs, h->j_template, h->j_shapedirs, h->parents, h->depth,
                   h->ell_idx, h->ell_w, h->extra_vids, h->lmk_faces, h->lmk_bary, h->need_vids, h->extra_pos,
                   h->lmk_pos, h->need_index};

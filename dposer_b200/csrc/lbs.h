@@ -62,6 +62,11 @@ struct dpb_lbs {
   int bt_rp = 0, bt_kp = 0;       // 3V padded to 64; feature rows padded to 256 / 512
   __half* basisT16 = nullptr;     // [bt_kp, 2*bt_rp] fp16 [hi | lo]
   CUtensorMap tm_bT;
+  // backward: skinning adjoint with dL/dA on tcgen05 (lbs_skin_bwd_tc.cu)
+  bool sb_ready = false;
+  int sb_vp = 0, sb_smem = 0;     // V padded to 64; dynamic shared memory of the kernel
+  __half* wT16 = nullptr;         // [128, 2*sb_vp] fp16 [hi | lo]: rows < J = weights^T, row J = ones
+  CUtensorMap tm_wT;
 };
 
 namespace dpb {
@@ -106,7 +111,12 @@ int lbs_fused3(dpb_lbs* h, const LbsVariant& v, __half* featop, __half* skinop, 
 int lbs_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_bwd_tc_release(dpb_lbs* h);
 int lbs_blendT_splits(const dpb_lbs* h, int64_t B);
-int lbs_blendT_tc(dpb_lbs* h, const __half* gvp16, float* cpart, float* gfeat, float* gbeta, int64_t B, cudaStream_t st);
+int lbs_blendT_tc(dpb_lbs* h, const __half* gvp16, const float* scale, float* cpart, float* gfeat, float* gbeta,
+                  int64_t B, cudaStream_t st);
+int lbs_skin_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m);
+void lbs_skin_bwd_tc_release(dpb_lbs* h);
+int lbs_skin_bwd_tc(dpb_lbs* h, const float* A, const float* vposed, const float* g_verts, const float* gextra,
+                    bool have_extra, __half* gvp16, float* gA, float* gbt, float* scale, int64_t B, cudaStream_t st);
 int lbs_bwd_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_bwd_release(dpb_lbs* h);
 }  // namespace dpb

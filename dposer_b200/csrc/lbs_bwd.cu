@@ -523,7 +523,8 @@ static size_t bwd_gvp_bytes(const dpb_lbs* h, int64_t B) {
 static size_t bwd_scratch_bytes(const dpb_lbs* h, int64_t B) {
   const size_t a = (size_t)B * h->bw_np * 4;
   const size_t b = h->bt_ready ? (size_t)lbs_blendT_splits(h, B) * B * h->bt_kp * 4 : 0;
-  return align_up((size_t)B * h->V * 3 * 4, 256) + bwd_gvp_bytes(h, B) + align_up(a > b ? a : b, 256);
+  return align_up((size_t)B * h->V * 3 * 4, 256) + bwd_gvp_bytes(h, B) + align_up(a > b ? a : b, 256) +
+         align_up((size_t)B * 4, 256);
 }
 
 }  // namespace dpb
@@ -571,24 +572,31 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
     float* vposed = reinterpret_cast<float*>(sp);
     float* gvp = reinterpret_cast<float*>(sp + align_up((size_t)B * h->V * 3 * 4, 256));
     float* gout = reinterpret_cast<float*>(sp + align_up((size_t)B * h->V * 3 * 4, 256) + bwd_gvp_bytes(h, B));
-    // the transposed blend on tcgen05 (fp16 [hi | lo] operand) unless DPB_LBS_BWD_SGEMM=1 asks for the fp32 SGEMM (A/B)
-    const bool tcT = h->bt_ready && !(getenv("DPB_LBS_BWD_SGEMM") && atoi(getenv("DPB_LBS_BWD_SGEMM")));
+    float* scale = reinterpret_cast<float*>(sp + bwd_scratch_bytes(h, B) - align_up((size_t)B * 4, 256));
+    // skinning adjoint (dL/dA) and transposed blend on tcgen05 unless DPB_LBS_BWD_FP32=1 asks for the round-1 kernels
+    // (shared-memory atomics + fp32 SGEMM; A/B timing)
+    const bool tcT = h->bt_ready && h->sb_ready && !(getenv("DPB_LBS_BWD_FP32") && atoi(getenv("DPB_LBS_BWD_FP32")));
     __half* gvp16 = tcT ? reinterpret_cast<__half*>(gvp) : nullptr;
     int rc = lbs_tc_blend(h, betas, w.feat, w.featop, vposed, B, st);
     if (rc != DPB_OK) return rc;
     if (tcT) DPB_CUDA_CHECK(cudaMemsetAsync(gvp16, 0, (size_t)B * 2 * h->bt_rp * 2, st));
     else DPB_CUDA_CHECK(cudaMemsetAsync(gvp, 0, (size_t)B * h->bw_kp * 4, st));
-    const size_t smem = ((size_t)2 * BW_TP * J * 12 + BW_TP * 3) * 4;
-    DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_skin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((h->V + BW_TV - 1) / BW_TV, (unsigned)((B + BW_TP - 1) / BW_TP));
-    DPB_REQUIRE(grid.y <= 65535u, "dpb_lbs_backward: batch too large for one call (max 65535*8 poses)");
-    lbs_skin_bwd_kernel<<<grid, BW_TV, smem, st>>>(w.A, vposed, h->ell_idx, h->ell_w,
-                                                   have_extra ? h->need_index : nullptr, h->n_need, h->V, J, S, h->nnz,
-                                                   g_verts, have_extra ? w.gextra : nullptr, w.gA, gvp, h->bw_kp,
-                                                   gvp16, h->bt_rp, w.gbeta, B);
-    DPB_CUDA_CHECK(cudaGetLastError());
     if (tcT) {
-      rc = lbs_blendT_tc(h, gvp16, gout, w.gfeat, w.gbeta, B, st);
+      rc = lbs_skin_bwd_tc(h, w.A, vposed, g_verts, w.gextra, have_extra, gvp16, w.gA, w.gbeta, scale, B, st);
+      if (rc != DPB_OK) return rc;
+    } else {
+    const size_t smem = ((size_t)2 * BW_TP * J * 12 + BW_TP * 3) * 4;
+      DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_skin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((h->V + BW_TV - 1) / BW_TV, (unsigned)((B + BW_TP - 1) / BW_TP));
+      DPB_REQUIRE(grid.y <= 65535u, "dpb_lbs_backward: batch too large for one call (max 65535*8 poses)");
+      lbs_skin_bwd_kernel<<<grid, BW_TV, smem, st>>>(w.A, vposed, h->ell_idx, h->ell_w,
+                                                     have_extra ? h->need_index : nullptr, h->n_need, h->V, J, S, h->nnz,
+                                                     g_verts, have_extra ? w.gextra : nullptr, w.gA, gvp, h->bw_kp,
+                                                     nullptr, 0, w.gbeta, B);
+      DPB_CUDA_CHECK(cudaGetLastError());
+    }
+    if (tcT) {
+      rc = lbs_blendT_tc(h, gvp16, scale, gout, w.gfeat, w.gbeta, B, st);
       if (rc != DPB_OK) return rc;
     } else {
       dim3 ggrid(h->bw_np / 64, (unsigned)((B + 63) / 64));

@@ -181,13 +181,15 @@ lbs_blendT_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
 
 // gfeat[b, k] += sum_s C[s, b, k] (k < P);  gbeta[b, k - P] += ... (P <= k < P + S): splits added in a fixed order
 __global__ void blendT_unpack_kernel(const float* __restrict__ C, int splits, int Kp, int P, int S,
-                                     float* __restrict__ gfeat, float* __restrict__ gbt, int64_t B) {
+                                     const float* __restrict__ scale, float* __restrict__ gfeat,
+                                     float* __restrict__ gbt, int64_t B) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * (P + S)) return;
   const int64_t b = i / (P + S);
   const int k = (int)(i % (P + S));
   float v = 0.f;
   for (int s = 0; s < splits; ++s) v += C[((size_t)s * B + b) * Kp + k];
+  if (scale) v /= scale[b];                             // the operand was scaled into fp16 range by a power of two
   if (k < P) gfeat[b * P + k] += v;
   else gbt[b * (S + 3) + (k - P)] += v;
 }
@@ -237,9 +239,9 @@ int lbs_blendT_splits(const dpb_lbs* h, int64_t B) {
   return (int)s;
 }
 
-// gvp16 [B, 2*Rp] fp16 [hi | lo] (pad columns zero) -> gfeat [B,P] += ..., gbeta [B,S+3][:S] += ...; cpart [splits,B,Kp]
-int lbs_blendT_tc(dpb_lbs* h, const __half* gvp16, float* cpart, float* gfeat, float* gbeta, int64_t B,
-                  cudaStream_t st) {
+// gvp16 [B, 2*Rp] fp16 [hi | lo] (pad columns zero; row b scaled by scale[b] if given) -> gfeat [B,P] += ..., gbeta [B,S+3][:S] += ...; cpart [splits,B,Kp]
+int lbs_blendT_tc(dpb_lbs* h, const __half* gvp16, const float* scale, float* cpart, float* gfeat, float* gbeta,
+                  int64_t B, cudaStream_t st) {
   CUtensorMap tm_g;
   int rc = make_tmap_2d(&tm_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, gvp16, (uint64_t)2 * h->bt_rp, (uint64_t)B, lbt::BK, 128, 2);
   if (rc != DPB_OK) return rc;
@@ -256,7 +258,7 @@ int lbs_blendT_tc(dpb_lbs* h, const __half* gvp16, float* cpart, float* gfeat, f
   else
     lbt::lbs_blendT_tc_kernel<4><<<grid, lbt::NUM_THREADS, lbt::SMEM_BYTES, st>>>(p, h->tm_bT, tm_g);
   const int64_t n = B * (h->P + h->S);
-  lbt::blendT_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cpart, p.splits, p.Kp, h->P, h->S, gfeat, gbeta, B);
+  lbt::blendT_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cpart, p.splits, p.Kp, h->P, h->S, scale, gfeat, gbeta, B);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }

@@ -1,0 +1,339 @@
+// LBS backward, the skinning adjoint with the joint-transform cotangent on tcgen05 (deterministic, no atomics).
+// Adjoint of  v_out = sum_j w[v,j] (R_j v_posed + t_j)  (smplx 0.1.28 lbs()) for dense vertex
+// cotangents g [B,V,3] (run/motion_denoising.py:255-268 differentiates through it):
+//
+//   g_vposed[b,v,:] = (sum_j w[v,j] R_j[b])^T g[b,v,:]                                  thread = (vertex, pose), CUDA cores
+//   dL/dA[b,j,(x,c)] = sum_v w[v,j] g[b,v,x] [v_posed[b,v,c] | 1]                       tensor cores:
+//       D[j, (pose,e)] = sum_v W^T[j,v] * Q[(pose,e), v],   Q = g (x) [v_posed | 1]  (12 entries per vertex and pose)
+//
+// Round 1 accumulated dL/dA with 48 shared-memory atomics per (vertex, pose) plus global atomics (15.5 ms per 15 360
+// SMPL-X poses, order-dependent sums).  Here a CTA owns 16 poses and sweeps the vertices in slabs of 64: eight compute
+// warps form Q for the slab and write it -- fp16 [hi | lo], SWIZZLE_128B K-major -- straight into shared memory as the
+// B operand (generic-proxy stores + fence.proxy.async), an issuing warp accumulates W^T . Q over all slabs in 192 TMEM
+// columns (hi.hi + hi.lo + lo.hi), and the epilogue writes dL/dA once.  Row J of W^T is all ones, so D[J, 9..11] is the
+// translation cotangent sum_v g.  g_vposed leaves as the fp16 [hi | lo] operand of the transposed blend (lbs_bwd_tc.cu).
+//
+//   warp 0  TMA: W^T slabs (hi + lo, double buffered);  warp 1  TMEM allocator + MMA issuer
+//   warps 2-9  compute (thread = vertex of the slab x 4 poses);  warps 2-5 also drain the accumulator at the end
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+
+#include <vector>
+
+#include "lbs.h"
+#include "ptx.cuh"
+
+namespace dpb {
+
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64_t inner, uint64_t rows,
+                 uint32_t box_inner, uint32_t box_rows, size_t elem_bytes);  // score_tc.cu
+
+namespace lsb {
+
+__global__ void lbs_rowscale_kernel(const float* __restrict__ g, int64_t n, const float* __restrict__ g2, int64_t n2,
+                                    float* __restrict__ scale);
+
+constexpr int BK = 64;                       // vertices per slab = K of one operand tile
+constexpr int NPG = 16;                      // poses per CTA
+constexpr int NQ = NPG * 12;                 // 192 = N of the MMAs
+constexpr int Q_TILE = NQ * BK * 2;          // 24 KB: [192 rows x 64 k] fp16, SWIZZLE_128B
+constexpr int W_TILE = 128 * BK * 2;         // 16 KB: [128 joint rows x 64 k]
+constexpr int NUM_THREADS = 320;
+constexpr int OFF_Q = 0;                     // 2 buffers x (hi, lo)
+constexpr int OFF_W = OFF_Q + 4 * Q_TILE;    // 2 stages x (hi, lo)
+constexpr int OFF_BAR = OFF_W + 4 * W_TILE;
+constexpr int NBARS = 9;
+constexpr int OFF_A = OFF_BAR + NBARS * 8 + 16;   // fp32 [NPG][J][12] skinning transforms of the CTA's poses
+static_assert(OFF_W % 1024 == 0 && OFF_BAR % 1024 == 0, "operand tiles are 1024-byte aligned");
+
+struct Params {
+  const float* A;            // [B,J,12]
+  const float* vposed;       // [B,V,3]
+  const float* g_verts;      // [B,V,3]
+  const float* gextra;       // [B,n_need,3] or nullptr
+  const int32_t* need_index; // [V] or nullptr
+  const int32_t* ell_idx;    // [nnz,V]
+  const float* ell_w;        // [nnz,V]
+  __half* gvp16;             // [B, 2*Rp]
+  float* gA;                 // [B,J,12]
+  float* gbt;                // [B,S+3]
+  const float* scale;        // [B] power-of-two scale of each pose's cotangents (fp16 range), see lbs_rowscale_kernel
+  int V, J, S, nnz, n_need, Rp, Vp;   // Vp = V padded to 64 (columns of one half of W^T)
+  int64_t B;
+};
+
+// byte offset of element (row r, column k) in a K-major SWIZZLE_128B tile of 64 fp16 columns
+__device__ __forceinline__ uint32_t sw128_off(int r, int k) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap tm_wT) {
+  constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, NQ, 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const uint32_t q_base = sb + OFF_Q, w_base = sb + OFF_W, bar = sb + OFF_BAR;
+  auto qfull = [&](uint32_t b) { return bar + 8u * b; };
+  auto qempty = [&](uint32_t b) { return bar + 8u * (2 + b); };
+  auto wfull = [&](uint32_t s) { return bar + 8u * (4 + s); };
+  auto wempty = [&](uint32_t s) { return bar + 8u * (6 + s); };
+  const uint32_t dfull = bar + 64;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBARS * 8);
+  float* A_s = reinterpret_cast<float*>(smem + OFF_A);
+  float* sc_s = A_s + (size_t)NPG * p.J * 12;       // [NPG] scale, [NPG] 1 / scale
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int J = p.J, V = p.V;
+  const int64_t b0 = (int64_t)blockIdx.x * NPG;
+  const int np = (int)min((int64_t)NPG, p.B - b0);
+  const int n_slabs = p.Vp / BK;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(qfull(b), 8); ptx::mbar_init(qempty(b), 1);
+      ptx::mbar_init(wfull(b), 1); ptx::mbar_init(wempty(b), 1);
+    }
+    ptx::mbar_init(dfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 256);
+  for (int i = threadIdx.x; i < NPG * J * 12; i += NUM_THREADS)
+    A_s[i] = i < np * J * 12 ? p.A[b0 * J * 12 + i] : 0.f;
+  if (threadIdx.x < NPG) {
+    const float sc = threadIdx.x < np ? p.scale[b0 + threadIdx.x] : 1.f;
+    sc_s[threadIdx.x] = sc;
+    sc_s[NPG + threadIdx.x] = 1.f / sc;              // a power of two: exact
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) ptx::prefetch_tmap(&tm_wT);
+    __syncwarp();
+    for (int s = 0; s < n_slabs; ++s) {
+      const uint32_t st = s & 1;
+      ptx::mbar_wait(wempty(st), ((s >> 1) & 1) ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(wfull(st), 2 * W_TILE);
+        ptx::tma_load_2d(w_base + (st * 2) * W_TILE, &tm_wT, wfull(st), s * BK, 0);
+        ptx::tma_load_2d(w_base + (st * 2 + 1) * W_TILE, &tm_wT, wfull(st), p.Vp + s * BK, 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    for (int s = 0; s < n_slabs; ++s) {
+      const uint32_t st = s & 1, ph = (s >> 1) & 1;
+      ptx::mbar_wait(qfull(st), ph);
+      ptx::mbar_wait(wfull(st), ph);
+      ptx::tc_fence_after();
+      const uint64_t whi = ptx::umma_desc_sw128(w_base + (st * 2) * W_TILE), wlo = whi + (uint64_t)(W_TILE >> 4);
+      const uint64_t qhi = ptx::umma_desc_sw128(q_base + (st * 2) * Q_TILE), qlo = qhi + (uint64_t)(Q_TILE >> 4);
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j) {
+          ptx::mma_f16_ss(tmem_base, whi + 2 * j, qhi + 2 * j, IDESC, (s == 0 && j == 0) ? 0u : 1u);
+          ptx::mma_f16_ss(tmem_base, whi + 2 * j, qlo + 2 * j, IDESC, 1u);
+          ptx::mma_f16_ss(tmem_base, wlo + 2 * j, qhi + 2 * j, IDESC, 1u);
+        }
+        ptx::mma_commit(wempty(st));
+        ptx::mma_commit(qempty(st));
+        if (s == n_slabs - 1) ptx::mma_commit(dfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- compute warps: thread = (vertex of the slab, 4 poses)
+    const int t = threadIdx.x - 64;
+    const int vl = t & 63, pg = t >> 6;
+    for (int s = 0; s < n_slabs; ++s) {
+      const uint32_t st = s & 1;
+      const int v = s * BK + vl;
+      const bool v_ok = v < V;
+      int jn[4];
+      float wn[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const bool ok = v_ok && n < p.nnz;
+        wn[n] = ok ? p.ell_w[(size_t)n * V + v] : 0.f;
+        jn[n] = ok ? p.ell_idx[(size_t)n * V + v] : 0;
+      }
+      const int qn = (v_ok && p.need_index) ? p.need_index[v] : -1;
+      float q[4][12];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pl = pg * 4 + i;
+        float g[3] = {0.f, 0.f, 0.f}, x[3] = {0.f, 0.f, 0.f};
+        if (v_ok && pl < np) {
+          const float* gv = p.g_verts + ((size_t)(b0 + pl) * V + v) * 3;
+          const float* xp = p.vposed + ((size_t)(b0 + pl) * V + v) * 3;
+          g[0] = gv[0]; g[1] = gv[1]; g[2] = gv[2];
+          x[0] = xp[0]; x[1] = xp[1]; x[2] = xp[2];
+          if (qn >= 0 && p.gextra) {
+            const float* ge = p.gextra + ((size_t)(b0 + pl) * p.n_need + qn) * 3;
+            g[0] += ge[0]; g[1] += ge[1]; g[2] += ge[2];
+          }
+          const float sc = sc_s[pl];                      // into fp16's normal range (exact: a power of two)
+          g[0] *= sc; g[1] *= sc; g[2] *= sc;
+          float TR[9];
+#pragma unroll
+          for (int e = 0; e < 9; ++e) TR[e] = 0.f;
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const float* Ap = A_s + ((size_t)pl * J + jn[n]) * 12;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) TR[e] = fmaf(wn[n], Ap[e], TR[e]);
+          }
+          const float o[3] = {TR[0] * g[0] + TR[3] * g[1] + TR[6] * g[2], TR[1] * g[0] + TR[4] * g[1] + TR[7] * g[2],
+                              TR[2] * g[0] + TR[5] * g[1] + TR[8] * g[2]};   // g_vposed = T_R^T g
+          __half* oh = p.gvp16 + (size_t)(b0 + pl) * 2 * p.Rp + (size_t)v * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const __half hi = __float2half_rn(o[c]);
+            oh[c] = hi;
+            oh[p.Rp + c] = __float2half_rn(o[c] - __half2float(hi));
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          q[i][3 * a + 0] = g[a] * x[0];
+          q[i][3 * a + 1] = g[a] * x[1];
+          q[i][3 * a + 2] = g[a] * x[2];
+          q[i][9 + a] = g[a];
+        }
+      }
+      ptx::mbar_wait(qempty(st), ((s >> 1) & 1) ^ 1);     // the MMAs of slab s - 2 are done with this buffer
+      uint8_t* qh = smem + OFF_Q + (st * 2) * Q_TILE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+          const uint32_t off = sw128_off((pg * 4 + i) * 12 + e, vl);
+          const __half hi = __float2half_rn(q[i][e]);
+          *reinterpret_cast<__half*>(qh + off) = hi;
+          *reinterpret_cast<__half*>(qh + Q_TILE + off) = __float2half_rn(q[i][e] - __half2float(hi));
+        }
+      ptx::fence_proxy_async_smem();                      // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(qfull(st));
+    }
+    if (warp < 6) {
+      // ---- drain: warp % 4 = TMEM lane quarter, lane = joint row (row J: the all-ones row = translation cotangent)
+      const int qd = warp & 3;
+      const int j = qd * 32 + lane;
+      ptx::mbar_wait(dfull, 0);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < NQ / 32; ++c) {
+        uint32_t d[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + c * 32, d);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = c * 32 + i, pl = col / 12, e = col % 12;
+          if (pl < np) {
+            const float val = __uint_as_float(d[i]) * sc_s[NPG + pl];
+            if (j < J) p.gA[((size_t)(b0 + pl) * J + j) * 12 + e] = val;
+            else if (j == J && e >= 9) p.gbt[(size_t)(b0 + pl) * (p.S + 3) + p.S + (e - 9)] += val;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace lsb
+
+// W^T [128, 2*Vp] fp16 [hi | lo]: row j < J = skinning weights of joint j over the vertices, row J = ones, rest zero
+int lbs_skin_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
+  const int V = h->V, J = h->J;
+  h->sb_ready = false;
+  if (J >= 128 || h->nnz > 4) return DPB_OK;            // needs a spare row for the ones; the kernel unrolls 4 ELL slots
+  h->sb_vp = (V + 63) / 64 * 64;
+  const size_t ld = (size_t)2 * h->sb_vp;
+  std::vector<__half> buf((size_t)128 * ld, __float2half_rn(0.f));
+  for (int v = 0; v < V; ++v) {
+    for (int j = 0; j < J; ++j) {
+      const float x = m->lbs_weights[(size_t)v * J + j];
+      const __half hi = __float2half_rn(x);
+      buf[(size_t)j * ld + v] = hi;
+      buf[(size_t)j * ld + h->sb_vp + v] = __float2half_rn(x - __half2float(hi));
+    }
+    buf[(size_t)J * ld + v] = __float2half_rn(1.f);
+  }
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->wT16, buf.size() * sizeof(__half)));
+  DPB_CUDA_CHECK(cudaMemcpy(h->wT16, buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  int rc = make_tmap_2d(&h->tm_wT, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->wT16, ld, 128, lsb::BK, 128, 2);
+  if (rc != DPB_OK) return rc;
+  const size_t smem = lsb::OFF_A + (size_t)lsb::NPG * J * 12 * 4 + 2 * lsb::NPG * 4 + 1024;
+  if (smem > 232448) return DPB_OK;
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(lsb::lbs_skin_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  h->sb_smem = (int)smem;
+  h->sb_ready = true;
+  return DPB_OK;
+}
+
+void lbs_skin_bwd_tc_release(dpb_lbs* h) {
+  if (h->wT16) cudaFree(h->wT16);
+  h->wT16 = nullptr;
+  h->sb_ready = false;
+}
+
+namespace lsb {
+// scale[b] = 2^k with max |cotangent of pose b| * scale in [32, 64): fp16 operands keep their full significand and the
+// [hi | lo] split its second half (cotangents of mean-reduced losses are ~1e-5: fp16-subnormal without it)
+__global__ void __launch_bounds__(256) lbs_rowscale_kernel(const float* __restrict__ g, int64_t n, const float* __restrict__ g2,
+                                                           int64_t n2, float* __restrict__ scale) {
+  const int64_t b = blockIdx.x;
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(g[b * n + i]));
+  float m2 = 0.f;
+  if (g2)
+    for (int64_t i = threadIdx.x; i < n2; i += 256) m2 = fmaxf(m2, fabsf(g2[b * n2 + i]));
+  m += m2;                                               // the two are added on some vertices
+  __shared__ float part[8];
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, part[i]);
+    int e = 0;
+    float sc = 1.f;
+    if (m > 0.f && m < 3.0e38f) {                          // finite and non-zero (NaN fails both comparisons)
+      frexpf(m, &e);                                       // m = f * 2^e, f in [0.5, 1)
+      e = 6 - e;
+      e = e < -100 ? -100 : (e > 100 ? 100 : e);
+      sc = ldexpf(1.f, e);
+    }
+    scale[b] = sc;
+  }
+}
+}  // namespace lsb
+
+// gA [B,J,12] is WRITTEN (no zeroing needed), gbt[:, S:S+3] += translation cotangent, gvp16 [B, 2*Rp] written for v < V
+// (scaled by scale[b]: lbs_blendT_tc divides it out again).  scale [B] is scratch.
+int lbs_skin_bwd_tc(dpb_lbs* h, const float* A, const float* vposed, const float* g_verts, const float* gextra,
+                    bool have_extra, __half* gvp16, float* gA, float* gbt, float* scale, int64_t B, cudaStream_t st) {
+  lsb::lbs_rowscale_kernel<<<(unsigned)B, 256, 0, st>>>(g_verts, (int64_t)h->V * 3, have_extra ? gextra : nullptr,
+                                                        (int64_t)h->n_need * 3, scale);
+  lsb::Params p{};
+  p.scale = scale;
+  p.A = A; p.vposed = vposed; p.g_verts = g_verts;
+  p.gextra = have_extra ? gextra : nullptr;
+  p.need_index = have_extra ? h->need_index : nullptr;
+  p.ell_idx = h->ell_idx; p.ell_w = h->ell_w;
+  p.gvp16 = gvp16; p.gA = gA; p.gbt = gbt;
+  p.V = h->V; p.J = h->J; p.S = h->S; p.nnz = h->nnz; p.n_need = h->n_need; p.Rp = h->bt_rp; p.Vp = h->sb_vp;
+  p.B = B;
+  lsb::lbs_skin_bwd_tc_kernel<<<(unsigned)((B + lsb::NPG - 1) / lsb::NPG), lsb::NUM_THREADS, h->sb_smem, st>>>(p, h->tm_wT);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+}  // namespace dpb
