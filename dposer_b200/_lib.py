@@ -43,7 +43,7 @@ EXPORTS = ['dpb_version', 'dpb_last_error', 'dpb_device_info', 'dpb_score_create
            'dpb_score_time_table', 'dpb_score_workspace_bytes', 'dpb_score_forward', 'dpb_sampler_run',
            'dpb_langevin_norms', 'dpb_langevin_update', 'dpb_normal_fill', 'dpb_prior_loss', 'dpb_lbs_create',
            'dpb_lbs_destroy', 'dpb_lbs_set_const_tail', 'dpb_lbs_num_joints_out', 'dpb_lbs_workspace_bytes', 'dpb_lbs_forward',
-           'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_apd_partial', 'dpb_mean_point_error', 'dpb_fit_loss',
+           'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_lbs_backward_scratch_bytes_joints', 'dpb_apd_partial', 'dpb_mean_point_error', 'dpb_fit_loss',
            'dpb_motion_loss', 'dpb_camera_fit_loss', 'dpb_adam_step', 'dpb_affine_cols', 'dpb_joint_map_gather',
            'dpb_joint_map_scatter', 'dpb_masked_mse_grad']
 
@@ -92,6 +92,8 @@ def load():
     lib.dpb_lbs_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, vp, sz, vp, sz, vp]
     lib.dpb_lbs_backward_scratch_bytes.argtypes = [vp, i64]
     lib.dpb_lbs_backward_scratch_bytes.restype = sz
+    lib.dpb_lbs_backward_scratch_bytes_joints.argtypes = [vp, i64]
+    lib.dpb_lbs_backward_scratch_bytes_joints.restype = sz
     lib.dpb_fit_loss.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, f32, f32, f32, f32, vp, vp, vp,
                                  vp, vp, i64, vp]
     lib.dpb_apd_partial.argtypes = [vp, i64, C.c_int, i64, i64, vp, vp]
@@ -107,7 +109,7 @@ def load():
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ('dpb_last_error', 'dpb_score_workspace_bytes', 'dpb_lbs_workspace_bytes',
-                        'dpb_lbs_backward_scratch_bytes'):
+                        'dpb_lbs_backward_scratch_bytes', 'dpb_lbs_backward_scratch_bytes_joints'):
             fn.restype = C.c_int
     _lib = lib
     return lib

@@ -101,10 +101,13 @@ class _LbsFn(torch.autograd.Function):
         g_transl = torch.empty(B, 3, dtype=torch.float32, device=dev) if ctx.has_transl else None
         ws = ctx.ws
         scratch, n_scratch = None, 0
-        if gv is not None:   # full-vertex cotangents: scratch for the split (tensor-core + SGEMM) vertex pass
+        # scratch of the tensor-core vertex pass: all vertices (vertex cotangents) or the few the joints read
+        if gv is not None:
             n_scratch = int(L.load().dpb_lbs_backward_scratch_bytes(h.ptr, B))
-            if n_scratch:
-                scratch = torch.empty(n_scratch, dtype=torch.uint8, device=dev)
+        elif B >= 64:
+            n_scratch = int(L.load().dpb_lbs_backward_scratch_bytes_joints(h.ptr, B))
+        if n_scratch:
+            scratch = torch.empty(n_scratch, dtype=torch.uint8, device=dev)
         L.check(L.load().dpb_lbs_backward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(gv), L.ptr(gj), L.ptr(g_pose),
                                           L.ptr(g_betas), L.ptr(g_transl), B, core.engine, L.ptr(ws), ws.numel(),
                                           L.ptr(scratch), n_scratch, L.current_stream(dev)))

@@ -367,7 +367,7 @@ bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_by
   out->compact = compact ? c.take<float>((size_t)B * h->n_need * 3) : nullptr;
   out->featop = nullptr;
   out->skinop = nullptr;
-  if (h->tc_ready && !compact) {
+  if (h->tc_ready && (!compact || h->sub)) {   // joints-only calls run the compact vertex set on the same operands
     c.off = align_up(c.off, 1024);
     out->featop = reinterpret_cast<__half*>(c.base + c.off);
     const int64_t B_pad = (B + 127) / 128 * 128;
@@ -488,6 +488,27 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
   if (rc == DPB_OK) rc = lbs_bwd_prepare(h, m);
   if (rc == DPB_OK && h->tc_ready) rc = lbs_bwd_tc_prepare(h, m);
   if (rc == DPB_OK && h->bt_ready) rc = lbs_skin_bwd_tc_prepare(h, m);
+  if (rc == DPB_OK && h->tc_ready && h->n_need > 0) {
+    // the compact vertex set as a small body model (no extra joints / landmarks of its own: no recursion)
+    const int Vn = h->n_need, P = h->P;
+    std::vector<float> vt((size_t)Vn * 3), sd((size_t)Vn * 3 * std::max(S, 1)), pd((size_t)P * Vn * 3),
+        lw((size_t)Vn * J), jr((size_t)J * Vn, 0.f);
+    for (int i = 0; i < Vn; ++i) {
+      const int v = need[i];
+      for (int c = 0; c < 3; ++c) {
+        vt[(size_t)i * 3 + c] = m->v_template[(size_t)v * 3 + c];
+        for (int k = 0; k < S; ++k) sd[((size_t)i * 3 + c) * S + k] = m->shapedirs[((size_t)v * 3 + c) * S + k];
+        for (int k = 0; k < P; ++k) pd[(size_t)k * Vn * 3 + (size_t)i * 3 + c] = m->posedirs[(size_t)k * V * 3 + (size_t)v * 3 + c];
+      }
+      for (int j = 0; j < J; ++j) lw[(size_t)i * J + j] = m->lbs_weights[(size_t)v * J + j];
+    }
+    dpb_body_tensors ms = *m;
+    ms.V = Vn;
+    ms.v_template = vt.data(); ms.shapedirs = sd.data(); ms.posedirs = pd.data();
+    ms.lbs_weights = lw.data(); ms.J_regressor = jr.data();
+    ms.n_extra = 0; ms.extra_vids = nullptr; ms.n_lmk = 0; ms.lmk_faces = nullptr; ms.lmk_bary = nullptr;
+    rc = dpb_lbs_create(&h->sub, &ms, device);
+  }
   if (rc != DPB_OK) { dpb_lbs_destroy(h); return rc; }
   *out = h;
   return DPB_OK;
@@ -496,6 +517,8 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
 extern "C" int dpb_lbs_destroy(dpb_lbs_t* h) {
   if (!h) return DPB_OK;
   DeviceGuard guard(h->device);
+  if (h->sub) dpb_lbs_destroy(h->sub);
+  h->sub = nullptr;
   lbs_tc_release(h);
   lbs_bwd_release(h);
   lbs_bwd_tc_release(h);
@@ -514,6 +537,10 @@ extern "C" int dpb_lbs_set_const_tail(dpb_lbs_t* h, int n_var, const float* tail
   if (!h) return fail(DPB_EINVAL, "dpb_lbs_set_const_tail: null handle");
   DPB_REQUIRE(n_var >= 1 && n_var < h->J && tail_pose, "dpb_lbs_set_const_tail: need 1 <= n_var < J and a tail pose");
   DeviceGuard guard(h->device);
+  if (h->sub) {
+    int rc = lbs_tc_make_tail(h->sub, n_var, tail_pose);
+    if (rc != DPB_OK) return rc;
+  }
   return lbs_tc_make_tail(h, n_var, tail_pose);
 }
 
@@ -537,18 +564,22 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
   const int engine = flags & DPB_ENGINE_MASK;
   const int n_verts = compact ? h->n_need : h->V;
   float* vout = compact ? w.compact : verts;
-  const bool use_tc = n_verts > 0 && !compact && h->tc_ready && w.featop &&
+  // hv = the body model whose vertices this call produces: the full one, or the compact set of the joints-only mode
+  dpb_lbs* hv = compact ? h->sub : h;
+  const bool use_tc = n_verts > 0 && hv && hv->tc_ready && w.featop &&
                       (engine == DPB_LBS_ENGINE_TC || (engine == DPB_ENGINE_AUTO && B >= 64));
   const int fused_sel = getenv("DPB_LBS_FUSED") ? atoi(getenv("DPB_LBS_FUSED")) : 3;   // A/B timing only: 0 two kernels, 1 first fused kernel, 2 / 3 CTA-pair kernels
   // const-tail calls (DPB_LBS_CONST_TAIL) read the pruned basis; everything else the full one
   const bool want_tail = (flags & DPB_LBS_CONST_TAIL) != 0;
   if (want_tail) DPB_REQUIRE(h->tailv.n_var > 0 || !h->tc_ready, "dpb_lbs_forward: DPB_LBS_CONST_TAIL without dpb_lbs_set_const_tail");
-  const LbsVariant var = (want_tail && h->tailv.dirs16) ? h->tailv : lbs_full_variant(h);
+  // (the compact model's variants have the same K layout: the pose kernel's operands serve both)
+  const LbsVariant var = !use_tc ? ((want_tail && h->tailv.dirs16) ? h->tailv : lbs_full_variant(h))
+                                 : ((want_tail && hv->tailv.dirs16) ? hv->tailv : lbs_full_variant(hv));
   // measured (profiles/r2_lbs_fused3_experiments.md): the 128-pose-group kernel wins for SMPL-sized joint counts (one
   // skinning K slab), the 96-pose-group kernel for SMPL-X (two slabs: its three T buffers hide the longer chunks)
-  const bool use_fused3 = use_tc && fused_sel == 3 && w.skinop && h->jp == 32 && lbs_fused3_fits(h, var);
-  const bool use_fused2 = use_fused3 || (use_tc && fused_sel >= 2 && w.skinop && lbs_fused2_fits(h, var));
-  const bool use_fused = use_fused2 || (use_tc && fused_sel != 0 && w.skinop && var.n_var == h->J && lbs_tc_fused_fits(h));
+  const bool use_fused3 = use_tc && fused_sel == 3 && w.skinop && h->jp == 32 && lbs_fused3_fits(hv, var);
+  const bool use_fused2 = use_fused3 || (use_tc && fused_sel >= 2 && w.skinop && lbs_fused2_fits(hv, var));
+  const bool use_fused = use_fused2 || (use_tc && !compact && fused_sel != 0 && w.skinop && var.n_var == h->J && lbs_tc_fused_fits(h));
   // the fused kernel's operands come straight out of the pose kernel (pad rows of the last pose group are zeroed)
   __half* fop = use_fused ? w.featop : nullptr;
   __half* sop = use_fused ? w.skinop : nullptr;
@@ -582,27 +613,27 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
     if (use_tc) {
       if (use_fused2) {
         // blend + skinning in one tcgen05 kernel on CTA pairs: the blended vertices stay in TMEM
-        int rc = use_fused3 ? lbs_fused3(h, var, w.featop, w.skinop, verts, B, st)
-                            : lbs_fused2(h, var, w.featop, w.skinop, verts, B, st);
+        int rc = use_fused3 ? lbs_fused3(hv, var, w.featop, w.skinop, vout, B, st)
+                            : lbs_fused2(hv, var, w.featop, w.skinop, vout, B, st);
         if (rc != DPB_OK) return rc;
       } else if (use_fused) {
         int rc = lbs_tc_fused(h, nullptr, nullptr, w.featop, nullptr, nullptr, w.skinop, verts, B, st);
         if (rc != DPB_OK) return rc;
       } else {
       // blend on tcgen05 (writes v_posed into verts), then skin in place with the transforms from the pose kernel
-      int rc = lbs_tc_blend(h, betas, w.feat, w.featop, verts, B, st);
+      int rc = lbs_tc_blend(hv, betas, w.feat, w.featop, vout, B, st);
       if (rc != DPB_OK) return rc;
-      if (lbs_tc_skin_fits(h)) {
-        rc = lbs_tc_skin(h, w.A, transl, w.skinop, verts, B, st);
+      if (lbs_tc_skin_fits(hv)) {
+        rc = lbs_tc_skin(hv, w.A, transl, w.skinop, vout, B, st);
         if (rc != DPB_OK) return rc;
       } else {
       size_t smem = ((size_t)LBS_TP * h->J * 12 + LBS_TP * 3) * 4;
       DPB_CUDA_CHECK(cudaFuncSetAttribute(lbs_vertex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid((n_verts + LBS_TV - 1) / LBS_TV, (unsigned)((B + LBS_TP - 1) / LBS_TP));
       DPB_REQUIRE(grid.y <= 65535u, "dpb_lbs_forward: batch too large for one call (max 65535*16 poses)");
-      lbs_vertex_kernel<<<grid, LBS_TV, smem, st>>>(betas, transl, w.feat, w.A, h->v_template, h->shapedirs,
-                                                    h->posedirs, h->ell_idx, h->ell_w, nullptr, n_verts, h->V, h->J,
-                                                    0, 0, h->nnz, verts, verts, B);
+      lbs_vertex_kernel<<<grid, LBS_TV, smem, st>>>(betas, transl, w.feat, w.A, hv->v_template, hv->shapedirs,
+                                                    hv->posedirs, hv->ell_idx, hv->ell_w, nullptr, n_verts, hv->V, h->J,
+                                                    0, 0, hv->nnz, vout, vout, B);
       DPB_CUDA_CHECK(cudaGetLastError());
       }
       }

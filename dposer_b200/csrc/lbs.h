@@ -67,6 +67,9 @@ struct dpb_lbs {
   int sb_vp = 0, sb_smem = 0;     // V padded to 64; dynamic shared memory of the kernel
   __half* wT16 = nullptr;         // [128, 2*sb_vp] fp16 [hi | lo]: rows < J = weights^T, row J = ones
   CUtensorMap tm_wT;
+  // joints-only mode on the tensor cores: the n_need vertices the extra joints / landmarks read, as a body model of
+  // their own (same joints, shape and pose spaces; vertex i = need_vids[i]) -- every vertex kernel runs on it unchanged
+  dpb_lbs* sub = nullptr;
 };
 
 namespace dpb {

@@ -536,6 +536,29 @@ extern "C" size_t dpb_lbs_backward_scratch_bytes(dpb_lbs_t* h, int64_t B) {
   return bwd_scratch_bytes(h, B);
 }
 
+extern "C" size_t dpb_lbs_backward_scratch_bytes_joints(dpb_lbs_t* h, int64_t B) {
+  if (!h || B <= 0 || !h->sub || !h->sub->bt_ready || !h->sub->sb_ready) return 0;
+  return bwd_scratch_bytes(h->sub, B);
+}
+
+namespace dpb {
+// vertex pass of the backward on the tensor cores for the vertex set of `hv` (the full model or the compact one):
+// v_posed recompute -> skinning adjoint (dL/dA, g_vposed) -> transposed blend (dL/dfeat, dL/dbeta)
+static int bwd_vertex_pass_tc(dpb_lbs* hv, const LbsWs& w, const float* betas, const float* g_verts, const float* gextra,
+                              bool have_extra, uint8_t* sp, int64_t B, cudaStream_t st) {
+  float* vposed = reinterpret_cast<float*>(sp);
+  __half* gvp16 = reinterpret_cast<__half*>(sp + align_up((size_t)B * hv->V * 3 * 4, 256));
+  float* gout = reinterpret_cast<float*>(sp + align_up((size_t)B * hv->V * 3 * 4, 256) + bwd_gvp_bytes(hv, B));
+  float* scale = reinterpret_cast<float*>(sp + bwd_scratch_bytes(hv, B) - align_up((size_t)B * 4, 256));
+  int rc = lbs_tc_blend(hv, betas, w.feat, w.featop, vposed, B, st);
+  if (rc != DPB_OK) return rc;
+  DPB_CUDA_CHECK(cudaMemsetAsync(gvp16, 0, (size_t)B * 2 * hv->bt_rp * 2, st));
+  rc = lbs_skin_bwd_tc(hv, w.A, vposed, g_verts, gextra, have_extra, gvp16, w.gA, w.gbeta, scale, B, st);
+  if (rc != DPB_OK) return rc;
+  return lbs_blendT_tc(hv, gvp16, scale, gout, w.gfeat, w.gbeta, B, st);
+}
+}  // namespace dpb
+
 extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* full_pose, const float* g_verts,
                                 const float* g_joints, float* g_pose, float* g_betas, float* g_transl, int64_t B,
                                 int flags, void* ws, size_t ws_bytes, void* scratch, size_t scratch_bytes,
@@ -605,6 +628,12 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
       bwd_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gout, h->bw_np, P, S, w.gfeat, w.gbeta, B);
       DPB_CUDA_CHECK(cudaGetLastError());
     }
+  } else if (!full && have_extra && h->sub && h->sub->bt_ready && h->sub->sb_ready && w.featop && scratch &&
+             scratch_bytes >= bwd_scratch_bytes(h->sub, B) &&
+             !(getenv("DPB_LBS_BWD_FP32") && atoi(getenv("DPB_LBS_BWD_FP32")))) {
+    // joints-only mode: the cotangents of the compact vertex set go through the same tensor-core pass
+    int rc = bwd_vertex_pass_tc(h->sub, w, betas, w.gextra, nullptr, false, static_cast<uint8_t*>(scratch), B, st);
+    if (rc != DPB_OK) return rc;
   } else if (full || have_extra) {
     size_t smem = ((size_t)P * BW_TP + (size_t)S * BW_TP + 2 * (size_t)BW_TP * J * 12 + (size_t)BW_TP * 3 * BW_TV +
                    BW_TP * 3) * 4;

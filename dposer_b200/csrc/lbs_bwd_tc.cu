@@ -234,8 +234,9 @@ void lbs_bwd_tc_release(dpb_lbs* h) {
 int lbs_blendT_splits(const dpb_lbs* h, int64_t B) {
   const int64_t nt = (B + 127) / 128;
   int64_t s = h->sm_count / (nt < 1 ? 1 : nt);
-  if (s < 1) s = 1;
   if (s > 8) s = 8;
+  if (s > h->bt_rp / lbt::BK) s = h->bt_rp / lbt::BK;   // every split owns at least one slab (an empty one would drain an
+  if (s < 1) s = 1;                                     // accumulator that no MMA ever wrote)
   return (int)s;
 }
 

@@ -818,7 +818,7 @@ int lbs_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   const int V = h->V, S = h->S, P = h->P;
   const int Kp = (S + P + 1 + 31) / 32 * 32;   // hi (= lo) width incl. the template slot: multiple of 32 so that [hi | lo] is whole 64-wide slabs
   const int K2 = 2 * Kp;
-  const int V_pad = (V + ltc::TILE_V - 1) / ltc::TILE_V * ltc::TILE_V;
+  const int V_pad = (V + 2 * ltc::TILE_V - 1) / (2 * ltc::TILE_V) * (2 * ltc::TILE_V);   // whole tile PAIRS (CTA-pair kernels)
   const int n_slabs = K2 / ltc::BK;
   if ((size_t)n_slabs * (64 * ltc::BK * 2) + 2 * ltc::A_SLAB + 2048 > 232448) return DPB_OK;  // too wide: fp32 engine only
   // blend basis, vertex-major per coordinate: row (c*V_pad + v) = [shapedirs[v,c,:] | posedirs[:,3v+c]] as [hi | lo]

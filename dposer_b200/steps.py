@@ -87,7 +87,8 @@ class LbsStep:
         self.g_transl = f(rows, 3)
         n = L.load().dpb_lbs_workspace_bytes(self.h.ptr, rows, 0)
         self.ws = torch.empty(int(n), dtype=torch.uint8, device=device)
-        ns = int(L.load().dpb_lbs_backward_scratch_bytes(self.h.ptr, rows)) if need_verts else 0
+        ns = int(L.load().dpb_lbs_backward_scratch_bytes(self.h.ptr, rows)) if need_verts else \
+            (int(L.load().dpb_lbs_backward_scratch_bytes_joints(self.h.ptr, rows)) if rows >= 64 else 0)
         self.scratch = torch.empty(ns, dtype=torch.uint8, device=device) if ns else None
         self.flags = core.engine | (L.LBS_CONST_TAIL if (const_tail and core.tail is not None) else 0)
 

@@ -215,8 +215,12 @@ int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* full_pose, co
  *   g_verts DEVICE [B,V,3] or NULL, g_joints DEVICE [B,J+n_extra+n_lmk,3] or NULL
  *   g_pose DEVICE [B,J*3], g_betas DEVICE [B,S], g_transl DEVICE [B,3] (each may be NULL)
  *   scratch DEVICE (optional, dpb_lbs_backward_scratch_bytes(h, B) bytes): with it and g_verts the vertex pass is
- *   split into tensor-core blend recompute + skinning adjoint + one SGEMM; without it a single slower kernel runs */
+ *   split into tensor-core blend recompute + skinning adjoint (dL/dA on tcgen05) + transposed blend on tcgen05;
+ *   without it a single slower kernel runs */
 size_t dpb_lbs_backward_scratch_bytes(dpb_lbs_t* h, int64_t B);
+/* scratch for the joints-only case (g_verts == NULL): the vertices the extra joints / landmarks read take the same
+ * tensor-core pass as a small body model of their own; 0 when unavailable (a single slower kernel runs without it) */
+size_t dpb_lbs_backward_scratch_bytes_joints(dpb_lbs_t* h, int64_t B);
 int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* full_pose, const float* g_verts,
                      const float* g_joints, float* g_pose, float* g_betas, float* g_transl, int64_t B,
                      int flags, void* ws, size_t ws_bytes, void* scratch, size_t scratch_bytes, void* stream);

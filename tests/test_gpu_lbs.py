@@ -253,3 +253,32 @@ def test_lbs_backward_split_path_across_tile_boundaries():
         ref, got = leaf[k].grad, dl[k].grad.cpu()
         scale = ref.abs().max().clamp_min(1e-6)
         assert (got - ref).abs().max() / scale < 2e-4, k
+
+
+@pytest.mark.parametrize('mt,B', [('smplx', 96), ('smpl', 130)])
+def test_lbs_joints_only_tensor_core_path(mt, B):
+    """Joints-only mode (need_verts=False, SMPLify's case) at a batch that takes the tensor-core path: the vertices the
+    extra joints / landmarks read run as a small body model of their own (forward AND the backward's vertex pass).
+    Joints <= 1e-5 m and gradients <= 2e-4 against autograd through the oracle."""
+    m = synthetic.make_body_tensors(mt)
+    inp = synthetic.lbs_inputs(B, mt, seed=13)
+    nj = 45 if mt == 'smpl' else 127
+    gj = torch.randn(B, nj, 3, generator=torch.Generator().manual_seed(29)) * 1e-3
+    leaf = {k: v.clone().requires_grad_(True) for k, v in inp.items()}
+    if mt == 'smpl':
+        pose, shape = torch.cat([leaf['root_orient'], leaf['pose_body']], 1), leaf['betas']
+    else:
+        pose = torch.cat([leaf['root_orient'], leaf['pose_body'], torch.zeros(B, 99)], 1)
+        shape = torch.cat([leaf['betas'], torch.zeros(B, 10)], 1)
+    _, j_ref = lbs_ref.body_forward(m, shape, pose, leaf['trans'])
+    (j_ref * gj).sum().backward()
+    bm = BodyModel(m, num_betas=10, batch_size=B, model_type=mt).cuda()
+    dl = {k: v.clone().cuda().requires_grad_(True) for k, v in inp.items()}
+    out = bm(need_verts=False, **dl)
+    assert out.v is None
+    assert float((out.Jtr.detach().cpu() - j_ref.detach()).abs().max()) < 1e-5
+    (out.Jtr * gj.cuda()).sum().backward()
+    for k in inp:
+        ref, got = leaf[k].grad, dl[k].grad.cpu()
+        scale = ref.abs().max().clamp_min(1e-12)
+        assert float((got - ref).abs().max() / scale) < 2e-4, k
