@@ -34,6 +34,8 @@ struct dpb_score {
   __half* act_t = nullptr;      // [slots*128, 1024] block intermediate
   CUtensorMap tm_act_h, tm_act_t;  // box {64, 128}
   int tc_slots = 0;
+  size_t act_bytes = 0, l2_window = 0;   // activation scratch size; bytes of the persisting-L2 access-policy window (0 = off)
+  float l2_hit = 1.f;
   float* gn_tc = nullptr;       // [5][2][1024] gamma | beta as staged by the tcgen05 epilogue
   int* tc_flags = nullptr;      // [slots] hand-off flags of the sampler's segment schedule (score_tc.cu: SegIter)
 };

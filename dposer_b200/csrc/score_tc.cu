@@ -414,6 +414,12 @@ score_tc_kernel(const __grid_constant__ KParams p,
   const int n_units = (p.n_tiles + CLUSTER * NSUB - 1) / (CLUSTER * NSUB);
   Seg sg;
   PROF_DECL
+  // the activation scratch is written and re-read once per layer and never needed in HBM: evict_last on its TMA
+  // stores and loads keeps the boxes in L2 (DPB_TC_L2HINT=0 at build time restores unhinted copies, A/B)
+#ifndef DPB_TC_L2HINT
+#define DPB_TC_L2HINT 1
+#endif
+  const uint64_t pol_act = DPB_TC_L2HINT == 2 ? ptx::l2_policy_evict_first() : ptx::l2_policy_evict_last();
 
   // register budget: the four single-lane roles (warpgroup 0) give registers to the 256 epilogue threads
   if (warp < 4) {
@@ -553,7 +559,11 @@ score_tc_kernel(const __grid_constant__ KParams p,
                     if (DBG(4) || direct) ptx::mbar_arrive_cluster(lbar);
                     else {
                       ptx::mbar_arrive_expect_tx_cluster(lbar, A_BYTES);
-                      ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, ks * BLOCK_K, slot_row0 + sub * TILE_M);
+                      if (DPB_TC_L2HINT)
+                        ptx::tma_load_2d_2sm_hint(smem_base + stage * STAGE_BYTES, tm, lbar, ks * BLOCK_K,
+                                                  slot_row0 + sub * TILE_M, pol_act);
+                      else
+                        ptx::tma_load_2d_2sm(smem_base + stage * STAGE_BYTES, tm, lbar, ks * BLOCK_K, slot_row0 + sub * TILE_M);
                     }
                   }
                 } else if (ptx::elect_one()) {
@@ -597,8 +607,14 @@ score_tc_kernel(const __grid_constant__ KParams p,
                   PROF_WAIT(0, ptx::mbar_wait(sfull_bar(hf, b), ph));
                   if (ptx::elect_one()) {
                     if (!DBG(16))
-                    ptx::tma_store_2d(tm, stg_base + (hf * STG_BUFS + b) * STG_BYTES,
-                                      chunk * CHUNK_N + hf * 128 + gp * 64, slot_row0 + sub * TILE_M);
+                    {
+                      if (DPB_TC_L2HINT)
+                        ptx::tma_store_2d_hint(tm, stg_base + (hf * STG_BUFS + b) * STG_BYTES,
+                                               chunk * CHUNK_N + hf * 128 + gp * 64, slot_row0 + sub * TILE_M, pol_act);
+                      else
+                        ptx::tma_store_2d(tm, stg_base + (hf * STG_BUFS + b) * STG_BYTES,
+                                          chunk * CHUNK_N + hf * 128 + gp * 64, slot_row0 + sub * TILE_M);
+                    }
                     ptx::tma_store_commit();
                     if (!last_released) {  // the previous store has finished READING its box: hand that box back
                       PROF_WAIT(1, ptx::tma_store_wait_read<1>());
@@ -1023,10 +1039,35 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
   // per-CTA activation scratch (one 128-row slot per SM)
   h->tc_slots = h->sm_count * tc::NSUB;
   const size_t rows = (size_t)h->tc_slots * tc::TILE_M;
-  DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_h, rows * H * sizeof(__half)));
-  DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_t, rows * H * sizeof(__half)));
-  DPB_CUDA_CHECK(cudaMemset(h->act_h, 0, rows * H * sizeof(__half)));
-  DPB_CUDA_CHECK(cudaMemset(h->act_t, 0, rows * H * sizeof(__half)));
+  // one allocation for both halves: a single L2 access-policy window covers the whole scratch
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->act_h, 2 * rows * H * sizeof(__half)));
+  h->act_t = h->act_h + rows * H;
+  DPB_CUDA_CHECK(cudaMemset(h->act_h, 0, 2 * rows * H * sizeof(__half)));
+  {
+    // The scratch is written and re-read once per layer and never needed in HBM: ask for it to stay in L2
+    // (persisting carve-out + access-policy window on the launch).  profiles/r1_ncu_full_summary_final.md: without
+    // it ~68 % of every activation box was written back to DRAM (1.05 GB per 37 888 rows x 4 steps).
+    cudaDeviceProp prop;
+    DPB_CUDA_CHECK(cudaGetDeviceProperties(&prop, h->device));
+    h->act_bytes = 2 * rows * H * sizeof(__half);
+    h->l2_window = 0;
+    // MEASURED (profiles/r2_sampler_l2_policy.md): reserving the carve-out costs more than it saves -- 535 ms without
+    // it, 565 ms with carve-out + window, 694 ms with the carve-out alone -- so it is opt-in (DPB_TC_L2PERSIST=1 when the
+    // handle is created) and the default leaves L2 to the hardware policy plus evict_last hints on the scratch traffic.
+    const char* e = getenv("DPB_TC_L2PERSIST");
+    if (e && atoi(e) == 1 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+      size_t carve = (size_t)prop.persistingL2CacheMaxSize;
+      if (carve > h->act_bytes) carve = h->act_bytes;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+        h->l2_window = h->act_bytes < (size_t)prop.accessPolicyMaxWindowSize ? h->act_bytes
+                                                                               : (size_t)prop.accessPolicyMaxWindowSize;
+        h->l2_hit = (float)((double)carve / (double)h->l2_window);
+        if (h->l2_hit > 1.f) h->l2_hit = 1.f;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
   {  // gamma | beta of the five GroupNorms as the epilogue stages them (beta halved for the tanh-form SiLU)
     std::vector<float> gn((size_t)NL * 2 * H);
     DPB_CUDA_CHECK(cudaMemcpy(gn.data(), h->gn_packed, gn.size() * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1060,7 +1101,7 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
 }
 
 void tc_release(dpb_score* h) {
-  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->act_t, h->tc_flags, h->gn_tc};
+  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->tc_flags, h->gn_tc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   h->tc_ready = false;
@@ -1098,9 +1139,28 @@ int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
   const int max_grid = (h->tc_slots / tc::NSUB) / tc::CLUSTER * tc::CLUSTER;
   if (grid > max_grid) grid = max_grid;
   if (j.n_steps > 1) DPB_CUDA_CHECK(cudaMemsetAsync(h->tc_flags, 0, sizeof(int) * h->tc_slots, st));
-  tc::score_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(p, h->tm_act_h, h->tm_act_t, h->tm_pre,
-                                                                    h->tm_w[0], h->tm_w[1], h->tm_w[2], h->tm_w[3],
-                                                                    h->tm_post);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(tc::NUM_THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int n_attr = 0;
+    if (h->l2_window > 0) {
+      attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[0].val.accessPolicyWindow.base_ptr = h->act_h;
+      attr[0].val.accessPolicyWindow.num_bytes = h->l2_window;
+      attr[0].val.accessPolicyWindow.hitRatio = h->l2_hit;
+      attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      n_attr = 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    DPB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::score_tc_kernel, p, h->tm_act_h, h->tm_act_t, h->tm_pre, h->tm_w[0],
+                                      h->tm_w[1], h->tm_w[2], h->tm_w[3], h->tm_post));
+  }
   DPB_CUDA_CHECK(cudaGetLastError());
 #ifdef DPB_TC_PROFILE
   {
