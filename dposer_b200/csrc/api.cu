@@ -183,6 +183,31 @@ extern "C" int dpb_score_forward(dpb_score_t* h, const float* x, const float* ta
   return launch_scale_out(w.raw, row_scale, scale, out, B, st);
 }
 
+extern "C" size_t dpb_score_jvp_workspace_bytes(dpb_score_t* h, int64_t B) {
+  if (!h || B <= 0) return 0;
+  return simt_forward_ws_bytes(2 * B) + align_up((size_t)2 * B * DP * 4, 256) + 1024;
+}
+
+extern "C" int dpb_score_jvp(dpb_score_t* h, const float* x, const float* v, const float* table, const int32_t* t_index,
+                             const float* row_scale, float scale, float* out, float* jv, int64_t B, void* ws,
+                             size_t ws_bytes, void* stream) {
+  if (!h) return fail(DPB_EINVAL, "dpb_score_jvp: null handle");
+  DeviceGuard guard(h->device);
+  DPB_REQUIRE(x && v && table && out && jv, "dpb_score_jvp: x, v, table, out and jv are required");
+  if (B <= 0) return DPB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  WsCarver c(ws, ws_bytes);
+  float* raw = c.take<float>((size_t)2 * B * DP);
+  if (!c.ok() || ws == nullptr || ws_bytes < dpb_score_jvp_workspace_bytes(h, B))
+    return fail(DPB_ENOMEM, "dpb_score_jvp: workspace too small");
+  void* rest = static_cast<uint8_t*>(ws) + c.off;
+  int rc = simt_forward_jvp_raw(h, x, v, table, t_index, raw, B, rest, ws_bytes - c.off, st);
+  if (rc != DPB_OK) return rc;
+  rc = launch_scale_out(raw, row_scale, scale, out, B, st);
+  if (rc != DPB_OK) return rc;
+  return launch_scale_out(raw + (size_t)B * DP, row_scale, scale, jv, B, st);   // the scaling is linear: same factor
+}
+
 extern "C" int dpb_sampler_run(dpb_score_t* h, float* x_io, const dpb_step_tables* tbl, const float* obs,
                                const float* mask, const float* noise, uint64_t seed, uint64_t step_offset,
                                float* traj, float* x_mean, int64_t B, int flags, void* ws, size_t ws_bytes,

@@ -46,6 +46,8 @@ namespace dpb {
 int simt_time_table(dpb_score* h, const float* labels, int n, float* table, cudaStream_t st);
 size_t simt_forward_ws_bytes(int64_t B);
 // raw[B,64] = post_dense output (column 63 is padding); buffers carved from ws
+int simt_forward_jvp_raw(dpb_score* h, const float* x, const float* v, const float* table, const int32_t* t_index,
+                         float* raw, int64_t B, void* ws, size_t ws_bytes, cudaStream_t st);
 int simt_forward_raw(dpb_score* h, const float* x, const float* table, const int32_t* t_index, float* raw,
                      int64_t B, void* ws, size_t ws_bytes, cudaStream_t st);
 

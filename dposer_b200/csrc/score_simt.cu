@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) sgemm_bias_kernel(const float* __restrict
                                                          float* __restrict__ C, int64_t M, int N, int K,
                                                          const float* __restrict__ bias,
                                                          const int32_t* __restrict__ t_index, int bias_stride,
-                                                         const float* __restrict__ col_bias) {
+                                                         const float* __restrict__ col_bias, int64_t bias_rows) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -129,8 +129,9 @@ __global__ void __launch_bounds__(256) sgemm_bias_kernel(const float* __restrict
   for (int i = 0; i < 4; ++i) {
     int64_t m = m0 + ty * 4 + i;
     if (m >= M) continue;
+    const bool biased = m < bias_rows;          // rows beyond carry tangents (JVP): the affine part drops out
     const float* brow = nullptr;
-    if (bias) brow = bias + (size_t)(t_index ? t_index[m] : 0) * bias_stride;
+    if (bias && biased) brow = bias + (size_t)(t_index ? t_index[m] : 0) * bias_stride;
     float4 o;
     float* op = &o.x;
 #pragma unroll
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) sgemm_bias_kernel(const float* __restrict
       int n = n0 + tx * 4 + j;
       float v = acc[i][j];
       if (brow) v += brow[n];
-      if (col_bias) v += col_bias[n];
+      if (col_bias && biased) v += col_bias[n];
       op[j] = v;
     }
     *reinterpret_cast<float4*>(C + m * N + n0 + tx * 4) = o;
@@ -178,6 +179,56 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ 
     o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
   }
   *reinterpret_cast<float4*>(out + m * H + c) = o;
+}
+
+// Forward-mode twin of gn_silu_kernel: row m of `in` is the primal pre-activation, row M + m its tangent; writes
+// SiLU(GN(h)) and its directional derivative (+ the residual stream's primal / tangent).  GroupNorm's JVP inside a
+// group: n = (h - mu) rstd,  dn = rstd (dh - mean(dh)) - n rstd mean(n dh);  SiLU'(y) = s + y s (1 - s), s = sigmoid(y).
+__global__ void __launch_bounds__(256) gn_silu_jvp_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* residual,
+                                                          float* out, int64_t M) {
+  const int64_t m = blockIdx.x;
+  if (m >= M) return;
+  const int c = threadIdx.x * 4;
+  const float4 v = *reinterpret_cast<const float4*>(in + m * H + c);
+  const float4 d = *reinterpret_cast<const float4*>(in + (M + m) * H + c);
+  auto gsum = [](float s) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    return s;
+  };
+  const float mean = gsum((v.x + v.y) + (v.z + v.w)) * (1.0f / GROUP);
+  const float dmean = gsum((d.x + d.y) + (d.z + d.w)) * (1.0f / GROUP);
+  const float hx[4] = {v.x - mean, v.y - mean, v.z - mean, v.w - mean};
+  const float dx[4] = {d.x - dmean, d.y - dmean, d.z - dmean, d.w - dmean};
+  const float q = gsum((hx[0] * hx[0] + hx[1] * hx[1]) + (hx[2] * hx[2] + hx[3] * hx[3]));
+  const float rstd = 1.0f / sqrtf(q * (1.0f / GROUP) + GN_EPS);
+  float n[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) n[i] = hx[i] * rstd;
+  const float ndh = gsum((n[0] * dx[0] + n[1] * dx[1]) + (n[2] * dx[2] + n[3] * dx[3])) * (1.0f / GROUP);
+  const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+  const float4 b = *reinterpret_cast<const float4*>(beta + c);
+  const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+  float4 o, od;
+  float *op = &o.x, *odp = &od.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float y = n[i] * gg[i] + bb[i];
+    const float dy = gg[i] * rstd * (dx[i] - n[i] * ndh);
+    const float sg = 1.0f / (1.0f + expf(-y));
+    op[i] = y * sg;
+    odp[i] = dy * (sg + y * sg * (1.0f - sg));
+  }
+  if (residual) {
+    const float4 r = *reinterpret_cast<const float4*>(residual + m * H + c);
+    const float4 rd = *reinterpret_cast<const float4*>(residual + (M + m) * H + c);
+    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    od.x += rd.x; od.y += rd.y; od.z += rd.z; od.w += rd.w;
+  }
+  *reinterpret_cast<float4*>(out + m * H + c) = o;
+  *reinterpret_cast<float4*>(out + (M + m) * H + c) = od;
 }
 
 // x [B,63] -> xpad [B,64]
@@ -221,20 +272,58 @@ int simt_forward_raw(dpb_score* h, const float* x, const float* table, const int
     pad_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, xp, B);
   }
   // pre_dense + pre_gnorm + act   (model.py:166-169)
-  sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(xp, h->pre_w, pre, B, H, DP, table, t_index, stride, nullptr);
+  sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(xp, h->pre_w, pre, B, H, DP, table, t_index, stride, nullptr, B);
   gn_silu_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[0], h->gn_b[0], nullptr, hbuf, B);
   for (int blk = 0; blk < 2; ++blk) {  // model.py:172-187
     int l1 = 1 + 2 * blk, l2 = 2 + 2 * blk;
     sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(hbuf, h->blk_w[l1 - 1], pre, B, H, H, table + (size_t)l1 * H,
-                                                 t_index, stride, nullptr);
+                                                 t_index, stride, nullptr, B);
     gn_silu_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[l1], h->gn_b[l1], nullptr, tbuf, B);
     sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(tbuf, h->blk_w[l2 - 1], pre, B, H, H, table + (size_t)l2 * H,
-                                                 t_index, stride, nullptr);
+                                                 t_index, stride, nullptr, B);
     gn_silu_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[l2], h->gn_b[l2], hbuf, hbuf, B);
   }
   // post_dense (model.py:189), N padded to 64
   dim3 post_grid(DP / BN, (unsigned)((B + BM - 1) / BM));
-  sgemm_bias_kernel<<<post_grid, 256, 0, st>>>(hbuf, h->post_w, raw, B, DP, H, nullptr, nullptr, 0, h->post_b);
+  sgemm_bias_kernel<<<post_grid, 256, 0, st>>>(hbuf, h->post_w, raw, B, DP, H, nullptr, nullptr, 0, h->post_b, B);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+// raw[0:B] = net(x) and raw[B:2B] = (d net / d x) v  (both before the sigma division), fp32 engine: every GEMM runs on
+// the stacked rows [primal ; tangent] (the tangent rows skip the bias), every GroupNorm + SiLU on its forward-mode twin.
+// ws: simt_forward_ws_bytes(2 B).  Serves the Hutchinson divergence of lib/algorithms/advanced/likelihood.py:26-37:
+// eps . (J eps) is the scalar the reference gets from autograd's eps . (J^T eps).
+int simt_forward_jvp_raw(dpb_score* h, const float* x, const float* v, const float* table, const int32_t* t_index,
+                         float* raw, int64_t B, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (B <= 0) return DPB_OK;
+  const int64_t B2 = 2 * B;
+  WsCarver c(ws, ws_bytes);
+  float* xp = c.take<float>((size_t)B2 * DP);
+  float* pre = c.take<float>((size_t)B2 * H);
+  float* hbuf = c.take<float>((size_t)B2 * H);
+  float* tbuf = c.take<float>((size_t)B2 * H);
+  if (!c.ok() || ws == nullptr) return fail(DPB_ENOMEM, "score jvp: workspace too small");
+  const int stride = NL * H;
+  dim3 gemm_grid(H / BN, (unsigned)((B2 + BM - 1) / BM));
+  {
+    int64_t n = B * DP;
+    pad_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, xp, B);
+    pad_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, xp + (size_t)B * DP, B);
+  }
+  sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(xp, h->pre_w, pre, B2, H, DP, table, t_index, stride, nullptr, B);
+  gn_silu_jvp_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[0], h->gn_b[0], nullptr, hbuf, B);
+  for (int blk = 0; blk < 2; ++blk) {
+    int l1 = 1 + 2 * blk, l2 = 2 + 2 * blk;
+    sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(hbuf, h->blk_w[l1 - 1], pre, B2, H, H, table + (size_t)l1 * H,
+                                                 t_index, stride, nullptr, B);
+    gn_silu_jvp_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[l1], h->gn_b[l1], nullptr, tbuf, B);
+    sgemm_bias_kernel<<<gemm_grid, 256, 0, st>>>(tbuf, h->blk_w[l2 - 1], pre, B2, H, H, table + (size_t)l2 * H,
+                                                 t_index, stride, nullptr, B);
+    gn_silu_jvp_kernel<<<(unsigned)B, 256, 0, st>>>(pre, h->gn_w[l2], h->gn_b[l2], hbuf, hbuf, B);
+  }
+  dim3 post_grid(DP / BN, (unsigned)((B2 + BM - 1) / BM));
+  sgemm_bias_kernel<<<post_grid, 256, 0, st>>>(hbuf, h->post_w, raw, B2, DP, H, nullptr, nullptr, 0, h->post_b, B);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }

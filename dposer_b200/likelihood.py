@@ -1,0 +1,81 @@
+"""Log-likelihood / latent code under the probability-flow ODE with the reference's call surface
+(lib/algorithms/advanced/likelihood.py:40-113).
+
+``get_likelihood_fn(sde, inverse_scaler, ...)`` returns ``likelihood_fn(model, data) -> (bpd, z, nfe)``.  scipy's RK45
+drives the ODE on the host exactly like the reference; every function evaluation is ONE native call,
+``dpb_score_jvp``: the score net and its forward-mode derivative along the Hutchinson probe (fp32 engine).  The
+reference gets ``eps . (J^T eps)`` from autograd (likelihood.py:26-37); the same scalar is ``eps . (J eps)``, so no
+backward pass through the network is needed.  drift and divergence follow from the affine form of the reverse SDE:
+
+    drift = f_x x - 0.5 g^2 score,   score = -raw / (sigma std)      div = f_x sum(eps^2) + 0.5 g^2 / (sigma std) eps.(J_raw eps)
+"""
+import numpy as np
+import torch
+from scipy import integrate
+
+from . import _lib as L
+from . import sde_lib
+from . import utils as mutils
+
+
+def drift_and_div(model, sde, x, t, epsilon, ws=None):
+    """(drift [B,63], div [B]) of the probability-flow ODE at the batch-uniform time ``t`` (python float)."""
+    L.require_cuda(x, 'x')
+    if not isinstance(sde, (sde_lib.VPSDE, sde_lib.subVPSDE)):
+        raise NotImplementedError('likelihood runs on VPSDE / subVPSDE')
+    B = x.shape[0]
+    ps = mutils.prior_scalars(sde, model, float(t), continuous=True)
+    tt = torch.tensor([float(t)], dtype=torch.float32)
+    fx, g = sde.sde(torch.ones(1, 1), tt)                  # f(x,t) = fx * x   (host fp32, like the reference's scalars)
+    fx, g2 = float(fx[0, 0]), float(g[0] ** 2)
+    table = model.time_table(ps['label'])
+    h = model.handle()
+    if ws is None:
+        ws = torch.empty(int(L.load().dpb_score_jvp_workspace_bytes(h.ptr, B)), dtype=torch.uint8, device=x.device)
+    score = torch.empty_like(x)
+    jv = torch.empty_like(x)
+    xc, ec = x.contiguous(), epsilon.contiguous()
+    L.check(L.load().dpb_score_jvp(h.ptr, L.ptr(xc), L.ptr(ec), L.ptr(table[0]), None, None, -ps['inv_sigma_std'],
+                                   L.ptr(score), L.ptr(jv), B, L.ptr(ws), ws.numel(), L.current_stream(x.device)))
+    drift = fx * xc - 0.5 * g2 * score
+    div = fx * (ec * ec).sum(dim=1) - 0.5 * g2 * (jv * ec).sum(dim=1)
+    return drift, div
+
+
+def get_likelihood_fn(sde, inverse_scaler, hutchinson_type='Rademacher', rtol=1e-5, atol=1e-5, method='RK45', eps=1e-5):
+    """likelihood.py:40-113.  ``likelihood_fn(model, data, epsilon=None)``: ``epsilon`` fixes the probe (parity tests)."""
+
+    def likelihood_fn(model, data, epsilon=None):
+        with torch.no_grad():
+            L.require_cuda(data, 'data')
+            data = data.to(torch.float32)
+            shape = data.shape
+            if epsilon is None:
+                if hutchinson_type == 'Gaussian':
+                    epsilon = torch.randn_like(data)
+                elif hutchinson_type == 'Rademacher':
+                    epsilon = torch.randint_like(data, low=0, high=2).float() * 2 - 1.
+                else:
+                    raise NotImplementedError(f"Hutchinson type {hutchinson_type} unknown.")
+            epsilon = epsilon.to(device=data.device, dtype=torch.float32)
+            h = model.handle()
+            ws = torch.empty(int(L.load().dpb_score_jvp_workspace_bytes(h.ptr, shape[0])), dtype=torch.uint8,
+                             device=data.device)
+
+            def ode_func(t, x):
+                sample = mutils.from_flattened_numpy(x[:-shape[0]], shape).to(data.device).type(torch.float32)
+                drift, div = drift_and_div(model, sde, sample, t, epsilon, ws)
+                return np.concatenate([mutils.to_flattened_numpy(drift), mutils.to_flattened_numpy(div)], axis=0)
+
+            init = np.concatenate([mutils.to_flattened_numpy(data), np.zeros((shape[0],))], axis=0)
+            solution = integrate.solve_ivp(ode_func, (eps, sde.T), init, rtol=rtol, atol=atol, method=method)
+            nfe = solution.nfev
+            zp = solution.y[:, -1]
+            z = mutils.from_flattened_numpy(zp[:-shape[0]], shape).to(data.device).type(torch.float32)
+            delta_logp = mutils.from_flattened_numpy(zp[-shape[0]:], (shape[0],)).to(data.device).type(torch.float32)
+            prior_logp = sde.prior_logp(z)
+            bpd = -(prior_logp + delta_logp) / np.log(2)
+            bpd = bpd / np.prod(shape[1:])
+            return bpd, z, nfe
+
+    return likelihood_fn

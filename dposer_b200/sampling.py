@@ -19,7 +19,7 @@ from . import _lib as L
 from . import sde_lib
 from . import utils as mutils
 
-_PREDICTORS = ('euler_maruyama', 'none')
+_PREDICTORS = ('euler_maruyama', 'reverse_diffusion', 'ancestral_sampling', 'none')
 _CORRECTORS = ('none', 'langevin')
 
 
@@ -35,9 +35,12 @@ def get_sampling_fn(config, sde, shape, inverse_scaler, eps, device=None, return
     if name == 'pc':
         pred, corr = config.sampling.predictor.lower(), config.sampling.corrector.lower()
         if pred not in _PREDICTORS:
-            # reverse_diffusion / ancestral_sampling cannot be driven by pc_sampler in the reference either
-            # (update_fn arity, sampling.py:215 vs :361) -- SURVEY 2 row 4
             raise NotImplementedError(f'predictor {pred!r} is not supported')
+        # reverse_diffusion / ancestral_sampling (sampling.py:210-259): the reference's own pc_sampler cannot drive them
+        # (update_fn arity, sampling.py:215 vs :361 -- SURVEY 2 row 4); here they are two more coefficient tables of the
+        # same fused kernel, pinned against the reference classes called directly (sde_variants_golden.npz)
+        if pred == 'ancestral_sampling' and not isinstance(sde, sde_lib.VPSDE):
+            raise NotImplementedError(f'SDE class {sde.__class__.__name__} not yet supported.')   # sampling.py:229
         if corr not in _CORRECTORS:
             raise NotImplementedError(f'corrector {corr!r} is not supported')
         return get_pc_sampler(sde, shape, pred, corr, inverse_scaler, config.sampling.snr,
@@ -88,7 +91,8 @@ def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_step
             timesteps = mutils.timestep_grid(sde, eps)
             if predictor == 'none':
                 raise NotImplementedError("predictor 'none' (corrector-only sampling) is not supported")
-            coef, labels = mutils.em_coefficients(sde, model, timesteps[start_t:], probability_flow, continuous)
+            coef, labels = mutils.em_coefficients(sde, model, timesteps[start_t:], probability_flow, continuous,
+                                                  predictor=predictor)
             coef = coef.to(device)
             table = model.time_table(labels)
             if impute:

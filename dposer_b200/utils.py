@@ -81,14 +81,20 @@ def sigma_at(model, labels):
     return model._sigmas_host()[labels.long()]
 
 
-def em_coefficients(sde, model, t, probability_flow=False, continuous=True):
-    """Per-step affine form of the Euler-Maruyama predictor (sampling.py:182-188 with
-    sde_lib.py:98-106 and utils.py:152-162) for a CPU fp32 vector of times ``t``:
+def em_coefficients(sde, model, t, probability_flow=False, continuous=True, predictor='euler_maruyama'):
+    """Per-step affine form of a predictor for a CPU fp32 vector of times ``t``:
 
         x_mean = a x + b raw ,  x = x_mean + c z ,  impute with alpha/std
 
-    where raw is the post_dense output before the sigma division.  Returns (coef [n,8], labels [n]).
+    where raw is the post_dense output before the sigma division (score = -raw / (sigma * std)).
+      euler_maruyama      sampling.py:182-188 with sde_lib.py:98-106 and utils.py:152-162
+      reverse_diffusion   sampling.py:210-220 with RSDE.discretize sde_lib.py:108-114 (f, G from SDE.discretize :52-69, or
+                          VPSDE's DDPM rule :129-134); the reference's probability-flow factor there is 1.0, not 0.5
+      ancestral_sampling  sampling.py:223-259, VPSDE only (x + beta score) / sqrt(1 - beta) + sqrt(beta) z
+    Returns (coef [n,8], labels [n]).
     """
+    if predictor not in ('euler_maruyama', 'reverse_diffusion', 'ancestral_sampling'):
+        raise NotImplementedError(f'predictor {predictor!r} is not supported')
     if not _is_vp(sde):
         raise NotImplementedError('fused sampler supports VPSDE / subVPSDE (VESDE runs the generic loop)')
     t = t.to(torch.float32).cpu()
@@ -102,11 +108,29 @@ def em_coefficients(sde, model, t, probability_flow=False, continuous=True):
         labels = t * (sde.N - 1)
         std_score = sde.sqrt_1m_alphas_cumprod[labels.long()]
     sig = sigma_at(model, labels)
-    dt = -1. / sde.N
-    w = 0.5 if probability_flow else 1.0
-    a = 1.0 + fx * dt
-    b = (g ** 2) * w * dt / (sig * std_score)    # score = -raw/(sig*std): -g^2*score*w*dt = +g^2 w dt raw/(sig std)
-    c = torch.zeros_like(g) if probability_flow else g * float(np.sqrt(-dt))
+    if predictor == 'euler_maruyama':
+        dt = -1. / sde.N
+        w = 0.5 if probability_flow else 1.0
+        a = 1.0 + fx * dt
+        b = (g ** 2) * w * dt / (sig * std_score)    # score = -raw/(sig*std): -g^2*score*w*dt = +g^2 w dt raw/(sig std)
+        c = torch.zeros_like(g) if probability_flow else g * float(np.sqrt(-dt))
+    elif predictor == 'reverse_diffusion':
+        if isinstance(sde, sde_lib.VPSDE):           # DDPM discretisation: f = (sqrt(alpha) - 1) x, G = sqrt(beta)
+            ts = (t * (sde.N - 1) / sde.T).long()
+            beta = sde.discrete_betas[ts]
+            fd, G = torch.sqrt(sde.alphas[ts]) - 1.0, torch.sqrt(beta)
+        else:                                        # f = drift / N, G = diffusion * sqrt(1 / N)
+            fd, G = fx * (1. / sde.N), g * torch.sqrt(torch.tensor(1. / sde.N))
+        a = 1.0 - fd                                 # x_mean = x - (f - G^2 score)
+        b = -(G ** 2) / (sig * std_score)
+        c = torch.zeros_like(G) if probability_flow else G
+    else:
+        if not isinstance(sde, sde_lib.VPSDE):
+            raise NotImplementedError(f'SDE class {sde.__class__.__name__} not yet supported.')
+        assert not probability_flow, 'Probability flow not supported by ancestral sampling'
+        beta = sde.discrete_betas[(t * (sde.N - 1) / sde.T).long()]
+        r = 1.0 / torch.sqrt(1. - beta)
+        a, b, c = r, -beta * r / (sig * std_score), torch.sqrt(beta)
     mean1, std_m = sde.marginal_prob(one, t)     # imputation: alpha*obs + std*z (sampling.py:415-416)
     coef = torch.zeros(t.numel(), L.COEF_STRIDE)
     coef[:, 0], coef[:, 1], coef[:, 2], coef[:, 3], coef[:, 4] = a, b, c, mean1[:, 0], std_m

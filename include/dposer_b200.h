@@ -106,6 +106,15 @@ int dpb_score_forward(dpb_score_t* h, const float* x, const float* table, const 
                       const float* row_scale, float scale, float* out, int64_t B, int flags,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* Forward-mode derivative of dpb_score_forward (fp32 engine): out [B,63] as dpb_score_forward, jv [B,63] =
+ * (d out / d x) v for a direction v [B,63], with the same row_scale / scale applied to both.  Replaces the autograd
+ * call of the Hutchinson-Skilling trace estimator in lib/algorithms/advanced/likelihood.py:26-37: the scalar
+ * eps . (J eps) it needs is what the reference computes as eps . (J^T eps).  ws: dpb_score_jvp_workspace_bytes. */
+size_t dpb_score_jvp_workspace_bytes(dpb_score_t* h, int64_t B);
+int dpb_score_jvp(dpb_score_t* h, const float* x, const float* v, const float* table, const int32_t* t_index,
+                  const float* row_scale, float scale, float* out, float* jv, int64_t B, void* ws, size_t ws_bytes,
+                  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused PC sampler  (replaces pc_sampler's hot loop, lib/algorithms/advanced/sampling.py:456-461,
  * EulerMaruyamaPredictor.update_fn :182-188, imputation :413-422, RSDE.sde sde_lib.py:98-106)

@@ -38,6 +38,46 @@ def main():
         torch.manual_seed(4321)
         noise = torch.stack([torch.randn(B, 63) for _ in range(N)])
         out.update(vp_em_z0=z0.numpy(), vp_em_noise=noise.numpy(), vp_em_out=xm.numpy(), vp_em_last=traj[-1].numpy())
+        # ReverseDiffusion / AncestralSampling predictors (sampling.py:210-259): the reference classes called directly, step
+        # by step over pc_sampler's time grid (its own pc_sampler cannot drive them: update_fn arity), draws replayed
+        # (N = 1000 schedules: VPSDE's discrete betas are only valid for beta_max / N < 1; the LAST 8 steps of the grid,
+        # entered like pc_sampler's 'denoise' task does with start_step = N - 8)
+        vp1k, sub1k = G.sde_lib.VPSDE(0.1, 20., N=1000), G.sde_lib.subVPSDE(0.1, 20., N=1000)
+        for tag, sde, cls in [('vp_rd', vp1k, G.sampling.ReverseDiffusionPredictor),
+                              ('vp_anc', vp1k, G.sampling.AncestralSamplingPredictor),
+                              ('sub_rd', sub1k, G.sampling.ReverseDiffusionPredictor)]:
+            score_fn = G.mutils.get_score_fn(sde, model, train=False, continuous=True)
+            sf = lambda xx, tt, _f=score_fn: _f(xx, tt, None, None)   # noqa: E731  (predictors call score_fn(x, t))
+            pred = cls(sde, sf, False)
+            if hasattr(pred, 'rsde'):
+                pred.rsde = sde.reverse(lambda xx, tt, c=None, m=None, _f=score_fn: _f(xx, tt, c, m), False)
+            xx = z0.clone()
+            torch.manual_seed(999)
+            for tt in torch.linspace(sde.T, 1e-3, sde.N)[sde.N - N:]:
+                xx, xm = pred.update_fn(xx, torch.ones(B) * tt)
+            torch.manual_seed(999)
+            noise = torch.stack([torch.randn(B, 63) for _ in range(N)])
+            out.update({f'{tag}_noise': noise.numpy(), f'{tag}_out': xm.numpy(), f'{tag}_last': xx.numpy()})
+    # likelihood / latent code under the probability-flow ODE (likelihood.py:40-113), Rademacher probe replayed
+    from lib.algorithms.advanced import likelihood as ref_lik
+    sub1000 = G.sde_lib.subVPSDE(0.1, 20., N=1000)
+    data = torch.tensor(np.load(os.path.join(G.REF, 'examples/toy_data.npz'))['pose_samples'][:4]).float()
+    norm = torch.load(os.path.join(G.REF, 'data/AMASS/amass_processed/version1/train/axis_normalize2.pt'))
+    data = (data - norm['mean_poses']) / norm['std_poses']
+    lfn = ref_lik.get_likelihood_fn(sub1000, lambda v: v, rtol=1e-5, atol=1e-5, eps=1e-5)
+    torch.manual_seed(77)
+    bpd, z, nfe = lfn(model, data.clone())
+    torch.manual_seed(77)
+    epsilon = torch.randint_like(data, low=0, high=2).float() * 2 - 1.
+    # one function evaluation too (drift and divergence at t = 0.3), the unit the kernel replaces
+    x_t = data * 0.7 + 0.2
+    vec_t = torch.ones(4) * 0.3
+    score_fn = G.mutils.get_score_fn(sub1000, model, train=False, continuous=True)
+    rs = sub1000.reverse(score_fn, probability_flow=True)
+    drift = rs.sde(x_t, vec_t, condition=None, mask=None)[0]
+    div = ref_lik.get_div_fn(lambda xx, tt: rs.sde(xx, tt, condition=None, mask=None)[0])(x_t.clone(), vec_t, epsilon)
+    out.update(lik_data=data.numpy(), lik_eps=epsilon.numpy(), lik_bpd=bpd.numpy(), lik_z=z.numpy(), lik_nfe=np.array(nfe),
+               lik_xt=x_t.numpy(), lik_drift=drift.detach().numpy(), lik_div=div.detach().numpy())
     np.savez(os.path.join(HERE, 'sde_variants_golden.npz'), **out)
     print('wrote sde_variants_golden.npz', {k: v.shape for k, v in out.items()})
 

@@ -212,3 +212,54 @@ def test_sampler_full_size_run_is_reproducible(gpu_model):
         gpu_model.engine = L.ENGINE_AUTO
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize('tag,sde_name,pred', [('vp_rd', 'vp', 'reverse_diffusion'), ('vp_anc', 'vp', 'ancestral_sampling'),
+                                              ('sub_rd', 'subvp', 'reverse_diffusion')])
+@pytest.mark.parametrize('engine,tol', [(L.ENGINE_FP32, 5e-5), (L.ENGINE_TC, 1e-3)])
+def test_other_predictors_vs_reference_golden(gpu_model, tag, sde_name, pred, engine, tol):
+    """ReverseDiffusion / AncestralSampling predictors (sampling.py:210-259) as coefficient tables of the fused sampler,
+    against the REAL reference classes called step by step over the last 8 steps of the N = 1000 grid with replayed draws
+    (sde_variants_golden.npz)."""
+    import types
+    g = golden('sde_variants_golden.npz')
+    N, B = 1000, 5
+    assert np.isfinite(g[f'{tag}_out']).all()
+    cfg = synthetic.default_config()
+    cfg.sampling.predictor = pred
+    sde = sde_lib.VPSDE(0.1, 20., N) if sde_name == 'vp' else sde_lib.subVPSDE(0.1, 20., N)
+    fn = sampling.get_sampling_fn(cfg, sde, (B, 63), lambda x: x, 1e-3, device='cuda')
+    noise = torch.tensor(g[f'{tag}_noise'])[:, None].cuda()
+    gpu_model.engine = engine
+    try:
+        traj, out = fn(gpu_model, z=torch.tensor(g['vp_em_z0']), noise=noise, start_step=N - 8,
+                       args=types.SimpleNamespace(task='denoise'))
+    finally:
+        gpu_model.engine = L.ENGINE_AUTO
+    assert max_rel(out, g[f'{tag}_out']) < tol
+    assert max_rel(traj[-1], g[f'{tag}_last']) < tol
+
+
+def test_likelihood_function_evaluation_vs_reference_golden(gpu_model):
+    """One ODE function evaluation of the likelihood (drift + Hutchinson divergence, likelihood.py:26-37,58-66) against
+    the REAL reference's autograd: dpb_score_jvp's eps . (J eps) is the reference's eps . (J^T eps)."""
+    from dposer_b200 import likelihood
+    g = golden('sde_variants_golden.npz')
+    sde = sde_lib.subVPSDE(0.1, 20., 1000)
+    drift, div = likelihood.drift_and_div(gpu_model, sde, torch.tensor(g['lik_xt']).cuda(), 0.3,
+                                          torch.tensor(g['lik_eps']).cuda())
+    assert max_rel(drift, g['lik_drift']) < 2e-5
+    assert max_rel(div, g['lik_div']) < 2e-4
+
+
+def test_likelihood_vs_reference_golden(gpu_model):
+    """get_likelihood_fn (likelihood.py:40-113): bits/dim, latent code and function-evaluation count against the REAL
+    reference on four AMASS poses with the same Rademacher probe (RK45 on the host on both sides)."""
+    from dposer_b200 import likelihood
+    g = golden('sde_variants_golden.npz')
+    sde = sde_lib.subVPSDE(0.1, 20., 1000)
+    fn = likelihood.get_likelihood_fn(sde, lambda v: v, rtol=1e-5, atol=1e-5, eps=1e-5)
+    bpd, z, nfe = fn(gpu_model, torch.tensor(g['lik_data']).cuda(), epsilon=torch.tensor(g['lik_eps']).cuda())
+    assert max_rel(bpd, g['lik_bpd']) < 2e-3
+    assert max_rel(z, g['lik_z']) < 5e-3
+    assert abs(nfe - int(g['lik_nfe'])) <= 0.25 * int(g['lik_nfe']), (nfe, int(g['lik_nfe']))

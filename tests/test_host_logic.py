@@ -178,3 +178,26 @@ def test_body_model_wrapper_shapes_and_joint_map():
     m = bmod.SMPLX(synthetic.make_body_tensors('smplx'))
     assert m.mean_poses.shape == (72,) and m.mean_shape.shape == (10,)
     assert torch.isfinite(m.mean_poses).all()
+
+
+def test_rot6d_transforms_properties():
+    """lib/utils/transforms.py:197-255 restated without torchgeometry (parity unpinned): round trips, orthonormality and
+    agreement with the LBS oracle's Rodrigues formula."""
+    from dposer_b200 import transforms as T
+    from oracle import lbs_ref
+    g = torch.Generator().manual_seed(5)
+    aa = torch.randn(200, 3, generator=g) * 1.2
+    aa[0] = 0.
+    aa[1] = torch.tensor([1e-8, 0., 0.])
+    aa[2] = torch.tensor([3.1, 0.1, -0.05])          # close to pi
+    R = T.axis_angle_to_mat3x3(aa)
+    assert float((R @ R.transpose(1, 2) - torch.eye(3)).abs().max()) < 1e-5
+    assert float((torch.linalg.det(R) - 1).abs().max()) < 1e-5
+    assert float((R[3:] - lbs_ref.batch_rodrigues(aa[3:])).abs().max()) < 1e-5
+    r6 = T.axis_angle_to_rot6d(aa)
+    assert r6.shape == (200, 6)
+    assert float((T.rot6d_to_mat3x3(r6) - R).abs().max()) < 1e-5
+    back = T.rot6d_to_axis_angle(r6)
+    assert float((T.axis_angle_to_mat3x3(back) - R).abs().max()) < 2e-5      # same rotation (axis-angle is 2-to-1 at pi)
+    small = aa.norm(dim=1) < 3.0
+    assert float((back[small] - aa[small]).abs().max()) < 2e-5
