@@ -88,16 +88,34 @@ class _PriorBase:
         return x_0_hat.detach(), alpha / torch.sqrt(sigma_2)[:, None]
 
     def multi_step_denoise(self, x_t, t, t_end, N=10):
-        """run/completion.py:112-129 (DDIM); N score evaluations on the GPU kernels."""
-        time_traj = linear_interpolation(t, t_end, N + 1)
-        cur = x_t.detach()
+        """run/completion.py:112-129 (DDIM).  Every DDIM step is affine in (x, raw network output):
+            x' = (a_b / a_c) x + [s_c (s_b - s_c a_b / a_c) / (sigma std)] raw
+        so the N steps are ONE ``dpb_sampler_run`` with an N-row coefficient table (noise coefficient 0): with the tcgen05
+        engine a single persistent kernel, like the reverse-SDE sampler."""
+        from . import sampling
+        t0, t1 = self._host_t(t), self._host_t(t_end)
+        traj = torch.linspace(0, 1, N + 1)
+        traj = (1 - traj) * t0 + traj * t1                      # linear_interpolation (lib/utils/misc.py:58-61)
+        coef = torch.zeros(N, L.COEF_STRIDE)
+        labels = []
         for i in range(N):
-            a_c, s_c = self.sde.return_alpha_sigma(time_traj[i])
-            a_b, s_b = self.sde.return_alpha_sigma(time_traj[i + 1])
-            eps_hat = -self.score_fn(cur, time_traj[i], None, None) * s_c[:, None]
-            cur = a_b / a_c * (cur - s_c[:, None] * eps_hat) + s_b[:, None] * eps_hat
-        alpha, sigma = self.sde.return_alpha_sigma(time_traj[0])
-        return cur.detach(), alpha / sigma[:, None]
+            tc, tb = traj[i:i + 1].float(), traj[i + 1:i + 2].float()
+            a_c, s_c = self.sde.return_alpha_sigma(tc)
+            a_b, s_b = self.sde.return_alpha_sigma(tb)
+            ps = mutils.prior_scalars(self.sde, self.model, float(tc), self.continuous)
+            ratio = (a_b / a_c).reshape(-1)[0]
+            coef[i, 0] = ratio
+            coef[i, 1] = s_c.reshape(-1)[0] * ps['inv_sigma_std'] * (s_b.reshape(-1)[0] - s_c.reshape(-1)[0] * ratio)
+            coef[i, 3], coef[i, 4] = 1.0, 0.0
+            labels.append(ps['label'])
+        cur = x_t.detach().to(torch.float32).contiguous().clone()
+        L.require_cuda(cur, 'x_t')
+        table = self.model.time_table(torch.cat(labels))
+        x_mean = torch.empty_like(cur)
+        sampling._run_steps(self.model, cur, coef.to(cur.device), table, None, None, None, 0, 0, None, x_mean, False)
+        alpha, sigma = self.sde.return_alpha_sigma(torch.tensor([t0], dtype=torch.float32))
+        snr = (alpha.reshape(-1)[0] / sigma.reshape(-1)[0]).to(cur.device).expand(cur.shape[0], 1)
+        return x_mean, snr
 
     def _ddim_loss(self, x_0, vec_t, weighted, divisor, n, z=None):
         """multi_denoise=True branch: only the final squared error is differentiable w.r.t. x_0."""
