@@ -33,6 +33,9 @@ struct dpb_score {
   __half* act_h = nullptr;      // [slots*128, 1024] residual stream
   __half* act_t = nullptr;      // [slots*128, 1024] block intermediate
   CUtensorMap tm_act_h, tm_act_t;  // box {64, 128}
+  // small-batch engine (score_small.cu): the same operands with 64-row boxes (one column slice per CTA)
+  CUtensorMap tms_w[4], tms_post, tms_pre;
+  bool tcs_ready = false;
   int tc_slots = 0;
   size_t act_bytes = 0, l2_window = 0;   // activation scratch size; bytes of the persisting-L2 access-policy window (0 = off)
   float l2_hit = 1.f;
@@ -72,5 +75,8 @@ struct TcJob {
   float* row_loss;
 };
 int tc_launch(dpb_score* h, const TcJob& job, cudaStream_t st);
+int tcs_prepare(dpb_score* h);
+bool tcs_wanted(const dpb_score* h, const TcJob& job);
+int tcs_launch(dpb_score* h, const TcJob& job, cudaStream_t st);
 
 }  // namespace dpb

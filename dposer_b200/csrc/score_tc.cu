@@ -1097,7 +1097,7 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
   DPB_CUDA_CHECK(cudaFuncSetAttribute(tc::score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       tc::SMEM_BYTES));
   h->tc_ready = true;
-  return DPB_OK;
+  return tcs_prepare(h);
 }
 
 void tc_release(dpb_score* h) {
@@ -1108,6 +1108,7 @@ void tc_release(dpb_score* h) {
 }
 
 int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
+  if (tcs_wanted(h, j)) return tcs_launch(h, j, st);   // few row tiles: split the output features over 16 CTAs per tile
   tc::KParams p{};
   p.mode = j.mode;
   p.n_steps = j.n_steps;
