@@ -76,6 +76,7 @@ class _LbsFn(torch.autograd.Function):
         L.check(L.load().dpb_lbs_forward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(t), L.ptr(verts), L.ptr(joints), B,
                                          flags, L.ptr(ws), ws.numel(), L.current_stream(dev)))
         ctx.core, ctx.need_verts, ctx.has_transl = core, need_verts, transl is not None
+        ctx.tail_flag = flags & L.LBS_CONST_TAIL
         # an output the loss never touches arrives as None in backward (not as a [B,V,3] tensor of zeros): with no
         # vertex gradient the backward runs over the <=174 vertices the extra joints read instead of all of them
         ctx.set_materialize_grads(False)
@@ -109,7 +110,7 @@ class _LbsFn(torch.autograd.Function):
         if n_scratch:
             scratch = torch.empty(n_scratch, dtype=torch.uint8, device=dev)
         L.check(L.load().dpb_lbs_backward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(gv), L.ptr(gj), L.ptr(g_pose),
-                                          L.ptr(g_betas), L.ptr(g_transl), B, core.engine, L.ptr(ws), ws.numel(),
+                                          L.ptr(g_betas), L.ptr(g_transl), B, core.engine | ctx.tail_flag, L.ptr(ws), ws.numel(),
                                           L.ptr(scratch), n_scratch, L.current_stream(dev)))
         return g_betas, g_pose, g_transl, None, None, None
 

@@ -621,7 +621,7 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
         if (rc != DPB_OK) return rc;
       } else {
       // blend on tcgen05 (writes v_posed into verts), then skin in place with the transforms from the pose kernel
-      int rc = lbs_tc_blend(hv, betas, w.feat, w.featop, vout, B, st);
+      int rc = lbs_tc_blend(hv, var, betas, w.feat, w.featop, vout, B, st);
       if (rc != DPB_OK) return rc;
       if (lbs_tc_skin_fits(hv)) {
         rc = lbs_tc_skin(hv, w.A, transl, w.skinop, vout, B, st);

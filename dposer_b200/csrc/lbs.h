@@ -91,8 +91,8 @@ struct LbsWs {
 size_t lbs_ws_bytes(const dpb_lbs* h, int64_t B, bool compact);
 bool lbs_carve(const dpb_lbs* h, int64_t B, bool compact, void* ws, size_t ws_bytes, LbsWs* out);
 size_t lbs_tc_ws_bytes(const dpb_lbs* h, int64_t B);
-int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* featop, float* verts, int64_t B,
-                 cudaStream_t st);
+int lbs_tc_blend(dpb_lbs* h, const LbsVariant& var, const float* betas, const float* feat, __half* featop, float* verts,
+                 int64_t B, cudaStream_t st);
 int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop, float* verts, int64_t B,
                 cudaStream_t st);
 bool lbs_tc_skin_fits(const dpb_lbs* h);

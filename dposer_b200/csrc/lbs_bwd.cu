@@ -544,13 +544,15 @@ extern "C" size_t dpb_lbs_backward_scratch_bytes_joints(dpb_lbs_t* h, int64_t B)
 namespace dpb {
 // vertex pass of the backward on the tensor cores for the vertex set of `hv` (the full model or the compact one):
 // v_posed recompute -> skinning adjoint (dL/dA, g_vposed) -> transposed blend (dL/dfeat, dL/dbeta)
-static int bwd_vertex_pass_tc(dpb_lbs* hv, const LbsWs& w, const float* betas, const float* g_verts, const float* gextra,
-                              bool have_extra, uint8_t* sp, int64_t B, cudaStream_t st) {
+static int bwd_vertex_pass_tc(dpb_lbs* hv, bool const_tail, const LbsWs& w, const float* betas, const float* g_verts,
+                              const float* gextra, bool have_extra, uint8_t* sp, int64_t B, cudaStream_t st) {
+  // v_posed recompute with the basis the forward used: the const-tail one (K = 224 for SMPL-X instead of 512) when declared
+  const LbsVariant var = (const_tail && hv->tailv.dirs16) ? hv->tailv : lbs_full_variant(hv);
   float* vposed = reinterpret_cast<float*>(sp);
   __half* gvp16 = reinterpret_cast<__half*>(sp + align_up((size_t)B * hv->V * 3 * 4, 256));
   float* gout = reinterpret_cast<float*>(sp + align_up((size_t)B * hv->V * 3 * 4, 256) + bwd_gvp_bytes(hv, B));
   float* scale = reinterpret_cast<float*>(sp + bwd_scratch_bytes(hv, B) - align_up((size_t)B * 4, 256));
-  int rc = lbs_tc_blend(hv, betas, w.feat, w.featop, vposed, B, st);
+  int rc = lbs_tc_blend(hv, var, betas, w.feat, w.featop, vposed, B, st);
   if (rc != DPB_OK) return rc;
   DPB_CUDA_CHECK(cudaMemsetAsync(gvp16, 0, (size_t)B * 2 * hv->bt_rp * 2, st));
   rc = lbs_skin_bwd_tc(hv, w.A, vposed, g_verts, gextra, have_extra, gvp16, w.gA, w.gbeta, scale, B, st);
@@ -563,7 +565,6 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
                                 const float* g_joints, float* g_pose, float* g_betas, float* g_transl, int64_t B,
                                 int flags, void* ws, size_t ws_bytes, void* scratch, size_t scratch_bytes,
                                 void* stream) {
-  (void)flags;
   if (!h) return fail(DPB_EINVAL, "dpb_lbs_backward: null handle");
   DeviceGuard guard(h->device);
   DPB_REQUIRE(betas && full_pose, "dpb_lbs_backward: betas and full_pose are required");
@@ -600,7 +601,9 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
     // (shared-memory atomics + fp32 SGEMM; A/B timing)
     const bool tcT = h->bt_ready && h->sb_ready && !(getenv("DPB_LBS_BWD_FP32") && atoi(getenv("DPB_LBS_BWD_FP32")));
     __half* gvp16 = tcT ? reinterpret_cast<__half*>(gvp) : nullptr;
-    int rc = lbs_tc_blend(h, betas, w.feat, w.featop, vposed, B, st);
+    // v_posed recompute with the basis the forward used (const-tail: K = 224 instead of 512 for SMPL-X)
+    const LbsVariant bvar = ((flags & DPB_LBS_CONST_TAIL) && h->tailv.dirs16) ? h->tailv : lbs_full_variant(h);
+    int rc = lbs_tc_blend(h, bvar, betas, w.feat, w.featop, vposed, B, st);
     if (rc != DPB_OK) return rc;
     if (tcT) DPB_CUDA_CHECK(cudaMemsetAsync(gvp16, 0, (size_t)B * 2 * h->bt_rp * 2, st));
     else DPB_CUDA_CHECK(cudaMemsetAsync(gvp, 0, (size_t)B * h->bw_kp * 4, st));
@@ -632,7 +635,8 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
              scratch_bytes >= bwd_scratch_bytes(h->sub, B) &&
              !(getenv("DPB_LBS_BWD_FP32") && atoi(getenv("DPB_LBS_BWD_FP32")))) {
     // joints-only mode: the cotangents of the compact vertex set go through the same tensor-core pass
-    int rc = bwd_vertex_pass_tc(h->sub, w, betas, w.gextra, nullptr, false, static_cast<uint8_t*>(scratch), B, st);
+    int rc = bwd_vertex_pass_tc(h->sub, (flags & DPB_LBS_CONST_TAIL) != 0, w, betas, w.gextra, nullptr, false,
+                                static_cast<uint8_t*>(scratch), B, st);
     if (rc != DPB_OK) return rc;
   } else if (full || have_extra) {
     size_t smem = ((size_t)P * BW_TP + (size_t)S * BW_TP + 2 * (size_t)BW_TP * J * 12 + (size_t)BW_TP * 3 * BW_TV +

@@ -284,8 +284,8 @@ lbs_blend_tc_kernel(const __grid_constant__ KParams p, const __grid_constant__ C
 }
 
 // [betas | feat] -> fp16 [hi | lo] operand rows (zero padded); one thread per (pose, k)
-__global__ void lbs_featop_kernel(const float* __restrict__ betas, const float* __restrict__ feat, int S, int P, int Kp,
-                                  __half* __restrict__ op, int64_t B, int64_t B_pad) {
+__global__ void lbs_featop_kernel(const float* __restrict__ betas, const float* __restrict__ feat, int S, int P, int Pf,
+                                  int Kp, __half* __restrict__ op, int64_t B, int64_t B_pad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B_pad * Kp) return;
   const int64_t b = i / Kp;
@@ -293,8 +293,8 @@ __global__ void lbs_featop_kernel(const float* __restrict__ betas, const float* 
   float x = 0.f;
   if (b < B) {
     if (k < S) x = betas[b * S + k];
-    else if (k < S + P) x = feat[b * P + (k - S)];
-    else if (k == S + P) x = 1.0f;      // the template slot
+    else if (k < S + Pf) x = feat[b * P + (k - S)];   // the first Pf of the P pose features vary (const-tail variants)
+    else if (k == S + Pf) x = 1.0f;     // the template slot
   }
   const __half hi = __float2half_rn(x);
   const __half lo = __float2half_rn(x - __half2float(hi));
@@ -1001,7 +1001,7 @@ int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   const int64_t B_pad = (B + ltc::PAD_POSES - 1) / ltc::PAD_POSES * ltc::PAD_POSES;
   if (feat && A) {   // operands not already written by the pose kernel
     const int64_t n = B_pad * Kp;
-    ltc::lbs_featop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(betas, feat, h->S, h->P, Kp, featop, B, B_pad);
+    ltc::lbs_featop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(betas, feat, h->S, h->P, h->P, Kp, featop, B, B_pad);
     const int64_t n2 = B_pad * 12 * Jp;
     ltc::lbs_skinop_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(A, transl, h->J, Jp, skinop, B, B_pad);
     DPB_CUDA_CHECK(cudaGetLastError());
@@ -1034,13 +1034,13 @@ int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* feat
 }
 
 // writes v_posed (template + shape blend + pose blend) into verts[B,V,3]
-int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* featop, float* verts, int64_t B,
-                 cudaStream_t st) {
-  const int K2 = h->kext, Kp = K2 / 2;
+int lbs_tc_blend(dpb_lbs* h, const LbsVariant& var, const float* betas, const float* feat, __half* featop, float* verts,
+                 int64_t B, cudaStream_t st) {
+  const int K2 = var.kext, Kp = K2 / 2;
   const int64_t B_pad = (B + ltc::PAD_POSES - 1) / ltc::PAD_POSES * ltc::PAD_POSES;
   {
     const int64_t n = B_pad * Kp;
-    ltc::lbs_featop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(betas, feat, h->S, h->P, Kp, featop, B, B_pad);
+    ltc::lbs_featop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(betas, feat, h->S, h->P, var.p_feat, Kp, featop, B, B_pad);
     DPB_CUDA_CHECK(cudaGetLastError());
   }
   const int n_slabs = K2 / ltc::BK;
@@ -1074,7 +1074,7 @@ int lbs_tc_blend(dpb_lbs* h, const float* betas, const float* feat, __half* feat
   else kern = (K2 == 1024) ? ltc::lbs_blend_tc_kernel<64, 32, 16>
             : (K2 == 448) ? ltc::lbs_blend_tc_kernel<64, 14, 7> : ltc::lbs_blend_tc_kernel<64>;
   DPB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_dirs, tm_feat);
+  kern<<<grid, ltc::NUM_THREADS, smem, st>>>(p, var.tm_dirs, tm_feat);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }

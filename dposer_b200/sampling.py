@@ -107,13 +107,14 @@ def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_step
                 _run_steps(model, x, coef, table, observation, mask, noise, seed, start_t, trajs, x_mean, impute)
             else:
                 _langevin_loop(model, sde, x, coef, table, timesteps[start_t:], observation, mask, noise, seed,
-                               start_t, trajs, x_mean, impute, snr)
+                               start_t, trajs, x_mean, impute, snr, continuous)
             return trajs, (x_mean if denoise else x)
 
     return pc_sampler
 
 
-def _langevin_loop(model, sde, x, coef, table, t_run, obs, mask, noise, seed, start_t, trajs, x_mean, impute, snr):
+def _langevin_loop(model, sde, x, coef, table, t_run, obs, mask, noise, seed, start_t, trajs, x_mean, impute, snr,
+                   continuous=True):
     """corrector -> (impute) -> predictor -> (impute) per step, sampling.py:459-460 with :282-302.
     Given-noise layout here is [n, K+1, B, 63] with the Langevin draw first."""
     lib = L.load()
@@ -125,8 +126,8 @@ def _langevin_loop(model, sde, x, coef, table, t_run, obs, mask, noise, seed, st
     else:
         lang_alpha = torch.ones_like(t_run)
     # grad = score = raw * (-1/(sigma*std)) = raw * b / (g^2 dt w) ; recompute the multiplier from the sde
-    labels = t_run * 999
-    ps = [mutils.prior_scalars(sde, model, float(t)) for t in t_run]
+    # same score scaling as the predictor (utils.get_score_fn: continuous marginal std, or the discrete VPSDE table)
+    ps = [mutils.prior_scalars(sde, model, float(t), continuous) for t in t_run]
     sums = torch.zeros(2, device=dev)
     grad = torch.empty_like(x)
     z = torch.empty_like(x)

@@ -96,7 +96,7 @@ def em_coefficients(sde, model, t, probability_flow=False, continuous=True, pred
     if predictor not in ('euler_maruyama', 'reverse_diffusion', 'ancestral_sampling'):
         raise NotImplementedError(f'predictor {predictor!r} is not supported')
     if not _is_vp(sde):
-        raise NotImplementedError('fused sampler supports VPSDE / subVPSDE (VESDE runs the generic loop)')
+        raise NotImplementedError('samplers support VPSDE / subVPSDE; VESDE is served by get_score_fn only')
     t = t.to(torch.float32).cpu()
     one = torch.ones(t.numel(), 1)
     fx, g = sde.sde(one, t)                     # drift for x = 1  ->  f(x,t) = fx * x
