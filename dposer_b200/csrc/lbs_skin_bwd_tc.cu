@@ -7,14 +7,14 @@
 //       D[j, (pose,e)] = sum_v W^T[j,v] * Q[(pose,e), v],   Q = g (x) [v_posed | 1]  (12 entries per vertex and pose)
 //
 // Round 1 accumulated dL/dA with 48 shared-memory atomics per (vertex, pose) plus global atomics (15.5 ms per 15 360
-// SMPL-X poses, order-dependent sums).  Here a CTA owns 16 poses and sweeps the vertices in slabs of 64: eight compute
+// SMPL-X poses, order-dependent sums).  Here a CTA owns 16 poses and sweeps the vertices in slabs of 64: sixteen compute
 // warps form Q for the slab and write it -- fp16 [hi | lo], SWIZZLE_128B K-major -- straight into shared memory as the
 // B operand (generic-proxy stores + fence.proxy.async), an issuing warp accumulates W^T . Q over all slabs in 192 TMEM
 // columns (hi.hi + hi.lo + lo.hi), and the epilogue writes dL/dA once.  Row J of W^T is all ones, so D[J, 9..11] is the
 // translation cotangent sum_v g.  g_vposed leaves as the fp16 [hi | lo] operand of the transposed blend (lbs_bwd_tc.cu).
 //
 //   warp 0  TMA: W^T slabs (hi + lo, double buffered);  warp 1  TMEM allocator + MMA issuer
-//   warps 2-9  compute (thread = vertex of the slab x 4 poses);  warps 2-5 also drain the accumulator at the end
+//   warps 2-17  compute (thread = vertex of the slab x 2 poses);  warps 2-5 also drain the accumulator at the end
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 
@@ -38,13 +38,14 @@ constexpr int NPG = 16;                      // poses per CTA
 constexpr int NQ = NPG * 12;                 // 192 = N of the MMAs
 constexpr int Q_TILE = NQ * BK * 2;          // 24 KB: [192 rows x 64 k] fp16, SWIZZLE_128B
 constexpr int W_TILE = 128 * BK * 2;         // 16 KB: [128 joint rows x 64 k]
-constexpr int NUM_THREADS = 320;
+constexpr int CW = 16;                       // compute warps: 4 per scheduler (8 ran one dependent instruction at a time)
+constexpr int PPT = NPG * BK / (CW * 32);    // (vertex, pose) pairs per compute thread and slab = 2
+constexpr int NUM_THREADS = 64 + CW * 32;    // 576
 constexpr int OFF_Q = 0;                     // 2 buffers x (hi, lo)
 constexpr int OFF_W = OFF_Q + 4 * Q_TILE;    // 2 stages x (hi, lo)
 constexpr int OFF_BAR = OFF_W + 4 * W_TILE;
 constexpr int NBARS = 9;
-constexpr int OFF_A = OFF_BAR + 96;   // fp32 [NPG][J][12] skinning transforms of the CTA's poses (16-byte aligned rows)
-static_assert(NBARS * 8 + 8 <= 96, "barriers + TMEM slot fit before the transforms");
+constexpr int OFF_A = OFF_BAR + NBARS * 8 + 16;   // fp32 [NPG][J][12] skinning transforms of the CTA's poses
 static_assert(OFF_W % 1024 == 0 && OFF_BAR % 1024 == 0, "operand tiles are 1024-byte aligned");
 
 struct Params {
@@ -90,7 +91,7 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
   const int n_slabs = p.Vp / BK;
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(qfull(b), 8); ptx::mbar_init(qempty(b), 1);
+      ptx::mbar_init(qfull(b), CW); ptx::mbar_init(qempty(b), 1);
       ptx::mbar_init(wfull(b), 1); ptx::mbar_init(wempty(b), 1);
     }
     ptx::mbar_init(dfull, 1);
@@ -144,59 +145,36 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
       __syncwarp();
     }
   } else {
-    // ---- compute warps: thread = (vertex of the slab, 4 poses)
+    // ---- compute warps: thread = (vertex of the slab, PPT poses)
     const int t = threadIdx.x - 64;
     const int vl = t & 63, pg = t >> 6;
-    // The global operands of slab s + 1 (sparse weights, cotangents, blended vertices: 32 loads per thread) are requested
-    // before slab s is processed: one CTA per SM keeps only 8 compute warps in flight, and without the prefetch every slab
-    // paid a full HBM round trip (8.2 k cycles per slab measured).
-    int jn[4], jn_n[4];
-    float wn[4], wn_n[4], gl[4][3], gl_n[4][3], xl[4][3], xl_n[4][3];
-    auto fetch = [&](int s, int* jj, float* ww, float (*gg)[3], float (*xx)[3]) {
-      const int v = s * BK + vl;
-      const bool v_ok = v < V;
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const bool ok = v_ok && n < p.nnz;
-        ww[n] = ok ? p.ell_w[(size_t)n * V + v] : 0.f;
-        jj[n] = ok ? p.ell_idx[(size_t)n * V + v] : 0;
-      }
-      const int qn = (v_ok && p.need_index) ? p.need_index[v] : -1;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pl = pg * 4 + i;
-        gg[i][0] = gg[i][1] = gg[i][2] = 0.f;
-        xx[i][0] = xx[i][1] = xx[i][2] = 0.f;
-        if (v_ok && pl < np) {
-          const float* gv = p.g_verts + ((size_t)(b0 + pl) * V + v) * 3;
-          const float* xp = p.vposed + ((size_t)(b0 + pl) * V + v) * 3;
-          gg[i][0] = __ldcs(gv); gg[i][1] = __ldcs(gv + 1); gg[i][2] = __ldcs(gv + 2);
-          xx[i][0] = __ldcs(xp); xx[i][1] = __ldcs(xp + 1); xx[i][2] = __ldcs(xp + 2);
-          if (qn >= 0 && p.gextra) {
-            const float* ge = p.gextra + ((size_t)(b0 + pl) * p.n_need + qn) * 3;
-            gg[i][0] += ge[0]; gg[i][1] += ge[1]; gg[i][2] += ge[2];
-          }
-        }
-      }
-    };
-    fetch(0, jn_n, wn_n, gl_n, xl_n);
     for (int s = 0; s < n_slabs; ++s) {
       const uint32_t st = s & 1;
       const int v = s * BK + vl;
       const bool v_ok = v < V;
+      int jn[4];
+      float wn[4];
 #pragma unroll
-      for (int n = 0; n < 4; ++n) { jn[n] = jn_n[n]; wn[n] = wn_n[n]; }
+      for (int n = 0; n < 4; ++n) {
+        const bool ok = v_ok && n < p.nnz;
+        wn[n] = ok ? p.ell_w[(size_t)n * V + v] : 0.f;
+        jn[n] = ok ? p.ell_idx[(size_t)n * V + v] : 0;
+      }
+      const int qn = (v_ok && p.need_index) ? p.need_index[v] : -1;
+      float q[PPT][12];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { gl[i][c] = gl_n[i][c]; xl[i][c] = xl_n[i][c]; }
-      if (s + 1 < n_slabs) fetch(s + 1, jn_n, wn_n, gl_n, xl_n);
-      float q[4][12];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pl = pg * 4 + i;
-        float g[3] = {gl[i][0], gl[i][1], gl[i][2]}, x[3] = {xl[i][0], xl[i][1], xl[i][2]};
+      for (int i = 0; i < PPT; ++i) {
+        const int pl = pg * PPT + i;
+        float g[3] = {0.f, 0.f, 0.f}, x[3] = {0.f, 0.f, 0.f};
         if (v_ok && pl < np) {
+          const float* gv = p.g_verts + ((size_t)(b0 + pl) * V + v) * 3;
+          const float* xp = p.vposed + ((size_t)(b0 + pl) * V + v) * 3;
+          g[0] = gv[0]; g[1] = gv[1]; g[2] = gv[2];
+          x[0] = xp[0]; x[1] = xp[1]; x[2] = xp[2];
+          if (qn >= 0 && p.gextra) {
+            const float* ge = p.gextra + ((size_t)(b0 + pl) * p.n_need + qn) * 3;
+            g[0] += ge[0]; g[1] += ge[1]; g[2] += ge[2];
+          }
           const float sc = sc_s[pl];                      // into fp16's normal range (exact: a power of two)
           g[0] *= sc; g[1] *= sc; g[2] *= sc;
           float TR[9];
@@ -204,11 +182,9 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
           for (int e = 0; e < 9; ++e) TR[e] = 0.f;
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
-            const float4* Ap = reinterpret_cast<const float4*>(A_s + ((size_t)pl * J + jn[n]) * 12);   // 3 x LDS.128
-            const float4 a0 = Ap[0], a1 = Ap[1], a2 = Ap[2];
-            const float ar[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
+            const float* Ap = A_s + ((size_t)pl * J + jn[n]) * 12;
 #pragma unroll
-            for (int e = 0; e < 9; ++e) TR[e] = fmaf(wn[n], ar[e], TR[e]);
+            for (int e = 0; e < 9; ++e) TR[e] = fmaf(wn[n], Ap[e], TR[e]);
           }
           const float o[3] = {TR[0] * g[0] + TR[3] * g[1] + TR[6] * g[2], TR[1] * g[0] + TR[4] * g[1] + TR[7] * g[2],
                               TR[2] * g[0] + TR[5] * g[1] + TR[8] * g[2]};   // g_vposed = T_R^T g
@@ -231,10 +207,10 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
       ptx::mbar_wait(qempty(st), ((s >> 1) & 1) ^ 1);     // the MMAs of slab s - 2 are done with this buffer
       uint8_t* qh = smem + OFF_Q + (st * 2) * Q_TILE;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < PPT; ++i)
 #pragma unroll
         for (int e = 0; e < 12; ++e) {
-          const uint32_t off = sw128_off((pg * 4 + i) * 12 + e, vl);
+          const uint32_t off = sw128_off((pg * PPT + i) * 12 + e, vl);
           const __half hi = __float2half_rn(q[i][e]);
           *reinterpret_cast<__half*>(qh + off) = hi;
           *reinterpret_cast<__half*>(qh + Q_TILE + off) = __float2half_rn(q[i][e] - __half2float(hi));
