@@ -96,6 +96,8 @@ int lbs_tc_blend(dpb_lbs* h, const LbsVariant& var, const float* betas, const fl
 int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop, float* verts, int64_t B,
                 cudaStream_t st);
 bool lbs_tc_skin_fits(const dpb_lbs* h);
+int lbs_tc_skin_adjoint(dpb_lbs* h, const float* A, __half* skinop, const float* g_verts, const float* gextra,
+                        bool have_extra, const float* scale, __half* gvp16, int64_t B, cudaStream_t st);
 bool lbs_tc_fused_fits(const dpb_lbs* h);
 int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* featop, const float* A, const float* transl,
                  __half* skinop, float* verts, int64_t B, cudaStream_t st);
@@ -118,8 +120,10 @@ int lbs_blendT_tc(dpb_lbs* h, const __half* gvp16, const float* scale, float* cp
                   int64_t B, cudaStream_t st);
 int lbs_skin_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_skin_bwd_tc_release(dpb_lbs* h);
-int lbs_skin_bwd_tc(dpb_lbs* h, const float* A, const float* vposed, const float* g_verts, const float* gextra,
-                    bool have_extra, __half* gvp16, float* gA, float* gbt, float* scale, int64_t B, cudaStream_t st);
+int lbs_bwd_rowscale(dpb_lbs* h, const float* g_verts, const float* gextra, bool have_extra, float* scale, int64_t B,
+                     cudaStream_t st);
+int lbs_skin_bwd_tc(dpb_lbs* h, const float* vposed, const float* g_verts, const float* gextra, bool have_extra,
+                    float* gA, float* gbt, const float* scale, int64_t B, cudaStream_t st);
 int lbs_bwd_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_bwd_release(dpb_lbs* h);
 }  // namespace dpb

@@ -555,7 +555,9 @@ static int bwd_vertex_pass_tc(dpb_lbs* hv, bool const_tail, const LbsWs& w, cons
   int rc = lbs_tc_blend(hv, var, betas, w.feat, w.featop, vposed, B, st);
   if (rc != DPB_OK) return rc;
   DPB_CUDA_CHECK(cudaMemsetAsync(gvp16, 0, (size_t)B * 2 * hv->bt_rp * 2, st));
-  rc = lbs_skin_bwd_tc(hv, w.A, vposed, g_verts, gextra, have_extra, gvp16, w.gA, w.gbeta, scale, B, st);
+  rc = lbs_bwd_rowscale(hv, g_verts, gextra, have_extra, scale, B, st);
+  if (rc == DPB_OK) rc = lbs_tc_skin_adjoint(hv, w.A, w.skinop, g_verts, gextra, have_extra, scale, gvp16, B, st);
+  if (rc == DPB_OK) rc = lbs_skin_bwd_tc(hv, vposed, g_verts, gextra, have_extra, w.gA, w.gbeta, scale, B, st);
   if (rc != DPB_OK) return rc;
   return lbs_blendT_tc(hv, gvp16, scale, gout, w.gfeat, w.gbeta, B, st);
 }
@@ -599,7 +601,7 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
     float* scale = reinterpret_cast<float*>(sp + bwd_scratch_bytes(h, B) - align_up((size_t)B * 4, 256));
     // skinning adjoint (dL/dA) and transposed blend on tcgen05 unless DPB_LBS_BWD_FP32=1 asks for the round-1 kernels
     // (shared-memory atomics + fp32 SGEMM; A/B timing)
-    const bool tcT = h->bt_ready && h->sb_ready && !(getenv("DPB_LBS_BWD_FP32") && atoi(getenv("DPB_LBS_BWD_FP32")));
+    const bool tcT = h->bt_ready && h->sb_ready && w.skinop && lbs_tc_skin_fits(h) && !(getenv("DPB_LBS_BWD_FP32") && atoi(getenv("DPB_LBS_BWD_FP32")));
     __half* gvp16 = tcT ? reinterpret_cast<__half*>(gvp) : nullptr;
     // v_posed recompute with the basis the forward used (const-tail: K = 224 instead of 512 for SMPL-X)
     const LbsVariant bvar = ((flags & DPB_LBS_CONST_TAIL) && h->tailv.dirs16) ? h->tailv : lbs_full_variant(h);
@@ -608,7 +610,9 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
     if (tcT) DPB_CUDA_CHECK(cudaMemsetAsync(gvp16, 0, (size_t)B * 2 * h->bt_rp * 2, st));
     else DPB_CUDA_CHECK(cudaMemsetAsync(gvp, 0, (size_t)B * h->bw_kp * 4, st));
     if (tcT) {
-      rc = lbs_skin_bwd_tc(h, w.A, vposed, g_verts, w.gextra, have_extra, gvp16, w.gA, w.gbeta, scale, B, st);
+      rc = lbs_bwd_rowscale(h, g_verts, w.gextra, have_extra, scale, B, st);
+      if (rc == DPB_OK) rc = lbs_tc_skin_adjoint(h, w.A, w.skinop, g_verts, w.gextra, have_extra, scale, gvp16, B, st);
+      if (rc == DPB_OK) rc = lbs_skin_bwd_tc(h, vposed, g_verts, w.gextra, have_extra, w.gA, w.gbeta, scale, B, st);
       if (rc != DPB_OK) return rc;
     } else {
     const size_t smem = ((size_t)2 * BW_TP * J * 12 + BW_TP * 3) * 4;
@@ -631,7 +635,8 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
       bwd_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gout, h->bw_np, P, S, w.gfeat, w.gbeta, B);
       DPB_CUDA_CHECK(cudaGetLastError());
     }
-  } else if (!full && have_extra && h->sub && h->sub->bt_ready && h->sub->sb_ready && w.featop && scratch &&
+  } else if (!full && have_extra && h->sub && h->sub->bt_ready && h->sub->sb_ready && w.featop && w.skinop &&
+             lbs_tc_skin_fits(h->sub) && scratch &&
              scratch_bytes >= bwd_scratch_bytes(h->sub, B) &&
              !(getenv("DPB_LBS_BWD_FP32") && atoi(getenv("DPB_LBS_BWD_FP32")))) {
     // joints-only mode: the cotangents of the compact vertex set go through the same tensor-core pass

@@ -2,8 +2,9 @@
 // Adjoint of  v_out = sum_j w[v,j] (R_j v_posed + t_j)  (smplx 0.1.28 lbs()) for dense vertex
 // cotangents g [B,V,3] (run/motion_denoising.py:255-268 differentiates through it):
 //
-//   g_vposed[b,v,:] = (sum_j w[v,j] R_j[b])^T g[b,v,:]                                  thread = (vertex, pose), CUDA cores
-//   dL/dA[b,j,(x,c)] = sum_v w[v,j] g[b,v,x] [v_posed[b,v,c] | 1]                       tensor cores:
+//   g_vposed[b,v,:] = (sum_j w[v,j] R_j[b])^T g[b,v,:]      ltc::lbs_skin_tc_kernel in adjoint mode (lbs_tc.cu): T = W A on the
+//                                                            tensor cores as in the forward, thread = vertex applies T_R^T
+//   dL/dA[b,j,(x,c)] = sum_v w[v,j] g[b,v,x] [v_posed[b,v,c] | 1]                       this kernel, tensor cores:
 //       D[j, (pose,e)] = sum_v W^T[j,v] * Q[(pose,e), v],   Q = g (x) [v_posed | 1]  (12 entries per vertex and pose)
 //
 // Round 1 accumulated dL/dA with 48 shared-memory atomics per (vertex, pose) plus global atomics (15.5 ms per 15 360
@@ -11,7 +12,9 @@
 // warps form Q for the slab and write it -- fp16 [hi | lo], SWIZZLE_128B K-major -- straight into shared memory as the
 // B operand (generic-proxy stores + fence.proxy.async), an issuing warp accumulates W^T . Q over all slabs in 192 TMEM
 // columns (hi.hi + hi.lo + lo.hi), and the epilogue writes dL/dA once.  Row J of W^T is all ones, so D[J, 9..11] is the
-// translation cotangent sum_v g.  g_vposed leaves as the fp16 [hi | lo] operand of the transposed blend (lbs_bwd_tc.cu).
+// translation cotangent sum_v g.  (The first version also rebuilt T_R per vertex and pose from the sparse weights with a
+// shared-memory gather of the joint transforms: 673 M shared-memory wavefronts per launch, 60 % of the LSU pipe,
+// profiles/r2_ncu_skin_bwd_tc.md -- that half now runs on the tensor cores in lbs_tc.cu.)
 //
 //   warp 0  TMA: W^T slabs (hi + lo, double buffered);  warp 1  TMEM allocator + MMA issuer
 //   warps 2-17  compute (thread = vertex of the slab x 2 poses);  warps 2-5 also drain the accumulator at the end
@@ -39,7 +42,6 @@ constexpr int NQ = NPG * 12;                 // 192 = N of the MMAs
 constexpr int Q_TILE = NQ * BK * 2;          // 24 KB: [192 rows x 64 k] fp16, SWIZZLE_128B
 constexpr int W_TILE = 128 * BK * 2;         // 16 KB: [128 joint rows x 64 k]
 constexpr int CW = 16;                       // compute warps: 4 per scheduler (8 ran one dependent instruction at a time)
-constexpr int PPT = NPG * BK / (CW * 32);    // (vertex, pose) pairs per compute thread and slab = 2
 constexpr int NUM_THREADS = 64 + CW * 32;    // 576
 constexpr int OFF_Q = 0;                     // 2 buffers x (hi, lo)
 constexpr int OFF_W = OFF_Q + 4 * Q_TILE;    // 2 stages x (hi, lo)
@@ -49,18 +51,14 @@ constexpr int OFF_A = OFF_BAR + NBARS * 8 + 16;   // fp32 [NPG][J][12] skinning 
 static_assert(OFF_W % 1024 == 0 && OFF_BAR % 1024 == 0, "operand tiles are 1024-byte aligned");
 
 struct Params {
-  const float* A;            // [B,J,12]
   const float* vposed;       // [B,V,3]
   const float* g_verts;      // [B,V,3]
   const float* gextra;       // [B,n_need,3] or nullptr
   const int32_t* need_index; // [V] or nullptr
-  const int32_t* ell_idx;    // [nnz,V]
-  const float* ell_w;        // [nnz,V]
-  __half* gvp16;             // [B, 2*Rp]
   float* gA;                 // [B,J,12]
   float* gbt;                // [B,S+3]
   const float* scale;        // [B] power-of-two scale of each pose's cotangents (fp16 range), see lbs_rowscale_kernel
-  int V, J, S, nnz, n_need, Rp, Vp;   // Vp = V padded to 64 (columns of one half of W^T)
+  int V, J, S, n_need, Vp;   // Vp = V padded to 64 (columns of one half of W^T)
   int64_t B;
 };
 
@@ -82,8 +80,7 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
   auto wempty = [&](uint32_t s) { return bar + 8u * (6 + s); };
   const uint32_t dfull = bar + 64;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBARS * 8);
-  float* A_s = reinterpret_cast<float*>(smem + OFF_A);
-  float* sc_s = A_s + (size_t)NPG * p.J * 12;       // [NPG] scale, [NPG] 1 / scale
+  float* sc_s = reinterpret_cast<float*>(smem + OFF_A);   // [NPG] scale, [NPG] 1 / scale
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int J = p.J, V = p.V;
   const int64_t b0 = (int64_t)blockIdx.x * NPG;
@@ -98,8 +95,6 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 256);
-  for (int i = threadIdx.x; i < NPG * J * 12; i += NUM_THREADS)
-    A_s[i] = i < np * J * 12 ? p.A[b0 * J * 12 + i] : 0.f;
   if (threadIdx.x < NPG) {
     const float sc = threadIdx.x < np ? p.scale[b0 + threadIdx.x] : 1.f;
     sc_s[threadIdx.x] = sc;
@@ -145,57 +140,41 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
       __syncwarp();
     }
   } else {
-    // ---- compute warps: thread = (vertex of the slab, PPT poses)
+    // ---- compute warps: thread = (two adjacent vertices of the slab, one pose): the two fp16 values of a Q row land in
+    // one 32-bit shared-memory store (a warp writes a whole 128-byte row; with one vertex per thread the kernel was bound
+    // by the count of 16-bit STS instructions, 768 per slab)
     const int t = threadIdx.x - 64;
-    const int vl = t & 63, pg = t >> 6;
-    for (int s = 0; s < n_slabs; ++s) {
-      const uint32_t st = s & 1;
-      const int v = s * BK + vl;
-      const bool v_ok = v < V;
-      int jn[4];
-      float wn[4];
+    const int vp2 = t & 31, pl = t >> 5;                  // vertex pair within the slab, pose within the CTA
+    static_assert(CW * 32 == NPG * (BK / 2), "one thread per (vertex pair, pose)");
+    float gn_[2][3], xn_[2][3];
+    auto fetch = [&](int s, float (*gg)[3], float (*xx)[3]) {
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const bool ok = v_ok && n < p.nnz;
-        wn[n] = ok ? p.ell_w[(size_t)n * V + v] : 0.f;
-        jn[n] = ok ? p.ell_idx[(size_t)n * V + v] : 0;
-      }
-      const int qn = (v_ok && p.need_index) ? p.need_index[v] : -1;
-      float q[PPT][12];
-#pragma unroll
-      for (int i = 0; i < PPT; ++i) {
-        const int pl = pg * PPT + i;
-        float g[3] = {0.f, 0.f, 0.f}, x[3] = {0.f, 0.f, 0.f};
-        if (v_ok && pl < np) {
+      for (int i = 0; i < 2; ++i) {
+        const int v = s * BK + 2 * vp2 + i;
+        gg[i][0] = gg[i][1] = gg[i][2] = 0.f;
+        xx[i][0] = xx[i][1] = xx[i][2] = 0.f;
+        if (v < V && pl < np) {
           const float* gv = p.g_verts + ((size_t)(b0 + pl) * V + v) * 3;
           const float* xp = p.vposed + ((size_t)(b0 + pl) * V + v) * 3;
-          g[0] = gv[0]; g[1] = gv[1]; g[2] = gv[2];
-          x[0] = xp[0]; x[1] = xp[1]; x[2] = xp[2];
+          gg[i][0] = gv[0]; gg[i][1] = gv[1]; gg[i][2] = gv[2];
+          xx[i][0] = xp[0]; xx[i][1] = xp[1]; xx[i][2] = xp[2];
+          const int qn = p.need_index ? p.need_index[v] : -1;
           if (qn >= 0 && p.gextra) {
             const float* ge = p.gextra + ((size_t)(b0 + pl) * p.n_need + qn) * 3;
-            g[0] += ge[0]; g[1] += ge[1]; g[2] += ge[2];
-          }
-          const float sc = sc_s[pl];                      // into fp16's normal range (exact: a power of two)
-          g[0] *= sc; g[1] *= sc; g[2] *= sc;
-          float TR[9];
-#pragma unroll
-          for (int e = 0; e < 9; ++e) TR[e] = 0.f;
-#pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            const float* Ap = A_s + ((size_t)pl * J + jn[n]) * 12;
-#pragma unroll
-            for (int e = 0; e < 9; ++e) TR[e] = fmaf(wn[n], Ap[e], TR[e]);
-          }
-          const float o[3] = {TR[0] * g[0] + TR[3] * g[1] + TR[6] * g[2], TR[1] * g[0] + TR[4] * g[1] + TR[7] * g[2],
-                              TR[2] * g[0] + TR[5] * g[1] + TR[8] * g[2]};   // g_vposed = T_R^T g
-          __half* oh = p.gvp16 + (size_t)(b0 + pl) * 2 * p.Rp + (size_t)v * 3;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const __half hi = __float2half_rn(o[c]);
-            oh[c] = hi;
-            oh[p.Rp + c] = __float2half_rn(o[c] - __half2float(hi));
+            gg[i][0] += ge[0]; gg[i][1] += ge[1]; gg[i][2] += ge[2];
           }
         }
+      }
+    };
+    fetch(0, gn_, xn_);
+    const float sc = sc_s[pl];                            // into fp16's normal range (exact: a power of two)
+    for (int s = 0; s < n_slabs; ++s) {
+      const uint32_t st = s & 1;
+      float q[2][12];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float g[3] = {gn_[i][0] * sc, gn_[i][1] * sc, gn_[i][2] * sc};
+        const float x[3] = {xn_[i][0], xn_[i][1], xn_[i][2]};
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           q[i][3 * a + 0] = g[a] * x[0];
@@ -204,17 +183,18 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
           q[i][9 + a] = g[a];
         }
       }
+      if (s + 1 < n_slabs) fetch(s + 1, gn_, xn_);        // next slab's operands in flight across the stores / barrier
       ptx::mbar_wait(qempty(st), ((s >> 1) & 1) ^ 1);     // the MMAs of slab s - 2 are done with this buffer
       uint8_t* qh = smem + OFF_Q + (st * 2) * Q_TILE;
 #pragma unroll
-      for (int i = 0; i < PPT; ++i)
-#pragma unroll
-        for (int e = 0; e < 12; ++e) {
-          const uint32_t off = sw128_off((pg * PPT + i) * 12 + e, vl);
-          const __half hi = __float2half_rn(q[i][e]);
-          *reinterpret_cast<__half*>(qh + off) = hi;
-          *reinterpret_cast<__half*>(qh + Q_TILE + off) = __float2half_rn(q[i][e] - __half2float(hi));
-        }
+      for (int e = 0; e < 12; ++e) {
+        const uint32_t off = sw128_off(pl * 12 + e, 2 * vp2);
+        const __half2 hi = __floats2half2_rn(q[0][e], q[1][e]);
+        const float2 hf = __half22float2(hi);
+        const __half2 lo = __floats2half2_rn(q[0][e] - hf.x, q[1][e] - hf.y);
+        *reinterpret_cast<__half2*>(qh + off) = hi;
+        *reinterpret_cast<__half2*>(qh + Q_TILE + off) = lo;
+      }
       ptx::fence_proxy_async_smem();                      // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(qfull(st));
@@ -256,7 +236,7 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
 int lbs_skin_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   const int V = h->V, J = h->J;
   h->sb_ready = false;
-  if (J >= 128 || h->nnz > 4) return DPB_OK;            // needs a spare row for the ones; the kernel unrolls 4 ELL slots
+  if (J >= 128) return DPB_OK;                          // needs a spare row for the ones
   h->sb_vp = (V + 63) / 64 * 64;
   const size_t ld = (size_t)2 * h->sb_vp;
   std::vector<__half> buf((size_t)128 * ld, __float2half_rn(0.f));
@@ -273,7 +253,7 @@ int lbs_skin_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   DPB_CUDA_CHECK(cudaMemcpy(h->wT16, buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
   int rc = make_tmap_2d(&h->tm_wT, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, h->wT16, ld, 128, lsb::BK, 128, 2);
   if (rc != DPB_OK) return rc;
-  const size_t smem = lsb::OFF_A + (size_t)lsb::NPG * J * 12 * 4 + 2 * lsb::NPG * 4 + 1024;
+  const size_t smem = lsb::OFF_A + 2 * lsb::NPG * 4 + 1024;
   if (smem > 232448) return DPB_OK;
   DPB_CUDA_CHECK(cudaFuncSetAttribute(lsb::lbs_skin_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   h->sb_smem = (int)smem;
@@ -318,20 +298,25 @@ __global__ void __launch_bounds__(256) lbs_rowscale_kernel(const float* __restri
 }
 }  // namespace lsb
 
-// gA [B,J,12] is WRITTEN (no zeroing needed), gbt[:, S:S+3] += translation cotangent, gvp16 [B, 2*Rp] written for v < V
-// (scaled by scale[b]: lbs_blendT_tc divides it out again).  scale [B] is scratch.
-int lbs_skin_bwd_tc(dpb_lbs* h, const float* A, const float* vposed, const float* g_verts, const float* gextra,
-                    bool have_extra, __half* gvp16, float* gA, float* gbt, float* scale, int64_t B, cudaStream_t st) {
+// scale [B] (scratch) = power-of-two scale of every pose's cotangents, shared by both halves of the skinning adjoint
+int lbs_bwd_rowscale(dpb_lbs* h, const float* g_verts, const float* gextra, bool have_extra, float* scale, int64_t B,
+                     cudaStream_t st) {
   lsb::lbs_rowscale_kernel<<<(unsigned)B, 256, 0, st>>>(g_verts, (int64_t)h->V * 3, have_extra ? gextra : nullptr,
                                                         (int64_t)h->n_need * 3, scale);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+// gA [B,J,12] is WRITTEN (no zeroing needed), gbt[:, S:S+3] += translation cotangent
+int lbs_skin_bwd_tc(dpb_lbs* h, const float* vposed, const float* g_verts, const float* gextra, bool have_extra,
+                    float* gA, float* gbt, const float* scale, int64_t B, cudaStream_t st) {
   lsb::Params p{};
   p.scale = scale;
-  p.A = A; p.vposed = vposed; p.g_verts = g_verts;
+  p.vposed = vposed; p.g_verts = g_verts;
   p.gextra = have_extra ? gextra : nullptr;
   p.need_index = have_extra ? h->need_index : nullptr;
-  p.ell_idx = h->ell_idx; p.ell_w = h->ell_w;
-  p.gvp16 = gvp16; p.gA = gA; p.gbt = gbt;
-  p.V = h->V; p.J = h->J; p.S = h->S; p.nnz = h->nnz; p.n_need = h->n_need; p.Rp = h->bt_rp; p.Vp = h->sb_vp;
+  p.gA = gA; p.gbt = gbt;
+  p.V = h->V; p.J = h->J; p.S = h->S; p.n_need = h->n_need; p.Vp = h->sb_vp;
   p.B = B;
   lsb::lbs_skin_bwd_tc_kernel<<<(unsigned)((B + lsb::NPG - 1) / lsb::NPG), lsb::NUM_THREADS, h->sb_smem, st>>>(p, h->tm_wT);
   DPB_CUDA_CHECK(cudaGetLastError());

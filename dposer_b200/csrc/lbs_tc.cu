@@ -323,7 +323,14 @@ struct SkinParams {
   int64_t B;
   int n_groups;
   const float* transl;      // [B,3] or nullptr
-  float* verts;             // [B,V,3] in: v_posed, out: skinned vertices
+  float* verts;             // [B,V,3] in: v_posed, out: skinned vertices (forward); in: vertex cotangents (adjoint)
+  // adjoint mode (gvp16 != nullptr): g_vposed = T_R^T g, scaled per pose, as the fp16 [hi | lo] operand [B, 2*Rp] of the
+  // transposed blend; gextra [B,n_need,3] (optional) adds the joint cotangents scattered onto the vertices they read
+  __half* gvp16;
+  int Rp, n_need;
+  const float* scale;       // [B]
+  const float* gextra;
+  const int32_t* need_index;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -453,6 +460,17 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
         const float* s = o + (size_t)((vok && bb + i < p.B) ? i : 0) * pstride;
         vp[i][0] = s[0]; vp[i][1] = s[1]; vp[i][2] = s[2];
       }
+      if (p.gvp16 && p.gextra && vok) {   // adjoint: joint cotangents of the vertices the extra joints / landmarks read
+        const int qn = p.need_index[b.vt * TILE_V + q * 32 + lane];
+        if (qn >= 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (bb + i < p.B) {
+              const float* ge = p.gextra + ((size_t)(bb + i) * p.n_need + qn) * 3;
+              vp[i][0] += ge[0]; vp[i][1] += ge[1]; vp[i][2] += ge[2];
+            }
+        }
+      }
     };
     constexpr int PF = 2;                 // blocks in flight beyond the current one (3 measured no faster)
     float vq[PF + 1][8][3];               // vq[0] = current block, vq[d] = d blocks ahead
@@ -483,6 +501,27 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+      if (p.gvp16) {
+        // skinning adjoint: g_vposed = T_R^T g, scaled into fp16's normal range, fp16 [hi | lo] halves of row (pose)
+        const int v = cur.vt * TILE_V + q * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (full || (vok && bb + i < p.B)) {
+            const float* T = reinterpret_cast<const float*>(t) + i * 12;
+            const float sc = p.scale[bb + i];
+            const float gx = vp[i][0] * sc, gy = vp[i][1] * sc, gz = vp[i][2] * sc;
+            const float o3[3] = {T[0] * gx + T[3] * gy + T[6] * gz, T[1] * gx + T[4] * gy + T[7] * gz,
+                                 T[2] * gx + T[5] * gy + T[8] * gz};
+            __half* oh = p.gvp16 + (size_t)(bb + i) * 2 * p.Rp + (size_t)v * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const __half hi = __float2half_rn(o3[c]);
+              oh[c] = hi;
+              oh[p.Rp + c] = __float2half_rn(o3[c] - __half2float(hi));
+            }
+          }
+        }
+      } else
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (full || (vok && bb + i < p.B)) {
@@ -984,6 +1023,47 @@ int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop,
   return DPB_OK;
 }
 
+
+// skinning adjoint, vertex side: gvp16 [B, 2*Rp] = fp16 [hi | lo] of scale[b] * T_R^T (g_verts + gextra) with the blended
+// transforms T = W A recomputed on the tensor cores (the forward's kernel with an adjoint epilogue)
+int lbs_tc_skin_adjoint(dpb_lbs* h, const float* A, __half* skinop, const float* g_verts, const float* gextra,
+                        bool have_extra, const float* scale, __half* gvp16, int64_t B, cudaStream_t st) {
+  const int Jp = h->jp;
+  const int64_t B_pad = (B + ltc::SK_GROUP - 1) / ltc::SK_GROUP * ltc::SK_GROUP;
+  {
+    const int64_t n = B_pad * 12 * Jp;
+    ltc::lbs_skinop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, nullptr, h->J, Jp, skinop, B, B_pad);
+    DPB_CUDA_CHECK(cudaGetLastError());
+  }
+  CUtensorMap tm_s;
+  int rc = make_tmap_2d(&tm_s, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, skinop, 2 * Jp, (uint64_t)B_pad * 12, ltc::BK, ltc::SK_N, 2);
+  if (rc != DPB_OK) return rc;
+  ltc::SkinParams p{};
+  p.V = h->V;
+  p.n_vt = h->n_cols_pad / ltc::TILE_V;
+  p.jsteps = Jp / 16;
+  p.n_slabs = 2 * Jp / ltc::BK;
+  p.B = B;
+  p.chunks = p.n_slabs == 1 ? 4 : 2;
+  p.n_groups = (int)(B_pad / (p.chunks * ltc::SK_POSES));
+  p.transl = nullptr;
+  p.verts = const_cast<float*>(g_verts);   // read-only in adjoint mode
+  p.gvp16 = gvp16;
+  p.Rp = h->bt_rp;
+  p.n_need = h->n_need;
+  p.scale = scale;
+  p.gextra = have_extra ? gextra : nullptr;
+  p.need_index = h->need_index;
+  const size_t smem = (size_t)p.chunks * p.n_slabs * ltc::SK_N * ltc::BK * 2 +
+                      (size_t)ltc::SK_WSTAGES * p.n_slabs * ltc::A_SLAB + (2 * ltc::SK_WSTAGES + 6) * 8 + 16 +
+                      8 * ltc::XSTAGE * 4 + 1024;
+  if (smem > 232448) return fail(DPB_EUNSUPPORTED, "lbs tc skin adjoint: transform operand does not fit shared memory");
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(ltc::lbs_skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = p.n_groups < h->sm_count ? p.n_groups : h->sm_count;
+  ltc::lbs_skin_tc_kernel<<<grid, ltc::NUM_THREADS, smem, st>>>(p, h->tm_wop, tm_s);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
 
 bool lbs_tc_fused_fits(const dpb_lbs* h) {
   if (!h->tc_ready || h->J >= h->jp || 2 * h->jp != ltc::BK) return false;   // one [hi | lo] slab incl. the transl slot
