@@ -15,3 +15,30 @@ for mt, B in [('smpl', 200), ('smplx', 130)]:
     bm = BodyModel(synthetic.make_body_tensors(mt), batch_size=B, model_type=mt).cuda()
     inp = {k: v.cuda().requires_grad_(True) for k, v in synthetic.lbs_inputs(B, mt).items()}
     o = bm(**inp); (o.v.sum() + o.Jtr.sum()).backward(); torch.cuda.synchronize(); print('lbs ok', mt)
+# round 2: joints-only tensor-core path (compact sub-model), small-batch engine, score-net JVP, native fitting steps
+for mt, B in [('smplx', 96), ('smpl', 130)]:
+    bm = BodyModel(synthetic.make_body_tensors(mt), batch_size=B, model_type=mt).cuda()
+    inp = {k: v.cuda().requires_grad_(True) for k, v in synthetic.lbs_inputs(B, mt).items()}
+    o = bm(need_verts=False, **inp); o.Jtr.sum().backward(); torch.cuda.synchronize(); print('lbs joints-only ok', mt)
+os.environ['DPB_TC_SMALL'] = '1'
+fn = sampling.get_sampling_fn(cfg, sde_lib.subVPSDE(0.1, 20., 3), (300, 63), lambda x: x, 1e-3, device='cuda')
+_, x = fn(model, z=torch.randn(300, 63)); torch.cuda.synchronize(); print('small engine ok', float(x.abs().mean()))
+os.environ['DPB_TC_SMALL'] = '0'
+from dposer_b200 import likelihood
+d, dv = likelihood.drift_and_div(model, sde_lib.subVPSDE(0.1, 20., 1000), torch.randn(70, 63).cuda(), 0.3,
+                                 torch.randn(70, 63).cuda())
+torch.cuda.synchronize(); print('jvp ok', float(dv.abs().mean()))
+import types
+from dposer_b200 import fitting
+from dposer_b200.misc import Posenormalizer
+mx = synthetic.make_body_tensors('smplx')
+rows, L_ = 128, 8
+bm = BodyModel(mx, num_betas=10, batch_size=rows, model_type='smplx').cuda()
+norm = Posenormalizer(None, device='cuda', normalize=True, min_max=False, rot_rep='axis')
+gt = synthetic.toy_poses()[:rows].cuda()
+with torch.no_grad():
+    jn = bm(pose_body=gt, need_verts=False).Jtr[:, :22]
+md = fitting.MotionDenoise(cfg, types.SimpleNamespace(device='cuda'), model, bm, sde_lib.subVPSDE(0.1, 20., 1000), norm,
+                           sde_N=500, batch_size=rows, seq_len=L_)
+r = md.optimize(jn, time_strategy='3', sample_trun=4.0, iterations=1, steps_per_iter=2)
+torch.cuda.synchronize(); print('motion denoise ok', bool(torch.isfinite(r['pose_body']).all()))
