@@ -41,7 +41,7 @@ class BodyTensors(C.Structure):
 
 EXPORTS = ['dpb_version', 'dpb_last_error', 'dpb_device_info', 'dpb_score_create', 'dpb_score_destroy',
            'dpb_score_time_table', 'dpb_score_workspace_bytes', 'dpb_score_forward', 'dpb_score_jvp',
-           'dpb_score_jvp_workspace_bytes', 'dpb_sampler_run',
+           'dpb_score_jvp_workspace_bytes', 'dpb_sampler_run_pc', 'dpb_sampler_pc_workspace_bytes', 'dpb_sampler_run',
            'dpb_langevin_norms', 'dpb_langevin_update', 'dpb_normal_fill', 'dpb_prior_loss', 'dpb_lbs_create',
            'dpb_lbs_destroy', 'dpb_lbs_set_const_tail', 'dpb_lbs_num_joints_out', 'dpb_lbs_workspace_bytes', 'dpb_lbs_forward',
            'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_lbs_backward_scratch_bytes_joints', 'dpb_apd_partial', 'dpb_mean_point_error', 'dpb_fit_loss',
@@ -83,6 +83,10 @@ def load():
     lib.dpb_normal_fill.argtypes = [vp, i64, u64, u64, C.c_int, vp]
     lib.dpb_prior_loss.argtypes = [vp, vp, vp, f32, f32, f32, C.c_int, f32, vp, u64, u64, vp, vp, vp, i64, C.c_int,
                                    vp, sz, vp]
+    lib.dpb_sampler_pc_workspace_bytes.argtypes = [vp, i64]
+    lib.dpb_sampler_pc_workspace_bytes.restype = sz
+    lib.dpb_sampler_run_pc.argtypes = [vp, vp, C.POINTER(StepTables), vp, vp, f32, vp, vp, vp, C.c_uint64, C.c_uint64, vp,
+                                       vp, i64, C.c_int, vp, sz, vp]
     lib.dpb_score_jvp_workspace_bytes.argtypes = [vp, i64]
     lib.dpb_score_jvp_workspace_bytes.restype = sz
     lib.dpb_score_jvp.argtypes = [vp, vp, vp, vp, vp, vp, f32, vp, vp, i64, vp, sz, vp]
@@ -114,7 +118,7 @@ def load():
         fn = getattr(lib, name)
         if name not in ('dpb_last_error', 'dpb_score_workspace_bytes', 'dpb_lbs_workspace_bytes',
                         'dpb_lbs_backward_scratch_bytes', 'dpb_lbs_backward_scratch_bytes_joints',
-                        'dpb_score_jvp_workspace_bytes'):
+                        'dpb_score_jvp_workspace_bytes', 'dpb_sampler_pc_workspace_bytes'):
             fn.restype = C.c_int
     _lib = lib
     return lib

@@ -183,6 +183,61 @@ extern "C" int dpb_score_forward(dpb_score_t* h, const float* x, const float* ta
   return launch_scale_out(w.raw, row_scale, scale, out, B, st);
 }
 
+// Predictor-corrector sampling with the Langevin corrector (sampling.py:456-461 with :282-302), all steps from one host
+// call: per step  score -> batch norms -> corrector update -> (one fused predictor step incl. imputation).  The corrector
+// needs batch-global norms between its score evaluation and its update, so a step is five launches, issued here without
+// returning to the caller (the Python loop of round 1 was bound by its per-step host work at small batches).
+extern "C" size_t dpb_sampler_pc_workspace_bytes(dpb_score_t* h, int64_t B) {
+  if (!h || B <= 0) return 0;
+  return dpb_score_workspace_bytes(h, B, 0) + 2 * align_up((size_t)B * D * 4, 256) + 256 + 1024;
+}
+
+extern "C" int dpb_sampler_run_pc(dpb_score_t* h, float* x_io, const dpb_step_tables* tbl, const float* score_scale,
+                                  const float* lang_alpha, float snr, const float* obs, const float* mask,
+                                  const float* noise, uint64_t seed, uint64_t step_offset, float* traj, float* x_mean,
+                                  int64_t B, int flags, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !tbl) return fail(DPB_EINVAL, "dpb_sampler_run_pc: null handle or tables");
+  DeviceGuard guard(h->device);
+  DPB_REQUIRE(x_io && tbl->coef && tbl->time_table && score_scale && lang_alpha && x_mean,
+              "dpb_sampler_run_pc: x_io, tables, score_scale, lang_alpha and x_mean are required");
+  if (B <= 0 || tbl->n_steps <= 0) return DPB_OK;
+  if (ws == nullptr || ws_bytes < dpb_sampler_pc_workspace_bytes(h, B))
+    return fail(DPB_ENOMEM, "dpb_sampler_run_pc: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool impute = (flags & DPB_SAMPLER_IMPUTE) != 0, given = (flags & DPB_SAMPLER_NOISE_GIVEN) != 0;
+  if (given) DPB_REQUIRE(noise, "dpb_sampler_run_pc: DPB_SAMPLER_NOISE_GIVEN without a noise tensor");
+  WsCarver c(ws, ws_bytes);
+  float* grad = c.take<float>((size_t)B * D);
+  float* z = c.take<float>((size_t)B * D);
+  float* sums = c.take<float>(2);
+  c.off = align_up(c.off, 256);
+  void* rest = static_cast<uint8_t*>(ws) + c.off;
+  const size_t rest_bytes = ws_bytes - c.off;
+  const int kp = impute ? 3 : 1;                       // predictor planes per step; the Langevin draw comes first
+  const size_t plane = (size_t)B * D;
+  for (int i = 0; i < tbl->n_steps; ++i) {
+    const float* table_i = tbl->time_table + (size_t)i * NL * H;
+    int rc = dpb_score_forward(h, x_io, table_i, nullptr, nullptr, score_scale[i], grad, B, flags & DPB_ENGINE_MASK, rest,
+                               rest_bytes, stream);
+    if (rc != DPB_OK) return rc;
+    const float* zi = z;
+    if (given) zi = noise + (size_t)i * (kp + 1) * plane;
+    else if ((rc = dpb_normal_fill(z, B, seed, step_offset + (uint64_t)i, 4, stream)) != DPB_OK) return rc;
+    DPB_CUDA_CHECK(cudaMemsetAsync(sums, 0, 2 * sizeof(float), st));
+    if ((rc = dpb_langevin_norms(grad, zi, sums, B, stream)) != DPB_OK) return rc;
+    if ((rc = dpb_langevin_update(x_io, nullptr, grad, zi, sums, snr, lang_alpha[i], B, stream)) != DPB_OK) return rc;
+    dpb_step_tables one{};
+    one.n_steps = 1;
+    one.coef = tbl->coef + (size_t)i * DPB_COEF_STRIDE;
+    one.time_table = table_i;
+    rc = dpb_sampler_run(h, x_io, &one, obs, mask, given ? noise + ((size_t)i * (kp + 1) + 1) * plane : nullptr, seed,
+                         step_offset + (uint64_t)i, traj ? traj + (size_t)i * plane : nullptr, x_mean, B, flags, rest,
+                         rest_bytes, stream);
+    if (rc != DPB_OK) return rc;
+  }
+  return DPB_OK;
+}
+
 extern "C" size_t dpb_score_jvp_workspace_bytes(dpb_score_t* h, int64_t B) {
   if (!h || B <= 0) return 0;
   return simt_forward_ws_bytes(2 * B) + align_up((size_t)2 * B * DP * 4, 256) + 1024;

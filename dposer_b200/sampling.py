@@ -115,39 +115,30 @@ def get_pc_sampler(sde, shape, predictor, corrector, inverse_scaler, snr, n_step
 
 def _langevin_loop(model, sde, x, coef, table, t_run, obs, mask, noise, seed, start_t, trajs, x_mean, impute, snr,
                    continuous=True):
-    """corrector -> (impute) -> predictor -> (impute) per step, sampling.py:459-460 with :282-302.
-    Given-noise layout here is [n, K+1, B, 63] with the Langevin draw first."""
+    """corrector -> (impute) -> predictor -> (impute) per step, sampling.py:459-460 with :282-302: ONE native call
+    (``dpb_sampler_run_pc`` issues the five launches of every step itself).  Given-noise layout here is
+    [n, K+1, B, 63] with the Langevin draw first."""
     lib = L.load()
     B = x.shape[0]
     dev = x.device
-    st = L.current_stream(dev)
     if isinstance(sde, (sde_lib.VPSDE, sde_lib.subVPSDE)):
         lang_alpha = sde.alphas[(t_run * (sde.N - 1) / sde.T).long()]      # sampling.py:287-289
     else:
         lang_alpha = torch.ones_like(t_run)
-    # grad = score = raw * (-1/(sigma*std)) = raw * b / (g^2 dt w) ; recompute the multiplier from the sde
     # same score scaling as the predictor (utils.get_score_fn: continuous marginal std, or the discrete VPSDE table)
-    ps = [mutils.prior_scalars(sde, model, float(t), continuous) for t in t_run]
-    sums = torch.zeros(2, device=dev)
-    grad = torch.empty_like(x)
-    z = torch.empty_like(x)
-    ws = model.workspace(B, dev)
+    scale = torch.tensor([-mutils.prior_scalars(sde, model, float(t), continuous)['inv_sigma_std'] for t in t_run],
+                         dtype=torch.float32)
+    lang_alpha = lang_alpha.to(torch.float32).contiguous()
     h = model.handle()
-    for i in range(t_run.numel()):
-        L.check(lib.dpb_score_forward(h.ptr, L.ptr(x), L.ptr(table[i]), None, None, -ps[i]['inv_sigma_std'],
-                                      L.ptr(grad), B, model.engine, L.ptr(ws), ws.numel(), st))
-        if noise is not None:
-            z = noise[i, 0]
-            nz = noise[i, 1:].contiguous()
-        else:
-            L.check(lib.dpb_normal_fill(L.ptr(z), B, C.c_uint64(seed), C.c_uint64(start_t + i), 4, st))
-            nz = None
-        sums.zero_()
-        L.check(lib.dpb_langevin_norms(L.ptr(grad), L.ptr(z), L.ptr(sums), B, st))
-        L.check(lib.dpb_langevin_update(L.ptr(x), None, L.ptr(grad), L.ptr(z), L.ptr(sums), float(snr),
-                                        float(lang_alpha[i]), B, st))
-        _run_steps(model, x, coef[i:i + 1], table[i:i + 1], obs, mask, nz, seed, start_t + i,
-                   None if trajs is None else trajs[i:i + 1], x_mean, impute)
+    ws = torch.empty(int(lib.dpb_sampler_pc_workspace_bytes(h.ptr, B)), dtype=torch.uint8, device=dev)
+    n = t_run.numel()
+    tbl = L.StepTables(n, C.c_void_p(coef.data_ptr()), C.c_void_p(table.data_ptr()))
+    flags = model.engine | (L.SAMPLER_IMPUTE if impute else 0) | (L.SAMPLER_NOISE_GIVEN if noise is not None else 0)
+    nz = None if noise is None else noise.contiguous()
+    L.check(lib.dpb_sampler_run_pc(h.ptr, L.ptr(x), C.byref(tbl), C.c_void_p(scale.data_ptr()),
+                                   C.c_void_p(lang_alpha.data_ptr()), float(snr), L.ptr(obs), L.ptr(mask), L.ptr(nz),
+                                   C.c_uint64(seed), C.c_uint64(start_t), L.ptr(trajs), L.ptr(x_mean), B, flags,
+                                   L.ptr(ws), ws.numel(), L.current_stream(dev)))
 
 
 def get_ode_sampler(sde, shape, inverse_scaler, denoise=False, rtol=1e-5, atol=1e-5, method='RK45', eps=1e-3,

@@ -152,6 +152,16 @@ int dpb_sampler_run(dpb_score_t* h, float* x_io, const dpb_step_tables* tbl, con
 int dpb_langevin_norms(const float* grad, const float* noise, float* sums, int64_t B, void* stream);
 int dpb_langevin_update(float* x_io, float* x_mean, const float* grad, const float* noise,
                         const float* sums, float snr, float alpha, int64_t B, void* stream);
+/* Predictor-corrector sampling with the Langevin corrector, all n_steps from ONE call (replaces the loop body
+ * sampling.py:456-461 with LangevinCorrector.update_fn :282-302 and the predictor of dpb_sampler_run):
+ *   score_scale HOST [n]: -1 / (sigma * std) of each step (score = raw * score_scale); lang_alpha HOST [n]: the alpha of
+ *   sampling.py:287-291; noise (DPB_SAMPLER_NOISE_GIVEN): DEVICE [n, K+1, B, 63], the Langevin draw first, then the K
+ *   planes of dpb_sampler_run; otherwise Philox slot 4 serves the corrector.  Batch norms are over the B rows given. */
+size_t dpb_sampler_pc_workspace_bytes(dpb_score_t* h, int64_t B);
+int dpb_sampler_run_pc(dpb_score_t* h, float* x_io, const dpb_step_tables* tbl, const float* score_scale,
+                       const float* lang_alpha, float snr, const float* obs, const float* mask, const float* noise,
+                       uint64_t seed, uint64_t step_offset, float* traj, float* x_mean, int64_t B, int flags, void* ws,
+                       size_t ws_bytes, void* stream);
 /* fills out[n] with N(0,1) draws of the library's Philox stream (row-major [B,63] addressing) */
 int dpb_normal_fill(float* out, int64_t B, uint64_t seed, uint64_t step, int slot, void* stream);
 
