@@ -206,6 +206,22 @@ extern "C" int dpb_sampler_run_pc(dpb_score_t* h, float* x_io, const dpb_step_ta
   cudaStream_t st = (cudaStream_t)stream;
   const bool impute = (flags & DPB_SAMPLER_IMPUTE) != 0, given = (flags & DPB_SAMPLER_NOISE_GIVEN) != 0;
   if (given) DPB_REQUIRE(noise, "dpb_sampler_run_pc: DPB_SAMPLER_NOISE_GIVEN without a noise tensor");
+  const int noise_k = impute ? 3 : 1;
+  if (pick_engine(h, flags, B, true) == DPB_ENGINE_TC && tc_pc_possible(h, B, tbl->n_steps)) {
+    // ONE persistent kernel for all steps: the corrector's batch norms cross the grid through a counter barrier
+    // (score_tc.cu, pc mode).  Columns 5 / 6 of the coefficient table take the per-step score scale and alpha.
+    float* coef = const_cast<float*>(tbl->coef);
+    DPB_CUDA_CHECK(cudaMemcpy2DAsync(coef + 5, DPB_COEF_STRIDE * sizeof(float), score_scale, sizeof(float), sizeof(float),
+                                     tbl->n_steps, cudaMemcpyHostToDevice, st));
+    DPB_CUDA_CHECK(cudaMemcpy2DAsync(coef + 6, DPB_COEF_STRIDE * sizeof(float), lang_alpha, sizeof(float), sizeof(float),
+                                     tbl->n_steps, cudaMemcpyHostToDevice, st));
+    TcJob j{};
+    j.mode = 1; j.B = B; j.x_io = x_io; j.table = tbl->time_table; j.coef = tbl->coef; j.n_steps = tbl->n_steps;
+    j.obs = obs; j.mask = mask; j.noise = given ? noise : nullptr; j.noise_k = noise_k;
+    j.seed = seed; j.step_offset = step_offset; j.traj = traj; j.x_mean = x_mean; j.impute = impute ? 1 : 0;
+    j.pc = 1; j.snr = snr;
+    return tc_launch(h, j, st);
+  }
   WsCarver c(ws, ws_bytes);
   float* grad = c.take<float>((size_t)B * D);
   float* z = c.take<float>((size_t)B * D);
@@ -213,7 +229,7 @@ extern "C" int dpb_sampler_run_pc(dpb_score_t* h, float* x_io, const dpb_step_ta
   c.off = align_up(c.off, 256);
   void* rest = static_cast<uint8_t*>(ws) + c.off;
   const size_t rest_bytes = ws_bytes - c.off;
-  const int kp = impute ? 3 : 1;                       // predictor planes per step; the Langevin draw comes first
+  const int kp = noise_k;                              // predictor planes per step; the Langevin draw comes first
   const size_t plane = (size_t)B * D;
   for (int i = 0; i < tbl->n_steps; ++i) {
     const float* table_i = tbl->time_table + (size_t)i * NL * H;

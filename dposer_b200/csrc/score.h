@@ -36,6 +36,7 @@ struct dpb_score {
   // small-batch engine (score_small.cu): the same operands with 64-row boxes (one column slice per CTA)
   CUtensorMap tms_w[4], tms_post, tms_pre;
   bool tcs_ready = false;
+  float* pc_buf = nullptr;      // predictor-corrector mode: [2 * PC_MAX_STEPS] batch norm sums + one int barrier counter
   int tc_slots = 0;
   size_t act_bytes = 0, l2_window = 0;   // activation scratch size; bytes of the persisting-L2 access-policy window (0 = off)
   float l2_hit = 1.f;
@@ -73,8 +74,11 @@ struct TcJob {
   // prior loss
   float alpha, std, inv_sigma_std, divisor; int weighted; const float* z; float* loss_out; float* grad_out;
   float* row_loss;
+  // predictor-corrector (Langevin) sampling fused into the sampler kernel: coef columns 5 / 6 carry score scale / alpha
+  int pc; float snr;
 };
 int tc_launch(dpb_score* h, const TcJob& job, cudaStream_t st);
+bool tc_pc_possible(const dpb_score* h, int64_t B, int n_steps);
 int tcs_prepare(dpb_score* h);
 bool tcs_wanted(const dpb_score* h, const TcJob& job);
 int tcs_launch(dpb_score* h, const TcJob& job, cudaStream_t st);

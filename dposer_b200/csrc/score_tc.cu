@@ -23,6 +23,8 @@
 #include "score.h"
 
 namespace dpb {
+constexpr int PC_MAX_STEPS = 4096;   // sampler steps the fused predictor-corrector mode keeps norm sums for
+
 namespace tc {
 
 constexpr int TILE_M = 128;
@@ -66,7 +68,8 @@ constexpr int OFF_STG = OFF_PAR + PAR_BYTES;     // 1024-aligned
 constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
 constexpr int OFF_POSTB = (OFF_BAR + NUM_BARS * 8 + 16 + 15) / 16 * 16;   // post_dense bias (64 floats)
 static_assert(OFF_POSTB % 16 == 0, "post_b is read with 128-bit loads");
-constexpr int SMEM_BYTES = OFF_POSTB + DP * 4 + 1024;  // + alignment slack
+constexpr int OFF_PCROW = OFF_POSTB + DP * 4;           // predictor-corrector mode: per-row squared norms [128][2]
+constexpr int SMEM_BYTES = OFF_PCROW + TILE_M * 2 * 4 + 1024;  // + alignment slack
 static_assert(OFF_STG % 1024 == 0, "staging boxes must be 1024-byte aligned for SWIZZLE_128B");
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr int MMA_M = TWO_SM ? 2 * TILE_M : TILE_M;
@@ -105,6 +108,13 @@ struct KParams {
   __half* act_h;
   __half* act_t;
   int* flags;   // one hand-off flag per CTA (zeroed before the launch), see SegIter
+  // predictor-corrector mode (Langevin corrector, sampling.py:282-302): n_steps counts SUB-steps, even = corrector, odd =
+  // predictor of step (sub >> 1); every CTA owns one tile for the whole run (lock step) and the batch-global norms go
+  // through pc_sums[step][2] and a counter barrier over the grid.  coef columns 5 / 6 = score scale / alpha of the step.
+  int pc;
+  float snr;
+  float* pc_sums;
+  int* pc_counter;
 };
 
 // ---- work distribution.  A "unit" is CLUSTER consecutive row tiles (one per CTA of a cluster) and a "chain" is
@@ -666,7 +676,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
     uint32_t pcnt = 0;             // hidden layers processed so far (parameter buffer = pcnt & 1)
     bool par_prefetched = false;
     auto stage_par = [&](int step_, int layer_, uint32_t slot) {
-      const float4* tb = reinterpret_cast<const float4*>(p.table + ((size_t)step_ * NL + layer_) * H);
+      const float4* tb = reinterpret_cast<const float4*>(p.table + ((size_t)(p.pc ? step_ >> 1 : step_) * NL + layer_) * H);
       const float4* gn = reinterpret_cast<const float4*>(p.gn + (size_t)(layer_ * 2) * H);  // gamma | beta (pre-halved)
       const uint32_t dst = ptx::smem_u32(par_base) + slot * (3 * H * 4);
       if (et < H / 4) ptx::cp_async_16(dst + et * 16, tb + et);
@@ -699,7 +709,7 @@ score_tc_kernel(const __grid_constant__ KParams p,
               int col = c0 + i;
               if (col < D) x[i] = __ldcg(p.x_io + row * D + col);
             }
-            if (p.impute && sg.s0 == 0) {  // imputation that follows the (none) corrector of step 0, sampling.py:459
+            if (p.impute && sg.s0 == 0 && !p.pc) {  // imputation that follows the (none) corrector of step 0, sampling.py:459
               float zc[TCOLS];
               draw_cols(p.noise ? p.noise : nullptr, row, c0, p.seed, (uint32_t)p.step_offset, 0, zc);
               const float al = p.coef[3], sd = p.coef[4];
@@ -826,17 +836,22 @@ score_tc_kernel(const __grid_constant__ KParams p,
           // everything of the sampler update that does not depend on the network output is prepared BEFORE the
           // accumulator wait: this step's coefficients and its Gaussian draws (Philox + Box-Muller)
           const bool last = (step + 1 == p.n_steps);
-          const float* cf = p.coef + (size_t)step * DPB_COEF_STRIDE;
-          const uint32_t gstep = (uint32_t)(p.step_offset + (unsigned long long)step);
+          const int lstep = p.pc ? (step >> 1) : step;           // the sampler step this sub-step belongs to
+          const bool corr = p.pc && !(step & 1);                 // corrector sub-step (its score evaluation just ran)
+          const float* cf = p.coef + (size_t)lstep * DPB_COEF_STRIDE;
+          const uint32_t gstep = (uint32_t)(p.step_offset + (unsigned long long)lstep);
           const size_t plane = (size_t)p.B * D;
           float ca = 0.f, cb = 0.f, cc = 0.f, al = 0.f, sd = 0.f;
-          const float* nz = p.noise ? p.noise + (size_t)step * p.noise_k * plane : nullptr;
+          // given noise: [n, K, B, 63] planes of the predictor; with the corrector [n, K + 1, B, 63], its draw first
+          const float* nzc = p.noise ? p.noise + (size_t)lstep * (p.noise_k + (p.pc ? 1 : 0)) * plane : nullptr;
+          const float* nz = (nzc && p.pc) ? nzc + plane : nzc;
           float zp[TCOLS];
 #pragma unroll
           for (int i = 0; i < TCOLS; ++i) zp[i] = 0.f;
           if (p.mode == 1 && valid) {
             ca = cf[0]; cb = cf[1]; cc = cf[2]; al = cf[3]; sd = cf[4];
-            draw_cols(nz ? nz + (p.noise_k == 3 ? plane : 0) : nullptr, row, c0, p.seed, gstep, 1, zp);
+            if (corr) draw_cols(nzc, row, c0, p.seed, gstep, 4, zp);          // the Langevin draw (Philox slot 4)
+            else draw_cols(nz ? nz + (p.noise_k == 3 ? plane : 0) : nullptr, row, c0, p.seed, gstep, 1, zp);
           }
           if (p.mode == 1) {  // pin the draws above the wait (the compiler would otherwise sink them below it)
 #pragma unroll
@@ -870,6 +885,73 @@ score_tc_kernel(const __grid_constant__ KParams p,
                 if (col < D) p.out[row * D + col] = raw[i] * sc;
               }
             }
+          } else if (p.mode == 1 && corr && DBG(8192)) {     // timing experiment: corrector sub-step without its tail
+            float x[TCOLS];
+#pragma unroll
+            for (int i = 0; i < TCOLS; ++i) x[i] = xs[sub][i] + 1e-9f * raw[i];
+            write_xa(xa_hi, xa_lo, r_in, c0, x);
+            signal(xa_bar(sub));
+          } else if (p.mode == 1 && corr) {
+            // ---- Langevin corrector (sampling.py:282-302): grad = score, batch-global mean norms, x += step grad + sqrt(2 step) z
+            float* rowsq = reinterpret_cast<float*>(smem + OFF_PCROW);
+            float gsq = 0.f, zsq = 0.f;
+            float grad[TCOLS];
+#pragma unroll
+            for (int i = 0; i < TCOLS; ++i) {
+              grad[i] = (valid && c0 + i < D) ? raw[i] * cf[5] : 0.f;
+              gsq = fmaf(grad[i], grad[i], gsq);
+              if (valid && c0 + i < D) zsq = fmaf(zp[i], zp[i], zsq);
+            }
+            if (c0 == 0) { rowsq[2 * r_in] = 0.f; rowsq[2 * r_in + 1] = 0.f; }
+            ptx::named_bar_sync(1, EPI_THREADS);
+            atomicAdd(rowsq + 2 * r_in, gsq);
+            atomicAdd(rowsq + 2 * r_in + 1, zsq);
+            ptx::named_bar_sync(1, EPI_THREADS);
+            if (c0 == 0) {                                   // one warp per row quarter: sum of the rows' norms
+              float ng = valid ? sqrtf(rowsq[2 * r_in]) : 0.f, nzz = valid ? sqrtf(rowsq[2 * r_in + 1]) : 0.f;
+              for (int o = 16; o > 0; o >>= 1) {
+                ng += __shfl_xor_sync(0xffffffffu, ng, o);
+                nzz += __shfl_xor_sync(0xffffffffu, nzz, o);
+              }
+              if (lane == 0) {
+                atomicAdd(p.pc_sums + 2 * lstep, ng);
+                atomicAdd(p.pc_sums + 2 * lstep + 1, nzz);
+              }
+            }
+            // grid barrier: every CTA has added its rows (lock step: all CTAs run the same sub-step sequence)
+            if (!DBG(1024)) __threadfence();
+            ptx::named_bar_sync(1, EPI_THREADS);
+            if (et == 0 && !DBG(2048)) {
+              atomicAdd(p.pc_counter, 1);
+              const int target = (lstep + 1) * (int)gridDim.x;
+              while (ptx::ld_acquire_gpu(p.pc_counter) < target) {
+              }
+              __threadfence();
+            }
+            ptx::named_bar_sync(1, EPI_THREADS);
+            const float sum_g = DBG(4096) ? 1.f : __ldcg(p.pc_sums + 2 * lstep), sum_z = DBG(4096) ? 1.f : __ldcg(p.pc_sums + 2 * lstep + 1);
+            const float rr = p.snr * sum_z / sum_g;          // both means share the divisor (sampling.py:296-298)
+            const float stp = rr * rr * 2.0f * cf[6];
+            const float sq = sqrtf(stp * 2.0f);
+            float x[TCOLS];
+#pragma unroll
+            for (int i = 0; i < TCOLS; ++i) x[i] = valid ? (xs[sub][i] + stp * grad[i]) + sq * zp[i] : 0.f;
+            if (valid && p.impute) {                         // imputation after the corrector (sampling.py:459, 413-422)
+              float zc[TCOLS];
+              draw_cols(nz, row, c0, p.seed, gstep, 0, zc);
+#pragma unroll
+              for (int i = 0; i < TCOLS; ++i) {
+                int col = c0 + i;
+                if (col < D) {
+                  float m = p.mask[row * D + col];
+                  x[i] = x[i] * (1.0f - m) + (al * p.obs[row * D + col] + zc[i] * sd) * m;
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < TCOLS; ++i) xs[sub][i] = x[i];
+            write_xa(xa_hi, xa_lo, r_in, c0, x);             // the predictor sub-step always follows
+            signal(xa_bar(sub));
           } else if (p.mode == 1) {
             float x[TCOLS];
 #pragma unroll
@@ -900,10 +982,10 @@ score_tc_kernel(const __grid_constant__ KParams p,
 #pragma unroll
                 for (int i = 0; i < TCOLS; ++i) {
                   int col = c0 + i;
-                  if (col < D) p.traj[((size_t)step * p.B + row) * D + col] = x[i];
+                  if (col < D) p.traj[((size_t)lstep * p.B + row) * D + col] = x[i];
                 }
               }
-              if (!last && p.impute) {  // imputation in the corrector slot of the NEXT step precedes its score eval
+              if (!last && p.impute && !p.pc) {  // imputation in the corrector slot of the NEXT step precedes its score eval
                 float zc[TCOLS];
                 const float* nz1 = p.noise ? p.noise + (size_t)(step + 1) * p.noise_k * plane : nullptr;
                 draw_cols(nz1, row, c0, p.seed, gstep + 1, 0, zc);
@@ -1096,22 +1178,38 @@ int tc_prepare(dpb_score* h, const dpb_score_weights* w) {
   if (rc != DPB_OK) return rc;
   DPB_CUDA_CHECK(cudaFuncSetAttribute(tc::score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       tc::SMEM_BYTES));
+  DPB_CUDA_CHECK(cudaMalloc((void**)&h->pc_buf, (2 * PC_MAX_STEPS + 4) * sizeof(float)));
   h->tc_ready = true;
   return tcs_prepare(h);
 }
 
+// the fused predictor-corrector mode needs every CTA to own one tile for the whole run (grid-wide norms per step)
+bool tc_pc_possible(const dpb_score* h, int64_t B, int n_steps) {
+  if (!h->tc_ready || !h->pc_buf || n_steps > PC_MAX_STEPS) return false;
+  const char* e = getenv("DPB_TC_PC");                            // A/B timing: 0 forces the per-step launch sequence
+  if (e && atoi(e) == 0) return false;
+  const int64_t n_tiles = (B + tc::TILE_M - 1) / tc::TILE_M;
+  const int64_t max_grid = (h->tc_slots / tc::NSUB) / tc::CLUSTER * tc::CLUSTER;
+  return (n_tiles + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER <= max_grid;
+}
+
 void tc_release(dpb_score* h) {
-  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->tc_flags, h->gn_tc};
+  void* ptrs[] = {h->w16[0], h->w16[1], h->w16[2], h->w16[3], h->post16, h->pre_split, h->act_h, h->tc_flags, h->gn_tc, h->pc_buf};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   h->tc_ready = false;
 }
 
 int tc_launch(dpb_score* h, const TcJob& j, cudaStream_t st) {
-  if (tcs_wanted(h, j)) return tcs_launch(h, j, st);   // few row tiles: split the output features over 16 CTAs per tile
+  if (!j.pc && tcs_wanted(h, j)) return tcs_launch(h, j, st);   // few row tiles: split the output features over 16 CTAs per tile
   tc::KParams p{};
   p.mode = j.mode;
-  p.n_steps = j.n_steps;
+  p.n_steps = j.pc ? 2 * j.n_steps : j.n_steps;
+  p.pc = j.pc;
+  p.snr = j.snr;
+  p.pc_sums = h->pc_buf;
+  p.pc_counter = reinterpret_cast<int*>(h->pc_buf + 2 * PC_MAX_STEPS);
+  if (j.pc) DPB_CUDA_CHECK(cudaMemsetAsync(h->pc_buf, 0, (2 * PC_MAX_STEPS + 4) * sizeof(float), st));
   p.impute = j.impute;
   p.noise_k = j.noise_k;
   p.B = j.B;

@@ -125,9 +125,9 @@ def _langevin_loop(model, sde, x, coef, table, t_run, obs, mask, noise, seed, st
         lang_alpha = sde.alphas[(t_run * (sde.N - 1) / sde.T).long()]      # sampling.py:287-289
     else:
         lang_alpha = torch.ones_like(t_run)
-    # same score scaling as the predictor (utils.get_score_fn: continuous marginal std, or the discrete VPSDE table)
-    scale = torch.tensor([-mutils.prior_scalars(sde, model, float(t), continuous)['inv_sigma_std'] for t in t_run],
-                         dtype=torch.float32)
+    # same score scaling as the predictor (utils.get_score_fn: continuous marginal std, or the discrete VPSDE table),
+    # evaluated for all steps at once by em_coefficients (column 5)
+    scale = coef[:, 5].detach().to('cpu', torch.float32).contiguous()
     lang_alpha = lang_alpha.to(torch.float32).contiguous()
     h = model.handle()
     ws = torch.empty(int(lib.dpb_sampler_pc_workspace_bytes(h.ptr, B)), dtype=torch.uint8, device=dev)

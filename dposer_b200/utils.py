@@ -134,6 +134,7 @@ def em_coefficients(sde, model, t, probability_flow=False, continuous=True, pred
     mean1, std_m = sde.marginal_prob(one, t)     # imputation: alpha*obs + std*z (sampling.py:415-416)
     coef = torch.zeros(t.numel(), L.COEF_STRIDE)
     coef[:, 0], coef[:, 1], coef[:, 2], coef[:, 3], coef[:, 4] = a, b, c, mean1[:, 0], std_m
+    coef[:, 5] = -1.0 / (sig * std_score)        # score = raw * coef[5]  (the Langevin corrector's gradient, utils.py:152-162)
     return coef, labels
 
 

@@ -156,7 +156,9 @@ int dpb_langevin_update(float* x_io, float* x_mean, const float* grad, const flo
  * sampling.py:456-461 with LangevinCorrector.update_fn :282-302 and the predictor of dpb_sampler_run):
  *   score_scale HOST [n]: -1 / (sigma * std) of each step (score = raw * score_scale); lang_alpha HOST [n]: the alpha of
  *   sampling.py:287-291; noise (DPB_SAMPLER_NOISE_GIVEN): DEVICE [n, K+1, B, 63], the Langevin draw first, then the K
- *   planes of dpb_sampler_run; otherwise Philox slot 4 serves the corrector.  Batch norms are over the B rows given. */
+ *   planes of dpb_sampler_run; otherwise Philox slot 4 serves the corrector.  Batch norms are over the B rows given.
+ *   With the tcgen05 engine and at most one 128-row tile per SM (B <= 18 944) all steps run in ONE persistent kernel;
+ *   columns 5 and 6 of tbl->coef (DEVICE, spare) are then overwritten with score_scale / lang_alpha. */
 size_t dpb_sampler_pc_workspace_bytes(dpb_score_t* h, int64_t B);
 int dpb_sampler_run_pc(dpb_score_t* h, float* x_io, const dpb_step_tables* tbl, const float* score_scale,
                        const float* lang_alpha, float snr, const float* obs, const float* mask, const float* noise,
