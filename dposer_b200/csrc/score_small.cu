@@ -336,7 +336,7 @@ score_small_kernel(const __grid_constant__ Params p, const __grid_constant__ CUt
               x[c] = xm + cc * z[c];
               if (last && p.x_mean) p.x_mean[row * D + c] = xm;
             }
-            if (p.impute) {
+            if (p.impute && (last || p.traj)) {   // else overwritten by the next step's pre-imputation before any read
               draw_row(nz ? nz + 2 * plane : nullptr, row, p.seed, gstep, 2, z);
 #pragma unroll
               for (int c = 0; c < D; ++c) {

@@ -966,7 +966,9 @@ score_tc_kernel(const __grid_constant__ KParams p,
                   if (last && p.x_mean) p.x_mean[row * D + col] = xm;
                 }
               }
-              if (p.impute) {
+              // (between steps without a trajectory the imputed columns are overwritten by the next step's pre-imputation
+              //  before anything reads them: the draw is skipped, results are identical)
+              if (p.impute && (last || p.traj || p.pc)) {
                 float zi[TCOLS];
                 draw_cols(nz ? nz + 2 * plane : nullptr, row, c0, p.seed, gstep, 2, zi);
 #pragma unroll
