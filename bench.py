@@ -317,20 +317,24 @@ def bench_configs(args, dev, model, peaks, flush, cpu_per_row_step):
     kw = dict(time_strategy='3', sample_trun=4.0, sample_time=490, iterations=3, steps_per_iter=60, graphs=True)
     md.optimize(jn, **kw)                      # first batch: allocates, captures the 180 step graphs
     torch.cuda.synchronize()
-    md.poses = torch.randn(rows, 63, device=dev) * 0.01
+    n_batches = args.c4_batches if args.c4_batches > 0 else max(1, 8192 // n_seq)
     flush.fill_(1)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = md.optimize(jn, gt_poses=None, **kw)   # a further batch of sequences: graph replays only
+    finite = True
+    for _ in range(n_batches):                 # further batches of sequences: graph replays only
+        md.poses = torch.randn(rows, 63, device=dev) * 0.01
+        res = md.optimize(jn, gt_poses=None, **kw)
+        finite = finite and bool(torch.isfinite(res['pose_body']).all())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out['c4_motion_denoise'] = {
         'workload': f'configs[3]: DPoser prior + temporal vertex term + joint data term, SMPL-X (10475 verts), Adam 3 x 60 '
-                    f'steps; ONE batch of {n_seq} independent 60-frame sequences (the config\'s 8192 sequences are '
-                    f'{8192 // n_seq} such batches replaying the same captured step graphs)',
-        'sequences': n_seq, 'frames': rows, 'adam_steps': 180, 'seconds': dt, 'value': rows / dt, 'unit': 'frames/s',
-        'ms_per_adam_step': dt * 1e3 / 180, 'seconds_for_8192_sequences': dt * 8192 / n_seq,
-        'finite': bool(torch.isfinite(res['pose_body']).all())}
+                    f'steps; {n_batches * n_seq} independent 60-frame sequences as {n_batches} batches of {n_seq} replaying '
+                    'the same captured step graphs (vertices + cotangents of one batch: 3.9 GB)',
+        'sequences': n_batches * n_seq, 'frames': n_batches * rows, 'adam_steps': 180, 'seconds': dt,
+        'value': n_batches * rows / dt, 'unit': 'frames/s', 'ms_per_adam_step': dt * 1e3 / (180 * n_batches),
+        'frames_per_batch': rows, 'finite': finite}
     del md, bm, jn, gt, res
     torch.cuda.empty_cache()
 
@@ -670,6 +674,7 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     ap.add_argument('--configs', default='all', choices=['all', 'none'], help='N=1: also measure every BASELINE config')
     ap.add_argument('--c4-sequences', type=int, default=256, help='sequences per batch of the motion-denoising config')
+    ap.add_argument('--c4-batches', type=int, default=0, help='batches to time (0 = the whole config: 8192 sequences)')
     ap.add_argument('--c5-images', type=int, default=131072, help='images on this GPU for the SMPLify config')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -67,6 +67,9 @@ struct dpb_lbs {
   int sb_vp = 0, sb_smem = 0;     // V padded to 64; dynamic shared memory of the kernel
   __half* wT16 = nullptr;         // [128, 2*sb_vp] fp16 [hi | lo]: rows < J = weights^T, row J = ones
   CUtensorMap tm_wT;
+  int32_t* csr_ptr = nullptr;     // [J+1] per-joint vertex lists of the sparse weights (V <= 1024: compact sets)
+  int32_t* csr_v = nullptr;
+  float* csr_w = nullptr;
   // joints-only mode on the tensor cores: the n_need vertices the extra joints / landmarks read, as a body model of
   // their own (same joints, shape and pose spaces; vertex i = need_vids[i]) -- every vertex kernel runs on it unchanged
   dpb_lbs* sub = nullptr;
@@ -124,6 +127,8 @@ int lbs_bwd_rowscale(dpb_lbs* h, const float* g_verts, const float* gextra, bool
                      cudaStream_t st);
 int lbs_skin_bwd_tc(dpb_lbs* h, const float* vposed, const float* g_verts, const float* gextra, bool have_extra,
                     float* gA, float* gbt, const float* scale, int64_t B, cudaStream_t st);
+int lbs_skin_bwd_small(dpb_lbs* h, const float* vposed, const float* g_verts, float* gA, float* gbt, int64_t B,
+                       cudaStream_t st);
 int lbs_bwd_prepare(dpb_lbs* h, const dpb_body_tensors* m);
 void lbs_bwd_release(dpb_lbs* h);
 }  // namespace dpb

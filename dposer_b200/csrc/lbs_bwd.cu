@@ -557,7 +557,11 @@ static int bwd_vertex_pass_tc(dpb_lbs* hv, bool const_tail, const LbsWs& w, cons
   DPB_CUDA_CHECK(cudaMemsetAsync(gvp16, 0, (size_t)B * 2 * hv->bt_rp * 2, st));
   rc = lbs_bwd_rowscale(hv, g_verts, gextra, have_extra, scale, B, st);
   if (rc == DPB_OK) rc = lbs_tc_skin_adjoint(hv, w.A, w.skinop, g_verts, gextra, have_extra, scale, gvp16, B, st);
-  if (rc == DPB_OK) rc = lbs_skin_bwd_tc(hv, vposed, g_verts, gextra, have_extra, w.gA, w.gbeta, scale, B, st);
+  if (rc == DPB_OK) {
+    // dL/dA: the GEMM, or for small vertex sets without extra cotangents (the compact set) the per-joint vertex lists
+    if (hv->csr_ptr && !have_extra) rc = lbs_skin_bwd_small(hv, vposed, g_verts, w.gA, w.gbeta, B, st);
+    else rc = lbs_skin_bwd_tc(hv, vposed, g_verts, gextra, have_extra, w.gA, w.gbeta, scale, B, st);
+  }
   if (rc != DPB_OK) return rc;
   return lbs_blendT_tc(hv, gvp16, scale, gout, w.gfeat, w.gbeta, B, st);
 }

@@ -21,6 +21,7 @@
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "lbs.h"
@@ -236,6 +237,25 @@ lbs_skin_bwd_tc_kernel(const __grid_constant__ Params p, const __grid_constant__
 int lbs_skin_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   const int V = h->V, J = h->J;
   h->sb_ready = false;
+  if (V <= 1024) {   // small vertex sets: per-joint vertex lists for lbs_skin_bwd_small_kernel
+    std::vector<int32_t> ptr(J + 1, 0), vs;
+    std::vector<float> ws;
+    for (int j = 0; j < J; ++j) {
+      for (int v = 0; v < V; ++v) {
+        const float x = m->lbs_weights[(size_t)v * J + j];
+        if (x != 0.f) { vs.push_back(v); ws.push_back(x); }
+      }
+      ptr[j + 1] = (int32_t)vs.size();
+    }
+    DPB_CUDA_CHECK(cudaMalloc((void**)&h->csr_ptr, ptr.size() * 4));
+    DPB_CUDA_CHECK(cudaMalloc((void**)&h->csr_v, std::max<size_t>(vs.size(), 1) * 4));
+    DPB_CUDA_CHECK(cudaMalloc((void**)&h->csr_w, std::max<size_t>(ws.size(), 1) * 4));
+    DPB_CUDA_CHECK(cudaMemcpy(h->csr_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+    if (!vs.empty()) {
+      DPB_CUDA_CHECK(cudaMemcpy(h->csr_v, vs.data(), vs.size() * 4, cudaMemcpyHostToDevice));
+      DPB_CUDA_CHECK(cudaMemcpy(h->csr_w, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
   if (J >= 128) return DPB_OK;                          // needs a spare row for the ones
   h->sb_vp = (V + 63) / 64 * 64;
   const size_t ld = (size_t)2 * h->sb_vp;
@@ -261,7 +281,58 @@ int lbs_skin_bwd_tc_prepare(dpb_lbs* h, const dpb_body_tensors* m) {
   return DPB_OK;
 }
 
+namespace lsb {
+// dL/dA for SMALL vertex sets (the compact set of the joints-only mode: 21 / 174 vertices): the GEMM above is all
+// prologue and drain there (2.1 ms per 131 072 poses for three slabs per CTA).  One block per pose; the pose's cotangents
+// and blended vertices sit in shared memory; thread = one of the J x 12 outputs walks the joint's vertex list (CSR of the
+// sparse weights, ascending vertex order: deterministic).
+__global__ void __launch_bounds__(256) lbs_skin_bwd_small_kernel(
+    const float* __restrict__ vposed, const float* __restrict__ g_verts, const int32_t* __restrict__ csr_ptr,
+    const int32_t* __restrict__ csr_v, const float* __restrict__ csr_w, int V, int J, int S, float* __restrict__ gA,
+    float* __restrict__ gbt, int64_t B) {
+  extern __shared__ float sm[];
+  float* g = sm;               // [V,3]
+  float* x = sm + (size_t)V * 3;
+  const int64_t b = blockIdx.x;
+  for (int i = threadIdx.x; i < V * 3; i += 256) {
+    g[i] = g_verts[(size_t)b * V * 3 + i];
+    x[i] = vposed[(size_t)b * V * 3 + i];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < J * 12; o += 256) {
+    const int j = o / 12, e = o % 12;
+    const int a = e < 9 ? e / 3 : e - 9, c = e % 3;
+    float acc = 0.f;
+    for (int k = csr_ptr[j]; k < csr_ptr[j + 1]; ++k) {
+      const int v = csr_v[k];
+      const float t = csr_w[k] * g[v * 3 + a];
+      acc = fmaf(t, e < 9 ? x[v * 3 + c] : 1.0f, acc);
+    }
+    gA[((size_t)b * J + j) * 12 + e] = acc;
+  }
+  if (threadIdx.x < 3) {       // translation cotangent = sum_v g (ascending vertex order)
+    float acc = 0.f;
+    for (int v = 0; v < V; ++v) acc += g[v * 3 + threadIdx.x];
+    gbt[(size_t)b * (S + 3) + S + threadIdx.x] += acc;
+  }
+}
+}  // namespace lsb
+
+int lbs_skin_bwd_small(dpb_lbs* h, const float* vposed, const float* g_verts, float* gA, float* gbt, int64_t B,
+                       cudaStream_t st) {
+  const size_t smem = (size_t)h->V * 6 * 4;
+  lsb::lbs_skin_bwd_small_kernel<<<(unsigned)B, 256, smem, st>>>(vposed, g_verts, h->csr_ptr, h->csr_v, h->csr_w, h->V,
+                                                               h->J, h->S, gA, gbt, B);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
 void lbs_skin_bwd_tc_release(dpb_lbs* h) {
+  if (h->csr_ptr) cudaFree(h->csr_ptr);
+  if (h->csr_v) cudaFree(h->csr_v);
+  if (h->csr_w) cudaFree(h->csr_w);
+  h->csr_ptr = h->csr_v = nullptr;
+  h->csr_w = nullptr;
   if (h->wT16) cudaFree(h->wT16);
   h->wT16 = nullptr;
   h->sb_ready = false;
