@@ -14,28 +14,28 @@ import torch
 from scipy import integrate
 
 from . import _lib as L
-from . import sde_lib
 from . import utils as mutils
 
 
 def drift_and_div(model, sde, x, t, epsilon, ws=None):
     """(drift [B,63], div [B]) of the probability-flow ODE at the batch-uniform time ``t`` (python float)."""
     L.require_cuda(x, 'x')
-    if not isinstance(sde, (sde_lib.VPSDE, sde_lib.subVPSDE)):
-        raise NotImplementedError('likelihood runs on VPSDE / subVPSDE')
     B = x.shape[0]
-    ps = mutils.prior_scalars(sde, model, float(t), continuous=True)
     tt = torch.tensor([float(t)], dtype=torch.float32)
+    # score = m * raw and the time label, evaluated by the same helper that builds the samplers' step tables
+    # (VP / subVP: m = -1 / (sigma std), label = 999 t;  VE: m = +1 / sigma, label = sigma(t))
+    coef, label = mutils.em_coefficients(sde, model, tt, probability_flow=True, continuous=True)
+    m = float(coef[0, 5])
     fx, g = sde.sde(torch.ones(1, 1), tt)                  # f(x,t) = fx * x   (host fp32, like the reference's scalars)
     fx, g2 = float(fx[0, 0]), float(g[0] ** 2)
-    table = model.time_table(ps['label'])
+    table = model.time_table(label)
     h = model.handle()
     if ws is None:
         ws = torch.empty(int(L.load().dpb_score_jvp_workspace_bytes(h.ptr, B)), dtype=torch.uint8, device=x.device)
     score = torch.empty_like(x)
     jv = torch.empty_like(x)
     xc, ec = x.contiguous(), epsilon.contiguous()
-    L.check(L.load().dpb_score_jvp(h.ptr, L.ptr(xc), L.ptr(ec), L.ptr(table[0]), None, None, -ps['inv_sigma_std'],
+    L.check(L.load().dpb_score_jvp(h.ptr, L.ptr(xc), L.ptr(ec), L.ptr(table[0]), None, None, m,
                                    L.ptr(score), L.ptr(jv), B, L.ptr(ws), ws.numel(), L.current_stream(x.device)))
     drift = fx * xc - 0.5 * g2 * score
     div = fx * (ec * ec).sum(dim=1) - 0.5 * g2 * (jv * ec).sum(dim=1)

@@ -38,9 +38,16 @@ def create_mask(body_poses, part='legs', observation_type='noise'):
     mask = body_poses.new_ones(body_poses.shape)
     mask[:, idx] = 0
     observation = body_poses.clone()
-    if observation_type != 'noise':
-        raise NotImplementedError("only observation_type='noise' is supported (mean-pose fill needs rot6d)")
-    observation[:, idx] = torch.randn_like(observation[:, idx])
+    if observation_type == 'noise':
+        observation[:, idx] = torch.randn_like(observation[:, idx])
+    else:
+        # the SMPL mean pose on the masked joints (misc.py:43-53): 'pose'[6:] of the reference's smpl_mean_params.npz
+        # (23 joints x rot6d), shipped in dposer_b200/data
+        from .transforms import rot6d_to_axis_angle
+        mean6 = torch.tensor(np.load(os.path.join(_DATA, 'smpl_mean_params.npz'))['pose'][6:], dtype=torch.float32,
+                             device=body_poses.device)
+        fill = rot6d_to_axis_angle(mean6.reshape(-1, 6)).reshape(-1) if rot_n == 3 else mean6
+        observation[:, idx] = fill[None, idx].repeat(body_poses.shape[0], 1)
     return mask, observation
 
 
@@ -60,21 +67,21 @@ def gaussian_smoothing(data, window_size, sigma):
 
 
 class Posenormalizer:
-    """lib/dataset/AMASS.py:187-259, axis-angle representation.  ``data_path`` may be the reference's
-    ``.../train`` directory (with axis_normalize{1,2}.pt) or None for the AMASS statistics shipped in
-    dposer_b200/data/amass_stats.npz (extracted from the reference's own files)."""
+    """lib/dataset/AMASS.py:187-259.  ``data_path`` may be the reference's ``.../train`` directory (with
+    {axis,rot6d}_normalize{1,2}.pt) or None for the AMASS statistics shipped in dposer_b200/data/amass_stats[_rot6d].npz
+    (extracted from the reference's own files).  ``rot_rep='rot6d'`` normalises 126-D poses (``from_axis`` / ``to_axis``
+    convert at the boundary, AMASS.py:200-201,254-256); the score-net kernels themselves are built for the shipped 63-D
+    axis-angle geometry only."""
 
     def __init__(self, data_path=None, device='cuda:0', normalize=True, min_max=True, rot_rep=None):
         assert rot_rep in ['rot6d', 'axis']
-        if rot_rep != 'axis':
-            raise NotImplementedError("rot_rep='rot6d' is out of scope (shipped config uses 'axis')")
         self.normalize, self.min_max, self.rot_rep = normalize, min_max, rot_rep
-        if data_path is not None and os.path.exists(os.path.join(data_path, 'axis_normalize1.pt')):
-            p1 = torch.load(os.path.join(data_path, 'axis_normalize1.pt'))
-            p2 = torch.load(os.path.join(data_path, 'axis_normalize2.pt'))
+        if data_path is not None and os.path.exists(os.path.join(data_path, f'{rot_rep}_normalize1.pt')):
+            p1 = torch.load(os.path.join(data_path, f'{rot_rep}_normalize1.pt'))
+            p2 = torch.load(os.path.join(data_path, f'{rot_rep}_normalize2.pt'))
             vals = [p1['min_poses'], p1['max_poses'], p2['mean_poses'], p2['std_poses']]
         else:
-            s = np.load(os.path.join(_DATA, 'amass_stats.npz'))
+            s = np.load(os.path.join(_DATA, 'amass_stats.npz' if rot_rep == 'axis' else 'amass_stats_rot6d.npz'))
             vals = [torch.tensor(s[k]) for k in ('min_poses', 'max_poses', 'mean_poses', 'std_poses')]
         self.min_poses, self.max_poses, self.mean_poses, self.std_poses = [v.to(device) for v in vals]
 
@@ -86,6 +93,9 @@ class Posenormalizer:
 
     def offline_normalize(self, poses, from_axis=False):
         assert len(poses.shape) in (2, 3)
+        if from_axis and self.rot_rep == 'rot6d':
+            from .transforms import axis_angle_to_rot6d
+            poses = axis_angle_to_rot6d(poses.reshape(-1, 3)).reshape(*poses.shape[:-1], -1)
         if not self.normalize:
             return poses
         if self.min_max:
@@ -96,13 +106,17 @@ class Posenormalizer:
 
     def offline_denormalize(self, poses, to_axis=False):
         assert len(poses.shape) in (2, 3)
-        if not self.normalize:
-            return poses
-        if self.min_max:
-            lo, hi = self._stats(poses, self.min_poses, self.max_poses)
-            return 0.5 * ((poses + 1) * (hi - lo) + 2 * lo)
-        mean, std = self._stats(poses, self.mean_poses, self.std_poses)
-        return poses * std + mean
+        if self.normalize:
+            if self.min_max:
+                lo, hi = self._stats(poses, self.min_poses, self.max_poses)
+                poses = 0.5 * ((poses + 1) * (hi - lo) + 2 * lo)
+            else:
+                mean, std = self._stats(poses, self.mean_poses, self.std_poses)
+                poses = poses * std + mean
+        if to_axis and self.rot_rep == 'rot6d':
+            from .transforms import rot6d_to_axis_angle
+            poses = rot6d_to_axis_angle(poses.reshape(-1, 6)).reshape(*poses.shape[:-1], -1)
+        return poses
 
 
 def shard_range(total, num_replicas, rank):

@@ -39,7 +39,7 @@ def get_sampling_fn(config, sde, shape, inverse_scaler, eps, device=None, return
         # reverse_diffusion / ancestral_sampling (sampling.py:210-259): the reference's own pc_sampler cannot drive them
         # (update_fn arity, sampling.py:215 vs :361 -- SURVEY 2 row 4); here they are two more coefficient tables of the
         # same fused kernel, pinned against the reference classes called directly (sde_variants_golden.npz)
-        if pred == 'ancestral_sampling' and not isinstance(sde, sde_lib.VPSDE):
+        if pred == 'ancestral_sampling' and not isinstance(sde, (sde_lib.VPSDE, sde_lib.VESDE)):
             raise NotImplementedError(f'SDE class {sde.__class__.__name__} not yet supported.')   # sampling.py:229
         if corr not in _CORRECTORS:
             raise NotImplementedError(f'corrector {corr!r} is not supported')

@@ -203,7 +203,7 @@ class VESDE(SDE):
 
     def discretize(self, x, t):
         timestep = (t * (self.N - 1) / self.T).long()
-        sigma = self.discrete_sigmas.to(t.device)[timestep]
-        adjacent = torch.where(timestep == 0, torch.zeros_like(t),
-                               self.discrete_sigmas[timestep - 1].to(t.device))
+        sigmas = self.discrete_sigmas.to(t.device)
+        sigma = sigmas[timestep]
+        adjacent = torch.where(timestep == 0, torch.zeros_like(t), sigmas[timestep - 1])
         return torch.zeros_like(x), torch.sqrt(sigma ** 2 - adjacent ** 2)

@@ -4,8 +4,9 @@ Data-preparation utilities (not on the hot path): plain torch ops on whatever de
 reference builds them on third-party ``torchgeometry`` (``angle_axis_to_rotation_matrix`` /
 ``rotation_matrix_to_angle_axis``), which is not installable offline -- PARITY UNPINNED: they are checked by
 properties (round trips, orthonormality, agreement with the LBS oracle's Rodrigues), not against the reference.
-The hot-path kernels take the shipped ``rot_rep='axis'`` (63-D) configuration only; ``Posenormalizer(rot_rep='rot6d')``
-keeps raising (a 126-D score net would need its own first / last layer geometry)."""
+``misc.Posenormalizer(rot_rep='rot6d')`` and ``misc.create_mask(observation_type='mean')`` call them at the data boundary;
+the hot-path kernels take the shipped ``rot_rep='axis'`` (63-D) configuration only (a 126-D score net would need its own
+first / last layer geometry)."""
 import torch
 import torch.nn.functional as F
 

@@ -90,51 +90,68 @@ def em_coefficients(sde, model, t, probability_flow=False, continuous=True, pred
       euler_maruyama      sampling.py:182-188 with sde_lib.py:98-106 and utils.py:152-162
       reverse_diffusion   sampling.py:210-220 with RSDE.discretize sde_lib.py:108-114 (f, G from SDE.discretize :52-69, or
                           VPSDE's DDPM rule :129-134); the reference's probability-flow factor there is 1.0, not 0.5
-      ancestral_sampling  sampling.py:223-259, VPSDE only (x + beta score) / sqrt(1 - beta) + sqrt(beta) z
+      ancestral_sampling  sampling.py:223-259, VPSDE (x + beta score) / sqrt(1 - beta) + sqrt(beta) z, VESDE the SMLD rule
+    VESDE (sde_lib.py:234-295) takes the same three forms with score = +raw / sigma and labels = sigma(t).
     Returns (coef [n,8], labels [n]).
     """
     if predictor not in ('euler_maruyama', 'reverse_diffusion', 'ancestral_sampling'):
         raise NotImplementedError(f'predictor {predictor!r} is not supported')
-    if not _is_vp(sde):
-        raise NotImplementedError('samplers support VPSDE / subVPSDE; VESDE is served by get_score_fn only')
+    ve = isinstance(sde, sde_lib.VESDE)
+    if not (_is_vp(sde) or ve):
+        raise NotImplementedError(f'SDE class {sde.__class__.__name__} not yet supported.')
     t = t.to(torch.float32).cpu()
     one = torch.ones(t.numel(), 1)
-    fx, g = sde.sde(one, t)                     # drift for x = 1  ->  f(x,t) = fx * x
+    fx, g = sde.sde(one, t)                     # drift for x = 1  ->  f(x,t) = fx * x  (0 for VE)
     fx = fx[:, 0]
-    if continuous or isinstance(sde, sde_lib.subVPSDE):
-        labels = t * 999
-        std_score = sde.marginal_prob(torch.zeros(t.numel(), 1), t)[1]
+    # m: score = m * raw, raw = post_dense output before the sigma division (utils.py:127-180)
+    if ve:
+        labels = sde.marginal_prob(one, t)[1] if continuous else torch.round((sde.T - t) * (sde.N - 1))
+        m = 1.0 / sigma_at(model, labels)
     else:
-        labels = t * (sde.N - 1)
-        std_score = sde.sqrt_1m_alphas_cumprod[labels.long()]
-    sig = sigma_at(model, labels)
+        if continuous or isinstance(sde, sde_lib.subVPSDE):
+            labels = t * 999
+            std_score = sde.marginal_prob(torch.zeros(t.numel(), 1), t)[1]
+        else:
+            labels = t * (sde.N - 1)
+            std_score = sde.sqrt_1m_alphas_cumprod[labels.long()]
+        m = -1.0 / (sigma_at(model, labels) * std_score)
     if predictor == 'euler_maruyama':
         dt = -1. / sde.N
         w = 0.5 if probability_flow else 1.0
         a = 1.0 + fx * dt
-        b = (g ** 2) * w * dt / (sig * std_score)    # score = -raw/(sig*std): -g^2*score*w*dt = +g^2 w dt raw/(sig std)
+        b = -(g ** 2) * w * dt * m                   # x + (f - g^2 w score) dt
         c = torch.zeros_like(g) if probability_flow else g * float(np.sqrt(-dt))
     elif predictor == 'reverse_diffusion':
+        ts = (t * (sde.N - 1) / sde.T).long()
         if isinstance(sde, sde_lib.VPSDE):           # DDPM discretisation: f = (sqrt(alpha) - 1) x, G = sqrt(beta)
-            ts = (t * (sde.N - 1) / sde.T).long()
-            beta = sde.discrete_betas[ts]
-            fd, G = torch.sqrt(sde.alphas[ts]) - 1.0, torch.sqrt(beta)
+            fd, G = torch.sqrt(sde.alphas[ts]) - 1.0, torch.sqrt(sde.discrete_betas[ts])
+        elif ve:                                     # SMLD discretisation (sde_lib.py:277-285): f = 0, G^2 = sigma_i^2 - sigma_{i-1}^2
+            sg = sde.discrete_sigmas[ts]
+            adj = torch.where(ts == 0, torch.zeros_like(sg), sde.discrete_sigmas[ts - 1])
+            fd, G = torch.zeros_like(sg), torch.sqrt(sg ** 2 - adj ** 2)
         else:                                        # f = drift / N, G = diffusion * sqrt(1 / N)
             fd, G = fx * (1. / sde.N), g * torch.sqrt(torch.tensor(1. / sde.N))
         a = 1.0 - fd                                 # x_mean = x - (f - G^2 score)
-        b = -(G ** 2) / (sig * std_score)
+        b = (G ** 2) * m
         c = torch.zeros_like(G) if probability_flow else G
     else:
-        if not isinstance(sde, sde_lib.VPSDE):
+        if not isinstance(sde, (sde_lib.VPSDE, sde_lib.VESDE)):
             raise NotImplementedError(f'SDE class {sde.__class__.__name__} not yet supported.')
         assert not probability_flow, 'Probability flow not supported by ancestral sampling'
-        beta = sde.discrete_betas[(t * (sde.N - 1) / sde.T).long()]
-        r = 1.0 / torch.sqrt(1. - beta)
-        a, b, c = r, -beta * r / (sig * std_score), torch.sqrt(beta)
+        ts = (t * (sde.N - 1) / sde.T).long()
+        if ve:                                       # sampling.py:232-241
+            sg = sde.discrete_sigmas[ts]
+            adj = torch.where(ts == 0, torch.zeros_like(sg), sde.discrete_sigmas[ts - 1])
+            d2 = sg ** 2 - adj ** 2
+            a, b, c = torch.ones_like(sg), d2 * m, torch.sqrt(adj ** 2 * d2 / sg ** 2)
+        else:                                        # sampling.py:243-251
+            beta = sde.discrete_betas[ts]
+            r = 1.0 / torch.sqrt(1. - beta)
+            a, b, c = r, beta * r * m, torch.sqrt(beta)
     mean1, std_m = sde.marginal_prob(one, t)     # imputation: alpha*obs + std*z (sampling.py:415-416)
     coef = torch.zeros(t.numel(), L.COEF_STRIDE)
     coef[:, 0], coef[:, 1], coef[:, 2], coef[:, 3], coef[:, 4] = a, b, c, mean1[:, 0], std_m
-    coef[:, 5] = -1.0 / (sig * std_score)        # score = raw * coef[5]  (the Langevin corrector's gradient, utils.py:152-162)
+    coef[:, 5] = m                               # score = raw * coef[5]  (the Langevin corrector's gradient)
     return coef, labels
 
 

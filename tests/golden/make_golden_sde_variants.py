@@ -58,6 +58,30 @@ def main():
             torch.manual_seed(999)
             noise = torch.stack([torch.randn(B, 63) for _ in range(N)])
             out.update({f'{tag}_noise': noise.numpy(), f'{tag}_out': xm.numpy(), f'{tag}_last': xx.numpy()})
+    # VESDE through the same three predictors (sde_lib.py:234-295; score_fn utils.py:164-180: labels = sigma(t), no std
+    # division): Euler-Maruyama through the reference's own pc_sampler, the other two called directly, draws replayed
+    with torch.no_grad():
+        ve8 = G.sde_lib.VESDE(0.01, 50., N=N)
+        sfn = G.sampling.get_sampling_fn(cfg, ve8, (B, 63), lambda v: v, 1e-5, device='cpu')
+        zv = z0 * 50.
+        torch.manual_seed(2468)
+        traj, xm = sfn(model, z=zv.clone())
+        torch.manual_seed(2468)
+        noise = torch.stack([torch.randn(B, 63) for _ in range(N)])
+        out.update(ve_em_z0=zv.numpy(), ve_em_noise=noise.numpy(), ve_em_out=xm.numpy(), ve_em_last=traj[-1].numpy())
+        for tag, cls in [('ve_rd', G.sampling.ReverseDiffusionPredictor), ('ve_anc', G.sampling.AncestralSamplingPredictor)]:
+            score_fn = G.mutils.get_score_fn(ve8, model, train=False, continuous=True)
+            sf = lambda xx, tt, _f=score_fn: _f(xx, tt, None, None)   # noqa: E731
+            pred = cls(ve8, sf, False)
+            if hasattr(pred, 'rsde'):
+                pred.rsde = ve8.reverse(lambda xx, tt, c=None, m=None, _f=score_fn: _f(xx, tt, c, m), False)
+            xx = zv.clone()
+            torch.manual_seed(1357)
+            for tt in torch.linspace(ve8.T, 1e-5, ve8.N):
+                xx, xm = pred.update_fn(xx, torch.ones(B) * tt)
+            torch.manual_seed(1357)
+            noise = torch.stack([torch.randn(B, 63) for _ in range(N)])
+            out.update({f'{tag}_noise': noise.numpy(), f'{tag}_out': xm.numpy(), f'{tag}_last': xx.numpy()})
     # likelihood / latent code under the probability-flow ODE (likelihood.py:40-113), Rademacher probe replayed
     from lib.algorithms.advanced import likelihood as ref_lik
     sub1000 = G.sde_lib.subVPSDE(0.1, 20., N=1000)

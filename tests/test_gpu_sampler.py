@@ -240,6 +240,29 @@ def test_other_predictors_vs_reference_golden(gpu_model, tag, sde_name, pred, en
     assert max_rel(traj[-1], g[f'{tag}_last']) < tol
 
 
+@pytest.mark.parametrize('tag,pred', [('ve_em', 'euler_maruyama'), ('ve_rd', 'reverse_diffusion'),
+                                      ('ve_anc', 'ancestral_sampling')])
+@pytest.mark.parametrize('engine,tol', [(L.ENGINE_FP32, 5e-5), (L.ENGINE_TC, 1e-3)])
+def test_vesde_predictors_vs_reference_golden(gpu_model, tag, pred, engine, tol):
+    """VESDE (sde_lib.py:234-295; score = +raw / sigma with labels = sigma(t), utils.py:164-180) through the three
+    predictors as coefficient tables of the fused sampler: 8 steps from 50 z, draws replayed, against the REAL
+    reference (its own pc_sampler for Euler-Maruyama, the predictor classes called directly for the other two)."""
+    g = golden('sde_variants_golden.npz')
+    N, B = 8, 5
+    cfg = synthetic.default_config()
+    cfg.sampling.predictor = pred
+    sde = sde_lib.VESDE(0.01, 50., N)
+    fn = sampling.get_sampling_fn(cfg, sde, (B, 63), lambda x: x, 1e-5, device='cuda')
+    noise = torch.tensor(g[f'{tag}_noise'])[:, None].cuda()
+    gpu_model.engine = engine
+    try:
+        traj, out = fn(gpu_model, z=torch.tensor(g['ve_em_z0']), noise=noise)
+    finally:
+        gpu_model.engine = L.ENGINE_AUTO
+    assert max_rel(out, g[f'{tag}_out']) < tol
+    assert max_rel(traj[-1], g[f'{tag}_last']) < tol
+
+
 def test_likelihood_function_evaluation_vs_reference_golden(gpu_model):
     """One ODE function evaluation of the likelihood (drift + Hutchinson divergence, likelihood.py:26-37,58-66) against
     the REAL reference's autograd: dpb_score_jvp's eps . (J eps) is the reference's eps . (J^T eps)."""

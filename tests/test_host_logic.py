@@ -79,6 +79,31 @@ def test_em_coefficients_reproduce_the_reference_update(oracle_sd):
             assert coef[i, 3] == mean[0, 0] and coef[i, 4] == std[0]
 
 
+@pytest.mark.parametrize('sde_name,tag,pred', [('ve', 've_em', 'euler_maruyama'), ('ve', 've_rd', 'reverse_diffusion'),
+                                               ('ve', 've_anc', 'ancestral_sampling'), ('vp', 'vp_rd', 'reverse_diffusion'),
+                                               ('vp', 'vp_anc', 'ancestral_sampling'), ('sub', 'sub_rd', 'reverse_diffusion')])
+def test_predictor_tables_reproduce_reference_chains(oracle_sd, sde_name, tag, pred):
+    """The per-step (a, b, c) tables of every predictor / SDE pair, iterated on the CPU with the oracle's network output
+    as ``raw``, land on the REAL reference's 8-step chains (sde_variants_golden.npz, replayed draws)."""
+    g = golden('sde_variants_golden.npz')
+    model = synthetic.make_score_model(42)
+    if sde_name == 've':
+        sde, eps, start, z0 = sde_lib.VESDE(0.01, 50., 8), 1e-5, 0, g['ve_em_z0']
+    else:
+        sde = sde_lib.VPSDE(0.1, 20., 1000) if sde_name == 'vp' else sde_lib.subVPSDE(0.1, 20., 1000)
+        eps, start, z0 = 1e-3, 992, g['vp_em_z0']
+    ts = mutils.timestep_grid(sde, eps)[start:]
+    coef, labels = mutils.em_coefficients(sde, model, ts, False, True, predictor=pred)
+    x = torch.tensor(z0)
+    noise = torch.tensor(g[f'{tag}_noise'])
+    for i in range(8):
+        raw = S.score_model_forward(oracle_sd, x, torch.ones(x.shape[0]) * labels[i], scale_by_sigma=False)
+        xm = coef[i, 0] * x + coef[i, 1] * raw
+        x = xm + coef[i, 2] * noise[i]
+    assert (xm - torch.tensor(g[f'{tag}_out'])).abs().max() <= 2e-4 * np.abs(g[f'{tag}_out']).max()
+    assert (x - torch.tensor(g[f'{tag}_last'])).abs().max() <= 2e-4 * np.abs(g[f'{tag}_last']).max()
+
+
 def test_prior_scalars_match_oracle():
     model = synthetic.make_score_model()
     sde, osde = sde_lib.subVPSDE(0.1, 20., 1000), S.SubVP()
@@ -133,8 +158,40 @@ def test_normalizer_roundtrip_and_stats():
     gen = torch.Generator().manual_seed(5)
     x7 = norm.offline_normalize(toy[:7]) + 0.3 * torch.randn(7, 63, generator=gen)
     assert np.array_equal(x7.numpy(), g['x'])
-    with pytest.raises(NotImplementedError):
-        misc.Posenormalizer(None, device='cpu', rot_rep='rot6d')
+
+
+def test_normalizer_rot6d_and_mean_pose_observation():
+    """Posenormalizer(rot_rep='rot6d') (AMASS.py:187-259 with the reference's own rot6d statistics) and create_mask's
+    mean-pose observation (misc.py:43-53).  The rot6d conversion itself is the restated torchgeometry path (unpinned)."""
+    from dposer_b200 import transforms as T
+    toy = synthetic.toy_poses()[:64]
+    for min_max in (False, True):
+        norm = misc.Posenormalizer(None, device='cpu', normalize=True, min_max=min_max, rot_rep='rot6d')
+        assert norm.mean_poses.shape == (126,) and norm.min_poses.shape == (126,)
+        x = norm.offline_normalize(toy, from_axis=True)
+        assert x.shape == (64, 126) and torch.isfinite(x).all()
+        r6 = T.axis_angle_to_rot6d(toy.reshape(-1, 3)).reshape(64, 126)
+        ref = (2 * (r6 - norm.min_poses) / (norm.max_poses - norm.min_poses) - 1) if min_max else \
+            (r6 - norm.mean_poses) / norm.std_poses
+        assert torch.equal(x, ref)
+        assert (norm.offline_denormalize(x) - r6).abs().max() < 1e-5
+        back = norm.offline_denormalize(x, to_axis=True)
+        assert (back - toy).abs().max() < 5e-4                # fp32 round trip; AMASS body poses are far from the pi branch
+        x3 = norm.offline_normalize(toy[None].repeat(2, 1, 1), from_axis=True)      # [t, b, dim]
+        assert torch.equal(x3[1], x)
+    # AMASS-like data should look standardised under the reference's mean / std
+    norm = misc.Posenormalizer(None, device='cpu', normalize=True, min_max=False, rot_rep='rot6d')
+    z = norm.offline_normalize(synthetic.toy_poses(), from_axis=True)
+    assert float(z.mean().abs()) < 0.5 and 0.3 < float(z.std()) < 3.0
+    # mean-pose observation: masked joints carry the SMPL mean pose, the rest is untouched
+    mean6 = torch.tensor(np.load(os.path.join(os.path.dirname(synthetic.__file__), 'data', 'smpl_mean_params.npz'))['pose'][6:])
+    for rot_n, data in ((3, toy), (6, r6)):
+        mask, obs = misc.create_mask(data, part='left_arm', observation_type='mean')
+        keep = mask.bool()
+        assert torch.equal(obs[keep], data[keep])
+        idx = (~keep[0]).nonzero().flatten()
+        fill = mean6.float() if rot_n == 6 else T.rot6d_to_axis_angle(mean6.float().reshape(-1, 6)).reshape(-1)
+        assert torch.equal(obs[:, idx], fill[idx][None].repeat(64, 1))
 
 
 def test_sde_objects_match_oracle_scalars():
