@@ -1,0 +1,233 @@
+// Split-fp16 GEMM on tcgen05 for the training step of the score network (reference: the nn.Linear forward / backward
+// that autograd runs under lib/algorithms/advanced/losses.py:61-137,187-275 -- y = x W^T + b, dX = dY W, dW = dY^T X).
+//
+//   C[m, n] = sum_k A[m, k] * B[n, k]  (+ bias1[n] + bias2[n] + add[m, n])
+//
+// Both operands are K-major fp16 [hi | lo] pairs (x = hi + lo, lo = fp16(x - hi)); three products hi.hi + lo.hi + hi.lo
+// accumulate in one fp32 TMEM tile (~1e-6 relative, the scheme every tensor-core kernel of this library uses), so the
+// result stands in for the reference's fp32 matmul.  Transposed products are formed from transposed operand copies
+// (split_kernel writes both layouts in one pass), which keeps one kernel and one shared-memory layout (SWIZZLE_128B).
+//
+//   warp 0     TMA producer: per k-block the four tiles A_hi, A_lo, B_hi, B_lo (64 KB stage, 3 stages)
+//   warp 1     TMEM allocator + MMA issuer: 12 UMMAs (M = 128, N = 128, K = 16) per stage
+//   warps 2-5  epilogue: TMEM -> registers -> C (thread = output row, 32 consecutive columns per TMEM load)
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+
+#include "score.h"
+#include "ptx.cuh"
+#include "train.h"
+
+namespace dpb {
+
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* ptr, uint64_t inner, uint64_t rows,
+                 uint32_t box_inner, uint32_t box_rows, size_t elem_bytes);  // score_tc.cu
+
+namespace gtc {
+
+constexpr int BK = 64;
+constexpr int TILE = 128 * BK * 2;      // 16 KB: [128 rows x 64 k] fp16, SWIZZLE_128B
+constexpr int ST = 3;                   // stages of four tiles
+constexpr int NUM_THREADS = 192;
+constexpr int OFF_BAR = ST * 4 * TILE;
+constexpr int NBARS = 2 * ST + 1;
+constexpr int SMEM_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;
+
+struct Params {
+  int M, N, kt;              // valid output extent, k-blocks of 64 per product
+  int a_r0, a_k0, a_lo;      // A operand: first row, first column of the hi half, column distance of the lo half
+  int b_r0, b_k0, b_lo;
+  float* C;
+  int64_t ldc;
+  const float* bias1;        // [N] or null
+  const float* bias2;        // [N] or null
+  const float* add;          // [M, ldadd] or null (may alias C)
+  int64_t ldadd;
+  int vec;                   // every pointer 16-byte aligned and every stride a multiple of 4: float4 epilogue
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap tm_a,
+                  const __grid_constant__ CUtensorMap tm_b) {
+  constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, 128, 0);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sb = ptx::smem_u32(smem);
+  const uint32_t bar = sb + OFF_BAR;
+  auto full = [&](uint32_t s) { return bar + 8u * s; };
+  auto empty = [&](uint32_t s) { return bar + 8u * (ST + s); };
+  const uint32_t dfull = bar + 8u * (2 * ST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBARS * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
+    ptx::mbar_init(dfull, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 128);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+
+  if (warp == 0) {
+    if (lane == 0) { ptx::prefetch_tmap(&tm_a); ptx::prefetch_tmap(&tm_b); }
+    __syncwarp();
+    uint32_t s = 0, ph = 0;
+    for (int k = 0; k < p.kt; ++k) {
+      ptx::mbar_wait(empty(s), ph ^ 1);
+      if (ptx::elect_one()) {
+        const uint32_t base = sb + s * 4 * TILE;
+        ptx::mbar_arrive_expect_tx(full(s), 4 * TILE);
+        ptx::tma_load_2d(base, &tm_a, full(s), p.a_k0 + k * BK, p.a_r0 + m0);
+        ptx::tma_load_2d(base + TILE, &tm_a, full(s), p.a_k0 + p.a_lo + k * BK, p.a_r0 + m0);
+        ptx::tma_load_2d(base + 2 * TILE, &tm_b, full(s), p.b_k0 + k * BK, p.b_r0 + n0);
+        ptx::tma_load_2d(base + 3 * TILE, &tm_b, full(s), p.b_k0 + p.b_lo + k * BK, p.b_r0 + n0);
+      }
+      __syncwarp();
+      if (++s == ST) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    uint32_t s = 0, ph = 0;
+    for (int k = 0; k < p.kt; ++k) {
+      ptx::mbar_wait(full(s), ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t ahi = ptx::umma_desc_sw128(sb + s * 4 * TILE), alo = ahi + (uint64_t)(TILE >> 4);
+        const uint64_t bhi = alo + (uint64_t)(TILE >> 4), blo = bhi + (uint64_t)(TILE >> 4);
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j) {
+          ptx::mma_f16_ss(tmem_base, alo + 2 * j, bhi + 2 * j, IDESC, (k == 0 && j == 0) ? 0u : 1u);
+          ptx::mma_f16_ss(tmem_base, ahi + 2 * j, blo + 2 * j, IDESC, 1u);
+          ptx::mma_f16_ss(tmem_base, ahi + 2 * j, bhi + 2 * j, IDESC, 1u);
+        }
+        ptx::mma_commit(empty(s));
+      }
+      __syncwarp();
+      if (++s == ST) { s = 0; ph ^= 1; }
+    }
+    if (ptx::elect_one()) ptx::mma_commit(dfull);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may read
+    const int m = m0 + q * 32 + lane;
+    ptx::mbar_wait(dfull, 0);
+    ptx::tc_fence_after();
+    const bool vec = p.vec != 0;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      ptx::tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (m >= p.M || nb >= p.N) continue;
+      float* crow = p.C + (size_t)m * p.ldc + nb;
+      const float* arow = p.add ? p.add + (size_t)m * p.ldadd + nb : nullptr;
+      if (vec && nb + 32 <= p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                 __uint_as_float(v[i + 3]));
+          if (p.bias1) { const float4 b = *reinterpret_cast<const float4*>(p.bias1 + nb + i); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (p.bias2) { const float4 b = *reinterpret_cast<const float4*>(p.bias2 + nb + i); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (arow) { const float4 b = *reinterpret_cast<const float4*>(arow + i); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          *reinterpret_cast<float4*>(crow + i) = o;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (nb + i < p.N) {
+            float o = __uint_as_float(v[i]);
+            if (p.bias1) o += p.bias1[nb + i];
+            if (p.bias2) o += p.bias2[nb + i];
+            if (arow) o += arow[i];
+            crow[i] = o;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// src fp32 [R, C] (row stride ld)  ->  row form  dst[(r0 + r), c0 + c | c0 + lo + c]   (stride dld, if dst)
+//                                      col form  dstT[(tr0 + c), tc0 + r | tc0 + tlo + r] (stride tld, if dstT)
+__global__ void split_kernel(const float* __restrict__ src, int R, int Cc, int64_t ld, __half* __restrict__ dst,
+                             int64_t dld, int r0, int c0, int lo, __half* __restrict__ dstT, int64_t tld, int tr0,
+                             int tc0, int tlo) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;           // bx: column block, by: row block
+  const int tx = threadIdx.x, ty = threadIdx.y;                   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = by + i, c = bx + tx;
+    float x = 0.f;
+    if (r < R && c < Cc) {
+      x = src[(size_t)r * ld + c];
+      if (dst) {
+        const __half hi = __float2half_rn(x);
+        __half* d = dst + (size_t)(r0 + r) * dld + c0 + c;
+        d[0] = hi;
+        d[lo] = __float2half_rn(x - __half2float(hi));
+      }
+    }
+    tile[i][tx] = x;
+  }
+  if (!dstT) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = bx + i, r = by + tx;
+    if (r < R && c < Cc) {
+      const float x = tile[tx][i];
+      const __half hi = __float2half_rn(x);
+      __half* d = dstT + (size_t)(tr0 + c) * tld + tc0 + r;
+      d[0] = hi;
+      d[tlo] = __float2half_rn(x - __half2float(hi));
+    }
+  }
+}
+
+}  // namespace gtc
+
+int gemm_tc_init() {
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(gtc::gemm_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
+  return DPB_OK;
+}
+
+int gemm_tc(const Op16& A, const Op16& B, int M, int N, int K, float* C, int64_t ldc, const float* bias1,
+            const float* bias2, const float* add, int64_t ldadd, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return DPB_OK;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A.ptr, (uint64_t)A.ld, (uint64_t)A.rows, gtc::BK, 128, 2);
+  if (rc != DPB_OK) return rc;
+  rc = make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, B.ptr, (uint64_t)B.ld, (uint64_t)B.rows, gtc::BK, 128, 2);
+  if (rc != DPB_OK) return rc;
+  gtc::Params p{};
+  p.M = M; p.N = N; p.kt = (K + gtc::BK - 1) / gtc::BK;
+  p.a_r0 = A.r0; p.a_k0 = A.k0; p.a_lo = A.lo;
+  p.b_r0 = B.r0; p.b_k0 = B.k0; p.b_lo = B.lo;
+  p.C = C; p.ldc = ldc; p.bias1 = bias1; p.bias2 = bias2; p.add = add; p.ldadd = ldadd;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.vec = al(C) && al(bias1) && al(bias2) && al(add) && (ldc & 3) == 0 && (!add || (ldadd & 3) == 0);
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + 127) / 128));
+  gtc::gemm_split_kernel<<<grid, gtc::NUM_THREADS, gtc::SMEM_BYTES, st>>>(p, ta, tb);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+int split16(const float* src, int R, int Cc, int64_t ld, const Op16* row, const Op16* col, cudaStream_t st) {
+  if (R <= 0 || Cc <= 0) return DPB_OK;
+  dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32)), block(32, 8);
+  gtc::split_kernel<<<grid, block, 0, st>>>(src, R, Cc, ld, row ? row->ptr : nullptr, row ? row->ld : 0, row ? row->r0 : 0,
+                                            row ? row->k0 : 0, row ? row->lo : 0, col ? col->ptr : nullptr,
+                                            col ? col->ld : 0, col ? col->r0 : 0, col ? col->k0 : 0, col ? col->lo : 0);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+}  // namespace dpb

@@ -1,0 +1,330 @@
+"""Loss, optimiser and one-step training / evaluation functions with the reference's call surface
+(lib/algorithms/advanced/losses.py:31-275), running on the native training path (csrc/train.cu + csrc/gemm_tc.cu).
+
+What differs from the reference, by construction:
+  * ``loss_fn`` evaluates the loss AND (for ``train=True``) writes every parameter's gradient into ``p.grad`` in ONE
+    native call -- the backward pass is hand-written, there is no autograd graph, so ``step_fn`` has no ``loss.backward()``;
+  * ``get_optimizer`` returns :class:`FlatAdam`, a ``torch.optim.Adam`` subclass (same ``param_groups`` / ``state_dict``
+    surface) whose parameters, gradients and moments are views into four flat buffers, so that gradient clipping + Adam
+    is one kernel chain and the EMA update another;
+  * the per-row time draws ``t`` come from torch's CPU generator (the schedule scalars are evaluated on the host in fp32
+    like everywhere else in this package); ``z`` and the dropout masks come from Philox on the device.  All three can be
+    passed in (``t=``, ``z=``, ``drop_mask=``) -- that is how the parity tests replay the reference's draws;
+  * the auxiliary v2v / j2j loss (``return_data=True``, "not recommended" in the reference's config) is not built.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import sde_lib
+from . import utils as mutils
+from .sde_lib import VESDE, VPSDE
+
+_DATA_DIM = L.POSE_DIM
+
+
+# ---------------------------------------------------------------------------------------------
+# native engine: one dpb_train handle per (model, batch size)
+# ---------------------------------------------------------------------------------------------
+def _f32p(t):
+    return C.cast(C.c_void_p(t.data_ptr()), L._f32p)
+
+
+def _tensor_struct(model, pick):
+    """dpb_train_tensors (device pointers) of the parameters (pick = lambda p: p.data) or gradients (lambda p: p.grad)."""
+    w = L.ScoreWeights()
+
+    def dp(p):
+        t = pick(p)
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
+        return _f32p(t)
+    w.pre_w, w.pre_b = dp(model.pre_dense.weight), dp(model.pre_dense.bias)
+    w.pre_t_w, w.pre_t_b = dp(model.pre_dense_t.weight), dp(model.pre_dense_t.bias)
+    w.pre_gn_w, w.pre_gn_b = dp(model.pre_gnorm.weight), dp(model.pre_gnorm.bias)
+    w.temb_w, w.temb_b = dp(model.shared_time_embed[0].weight), dp(model.shared_time_embed[0].bias)
+    names = [('b1_dense1', 'b1_gnorm1'), ('b1_dense2', 'b1_gnorm2'), ('b2_dense1', 'b2_gnorm1'), ('b2_dense2', 'b2_gnorm2')]
+    for i, (dn, gn) in enumerate(names):
+        w.blk_w[i], w.blk_b[i] = dp(getattr(model, dn).weight), dp(getattr(model, dn).bias)
+        w.blk_t_w[i], w.blk_t_b[i] = dp(getattr(model, dn + '_t').weight), dp(getattr(model, dn + '_t').bias)
+        w.blk_gn_w[i], w.blk_gn_b[i] = dp(getattr(model, gn).weight), dp(getattr(model, gn).bias)
+    w.post_w, w.post_b = dp(model.post_dense.weight), dp(model.post_dense.bias)
+    return w
+
+
+class _Engine:
+    def __init__(self, model, B, device):
+        from .model import embedding_freqs
+        if not model._geometry_ok:
+            raise NotImplementedError('the training kernels are built for the shipped geometry (63-D pose, hidden 1024, '
+                                      'embed 512, 2 blocks)')
+        self.B, self.device = int(B), device
+        self.freqs = embedding_freqs(L.EMBED).to(device=device, dtype=torch.float32).contiguous()
+        out = C.c_void_p()
+        L.check(L.load().dpb_train_create(C.byref(out), self.B, device.index or 0), 'dpb_train_create')
+        self.ptr = out
+        self.loss = torch.zeros(1, device=device)
+        self.loss_rows = torch.zeros(self.B, device=device)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'ptr', None):
+                L.load().dpb_train_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+def _engine(model, B, device):
+    eng = getattr(model, '_train_engine', None)
+    if eng is None or eng.B != int(B) or eng.device != device:
+        eng = _Engine(model, B, device)
+        model._train_engine = eng
+    return eng
+
+
+def native_loss(model, batch, rows, z=None, drop_mask=None, drop_p=0.0, seed=0, grads=True):
+    """One ``dpb_train_loss_grad`` call.  rows: host or device fp32 [6,B] (label, mean_c, std_c, res_c, z_c, row_w).
+    Returns the loss as a [] device tensor (a fresh copy); per-row losses stay in ``model._train_engine.loss_rows``."""
+    L.require_cuda(batch, 'batch')
+    dev = batch.device
+    B = batch.shape[0]
+    if batch.shape[1] != _DATA_DIM:
+        raise NotImplementedError('the training kernels take the 63-D axis-angle representation')
+    eng = _engine(model, B, dev)
+    batch = batch.detach().to(torch.float32).contiguous()
+    rows = rows.to(device=dev, dtype=torch.float32).contiguous()
+    assert rows.shape == (6, B)
+    P = _tensor_struct(model, lambda p: p.data)
+    P.emb_freqs = _f32p(eng.freqs)
+    G = None
+    if grads:
+        for p in model.parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        G = _tensor_struct(model, lambda p: p.grad)
+    if z is not None:
+        z = z.to(device=dev, dtype=torch.float32).contiguous()
+    if drop_mask is not None:
+        drop_mask = drop_mask.to(device=dev, dtype=torch.uint8).contiguous()
+        assert drop_mask.shape == (L.NUM_DENSE, B, L.HIDDEN)
+    L.check(L.load().dpb_train_loss_grad(eng.ptr, C.byref(P), C.byref(G) if G is not None else None, L.ptr(batch),
+                                         L.ptr(rows), L.ptr(z), L.ptr(drop_mask), float(drop_p), C.c_uint64(seed),
+                                         L.ptr(eng.loss), L.ptr(eng.loss_rows), L.current_stream(dev)))
+    return eng.loss[0].clone()
+
+
+# ---------------------------------------------------------------------------------------------
+# optimiser
+# ---------------------------------------------------------------------------------------------
+class FlatAdam(torch.optim.Adam):
+    """torch.optim.Adam (amsgrad off) over flat parameter / gradient / moment buffers; ``step`` is native."""
+
+    def __init__(self, params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
+        params = list(params)
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self._params = params
+        L.require_cuda(params[0], 'parameters')
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat_p = torch.empty(n, device=dev)
+        self.flat_g = torch.zeros(n, device=dev)
+        self.flat_m = torch.zeros(n, device=dev)
+        self.flat_v = torch.zeros(n, device=dev)
+        self._step = 0
+        self._scratch = torch.empty(int(L.load().dpb_train_adam_scratch_bytes()), dtype=torch.uint8, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.flat_p[off:off + k].view_as(p)
+                p.grad = self.flat_g[off:off + k].view_as(p)
+                off += k
+        self._publish_state()
+
+    def _views(self, flat):
+        out, off = [], 0
+        for p in self._params:
+            out.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return out
+
+    def _publish_state(self):
+        """Expose the moments through torch's per-parameter ``state`` so that ``state_dict()`` has the usual layout."""
+        for p, m, v in zip(self._params, self._views(self.flat_m), self._views(self.flat_v)):
+            self.state[p] = {'step': torch.tensor(float(self._step)), 'exp_avg': m, 'exp_avg_sq': v}
+
+    def zero_grad(self, set_to_none=True):
+        """Nothing to do: every gradient is overwritten by the next native backward pass (the views must stay)."""
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_clip=-1.0):
+        g = self.param_groups[0]
+        self._step += 1
+        L.check(L.load().dpb_train_adam(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
+                                        self.flat_p.numel(), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]),
+                                        float(g['eps']), float(g['weight_decay']), self._step, float(grad_clip),
+                                        L.ptr(self._scratch), L.current_stream(self.flat_p.device)))
+        for st in self.state.values():
+            st['step'] = torch.tensor(float(self._step))
+
+    def grad_norm(self):
+        """||g||_2 over all parameters (what clip_grad_norm_ returns); synchronises."""
+        L.check(L.load().dpb_train_grad_norm(L.ptr(self.flat_g), self.flat_g.numel(), L.ptr(self._scratch),
+                                             L.current_stream(self.flat_g.device)))
+        return float(self._scratch[:8].view(torch.float64)[0].sqrt())
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        steps = []
+        with torch.no_grad():
+            for p, m, v in zip(self._params, self._views(self.flat_m), self._views(self.flat_v)):
+                st = self.state.get(p)
+                if st:                                   # parameters torch never stepped (no gradient) have no entry
+                    m.copy_(st['exp_avg'])
+                    v.copy_(st['exp_avg_sq'])
+                    steps.append(int(float(st['step'])))
+                else:
+                    m.zero_()
+                    v.zero_()
+        self._step = max(steps) if steps else 0
+        self._publish_state()
+
+
+def get_optimizer(config, params):
+    """losses.py:31-41."""
+    if config.optim.optimizer == 'Adam':
+        return FlatAdam(params, lr=config.optim.lr, betas=(config.optim.beta1, 0.999), eps=config.optim.eps,
+                        weight_decay=config.optim.weight_decay)
+    raise NotImplementedError(f'Optimizer {config.optim.optimizer} not supported yet!')
+
+
+def optimization_manager(config):
+    """losses.py:44-57: warm-up, gradient clipping (disabled if negative), optimiser step."""
+
+    def optimize_fn(optimizer, params, step, lr=config.optim.lr, warmup=config.optim.warmup,
+                    grad_clip=config.optim.grad_clip):
+        if warmup > 0:
+            for g in optimizer.param_groups:
+                g['lr'] = lr * np.minimum(step / warmup, 1.0)
+        optimizer.step(grad_clip=grad_clip)
+
+    return optimize_fn
+
+
+# ---------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------
+def _draw_seed():
+    return mutils.host_seed()
+
+
+def _run(model, batch, rows, train, z, drop_mask):
+    p = float(model.config.model.dropout) if train else 0.0
+    loss = native_loss(model, batch, rows, z=z, drop_mask=drop_mask if train else None, drop_p=p, seed=_draw_seed(),
+                       grads=train)
+    return loss
+
+
+def get_sde_loss_fn(sde, train, reduce_mean=False, continuous=True, likelihood_weighting=False, eps=1e-5,
+                    return_data=False, denoise_steps=5):
+    """losses.py:61-137.  ``loss_fn(model, batch, condition, mask, t=None, z=None, drop_mask=None)``."""
+    if return_data:
+        raise NotImplementedError('the auxiliary (multi-step denoise + body model) loss is not built')
+    red = (1.0 / _DATA_DIM) if reduce_mean else 0.5
+
+    def loss_fn(model, batch, condition=None, mask=None, t=None, z=None, drop_mask=None):
+        B = batch.shape[0]
+        if t is None:
+            t = torch.rand(B) * (sde.T - eps) + eps                  # losses.py:111 (CPU generator here)
+        t = t.detach().to('cpu', torch.float32)
+        # labels, score multiplier m (score = m * res), marginal mean coefficient and std: the samplers' table helper
+        coef, labels = mutils.em_coefficients(sde, model, t, probability_flow=True, continuous=continuous)
+        m, mean_c, std = coef[:, 5], coef[:, 3], coef[:, 4]
+        if not likelihood_weighting:
+            res_c, z_c, w = m * std, torch.ones(B), torch.full((B,), red)           # (score std + z)^2
+        else:
+            g2 = sde.sde(torch.zeros(B, 1), t)[1] ** 2
+            res_c, z_c, w = m, 1.0 / std, red * g2                                  # (score + z / std)^2 g^2
+        rows = torch.stack([labels.float(), mean_c, std, res_c, z_c, w])
+        return _run(model, batch, rows, train, z, drop_mask)
+
+    return loss_fn
+
+
+def get_smld_loss_fn(vesde, train, reduce_mean=False):
+    """losses.py:140-161 (legacy NCSN objective; labels index the DESCENDING sigma array)."""
+    assert isinstance(vesde, VESDE), "SMLD training only works for VESDEs."
+    smld_sigma_array = torch.flip(vesde.discrete_sigmas, dims=(0,))
+    red = (1.0 / _DATA_DIM) if reduce_mean else 0.5
+
+    def loss_fn(model, batch, condition=None, mask=None, labels=None, z=None, drop_mask=None):
+        B = batch.shape[0]
+        if labels is None:
+            labels = torch.randint(0, vesde.N, (B,))
+        labels = labels.cpu()
+        sig = smld_sigma_array[labels]
+        inv_s = 1.0 / mutils.sigma_at(model, labels.float())
+        # score = res / sigmas[label]; target = -z / sig; (score - target)^2 sig^2
+        rows = torch.stack([labels.float(), torch.ones(B), sig, inv_s, 1.0 / sig, red * sig ** 2])
+        return _run(model, batch, rows, train, z, drop_mask)
+
+    return loss_fn
+
+
+def get_ddpm_loss_fn(vpsde, train, reduce_mean=True):
+    """losses.py:164-184 (legacy DDPM objective)."""
+    assert isinstance(vpsde, VPSDE), "DDPM training only works for VPSDEs."
+    red = (1.0 / _DATA_DIM) if reduce_mean else 0.5
+
+    def loss_fn(model, batch, condition=None, mask=None, labels=None, z=None, drop_mask=None):
+        B = batch.shape[0]
+        if labels is None:
+            labels = torch.randint(0, vpsde.N, (B,))
+        labels = labels.cpu()
+        inv_s = 1.0 / mutils.sigma_at(model, labels.float())
+        rows = torch.stack([labels.float(), vpsde.sqrt_alphas_cumprod[labels], vpsde.sqrt_1m_alphas_cumprod[labels],
+                            inv_s, -torch.ones(B), torch.full((B,), red)])            # (score - noise)^2
+        return _run(model, batch, rows, train, z, drop_mask)
+
+    return loss_fn
+
+
+def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True, likelihood_weighting=False,
+                auxiliary_loss=False, denormalize=None, body_model=None, rot_rep='rot6d', denoise_steps=5):
+    """losses.py:187-275: ``step_fn(state, batch)`` with ``state = dict(optimizer, model, ema, step)``."""
+    if auxiliary_loss:
+        raise NotImplementedError('the auxiliary (multi-step denoise + body model) loss is not built')
+    if continuous:
+        loss_fn = get_sde_loss_fn(sde, train, reduce_mean=reduce_mean, continuous=True,
+                                  likelihood_weighting=likelihood_weighting)
+    else:
+        assert not likelihood_weighting, "Likelihood weighting is not supported for original SMLD/DDPM training."
+        if isinstance(sde, VESDE):
+            loss_fn = get_smld_loss_fn(sde, train, reduce_mean=reduce_mean)
+        elif isinstance(sde, VPSDE):
+            loss_fn = get_ddpm_loss_fn(sde, train, reduce_mean=reduce_mean)
+        else:
+            raise ValueError(f"Discrete training for {sde.__class__.__name__} is not recommended.")
+
+    def step_fn(state, batch, condition=None, mask=None, **draws):
+        model = state['model']
+        if train:
+            optimizer = state['optimizer']
+            optimizer.zero_grad()
+            loss = loss_fn(model, batch, condition, mask, **draws)       # loss and every p.grad in one native call
+            optimize_fn(optimizer, model.parameters(), step=state['step'])
+            state['step'] += 1
+            model.mark_updated()
+            state['ema'].update(model.parameters())
+        else:
+            with torch.no_grad():
+                ema = state['ema']
+                ema.store(model.parameters())
+                ema.copy_to(model.parameters())
+                loss = loss_fn(model, batch, condition, mask, **draws)
+                ema.restore(model.parameters())
+        return {'step_loss': loss, 'score_loss': loss}
+
+    return step_fn

@@ -88,11 +88,16 @@ class ScoreModelFC(nn.Module):
                              embed_dim == L.EMBED and n_blocks == 2)
         self._h = None
         self._ws = {}
+        self._native_updates = 0
         self.engine = L.ENGINE_AUTO      # ENGINE_FP32 forces the exact path, ENGINE_TC the tensor-core path
 
     # ------------------------------------------------------------------ handle management
     def _param_versions(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self._native_updates,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def mark_updated(self):
+        """The native optimiser wrote the weights in place (no torch version bump): rebuild the handle on next use."""
+        self._native_updates += 1
 
     def handle(self):
         """Create (or refresh after a weight update) the device handle built from the current weights."""
@@ -187,7 +192,8 @@ class ScoreModelFC(nn.Module):
     def forward(self, batch, t, condition=None, mask=None):
         """batch [B,63], t [B] (labels, i.e. t*999 when called through score_fn) -> [B,63]  (model.py:141-196)."""
         if self.training:
-            raise NotImplementedError('dposer_b200.ScoreModelFC is inference-only (dropout/training are out of scope)')
+            raise NotImplementedError('ScoreModelFC.forward is the inference path; training goes through dposer_b200.losses '
+                                      '(get_step_fn / get_sde_loss_fn: loss and gradients in one native call)')
         t = t.detach().to('cpu', torch.float32)
         row_mult = None
         if self.config.model.scale_by_sigma:

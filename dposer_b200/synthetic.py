@@ -20,7 +20,9 @@ def default_config():
     ns = types.SimpleNamespace
     return ns(
         data=ns(normalize=True, rot_rep='axis', min_max=False),
-        training=ns(sde='subvpsde', continuous=True, batch_size=1280),
+        training=ns(sde='subvpsde', continuous=True, batch_size=1280, n_iters=400001, auxiliary_loss=False, denoise_steps=10,
+                    likelihood_weighting=False, reduce_mean=True),
+        optim=ns(weight_decay=0, optimizer='Adam', lr=2e-4, beta1=0.9, eps=1e-8, warmup=5000, grad_clip=1.),
         sampling=ns(method='pc', predictor='euler_maruyama', corrector='none', n_steps_each=1, noise_removal=True,
                     probability_flow=False, snr=0.16),
         model=ns(type='ScoreModelFC', HIDDEN_DIM=1024, EMBED_DIM=512, N_BLOCKS=2, dropout=0.1, fourier_scale=16,

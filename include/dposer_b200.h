@@ -305,6 +305,44 @@ int dpb_joint_map_scatter(const float* g_out, int n_map, const int32_t* map, int
                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training step of the score network (replaces loss_fn + loss.backward() + optimize_fn + ema.update of
+ * lib/algorithms/advanced/losses.py:31-57,61-137,187-275 with model.py:141-196 in train mode and
+ * lib/algorithms/ema.py:35-50).  Every contraction of the forward and backward pass is a split-fp16 tcgen05 GEMM.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct dpb_train dpb_train_t;
+/* the fields of dpb_score_weights, but DEVICE fp32 pointers: parameters (read) or their gradients (written).
+ * emb_freqs (parameters only) = DEVICE [256]. */
+typedef dpb_score_weights dpb_train_tensors;
+
+/* scratch for steps of exactly `batch` rows (activations, cotangents, fp16 operand copies) */
+int dpb_train_create(dpb_train_t** h, int64_t batch, int device);
+int dpb_train_destroy(dpb_train_t* h);
+/* loss = mean_b row_w[b] sum_k (res_c[b] res[b,k] + z_c[b] z[b,k])^2 on perturbed = mean_c x + std_c z, where res is the
+ * network's post_dense output at the per-row label (losses.py:108-131; the sigma / std divisions and the reduce_mean /
+ * likelihood-weighting factors are folded into the row scalars by the host).
+ *   params    DEVICE parameter pointers;  grads  DEVICE gradient pointers (every one overwritten) or NULL = loss only
+ *   batch     DEVICE fp32 [B,63] clean (normalised) poses
+ *   rows      DEVICE fp32 [6,B]: label (= 999 t), mean_c, std_c, res_c, z_c, row_w
+ *   z_given   DEVICE fp32 [B,63] Gaussian draws (parity mode) or NULL: Philox4x32-10 keyed by (seed, row)
+ *   mask_given DEVICE uint8 [5,B,1024] dropout keep-masks in layer order (parity mode) or NULL: Philox
+ *   drop_p    dropout probability (0 = eval mode)
+ *   loss      DEVICE fp32 [1];  loss_rows DEVICE fp32 [B] or NULL */
+int dpb_train_loss_grad(dpb_train_t* h, const dpb_train_tensors* params, const dpb_train_tensors* grads,
+                        const float* batch, const float* rows, const float* z_given, const uint8_t* mask_given,
+                        float drop_p, uint64_t seed, float* loss, float* loss_rows, void* stream);
+/* scratch for the two calls below (DEVICE, any contents) */
+size_t dpb_train_adam_scratch_bytes(void);
+/* ((double*)scratch)[0] = sum of squares of a flat gradient buffer, added in a fixed order */
+int dpb_train_grad_norm(const float* g, int64_t n, void* scratch, void* stream);
+/* torch.optim.Adam's update on flat buffers (losses.py:31-41), preceded by torch.nn.utils.clip_grad_norm_ when
+ * grad_clip >= 0 (losses.py:53-54): the clip coefficient is evaluated on the device, no host synchronisation.
+ * `lr` already contains the warm-up factor (losses.py:50-52); step >= 1 is Adam's own step count. */
+int dpb_train_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int64_t step, float grad_clip, void* scratch, void* stream);
+/* shadow -= one_minus_decay * (shadow - p)   (ExponentialMovingAverage.update, ema.py:35-50) */
+int dpb_ema_update(float* shadow, const float* p, int64_t n, float one_minus_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Metrics (replaces average_pairwise_distance lib/utils/metric.py:8-37 and the per-sample
  * reductions of Evaler.eval_bodys lib/dataset/AMASS.py:275-298)
  * ---------------------------------------------------------------------------------------- */
