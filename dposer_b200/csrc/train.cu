@@ -408,6 +408,36 @@ extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, con
   return DPB_OK;
 }
 
+// ---- C = A B^T through the same split-fp16 tensor-core GEMM (utility / unit-test entry; operands converted per call)
+static size_t gemm_nt_layout(int M, int N, int K, void* base, size_t cap, Op16* a, Op16* b) {
+  WsCarver ws(base, cap);
+  const int64_t kp = (K + 63) / 64 * 64;
+  *a = trn::carve16(ws, M, kp);
+  *b = trn::carve16(ws, N, kp);
+  return align_up(ws.off, 256);
+}
+
+extern "C" size_t dpb_gemm_nt_workspace_bytes(int M, int N, int K) {
+  Op16 a, b;
+  return gemm_nt_layout(M, N, K, nullptr, ~(size_t)0, &a, &b);
+}
+
+extern "C" int dpb_gemm_nt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, void* ws,
+                           size_t ws_bytes, void* stream) {
+  DPB_REQUIRE(A && B && C && ws && M > 0 && N > 0 && K > 0, "dpb_gemm_nt: bad argument");
+  DPB_REQUIRE(ws_bytes >= dpb_gemm_nt_workspace_bytes(M, N, K), "dpb_gemm_nt: workspace too small");
+  PtrDeviceGuard guard(C);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = gemm_tc_init();
+  if (rc != DPB_OK) return rc;
+  Op16 a, b;
+  const size_t used = gemm_nt_layout(M, N, K, ws, ws_bytes, &a, &b);
+  DPB_CUDA_CHECK(cudaMemsetAsync(ws, 0, used, st));
+  if ((rc = split16(A, M, K, K, &a, nullptr, st)) != DPB_OK) return rc;
+  if ((rc = split16(B, N, K, K, &b, nullptr, st)) != DPB_OK) return rc;
+  return gemm_tc(a, b, M, N, K, C, N, bias, nullptr, nullptr, 0, st);
+}
+
 extern "C" size_t dpb_train_adam_scratch_bytes(void) { return (size_t)(trn::SS_BLOCKS + 1) * sizeof(double); }
 
 // scratch[0] = sum_i g_i^2 (double), partial sums added in a fixed order

@@ -330,6 +330,11 @@ int dpb_train_destroy(dpb_train_t* h);
 int dpb_train_loss_grad(dpb_train_t* h, const dpb_train_tensors* params, const dpb_train_tensors* grads,
                         const float* batch, const float* rows, const float* z_given, const uint8_t* mask_given,
                         float drop_p, uint64_t seed, float* loss, float* loss_rows, void* stream);
+/* C[M,N] = A[M,K] B[N,K]^T (+ bias[n]) on the split-fp16 tcgen05 GEMM the training step is built from (DEVICE fp32,
+ * row-major, ~1e-6 relative); utility / unit-test entry, the operands are converted on every call */
+size_t dpb_gemm_nt_workspace_bytes(int M, int N, int K);
+int dpb_gemm_nt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, void* ws,
+                size_t ws_bytes, void* stream);
 /* scratch for the two calls below (DEVICE, any contents) */
 size_t dpb_train_adam_scratch_bytes(void);
 /* ((double*)scratch)[0] = sum of squares of a flat gradient buffer, added in a fixed order */

@@ -248,3 +248,37 @@ def test_load_body_tensors_smplx_layout(tmp_path):
     for k in ['v_template', 'shapedirs', 'posedirs', 'J_regressor', 'lbs_weights', 'lmk_bary', 'hands_mean']:
         assert torch.equal(t[k], m[k]), k
     assert t['parents'] == m['parents'] and torch.equal(t['lmk_faces'], m['lmk_faces'])
+
+
+def test_training_oracle_reproduces_reference_steps():
+    """oracle/train_ref.py against the REAL reference's three training steps (train_golden.npz): loss, gradient norm and
+    sampled gradients per step, sampled parameter / EMA deltas at the end."""
+    from oracle import score_ref as S
+    from oracle import train_ref as T
+    g = golden('train_golden.npz')
+    B, STEPS = 96, 3
+    sd = S.make_state_dict(42)
+    names = T.param_names(sd)
+    sd0 = {k: sd[k].clone() for k in names}
+    opt = {k: (torch.zeros_like(sd[k]), torch.zeros_like(sd[k])) for k in names}
+    opt['step'] = 0
+    ema = {k: sd[k].clone() for k in names}
+    ema['num_updates'] = 0
+    osde = S.SubVP(0.1, 20., 1000)
+    data = torch.tensor(g['data'])
+    idx = lambda n: torch.linspace(0, n - 1, min(48, n)).long()     # noqa: E731
+    for s in range(STEPS):
+        masks = torch.tensor(np.unpackbits(g[f's{s}_masks'], axis=-1)).reshape(5, B, 1024)
+        loss, grads, total = T.train_step(sd, opt, ema, osde, data[s * B:(s + 1) * B], torch.tensor(g[f's{s}_t']),
+                                          torch.tensor(g[f's{s}_z']), masks, int(g['step0']) + s)
+        assert abs(float(loss) - float(g[f's{s}_loss'])) < 1e-5 * float(g[f's{s}_loss'])
+        assert abs(float(total) - float(g[f's{s}_gnorm'])) < 1e-4 * float(g[f's{s}_gnorm'])
+        for n, gr in grads.items():
+            flat = gr.reshape(-1)
+            assert float((flat[idx(flat.numel())] - torch.tensor(g[f's{s}_g_{n}'])).abs().max()) <= 1e-4 * float(flat.abs().max()) + 1e-9, n
+    for n in names:
+        d = (sd[n] - sd0[n]).reshape(-1)
+        dmax = max(float(np.abs(g[f'dp_{n}']).max()), 1e-12)
+        assert float((d[idx(d.numel())] - torch.tensor(g[f'dp_{n}'])).abs().max()) <= 2e-2 * dmax + 1e-12, n
+        e = (ema[n] - sd0[n]).reshape(-1)
+        assert float((e[idx(e.numel())] - torch.tensor(g[f'dema_{n}'])).abs().max()) <= 2e-2 * dmax + 1e-12, n
