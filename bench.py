@@ -374,6 +374,50 @@ def bench_configs(args, dev, model, peaks, flush, cpu_per_row_step):
                     f'camera + 5 x 100 body Adam steps, {B} independent images on one GPU (1M images = 8 such shards)',
         'images': B, 'adam_steps': 600, 'seconds': dt, 'value': B / dt, 'unit': 'poses/s',
         'ms_per_adam_step': dt * 1e3 / 600, 'finite': bool(torch.isfinite(pose).all() and torch.isfinite(reproj).all())}
+    del fit, warm, pp, smpl
+    torch.cuda.empty_cache()
+
+    # ---- the training step (losses.get_step_fn(train=True)): loss + hand-written backward on the
+    # split-fp16 tcgen05 GEMM, clip + Adam, EMA; the reference's batch size (configs/default_amass_configs.py:22) and a large one
+    from dposer_b200 import losses
+    from dposer_b200.ema import ExponentialMovingAverage
+    FLOP_ROW = 3 * (SCORE_FLOP_PER_ROW + 2 * (512 * 512 + 512 * 5120))     # forward + two backward products, x and time path
+    tr = {}
+    for tag, Bt, nst in (('reference_batch', cfg.training.batch_size, 200), ('large_batch', 16384, 30)):
+        tm = synthetic.make_score_model(42).to(dev)
+        tm.train()
+        state = dict(optimizer=losses.get_optimizer(cfg, tm.parameters()), model=tm,
+                     ema=ExponentialMovingAverage(tm.parameters(), decay=cfg.model.ema_rate), step=0)
+        step_fn = losses.get_step_fn(sde, True, losses.optimization_manager(cfg), reduce_mean=cfg.training.reduce_mean)
+        toy = synthetic.toy_poses()
+        host = norm.offline_normalize(toy[torch.randint(0, toy.shape[0], (Bt,))].to(dev)).cpu().pin_memory()
+        data = host.to(dev)
+        for _ in range(5):
+            step_fn(state, data)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(nst):
+            ld = step_fn(state, data)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / nst
+        t0 = time.perf_counter()                      # end to end: batch from pinned host memory, loss back to the host
+        for _ in range(nst):
+            lv = float(step_fn(state, host.to(dev, non_blocking=True))['step_loss'])
+        ms_e2e = (time.perf_counter() - t0) * 1e3 / nst
+        tf = FLOP_ROW * Bt / (ms * 1e-3) / 1e12
+        tr[tag] = {'batch': Bt, 'ms_per_step': ms, 'value': Bt / (ms * 1e-3), 'unit': 'poses/s', 'steps_per_s': 1e3 / ms,
+                   'e2e_ms_per_step': ms_e2e, 'e2e_value': Bt / (ms_e2e * 1e-3), 'loss': lv, 'finite': bool(lv == lv and abs(lv) != float("inf")),
+                   'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peaks['tc_sustained'], 'unit': 'TFLOP/s',
+                                'frac': tf / peaks['tc_sustained'],
+                                'note': 'algorithmic FLOP (one product); the split-fp16 GEMM executes three'}}
+        del state, tm, data, host
+        torch.cuda.empty_cache()
+    out['f3_train_step'] = {
+        'workload': 'SURVEY 8(f)3: one training step of ScoreModelFC (sub-VP denoising score matching, per-row t, dropout 0.1, '
+                    'grad clip 1.0, Adam, EMA) -- 27 tcgen05 GEMMs + elementwise kernels per step; synthetic AMASS-like poses',
+        'flop_per_row_step': FLOP_ROW, **tr['reference_batch'], 'large_batch': tr['large_batch']}
     return out
 
 
@@ -424,6 +468,30 @@ def cpu_task_loops(budget_s=12.0):
     dt = (time.perf_counter() - t0) / (6 * iters)
     res['c5_smplify'] = {'value': B / (dt * 600), 'unit': 'poses/s', 'cores': os.cpu_count(), 'kind': 'port',
                          'sample': f'{B} images, {6 * iters} of 600 Adam steps, {dt:.2f} s per step'}
+    # training step: the oracle restatement (autograd on the host cores; pinned to the real losses.get_step_fn by
+    # tests/golden/train_golden.npz) at the reference's batch size
+    from oracle import train_ref
+    Bt, nst = 1280, 3
+    osde = score_ref.SubVP(0.1, 20., 1000)
+    tsd = {k: v.clone() for k, v in sd.items()}
+    names = train_ref.param_names(tsd)
+    opt = {k: (torch.zeros_like(tsd[k]), torch.zeros_like(tsd[k])) for k in names}
+    opt['step'] = 0
+    ema = {k: tsd[k].clone() for k in names}
+    ema['num_updates'] = 0
+    toy = synthetic.toy_poses()
+    batch = (toy[torch.randint(0, toy.shape[0], (Bt,), generator=g)] - mean) / std
+    times = []
+    for i in range(nst + 1):
+        t = torch.rand(Bt, generator=g) * (1 - 1e-5) + 1e-5
+        z = torch.randn(Bt, 63, generator=g)
+        masks = (torch.rand(5, Bt, 1024, generator=g) >= 0.1).to(torch.uint8)
+        t0 = time.perf_counter()
+        train_ref.train_step(tsd, opt, ema, osde, batch, t, z, masks, 4000 + i)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times[1:]) / nst
+    res['f3_train_step'] = {'value': Bt / dt, 'unit': 'poses/s', 'cores': os.cpu_count(), 'kind': 'port',
+                            'sample': f'{nst} steps of {Bt} rows after one warm-up step, {dt * 1e3:.0f} ms per step'}
     return res
 
 

@@ -27,6 +27,9 @@ struct dpb_train {
   float *mean[5], *rstd[5], *loss_rows;
   dpb::Op16 xp16, xpT16, temb0_16, temb0T16, temb16, tembT16, X16[5], XT16[5], G16, GT16, gres16, gresT16, gqT16;
   dpb::Op16 Wpre16, W16[4], WT16[4], Wpost16, WpostT16, Ws16, Wt16, WtT16;
+  const uint64_t* seed_dev = nullptr;     // when set, the Philox seed is read from device memory (graph replay)
+  cudaStream_t side = nullptr;            // weight-gradient GEMMs run beside the cotangent chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace dpb {
@@ -37,8 +40,10 @@ constexpr int SS_BLOCKS = 512;
 // perturbed = mean_c x + std_c z (losses.py:112-115), z from Philox or given; sinusoidal embedding of the label (model.py:37-51)
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ batch, const float* __restrict__ rows,
                                                    const float* __restrict__ z_given, uint64_t seed,
+                                                   const uint64_t* __restrict__ seed_dev,
                                                    const float* __restrict__ freqs, float* __restrict__ xp,
                                                    float* __restrict__ z, float* __restrict__ temb0, int64_t B) {
+  if (seed_dev) seed = *seed_dev;
   const int64_t b = blockIdx.x;
   const int t = threadIdx.x;
   const float label = rows[b], mc = rows[B + b], sc = rows[2 * B + b];
@@ -96,7 +101,9 @@ __global__ void __launch_bounds__(256) gn_act_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ beta, const float* __restrict__ resid,
                                                          float* __restrict__ out, float* __restrict__ mean,
                                                          float* __restrict__ rstd, const uint8_t* __restrict__ mask_given,
-                                                         uint64_t seed, int stage, float p, int64_t B) {
+                                                         uint64_t seed, const uint64_t* __restrict__ seed_dev, int stage,
+                                                         float p, int64_t B) {
+  if (seed_dev) seed = *seed_dev;
   const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * 32) return;
@@ -123,7 +130,9 @@ __global__ void __launch_bounds__(256) gn_act_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                          float* __restrict__ gu, int64_t ldg, float* __restrict__ t1,
                                                          float* __restrict__ t2, const uint8_t* __restrict__ mask_given,
-                                                         uint64_t seed, int stage, float p, int64_t B) {
+                                                         uint64_t seed, const uint64_t* __restrict__ seed_dev, int stage,
+                                                         float p, int64_t B) {
+  if (seed_dev) seed = *seed_dev;
   const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * 32) return;
@@ -219,9 +228,10 @@ __global__ void __launch_bounds__(256) sumsq_final_kernel(const double* __restri
 __global__ void adam_weights_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                     float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2,
                                     float inv_sqrt_bc2, float eps, float wd, const double* __restrict__ gnorm_sq,
-                                    float grad_clip) {
+                                    float grad_clip, const float* __restrict__ hyper_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (hyper_dev) { step_size = hyper_dev[0]; inv_sqrt_bc2 = hyper_dev[1]; }
   float coef = 1.0f;
   if (gnorm_sq && grad_clip >= 0.f) coef = fminf(grad_clip / ((float)sqrt(*gnorm_sq) + 1e-6f), 1.0f);
   float gi = g[i] * coef;
@@ -234,8 +244,10 @@ __global__ void adam_weights_kernel(float* __restrict__ p, const float* __restri
 }
 
 // s -= (1 - decay) (s - p)   (ema.py:48-50)
-__global__ void ema_kernel(float* __restrict__ s, const float* __restrict__ p, int64_t n, float omd) {
+__global__ void ema_kernel(float* __restrict__ s, const float* __restrict__ p, int64_t n, float omd,
+                           const float* __restrict__ omd_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (omd_dev) omd = *omd_dev;
   if (i < n) s[i] -= omd * (s[i] - p[i]);
 }
 
@@ -298,7 +310,16 @@ extern "C" int dpb_train_create(dpb_train** out, int64_t batch, int device) {
   if (e != cudaSuccess) { delete h; return fail(DPB_ENOMEM, std::string("dpb_train_create: ") + cudaGetErrorString(e)); }
   cudaMemset(h->pool, 0, h->pool_bytes);                  // operand pads (k >= K, rows >= valid) stay zero for good
   trn::layout(h, h->pool, h->pool_bytes);
+  cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   *out = h;
+  return DPB_OK;
+}
+
+extern "C" int dpb_train_set_seed_pointer(dpb_train* h, const uint64_t* seed_dev) {
+  DPB_REQUIRE(h, "dpb_train_set_seed_pointer: bad argument");
+  h->seed_dev = seed_dev;
   return DPB_OK;
 }
 
@@ -306,6 +327,9 @@ extern "C" int dpb_train_destroy(dpb_train* h) {
   if (!h) return DPB_OK;
   DeviceGuard guard(h->device);
   if (h->pool) cudaFree(h->pool);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return DPB_OK;
 }
@@ -340,7 +364,7 @@ extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, con
     TRY(split16(Wt[s], H, E, E, &r, G ? &c : nullptr, st));
   }
   // ---- forward
-  trn::prep_kernel<<<(unsigned)B, 256, 0, st>>>(batch, rows, z_given, seed, P->emb_freqs, h->xp, h->z, h->temb0, B);
+  trn::prep_kernel<<<(unsigned)B, 256, 0, st>>>(batch, rows, z_given, seed, h->seed_dev, P->emb_freqs, h->xp, h->z, h->temb0, B);
   TRY(split16(h->xp, Bi, DP, DP, &h->xp16, G ? &h->xpT16 : nullptr, st));
   TRY(split16(h->temb0, Bi, E, E, &h->temb0_16, G ? &h->temb0T16 : nullptr, st));
   TRY(gemm_tc(h->temb0_16, h->Ws16, Bi, E, E, h->q, E, P->temb_b, nullptr, nullptr, 0, st));
@@ -353,7 +377,7 @@ extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, con
     TRY(gemm_tc(in, w, Bi, H, s == 0 ? DP : H, h->u[s], H, bl[s], bt[s], h->tproj + (size_t)s * H, NL * H, st));
     const float* resid = (s == 2) ? h->act[0] : (s == 4) ? h->act[2] : nullptr;
     trn::gn_act_fwd_kernel<<<gw, 256, 0, st>>>(h->u[s], gam[s], bet[s], resid, h->act[s], h->mean[s], h->rstd[s],
-                                               mask_given, seed, s, drop_p, B);
+                                               mask_given, seed, h->seed_dev, s, drop_p, B);
     TRY(split16(h->act[s], Bi, H, H, &h->X16[s], G ? &h->XT16[s] : nullptr, st));
   }
   TRY(gemm_tc(h->X16[4], h->Wpost16, Bi, D, H, h->res, DP, P->post_b, nullptr, nullptr, 0, st));
@@ -372,7 +396,12 @@ extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, con
   float* gbet[5] = {(float*)G->pre_gn_b, (float*)G->blk_gn_b[0], (float*)G->blk_gn_b[1], (float*)G->blk_gn_b[2], (float*)G->blk_gn_b[3]};
   const dim3 cs(32, 32);
   TRY(split16(h->gres, Bi, DP, DP, &h->gres16, &h->gresT16, st));
-  TRY(gemm_tc(h->gresT16, h->XT16[4], D, H, Bi, (float*)G->post_w, H, nullptr, nullptr, nullptr, 0, st));       // dW_post
+  // weight-gradient GEMMs leave the critical path (the cotangent chain): they run on a side stream, forked after the
+  // operand they read is written and joined at the end (works the same under stream capture)
+  cudaStream_t sd = h->side ? h->side : st;
+  auto fork = [&]() { if (sd != st) { cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(sd, h->ev_fork, 0); } };
+  fork();
+  TRY(gemm_tc(h->gresT16, h->XT16[4], D, H, Bi, (float*)G->post_w, H, nullptr, nullptr, nullptr, 0, sd));       // dW_post
   trn::colsum_kernel<<<2, cs, 0, st>>>(h->gres, B, D, DP, 1.0f, (float*)G->post_b, nullptr);
   TRY(gemm_tc(h->gres16, h->WpostT16, Bi, H, DP, h->gA, H, nullptr, nullptr, nullptr, 0, st));                   // d h''
   // cotangent buffers: gA carries d h'' -> d h' -> d h (outputs of the even stages), gB the odd stages' outputs
@@ -380,22 +409,23 @@ extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, con
     float* gu = h->Gall + (size_t)s * H;
     const float* gout = (s & 1) ? h->gB : h->gA;
     trn::gn_act_bwd_kernel<<<gw, 256, 0, st>>>(gout, h->u[s], gam[s], bet[s], h->mean[s], h->rstd[s], gu, NL * H, h->t1,
-                                               h->t2, mask_given, seed, s, drop_p, B);
+                                               h->t2, mask_given, seed, h->seed_dev, s, drop_p, B);
     trn::colsum_kernel<<<H / 32, cs, 0, st>>>(h->t1, B, H, H, 1.0f, gbet[s], nullptr);
     trn::colsum_kernel<<<H / 32, cs, 0, st>>>(h->t2, B, H, H, 1.0f, ggam[s], nullptr);
     trn::colsum_kernel<<<H / 32, cs, 0, st>>>(gu, B, H, NL * H, 1.0f, gbl[s], gbt[s]);
     const Op16 grow = h->G16.block(0, s * H), gcol = h->GT16.block(s * H, 0);
     TRY(split16(gu, Bi, H, NL * H, &grow, &gcol, st));
+    fork();
     if (s == 0) {
-      TRY(gemm_tc(gcol, h->xpT16, H, D, Bi, (float*)G->pre_w, D, nullptr, nullptr, nullptr, 0, st));             // dW_pre
+      TRY(gemm_tc(gcol, h->xpT16, H, D, Bi, (float*)G->pre_w, D, nullptr, nullptr, nullptr, 0, sd));             // dW_pre
     } else {
-      TRY(gemm_tc(gcol, h->XT16[s - 1], H, H, Bi, gWl[s - 1], H, nullptr, nullptr, nullptr, 0, st));             // dW_s
+      TRY(gemm_tc(gcol, h->XT16[s - 1], H, H, Bi, gWl[s - 1], H, nullptr, nullptr, nullptr, 0, sd));             // dW_s
       if (s & 1)     // input of stage 3 / 1 is h' / h, which also feeds the residual: d h' = g_u3 W_3 + d h''  (in place)
         TRY(gemm_tc(grow, h->WT16[s - 1], Bi, H, H, h->gA, H, nullptr, nullptr, h->gA, H, st));
       else           // input of stage 4 / 2 is a_3 / a_1
         TRY(gemm_tc(grow, h->WT16[s - 1], Bi, H, H, h->gB, H, nullptr, nullptr, nullptr, 0, st));
     }
-    TRY(gemm_tc(gcol, h->tembT16, H, E, Bi, gWt[s], E, nullptr, nullptr, nullptr, 0, st));                       // dWt_s
+    TRY(gemm_tc(gcol, h->tembT16, H, E, Bi, gWt[s], E, nullptr, nullptr, nullptr, 0, sd));                       // dWt_s
   }
   // time path: d temb = sum_s g_u_s Wt_s (one GEMM over the concatenated cotangents), through SiLU, into the shared layer
   TRY(gemm_tc(h->G16, h->WtT16, Bi, E, NL * H, h->gtemb, E, nullptr, nullptr, nullptr, 0, st));
@@ -403,6 +433,7 @@ extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, con
   TRY(split16(h->gq, Bi, E, E, nullptr, &h->gqT16, st));
   TRY(gemm_tc(h->gqT16, h->temb0T16, E, E, Bi, (float*)G->temb_w, E, nullptr, nullptr, nullptr, 0, st));         // dW_s
   trn::colsum_kernel<<<E / 32, cs, 0, st>>>(h->gq, B, E, E, 1.0f, (float*)G->temb_b, nullptr);
+  if (sd != st) { cudaEventRecord(h->ev_join, sd); cudaStreamWaitEvent(st, h->ev_join, 0); }
   DPB_CUDA_CHECK(cudaGetLastError());
 #undef TRY
   return DPB_OK;
@@ -453,7 +484,8 @@ extern "C" int dpb_train_grad_norm(const float* g, int64_t n, void* scratch, voi
 }
 
 extern "C" int dpb_train_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                              float eps, float weight_decay, int64_t step, float grad_clip, void* scratch, void* stream) {
+                              float eps, float weight_decay, int64_t step, float grad_clip, const float* hyper_dev,
+                              void* scratch, void* stream) {
   DPB_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "dpb_train_adam: bad argument");
   DPB_REQUIRE(grad_clip < 0.f || scratch, "dpb_train_adam: gradient clipping needs the scratch buffer");
   PtrDeviceGuard guard(p);
@@ -467,16 +499,17 @@ extern "C" int dpb_train_adam(float* p, const float* g, float* m, float* v, int6
   const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
   trn::adam_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
       p, g, m, v, n, step_size, beta1, beta2, inv_sqrt_bc2, eps, weight_decay,
-      grad_clip >= 0.f ? static_cast<const double*>(scratch) : nullptr, grad_clip);
+      grad_clip >= 0.f ? static_cast<const double*>(scratch) : nullptr, grad_clip, hyper_dev);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }
 
-extern "C" int dpb_ema_update(float* shadow, const float* p, int64_t n, float one_minus_decay, void* stream) {
+extern "C" int dpb_ema_update(float* shadow, const float* p, int64_t n, float one_minus_decay, const float* omd_dev,
+                              void* stream) {
   DPB_REQUIRE(shadow && p && n >= 0, "dpb_ema_update: bad argument");
   if (n == 0) return DPB_OK;
   PtrDeviceGuard guard(shadow);
-  trn::ema_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(shadow, p, n, one_minus_decay);
+  trn::ema_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(shadow, p, n, one_minus_decay, omd_dev);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }

@@ -47,8 +47,16 @@ class ExponentialMovingAverage:
             return None
         return torch.as_strided(base.detach(), (n,), (1,))
 
-    def update(self, parameters):
-        """ema.py:35-50: s -= (1 - decay) (s - p), decay capped by (1 + n) / (10 + n)."""
+    def next_one_minus_decay(self):
+        """1 - decay of the NEXT update (ema.py:44-47), without advancing the counter."""
+        decay = self.decay
+        if self.num_updates is not None:
+            decay = min(decay, (2 + self.num_updates) / (11 + self.num_updates))
+        return 1.0 - decay
+
+    def update(self, parameters, omd_dev=None):
+        """ema.py:35-50: s -= (1 - decay) (s - p), decay capped by (1 + n) / (10 + n).  ``omd_dev`` (device fp32 [1]): the
+        kernel reads 1 - decay from device memory (CUDA-graph replay; the caller filled it with next_one_minus_decay())."""
         decay = self.decay
         if self.num_updates is not None:
             self.num_updates += 1
@@ -62,12 +70,13 @@ class ExponentialMovingAverage:
         flat = self._flat_view(params) if params[0].dtype == torch.float32 else None
         with torch.no_grad():
             if flat is not None and flat.numel() == self._flat.numel():
-                L.check(lib.dpb_ema_update(L.ptr(self._flat), L.ptr(flat), flat.numel(), float(omd),
+                L.check(lib.dpb_ema_update(L.ptr(self._flat), L.ptr(flat), flat.numel(), float(omd), L.ptr(omd_dev),
                                            L.current_stream(flat.device)))
             else:
                 for s, p in zip(self.shadow_params, params):
                     pc = p.detach().contiguous()
-                    L.check(lib.dpb_ema_update(L.ptr(s), L.ptr(pc), s.numel(), float(omd), L.current_stream(s.device)))
+                    L.check(lib.dpb_ema_update(L.ptr(s), L.ptr(pc), s.numel(), float(omd), L.ptr(omd_dev),
+                                               L.current_stream(s.device)))
 
     def copy_to(self, parameters):
         """ema.py:52-63 (in-place ``copy_`` on the parameter itself, so that the model notices the new weights)."""

@@ -83,9 +83,10 @@ def _engine(model, B, device):
     return eng
 
 
-def native_loss(model, batch, rows, z=None, drop_mask=None, drop_p=0.0, seed=0, grads=True):
+def native_loss(model, batch, rows, z=None, drop_mask=None, drop_p=0.0, seed=0, grads=True, clone=True, seed_dev=None):
     """One ``dpb_train_loss_grad`` call.  rows: host or device fp32 [6,B] (label, mean_c, std_c, res_c, z_c, row_w).
-    Returns the loss as a [] device tensor (a fresh copy); per-row losses stay in ``model._train_engine.loss_rows``."""
+    Returns the loss as a [] device tensor (a fresh copy unless ``clone=False``); per-row losses stay in
+    ``model._train_engine.loss_rows``."""
     L.require_cuda(batch, 'batch')
     dev = batch.device
     B = batch.shape[0]
@@ -108,10 +109,12 @@ def native_loss(model, batch, rows, z=None, drop_mask=None, drop_p=0.0, seed=0, 
     if drop_mask is not None:
         drop_mask = drop_mask.to(device=dev, dtype=torch.uint8).contiguous()
         assert drop_mask.shape == (L.NUM_DENSE, B, L.HIDDEN)
+    # where the Philox seed comes from: the argument, or (graph replay) device memory
+    L.check(L.load().dpb_train_set_seed_pointer(eng.ptr, seed_dev))
     L.check(L.load().dpb_train_loss_grad(eng.ptr, C.byref(P), C.byref(G) if G is not None else None, L.ptr(batch),
                                          L.ptr(rows), L.ptr(z), L.ptr(drop_mask), float(drop_p), C.c_uint64(seed),
                                          L.ptr(eng.loss), L.ptr(eng.loss_rows), L.current_stream(dev)))
-    return eng.loss[0].clone()
+    return eng.loss[0].clone() if clone else eng.loss[0]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -159,15 +162,30 @@ class FlatAdam(torch.optim.Adam):
         """Nothing to do: every gradient is overwritten by the next native backward pass (the views must stay)."""
 
     @torch.no_grad()
-    def step(self, closure=None, grad_clip=-1.0):
+    def step(self, closure=None, grad_clip=-1.0, hyper_dev=None):
+        """``hyper_dev`` (device fp32 [2], see :meth:`hyper`): the kernel reads the step size / bias correction from device
+        memory -- what a captured CUDA graph of the step needs."""
         g = self.param_groups[0]
         self._step += 1
         L.check(L.load().dpb_train_adam(L.ptr(self.flat_p), L.ptr(self.flat_g), L.ptr(self.flat_m), L.ptr(self.flat_v),
                                         self.flat_p.numel(), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]),
                                         float(g['eps']), float(g['weight_decay']), self._step, float(grad_clip),
-                                        L.ptr(self._scratch), L.current_stream(self.flat_p.device)))
+                                        L.ptr(hyper_dev), L.ptr(self._scratch), L.current_stream(self.flat_p.device)))
+
+    def _stamp(self):
         for st in self.state.values():
             st['step'] = torch.tensor(float(self._step))
+
+    def state_dict(self):
+        self._stamp()                      # the per-parameter 'step' entries are written when somebody looks
+        return super().state_dict()
+
+    def hyper(self, step):
+        """(lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step)) of Adam's ``step``-th update, rounded exactly like the native
+        entry point does it (fp32 arguments, double arithmetic, fp32 results)."""
+        g = self.param_groups[0]
+        lr, b1, b2 = (float(np.float32(v)) for v in (g['lr'], g['betas'][0], g['betas'][1]))
+        return float(np.float32(lr / (1.0 - b1 ** step))), float(np.float32(1.0 / np.sqrt(1.0 - b2 ** step)))
 
     def grad_norm(self):
         """||g||_2 over all parameters (what clip_grad_norm_ returns); synchronises."""
@@ -204,12 +222,13 @@ def optimization_manager(config):
     """losses.py:44-57: warm-up, gradient clipping (disabled if negative), optimiser step."""
 
     def optimize_fn(optimizer, params, step, lr=config.optim.lr, warmup=config.optim.warmup,
-                    grad_clip=config.optim.grad_clip):
+                    grad_clip=config.optim.grad_clip, hyper_dev=None):
         if warmup > 0:
             for g in optimizer.param_groups:
                 g['lr'] = lr * np.minimum(step / warmup, 1.0)
-        optimizer.step(grad_clip=grad_clip)
+        optimizer.step(grad_clip=grad_clip, hyper_dev=hyper_dev)
 
+    optimize_fn.warmup, optimize_fn.lr, optimize_fn.grad_clip = config.optim.warmup, config.optim.lr, config.optim.grad_clip
     return optimize_fn
 
 
@@ -234,8 +253,7 @@ def get_sde_loss_fn(sde, train, reduce_mean=False, continuous=True, likelihood_w
         raise NotImplementedError('the auxiliary (multi-step denoise + body model) loss is not built')
     red = (1.0 / _DATA_DIM) if reduce_mean else 0.5
 
-    def loss_fn(model, batch, condition=None, mask=None, t=None, z=None, drop_mask=None):
-        B = batch.shape[0]
+    def make_rows(model, B, t=None):
         if t is None:
             t = torch.rand(B) * (sde.T - eps) + eps                  # losses.py:111 (CPU generator here)
         t = t.detach().to('cpu', torch.float32)
@@ -247,9 +265,12 @@ def get_sde_loss_fn(sde, train, reduce_mean=False, continuous=True, likelihood_w
         else:
             g2 = sde.sde(torch.zeros(B, 1), t)[1] ** 2
             res_c, z_c, w = m, 1.0 / std, red * g2                                  # (score + z / std)^2 g^2
-        rows = torch.stack([labels.float(), mean_c, std, res_c, z_c, w])
-        return _run(model, batch, rows, train, z, drop_mask)
+        return torch.stack([labels.float(), mean_c, std, res_c, z_c, w])
 
+    def loss_fn(model, batch, condition=None, mask=None, t=None, z=None, drop_mask=None):
+        return _run(model, batch, make_rows(model, batch.shape[0], t), train, z, drop_mask)
+
+    loss_fn.make_rows = make_rows
     return loss_fn
 
 
@@ -259,17 +280,19 @@ def get_smld_loss_fn(vesde, train, reduce_mean=False):
     smld_sigma_array = torch.flip(vesde.discrete_sigmas, dims=(0,))
     red = (1.0 / _DATA_DIM) if reduce_mean else 0.5
 
-    def loss_fn(model, batch, condition=None, mask=None, labels=None, z=None, drop_mask=None):
-        B = batch.shape[0]
+    def make_rows(model, B, labels=None):
         if labels is None:
             labels = torch.randint(0, vesde.N, (B,))
         labels = labels.cpu()
         sig = smld_sigma_array[labels]
         inv_s = 1.0 / mutils.sigma_at(model, labels.float())
         # score = res / sigmas[label]; target = -z / sig; (score - target)^2 sig^2
-        rows = torch.stack([labels.float(), torch.ones(B), sig, inv_s, 1.0 / sig, red * sig ** 2])
-        return _run(model, batch, rows, train, z, drop_mask)
+        return torch.stack([labels.float(), torch.ones(B), sig, inv_s, 1.0 / sig, red * sig ** 2])
 
+    def loss_fn(model, batch, condition=None, mask=None, labels=None, z=None, drop_mask=None):
+        return _run(model, batch, make_rows(model, batch.shape[0], labels), train, z, drop_mask)
+
+    loss_fn.make_rows = make_rows
     return loss_fn
 
 
@@ -278,22 +301,69 @@ def get_ddpm_loss_fn(vpsde, train, reduce_mean=True):
     assert isinstance(vpsde, VPSDE), "DDPM training only works for VPSDEs."
     red = (1.0 / _DATA_DIM) if reduce_mean else 0.5
 
-    def loss_fn(model, batch, condition=None, mask=None, labels=None, z=None, drop_mask=None):
-        B = batch.shape[0]
+    def make_rows(model, B, labels=None):
         if labels is None:
             labels = torch.randint(0, vpsde.N, (B,))
         labels = labels.cpu()
         inv_s = 1.0 / mutils.sigma_at(model, labels.float())
-        rows = torch.stack([labels.float(), vpsde.sqrt_alphas_cumprod[labels], vpsde.sqrt_1m_alphas_cumprod[labels],
+        return torch.stack([labels.float(), vpsde.sqrt_alphas_cumprod[labels], vpsde.sqrt_1m_alphas_cumprod[labels],
                             inv_s, -torch.ones(B), torch.full((B,), red)])            # (score - noise)^2
-        return _run(model, batch, rows, train, z, drop_mask)
 
+    def loss_fn(model, batch, condition=None, mask=None, labels=None, z=None, drop_mask=None):
+        return _run(model, batch, make_rows(model, batch.shape[0], labels), train, z, drop_mask)
+
+    loss_fn.make_rows = make_rows
     return loss_fn
 
 
+class _GraphedStep:
+    """loss + backward + clip + Adam + EMA of one batch size as ONE captured CUDA graph.  What changes from step to step --
+    the per-row schedule scalars, the Philox seed, Adam's step size / bias correction, the EMA decay -- lives in one
+    device buffer that a single small host-to-device copy refreshes before every replay."""
+
+    def __init__(self, model, optimizer, ema, B, dev, grad_clip):
+        self.B, self.dev = B, dev
+        self.eng = _engine(model, B, dev)
+        self.buf = torch.zeros(8 + 6 * B, device=dev)            # [step_size, inv_sqrt_bc2, omd, -, seed lo, seed hi, -, -, rows]
+        self.host = torch.zeros(8 + 6 * B)
+        self.batch = torch.zeros(B, _DATA_DIM, device=dev)
+        rows, hyper = self.buf[8:].view(6, B), self.buf[:3]
+        seed_dev = C.c_void_p(self.buf.data_ptr() + 16)
+        p = float(model.config.model.dropout)
+        keep = (optimizer._step, ema.num_updates)
+
+        def body():
+            native_loss(model, self.batch, rows, drop_p=p, seed=0, grads=True, clone=False, seed_dev=seed_dev)
+            optimizer.step(grad_clip=grad_clip, hyper_dev=hyper[:2])
+            ema.update(model.parameters(), omd_dev=hyper[2:])
+        self.graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(self.graph):
+            body()
+        optimizer._step, ema.num_updates = keep                  # capture launched nothing: undo the host-side counters
+
+    def run(self, optimizer, ema, batch, rows, lr_t):
+        for g in optimizer.param_groups:
+            g['lr'] = lr_t
+        optimizer._step += 1
+        h = self.host
+        h[0], h[1] = optimizer.hyper(optimizer._step)
+        h[2] = ema.next_one_minus_decay()
+        h[4:6] = torch.tensor([_draw_seed()], dtype=torch.int64).view(torch.float32)
+        h[8:] = rows.reshape(-1)
+        self.buf.copy_(h)                                        # pageable source: the copy is complete when this returns
+        self.batch.copy_(batch, non_blocking=True)
+        self.graph.replay()
+        if ema.num_updates is not None:
+            ema.num_updates += 1
+        return self.eng.loss[0].clone()
+
+
 def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True, likelihood_weighting=False,
-                auxiliary_loss=False, denormalize=None, body_model=None, rot_rep='rot6d', denoise_steps=5):
-    """losses.py:187-275: ``step_fn(state, batch)`` with ``state = dict(optimizer, model, ema, step)``."""
+                auxiliary_loss=False, denormalize=None, body_model=None, rot_rep='rot6d', denoise_steps=5, graph=False):
+    """losses.py:187-275: ``step_fn(state, batch)`` with ``state = dict(optimizer, model, ema, step)``.
+    ``graph=True``: the training step of each batch size is captured once as a CUDA graph and replayed (needs the
+    optimize_fn of :func:`optimization_manager`; steps that replay given draws -- ``z=`` / ``drop_mask=`` -- run eagerly)."""
     if auxiliary_loss:
         raise NotImplementedError('the auxiliary (multi-step denoise + body model) loss is not built')
     if continuous:
@@ -308,9 +378,23 @@ def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True
         else:
             raise ValueError(f"Discrete training for {sde.__class__.__name__} is not recommended.")
 
+    graphs = {}
+
     def step_fn(state, batch, condition=None, mask=None, **draws):
         model = state['model']
-        if train:
+        if train and graph and 'z' not in draws and 'drop_mask' not in draws:
+            optimizer, ema, B = state['optimizer'], state['ema'], batch.shape[0]
+            L.require_cuda(batch, 'batch')
+            g = graphs.get(B)
+            if g is None:
+                g = graphs[B] = _GraphedStep(model, optimizer, ema, B, batch.device, optimize_fn.grad_clip)
+            rows = loss_fn.make_rows(model, B, **draws)
+            warm, lr = optimize_fn.warmup, optimize_fn.lr
+            lr_t = lr * min(state['step'] / warm, 1.0) if warm > 0 else lr
+            loss = g.run(optimizer, ema, batch.detach().to(torch.float32), rows, lr_t)
+            state['step'] += 1
+            model.mark_updated()
+        elif train:
             optimizer = state['optimizer']
             optimizer.zero_grad()
             loss = loss_fn(model, batch, condition, mask, **draws)       # loss and every p.grad in one native call

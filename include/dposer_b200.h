@@ -343,9 +343,16 @@ int dpb_train_grad_norm(const float* g, int64_t n, void* scratch, void* stream);
  * grad_clip >= 0 (losses.py:53-54): the clip coefficient is evaluated on the device, no host synchronisation.
  * `lr` already contains the warm-up factor (losses.py:50-52); step >= 1 is Adam's own step count. */
 int dpb_train_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, int64_t step, float grad_clip, void* scratch, void* stream);
+                   float eps, float weight_decay, int64_t step, float grad_clip, const float* hyper_dev, void* scratch,
+                   void* stream);
+/* hyper_dev (optional, for CUDA-graph replay): DEVICE fp32 [2] = { lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step) }
+ * read by the kernel instead of the values derived from lr / step on the host */
 /* shadow -= one_minus_decay * (shadow - p)   (ExponentialMovingAverage.update, ema.py:35-50) */
-int dpb_ema_update(float* shadow, const float* p, int64_t n, float one_minus_decay, void* stream);
+int dpb_ema_update(float* shadow, const float* p, int64_t n, float one_minus_decay, const float* omd_dev, void* stream);
+/* omd_dev (optional): DEVICE fp32 [1] read instead of one_minus_decay.  dpb_train_set_seed_pointer: the Philox seed of
+ * dpb_train_loss_grad is read from DEVICE memory from now on (NULL switches back to the argument) -- with both, a
+ * captured CUDA graph of one training step can be replayed with fresh draws and schedule values. */
+int dpb_train_set_seed_pointer(dpb_train_t* h, const uint64_t* seed_dev);
 
 /* ------------------------------------------------------------------------------------------
  * Metrics (replaces average_pairwise_distance lib/utils/metric.py:8-37 and the per-sample
