@@ -46,10 +46,12 @@ struct Params {
   int vec;                   // every pointer 16-byte aligned and every stride a multiple of 4: float4 epilogue
 };
 
+template <int BN>      // output tile 128 x BN: BN = 64 doubles the CTA count of the small GEMMs (a step at batch 1280 is latency-bound)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUtensorMap tm_a,
                   const __grid_constant__ CUtensorMap tm_b) {
-  constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, 128, 0);
+  constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, BN, 0);
+  constexpr uint32_t BTILE = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sb = ptx::smem_u32(smem);
@@ -64,12 +66,12 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
     ptx::mbar_init(dfull, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 128);
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), BN);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
 
   if (warp == 0) {
     if (lane == 0) { ptx::prefetch_tmap(&tm_a); ptx::prefetch_tmap(&tm_b); }
@@ -79,7 +81,7 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
       ptx::mbar_wait(empty(s), ph ^ 1);
       if (ptx::elect_one()) {
         const uint32_t base = sb + s * 4 * TILE;
-        ptx::mbar_arrive_expect_tx(full(s), 4 * TILE);
+        ptx::mbar_arrive_expect_tx(full(s), 2 * TILE + 2 * BTILE);
         ptx::tma_load_2d(base, &tm_a, full(s), p.a_k0 + k * BK, p.a_r0 + m0);
         ptx::tma_load_2d(base + TILE, &tm_a, full(s), p.a_k0 + p.a_lo + k * BK, p.a_r0 + m0);
         ptx::tma_load_2d(base + 2 * TILE, &tm_b, full(s), p.b_k0 + k * BK, p.b_r0 + n0);
@@ -116,7 +118,7 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
     ptx::tc_fence_after();
     const bool vec = p.vec != 0;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
       ptx::tmem_ld_wait();
@@ -152,7 +154,7 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 128);
+    ptx::tmem_dealloc(tmem_base, BN);
   }
 }
 
@@ -195,7 +197,8 @@ __global__ void split_kernel(const float* __restrict__ src, int R, int Cc, int64
 }  // namespace gtc
 
 int gemm_tc_init() {
-  DPB_CUDA_CHECK(cudaFuncSetAttribute(gtc::gemm_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(gtc::gemm_split_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(gtc::gemm_split_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gtc::SMEM_BYTES));
   return DPB_OK;
 }
 
@@ -203,9 +206,12 @@ int gemm_tc(const Op16& A, const Op16& B, int M, int N, int K, float* C, int64_t
             const float* bias2, const float* add, int64_t ldadd, cudaStream_t st) {
   if (M <= 0 || N <= 0) return DPB_OK;
   CUtensorMap ta, tb;
+  const int mt = (M + 127) / 128;
+  const int bn = (mt * ((N + 127) / 128) < 48) ? 64 : 128;     // under a third of a wave of 128 x 128 tiles: halve the tile
+  // (measured: at 80 CTAs the 128-wide tile is as fast -- the kernel is bound by the bytes each SM pulls from L2 per k-block)
   int rc = make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, A.ptr, (uint64_t)A.ld, (uint64_t)A.rows, gtc::BK, 128, 2);
   if (rc != DPB_OK) return rc;
-  rc = make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, B.ptr, (uint64_t)B.ld, (uint64_t)B.rows, gtc::BK, 128, 2);
+  rc = make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, B.ptr, (uint64_t)B.ld, (uint64_t)B.rows, gtc::BK, (uint32_t)bn, 2);
   if (rc != DPB_OK) return rc;
   gtc::Params p{};
   p.M = M; p.N = N; p.kt = (K + gtc::BK - 1) / gtc::BK;
@@ -214,8 +220,11 @@ int gemm_tc(const Op16& A, const Op16& B, int M, int N, int K, float* C, int64_t
   p.C = C; p.ldc = ldc; p.bias1 = bias1; p.bias2 = bias2; p.add = add; p.ldadd = ldadd;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec = al(C) && al(bias1) && al(bias2) && al(add) && (ldc & 3) == 0 && (!add || (ldadd & 3) == 0);
-  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((N + 127) / 128));
-  gtc::gemm_split_kernel<<<grid, gtc::NUM_THREADS, gtc::SMEM_BYTES, st>>>(p, ta, tb);
+  dim3 grid((unsigned)mt, (unsigned)((N + bn - 1) / bn));
+  if (bn == 64)
+    gtc::gemm_split_kernel<64><<<grid, gtc::NUM_THREADS, gtc::SMEM_BYTES, st>>>(p, ta, tb);
+  else
+    gtc::gemm_split_kernel<128><<<grid, gtc::NUM_THREADS, gtc::SMEM_BYTES, st>>>(p, ta, tb);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }

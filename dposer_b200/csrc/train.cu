@@ -174,6 +174,30 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
   }
 }
 
+// the three column sums of one stage's backward in one launch (blockIdx.y picks the source): d beta, d gamma, d bias
+__global__ void __launch_bounds__(1024) colsum3_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
+                                                       const float* __restrict__ s2, int64_t ld2, int64_t R,
+                                                       float* __restrict__ d0, float* __restrict__ d1,
+                                                       float* __restrict__ d2a, float* __restrict__ d2b) {
+  __shared__ float part[32][33];
+  const int which = blockIdx.y;
+  const float* src = which == 0 ? s0 : which == 1 ? s1 : s2;
+  const int64_t ld = which == 2 ? ld2 : H;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  for (int64_t r = threadIdx.y; r < R; r += 32) s += src[r * ld + c];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += part[i][threadIdx.x];
+    if (which == 0) d0[c] = t;
+    else if (which == 1) d1[c] = t;
+    else { d2a[c] = t; d2b[c] = t; }
+  }
+}
+
 // e = res_c res + z_c z ; loss_row = row_w sum e^2 ; d loss / d res = 2 row_w res_c e / B   (losses.py:124-131)
 __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ res, const float* __restrict__ z,
                                                    const float* __restrict__ rows, float* __restrict__ gres,
@@ -410,9 +434,7 @@ extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, con
     const float* gout = (s & 1) ? h->gB : h->gA;
     trn::gn_act_bwd_kernel<<<gw, 256, 0, st>>>(gout, h->u[s], gam[s], bet[s], h->mean[s], h->rstd[s], gu, NL * H, h->t1,
                                                h->t2, mask_given, seed, h->seed_dev, s, drop_p, B);
-    trn::colsum_kernel<<<H / 32, cs, 0, st>>>(h->t1, B, H, H, 1.0f, gbet[s], nullptr);
-    trn::colsum_kernel<<<H / 32, cs, 0, st>>>(h->t2, B, H, H, 1.0f, ggam[s], nullptr);
-    trn::colsum_kernel<<<H / 32, cs, 0, st>>>(gu, B, H, NL * H, 1.0f, gbl[s], gbt[s]);
+    trn::colsum3_kernel<<<dim3(H / 32, 3), cs, 0, st>>>(h->t1, h->t2, gu, NL * H, B, gbet[s], ggam[s], gbl[s], gbt[s]);
     const Op16 grow = h->G16.block(0, s * H), gcol = h->GT16.block(s * H, 0);
     TRY(split16(gu, Bi, H, NL * H, &grow, &gcol, st));
     fork();
