@@ -388,7 +388,8 @@ def bench_configs(args, dev, model, peaks, flush, cpu_per_row_step):
         tm.train()
         state = dict(optimizer=losses.get_optimizer(cfg, tm.parameters()), model=tm,
                      ema=ExponentialMovingAverage(tm.parameters(), decay=cfg.model.ema_rate), step=0)
-        step_fn = losses.get_step_fn(sde, True, losses.optimization_manager(cfg), reduce_mean=cfg.training.reduce_mean)
+        step_fn = losses.get_step_fn(sde, True, losses.optimization_manager(cfg), reduce_mean=cfg.training.reduce_mean,
+                                     graph=True)
         toy = synthetic.toy_poses()
         host = norm.offline_normalize(toy[torch.randint(0, toy.shape[0], (Bt,))].to(dev)).cpu().pin_memory()
         data = host.to(dev)
@@ -416,7 +417,7 @@ def bench_configs(args, dev, model, peaks, flush, cpu_per_row_step):
         torch.cuda.empty_cache()
     out['f3_train_step'] = {
         'workload': 'SURVEY 8(f)3: one training step of ScoreModelFC (sub-VP denoising score matching, per-row t, dropout 0.1, '
-                    'grad clip 1.0, Adam, EMA) -- 27 tcgen05 GEMMs + elementwise kernels per step; synthetic AMASS-like poses',
+                    'grad clip 1.0, Adam, EMA) -- 27 tcgen05 GEMMs + elementwise kernels per step, replayed as one CUDA graph; AMASS toy poses',
         'flop_per_row_step': FLOP_ROW, **tr['reference_batch'], 'large_batch': tr['large_batch']}
     return out
 

@@ -10,7 +10,7 @@
 //
 //   warp 0     TMA producer: per k-block the four tiles A_hi, A_lo, B_hi, B_lo (64 KB stage, 3 stages)
 //   warp 1     TMEM allocator + MMA issuer: 12 UMMAs (M = 128, N = 128, K = 16) per stage
-//   warps 2-5  epilogue: TMEM -> registers -> C (thread = output row, 32 consecutive columns per TMEM load)
+//   warps 2-5  epilogue: TMEM -> registers -> 32 x 32 transpose in shared memory -> C (a warp stores whole row segments)
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 
@@ -43,7 +43,6 @@ struct Params {
   const float* bias2;        // [N] or null
   const float* add;          // [M, ldadd] or null (may alias C)
   int64_t ldadd;
-  int vec;                   // every pointer 16-byte aligned and every stride a multiple of 4: float4 epilogue
 };
 
 template <int BN>      // output tile 128 x BN: BN = 64 doubles the CTA count of the small GEMMs (a step at batch 1280 is latency-bound)
@@ -113,40 +112,50 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
     __syncwarp();
   } else {
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
-    const int m = m0 + q * 32 + lane;
+    // Each 32 x 32 block is transposed through shared memory (the operand stages are idle by then) so that a warp writes
+    // 128 contiguous bytes of one output row per instruction.  Everything the epilogue reads from global memory (bias,
+    // the added matrix) is requested BEFORE the accumulator is waited for / loaded: the loads of a block are independent.
+    float* tr = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    const int mrow0 = m0 + q * 32;
+    const int rmax = min(32, p.M - mrow0);
+    float bsum[BN / 32];
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      const int n = n0 + c * 32 + lane;
+      bsum[c] = 0.f;
+      if (n < p.N) {
+        if (p.bias1) bsum[c] += p.bias1[n];
+        if (p.bias2) bsum[c] += p.bias2[n];
+      }
+    }
+    auto load_add = [&](int c, float (&a)[32]) {
+      const int n = n0 + c * 32 + lane;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        a[r] = (p.add && n < p.N && r < rmax) ? p.add[(size_t)(mrow0 + r) * p.ldadd + n] : 0.f;
+    };
+    float a[32];
+    load_add(0, a);
     ptx::mbar_wait(dfull, 0);
     ptx::tc_fence_after();
-    const bool vec = p.vec != 0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
       ptx::tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (m >= p.M || nb >= p.N) continue;
-      float* crow = p.C + (size_t)m * p.ldc + nb;
-      const float* arow = p.add ? p.add + (size_t)m * p.ldadd + nb : nullptr;
-      if (vec && nb + 32 <= p.N) {
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                 __uint_as_float(v[i + 3]));
-          if (p.bias1) { const float4 b = *reinterpret_cast<const float4*>(p.bias1 + nb + i); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-          if (p.bias2) { const float4 b = *reinterpret_cast<const float4*>(p.bias2 + nb + i); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-          if (arow) { const float4 b = *reinterpret_cast<const float4*>(arow + i); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-          *reinterpret_cast<float4*>(crow + i) = o;
-        }
-      } else {
+      for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = __uint_as_float(v[i]);
+      __syncwarp();
+      const int n = n0 + c * 32 + lane;
+      float o[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (nb + i < p.N) {
-            float o = __uint_as_float(v[i]);
-            if (p.bias1) o += p.bias1[nb + i];
-            if (p.bias2) o += p.bias2[nb + i];
-            if (arow) o += arow[i];
-            crow[i] = o;
-          }
-        }
+      for (int r = 0; r < 32; ++r) o[r] = tr[r * 33 + lane] + bsum[c] + a[r];
+      if (c + 1 < BN / 32) load_add(c + 1, a);            // next block's loads fly while this one is stored
+      if (n < p.N) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (r < rmax) p.C[(size_t)(mrow0 + r) * p.ldc + n] = o[r];
       }
     }
   }
@@ -218,8 +227,6 @@ int gemm_tc(const Op16& A, const Op16& B, int M, int N, int K, float* C, int64_t
   p.a_r0 = A.r0; p.a_k0 = A.k0; p.a_lo = A.lo;
   p.b_r0 = B.r0; p.b_k0 = B.k0; p.b_lo = B.lo;
   p.C = C; p.ldc = ldc; p.bias1 = bias1; p.bias2 = bias2; p.add = add; p.ldadd = ldadd;
-  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  p.vec = al(C) && al(bias1) && al(bias2) && al(add) && (ldc & 3) == 0 && (!add || (ldadd & 3) == 0);
   dim3 grid((unsigned)mt, (unsigned)((N + bn - 1) / bn));
   if (bn == 64)
     gtc::gemm_split_kernel<64><<<grid, gtc::NUM_THREADS, gtc::SMEM_BYTES, st>>>(p, ta, tb);

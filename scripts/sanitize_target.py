@@ -42,3 +42,24 @@ md = fitting.MotionDenoise(cfg, types.SimpleNamespace(device='cuda'), model, bm,
                            sde_N=500, batch_size=rows, seq_len=L_)
 r = md.optimize(jn, time_strategy='3', sample_trun=4.0, iterations=1, steps_per_iter=2)
 torch.cuda.synchronize(); print('motion denoise ok', bool(torch.isfinite(r['pose_body']).all()))
+# round 2, training step (8(f) row 3): eager (side stream) and graph replay, ragged batch; the GEMM utility entry at ragged sizes
+from dposer_b200 import losses
+from dposer_b200.ema import ExponentialMovingAverage
+cfg.optim.warmup = 2
+tm = synthetic.make_score_model(42).cuda(); tm.train()
+state = dict(optimizer=losses.get_optimizer(cfg, tm.parameters()), model=tm,
+             ema=ExponentialMovingAverage(tm.parameters(), decay=cfg.model.ema_rate), step=0)
+sde1k = sde_lib.subVPSDE(0.1, 20., 1000)
+data = synthetic.toy_poses()[:200].cuda()
+for graph in (False, True):
+    fn = losses.get_step_fn(sde1k, True, losses.optimization_manager(cfg), reduce_mean=True, graph=graph)
+    for i in range(3):
+        ld = fn(state, data[:130 + 35 * (i % 2)])
+    torch.cuda.synchronize(); print('train step ok graph=%s' % graph, float(ld['step_loss']))
+import ctypes
+lib = L.load()
+for (M, N, K) in [(257, 129, 200), (63, 1024, 96)]:
+    A, Bm, out = torch.randn(M, K).cuda(), torch.randn(N, K).cuda(), torch.empty(M, N).cuda()
+    ws = torch.empty(int(lib.dpb_gemm_nt_workspace_bytes(M, N, K)), dtype=torch.uint8, device='cuda')
+    L.check(lib.dpb_gemm_nt(L.ptr(A), L.ptr(Bm), None, L.ptr(out), M, N, K, L.ptr(ws), ws.numel(), L.current_stream(A.device)))
+    torch.cuda.synchronize(); print('gemm ok', float((out - A @ Bm.T).abs().max()))
