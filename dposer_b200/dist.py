@@ -67,6 +67,18 @@ def all_reduce_sum(t):
     return t
 
 
+def all_reduce_mean_(t):
+    """In-place mean over ranks: the data-parallel gradient all-reduce of the training step (one flat buffer, one
+    collective).  NCCL averages inside the collective; gloo (CPU tests) sums and divides."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_backend() == 'nccl':
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(t)
+            t.div_(dist.get_world_size())
+    return t
+
+
 def max_over_ranks(value, device):
     """Max of a python float over ranks (timing rule: report the slowest rank)."""
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)

@@ -360,10 +360,15 @@ class _GraphedStep:
 
 
 def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True, likelihood_weighting=False,
-                auxiliary_loss=False, denormalize=None, body_model=None, rot_rep='rot6d', denoise_steps=5, graph=False):
+                auxiliary_loss=False, denormalize=None, body_model=None, rot_rep='rot6d', denoise_steps=5, graph=False,
+                data_parallel=False):
     """losses.py:187-275: ``step_fn(state, batch)`` with ``state = dict(optimizer, model, ema, step)``.
     ``graph=True``: the training step of each batch size is captured once as a CUDA graph and replayed (needs the
-    optimize_fn of :func:`optimization_manager`; steps that replay given draws -- ``z=`` / ``drop_mask=`` -- run eagerly)."""
+    optimize_fn of :func:`optimization_manager`; steps that replay given draws -- ``z=`` / ``drop_mask=`` -- run eagerly).
+    ``data_parallel=True`` (one process per GPU, ``torch.distributed`` initialised): every rank steps on its own shard of the
+    batch and the flat gradient buffer is averaged over ranks with ONE all-reduce before clipping / Adam -- the reference
+    trains on one GPU (run/train.py), this is the collective SURVEY 8(e)/(f)3 names for scaling it out."""
+    from . import dist as D
     if auxiliary_loss:
         raise NotImplementedError('the auxiliary (multi-step denoise + body model) loss is not built')
     if continuous:
@@ -382,7 +387,7 @@ def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True
 
     def step_fn(state, batch, condition=None, mask=None, **draws):
         model = state['model']
-        if train and graph and 'z' not in draws and 'drop_mask' not in draws:
+        if train and graph and not data_parallel and 'z' not in draws and 'drop_mask' not in draws:
             optimizer, ema, B = state['optimizer'], state['ema'], batch.shape[0]
             L.require_cuda(batch, 'batch')
             g = graphs.get(B)
@@ -398,6 +403,8 @@ def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True
             optimizer = state['optimizer']
             optimizer.zero_grad()
             loss = loss_fn(model, batch, condition, mask, **draws)       # loss and every p.grad in one native call
+            if data_parallel:
+                D.all_reduce_mean_(optimizer.flat_g)
             optimize_fn(optimizer, model.parameters(), step=state['step'])
             state['step'] += 1
             model.mark_updated()

@@ -32,6 +32,9 @@ def _worker(rank, world, port, total, q):
     part = torch.tensor([float(full[s:s + n].sum())], dtype=torch.float64)
     tot = D.all_reduce_sum(part)
     ok = ok and abs(float(tot) - float(full.sum())) < 1e-6
+    g = torch.full((5,), float(rank + 1))
+    D.all_reduce_mean_(g)                       # the training step's gradient all-reduce (mean over ranks)
+    ok = ok and bool((g == (world + 1) / 2).all())
     mx = D.max_over_ranks(10.0 + rank, 'cpu')
     ok = ok and mx == 10.0 + world - 1
     q.put((rank, bool(ok), s, n))
