@@ -223,3 +223,41 @@ def test_graphed_train_step_matches_eager_step():
     assert a[0] == b[0], (a[0], b[0])
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
     assert a[4:] == b[4:] == (6, 6, 6)
+
+
+def test_checkpoint_resume_continues_identically(tmp_path):
+    """run/train.py:182-191,392-403: a checkpoint in the reference's layout (model_state_dict / optimizer_state_dict / ema /
+    step) written after two steps and loaded into a fresh model + optimiser + EMA continues bit for bit."""
+    cfg = synthetic.default_config()
+    cfg.optim.warmup = 3
+    sde = sde_lib.subVPSDE(0.1, 20., 1000)
+    data = synthetic.toy_poses()[:128].cuda()
+
+    def fresh(seed):
+        model = synthetic.make_score_model(seed).cuda()
+        model.train()
+        return _state(cfg, model)
+    step_fn = losses.get_step_fn(sde, train=True, optimize_fn=losses.optimization_manager(cfg), reduce_mean=True)
+    a = fresh(42)
+    torch.manual_seed(1)
+    for _ in range(2):
+        step_fn(a, data)
+    path = str(tmp_path / 'checkpoint-step2.pth')
+    torch.save({'epoch': 1, 'model_state_dict': a['model'].state_dict(), 'optimizer_state_dict': a['optimizer'].state_dict(),
+                'ema': a['ema'].state_dict(), 'step': a['step']}, path)
+    torch.manual_seed(2)
+    la = float(step_fn(a, data)['step_loss'])
+    b = fresh(7)                                            # different weights: everything must come from the file
+    ck = torch.load(path, map_location='cuda', weights_only=False)
+    b['model'].load_state_dict(ck['model_state_dict'])
+    b['optimizer'].load_state_dict(ck['optimizer_state_dict'])
+    b['ema'].load_state_dict(ck['ema'])
+    b['step'] = ck['step']
+    torch.manual_seed(2)
+    lb = float(step_fn(b, data)['step_loss'])
+    assert la == lb and b['step'] == 3 and b['ema'].num_updates == 3
+    assert torch.equal(a['optimizer'].flat_p, b['optimizer'].flat_p)
+    assert torch.equal(a['optimizer'].flat_m, b['optimizer'].flat_m) and torch.equal(a['optimizer'].flat_v, b['optimizer'].flat_v)
+    assert all(torch.equal(x, y) for x, y in zip(a['ema'].shadow_params, b['ema'].shadow_params))
+    # the EMA update after a load runs on the re-allocated flat shadow buffer too
+    assert b['ema']._flat.numel() == a['ema']._flat.numel()
