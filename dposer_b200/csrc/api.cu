@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "score.h"
+#include "train.h"
 
 namespace dpb {
 
@@ -115,6 +116,7 @@ extern "C" int dpb_score_destroy(dpb_score_t* h) {
   if (!h) return DPB_OK;
   DeviceGuard guard(h->device);
   tc_release(h);
+  score_jvp_tc_release(h);
   std::vector<void*> ptrs = {h->pre_w, h->post_w, h->post_b, h->temb_w, h->temb_b, h->emb_freqs, h->gn_packed};
   for (int i = 0; i < 4; ++i) ptrs.push_back(h->blk_w[i]);
   for (int l = 0; l < NL; ++l) {
@@ -256,7 +258,8 @@ extern "C" int dpb_sampler_run_pc(dpb_score_t* h, float* x_io, const dpb_step_ta
 
 extern "C" size_t dpb_score_jvp_workspace_bytes(dpb_score_t* h, int64_t B) {
   if (!h || B <= 0) return 0;
-  return simt_forward_ws_bytes(2 * B) + align_up((size_t)2 * B * DP * 4, 256) + 1024;
+  const size_t simt = simt_forward_ws_bytes(2 * B), tc = score_jvp_tc_ws_bytes(B);
+  return (simt > tc ? simt : tc) + align_up((size_t)2 * B * DP * 4, 256) + 1024;
 }
 
 extern "C" int dpb_score_jvp(dpb_score_t* h, const float* x, const float* v, const float* table, const int32_t* t_index,
@@ -272,7 +275,10 @@ extern "C" int dpb_score_jvp(dpb_score_t* h, const float* x, const float* v, con
   if (!c.ok() || ws == nullptr || ws_bytes < dpb_score_jvp_workspace_bytes(h, B))
     return fail(DPB_ENOMEM, "dpb_score_jvp: workspace too small");
   void* rest = static_cast<uint8_t*>(ws) + c.off;
-  int rc = simt_forward_jvp_raw(h, x, v, table, t_index, raw, B, rest, ws_bytes - c.off, st);
+  // batch-uniform time (the likelihood's case): every contraction on tcgen05; per-row tables keep the fp32 SGEMM path
+  static const bool force_fp32 = getenv("DPB_JVP_FP32") && atoi(getenv("DPB_JVP_FP32")) != 0;
+  int rc = (!t_index && !force_fp32) ? score_jvp_tc_raw(h, x, v, table, raw, B, rest, ws_bytes - c.off, st)
+                                     : simt_forward_jvp_raw(h, x, v, table, t_index, raw, B, rest, ws_bytes - c.off, st);
   if (rc != DPB_OK) return rc;
   rc = launch_scale_out(raw, row_scale, scale, out, B, st);
   if (rc != DPB_OK) return rc;

@@ -43,6 +43,7 @@ struct Params {
   const float* bias2;        // [N] or null
   const float* add;          // [M, ldadd] or null (may alias C)
   int64_t ldadd;
+  int bias_rows;             // the biases apply to rows < bias_rows (stacked [primal ; tangent] rows of the JVP)
 };
 
 template <int BN>      // output tile 128 x BN: BN = 64 doubles the CTA count of the small GEMMs (a step at batch 1280 is latency-bound)
@@ -150,7 +151,7 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
       const int n = n0 + c * 32 + lane;
       float o[32];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) o[r] = tr[r * 33 + lane] + bsum[c] + a[r];
+      for (int r = 0; r < 32; ++r) o[r] = tr[r * 33 + lane] + (mrow0 + r < p.bias_rows ? bsum[c] : 0.f) + a[r];
       if (c + 1 < BN / 32) load_add(c + 1, a);            // next block's loads fly while this one is stored
       if (n < p.N) {
 #pragma unroll
@@ -212,7 +213,7 @@ int gemm_tc_init() {
 }
 
 int gemm_tc(const Op16& A, const Op16& B, int M, int N, int K, float* C, int64_t ldc, const float* bias1,
-            const float* bias2, const float* add, int64_t ldadd, cudaStream_t st) {
+            const float* bias2, const float* add, int64_t ldadd, cudaStream_t st, int bias_rows) {
   if (M <= 0 || N <= 0) return DPB_OK;
   CUtensorMap ta, tb;
   const int mt = (M + 127) / 128;
@@ -227,6 +228,7 @@ int gemm_tc(const Op16& A, const Op16& B, int M, int N, int K, float* C, int64_t
   p.a_r0 = A.r0; p.a_k0 = A.k0; p.a_lo = A.lo;
   p.b_r0 = B.r0; p.b_k0 = B.k0; p.b_lo = B.lo;
   p.C = C; p.ldc = ldc; p.bias1 = bias1; p.bias2 = bias2; p.add = add; p.ldadd = ldadd;
+  p.bias_rows = bias_rows;
   dim3 grid((unsigned)mt, (unsigned)((N + bn - 1) / bn));
   if (bn == 64)
     gtc::gemm_split_kernel<64><<<grid, gtc::NUM_THREADS, gtc::SMEM_BYTES, st>>>(p, ta, tb);

@@ -42,6 +42,7 @@ struct dpb_score {
   float l2_hit = 1.f;
   float* gn_tc = nullptr;       // [5][2][1024] gamma | beta as staged by the tcgen05 epilogue
   int* tc_flags = nullptr;      // [slots] hand-off flags of the sampler's segment schedule (score_tc.cu: SegIter)
+  void* jvp_ops = nullptr;      // fp16 [hi | lo] weight operands of the tensor-core JVP (jvp_tc.cu), built on first use
 };
 
 namespace dpb {

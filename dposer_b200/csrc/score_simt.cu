@@ -5,6 +5,7 @@
 //
 // Math follows ScoreModelFC.forward (reference lib/algorithms/advanced/model.py:141-196).
 #include "score.h"
+#include "train.h"
 
 namespace dpb {
 
@@ -324,6 +325,108 @@ int simt_forward_jvp_raw(dpb_score* h, const float* x, const float* v, const flo
   }
   dim3 post_grid(DP / BN, (unsigned)((B2 + BM - 1) / BM));
   sgemm_bias_kernel<<<post_grid, 256, 0, st>>>(hbuf, h->post_w, raw, B2, DP, H, nullptr, nullptr, 0, h->post_b, B);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+
+// ------------------------------------------------------------------ the same JVP with every contraction on tcgen05
+// (gemm_tc.cu: fp16 [hi | lo] operands, three products, fp32 accumulation in TMEM -- ~1e-6 relative, so it stands in for
+// the fp32 SGEMM above).  Batch-uniform time only (one table row, the likelihood's case): the affine part of a layer is a
+// column bias applied to the primal rows.  The weight operands are built once per handle.
+struct JvpOps {
+  __half* pool = nullptr;
+  Op16 Wpre, W[4], Wpost;
+};
+
+static Op16 carve_op16(WsCarver& ws, int64_t rows, int64_t kp) {
+  Op16 o;
+  o.ptr = ws.take<__half>((size_t)rows * 2 * kp);
+  o.ld = 2 * kp;
+  o.rows = rows;
+  o.lo = (int)kp;
+  return o;
+}
+
+static size_t jvp_weight_layout(JvpOps* o, void* base, size_t cap) {
+  WsCarver ws(base, cap);
+  o->Wpre = carve_op16(ws, H, DP);
+  for (int l = 0; l < 4; ++l) o->W[l] = carve_op16(ws, H, H);
+  o->Wpost = carve_op16(ws, DP, H);
+  return align_up(ws.off, 256);
+}
+
+struct JvpWs {
+  float *xp, *pre, *hbuf, *tbuf;
+  Op16 xp16, a16;
+};
+
+static size_t jvp_ws_layout(JvpWs* w, int64_t B2, void* base, size_t cap) {
+  WsCarver ws(base, cap);
+  w->xp = ws.take<float>((size_t)B2 * DP);
+  w->pre = ws.take<float>((size_t)B2 * H);
+  w->hbuf = ws.take<float>((size_t)B2 * H);
+  w->tbuf = ws.take<float>((size_t)B2 * H);
+  w->xp16 = carve_op16(ws, B2, DP);
+  w->a16 = carve_op16(ws, B2, H);
+  return align_up(ws.off, 256);
+}
+
+size_t score_jvp_tc_ws_bytes(int64_t B) {
+  JvpWs w;
+  return jvp_ws_layout(&w, 2 * B, nullptr, ~(size_t)0) + 1024;
+}
+
+void score_jvp_tc_release(dpb_score* h) {
+  JvpOps* o = static_cast<JvpOps*>(h->jvp_ops);
+  if (!o) return;
+  if (o->pool) cudaFree(o->pool);
+  delete o;
+  h->jvp_ops = nullptr;
+}
+
+int score_jvp_tc_raw(dpb_score* h, const float* x, const float* v, const float* table, float* raw, int64_t B, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+  if (B <= 0) return DPB_OK;
+  int rc = DPB_OK;
+  JvpOps* o = static_cast<JvpOps*>(h->jvp_ops);
+  if (!o) {
+    if ((rc = gemm_tc_init()) != DPB_OK) return rc;
+    o = new JvpOps();
+    const size_t bytes = jvp_weight_layout(o, nullptr, ~(size_t)0);
+    if (cudaMalloc((void**)&o->pool, bytes) != cudaSuccess) { delete o; return fail(DPB_ENOMEM, "score jvp: weight operands"); }
+    jvp_weight_layout(o, o->pool, bytes);
+    h->jvp_ops = o;
+    if ((rc = split16(h->pre_w, H, DP, DP, &o->Wpre, nullptr, st)) != DPB_OK) return rc;
+    for (int l = 0; l < 4; ++l)
+      if ((rc = split16(h->blk_w[l], H, H, H, &o->W[l], nullptr, st)) != DPB_OK) return rc;
+    if ((rc = split16(h->post_w, DP, H, H, &o->Wpost, nullptr, st)) != DPB_OK) return rc;
+  }
+  const int64_t B2 = 2 * B;
+  JvpWs w;
+  if (ws == nullptr || jvp_ws_layout(&w, B2, ws, ws_bytes) > ws_bytes) return fail(DPB_ENOMEM, "score jvp: workspace too small");
+  const int M = (int)B2, Bi = (int)B;
+  {
+    int64_t n = B * DP;
+    pad_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, w.xp, B);
+    pad_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, w.xp + (size_t)B * DP, B);
+  }
+#define JTRY(expr) do { rc = (expr); if (rc != DPB_OK) return rc; } while (0)
+  JTRY(split16(w.xp, M, DP, DP, &w.xp16, nullptr, st));
+  JTRY(gemm_tc(w.xp16, o->Wpre, M, H, DP, w.pre, H, table, nullptr, nullptr, 0, st, Bi));
+  gn_silu_jvp_kernel<<<(unsigned)B, 256, 0, st>>>(w.pre, h->gn_w[0], h->gn_b[0], nullptr, w.hbuf, B);
+  for (int blk = 0; blk < 2; ++blk) {
+    const int l1 = 1 + 2 * blk, l2 = 2 + 2 * blk;
+    JTRY(split16(w.hbuf, M, H, H, &w.a16, nullptr, st));
+    JTRY(gemm_tc(w.a16, o->W[l1 - 1], M, H, H, w.pre, H, table + (size_t)l1 * H, nullptr, nullptr, 0, st, Bi));
+    gn_silu_jvp_kernel<<<(unsigned)B, 256, 0, st>>>(w.pre, h->gn_w[l1], h->gn_b[l1], nullptr, w.tbuf, B);
+    JTRY(split16(w.tbuf, M, H, H, &w.a16, nullptr, st));
+    JTRY(gemm_tc(w.a16, o->W[l2 - 1], M, H, H, w.pre, H, table + (size_t)l2 * H, nullptr, nullptr, 0, st, Bi));
+    gn_silu_jvp_kernel<<<(unsigned)B, 256, 0, st>>>(w.pre, h->gn_w[l2], h->gn_b[l2], w.hbuf, w.hbuf, B);
+  }
+  JTRY(split16(w.hbuf, M, H, H, &w.a16, nullptr, st));
+  JTRY(gemm_tc(w.a16, o->Wpost, M, DP, H, raw, DP, h->post_b, nullptr, nullptr, 0, st, Bi));
+#undef JTRY
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }

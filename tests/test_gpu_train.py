@@ -145,6 +145,7 @@ def test_train_step_vs_oracle_other_batch_sizes():
         og = dict(zip(used, torch.autograd.grad(ol, [leaves[k] for k in used])))
         fn = losses.get_sde_loss_fn(sde, True, reduce_mean=True, likelihood_weighting=lw)
         loss = fn(model, batch.cuda(), None, None, t=t, z=z, drop_mask=masks)
+        ol = ol.detach()
         assert abs(float(loss) - float(ol)) < 2e-4 * abs(float(ol)), Bn
         for n, p in model.named_parameters():
             if n in og:
