@@ -3,7 +3,7 @@
 
 ``get_likelihood_fn(sde, inverse_scaler, ...)`` returns ``likelihood_fn(model, data) -> (bpd, z, nfe)``.  scipy's RK45
 drives the ODE on the host exactly like the reference; every function evaluation is ONE native call,
-``dpb_score_jvp``: the score net and its forward-mode derivative along the Hutchinson probe (fp32 engine).  The
+``dpb_score_jvp``: the score net and its forward-mode derivative along the Hutchinson probe (split-fp16 tcgen05 GEMMs).  The
 reference gets ``eps . (J^T eps)`` from autograd (likelihood.py:26-37); the same scalar is ``eps . (J eps)``, so no
 backward pass through the network is needed.  drift and divergence follow from the affine form of the reverse SDE:
 
