@@ -415,6 +415,25 @@ def bench_configs(args, dev, model, peaks, flush, cpu_per_row_step):
                                 'note': 'algorithmic FLOP (one product); the split-fp16 GEMM executes three'}}
         del state, tm, data, host
         torch.cuda.empty_cache()
+    # ---- bits/dim + latent code under the probability-flow ODE (likelihood.get_likelihood_fn, device RK45)
+    from dposer_b200 import likelihood
+    lfn = likelihood.get_likelihood_fn(sde, lambda v: v, rtol=1e-5, atol=1e-5, eps=1e-5)
+    toy = synthetic.toy_poses()
+    Bl = 16384
+    ldata = norm.offline_normalize(toy[torch.randint(0, toy.shape[0], (Bl,))].to(dev))
+    lfn(model, ldata[:64])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    bpd, _, nfe = lfn(model, ldata)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out['f2_likelihood'] = {
+        'workload': 'SURVEY 8(f)2: log-likelihood (bits/dim) and latent code of 16 384 poses, probability-flow ODE with Hutchinson '
+                    'divergence, RK45 rtol = atol = 1e-5 (device-side stages / error norm, JVP contractions on tcgen05)',
+        'rows': Bl, 'nfe': int(nfe), 'seconds': dt, 'value': Bl / dt, 'unit': 'poses/s', 'ms_per_function_evaluation': dt * 1e3 / nfe,
+        'finite': bool(torch.isfinite(bpd).all())}
+    del ldata, bpd
+
     out['f3_train_step'] = {
         'workload': 'SURVEY 8(f)3: one training step of ScoreModelFC (sub-VP denoising score matching, per-row t, dropout 0.1, '
                     'grad clip 1.0, Adam, EMA) -- 27 tcgen05 GEMMs + elementwise kernels per step, replayed as one CUDA graph; AMASS toy poses',
@@ -469,6 +488,29 @@ def cpu_task_loops(budget_s=12.0):
     dt = (time.perf_counter() - t0) / (6 * iters)
     res['c5_smplify'] = {'value': B / (dt * 600), 'unit': 'poses/s', 'cores': os.cpu_count(), 'kind': 'port',
                          'sample': f'{B} images, {6 * iters} of 600 Adam steps, {dt:.2f} s per step'}
+    # likelihood: the REAL reference's get_likelihood_fn (oracle/_ref, autograd divergence, scipy RK45) on 32 poses
+    try:
+        from oracle import make_ref
+        mods = make_ref.import_reference()
+        if mods is not None:
+            ref_model_mod, ref_sde, _, _ = mods
+            from lib.algorithms.advanced import likelihood as ref_lik
+            cfg = synthetic.default_config()
+            cfg.device = torch.device('cpu')
+            torch.manual_seed(42)
+            rm = ref_model_mod.ScoreModelFC(cfg, n_poses=21, pose_dim=3, hidden_dim=1024, embed_dim=512, n_blocks=2)
+            rm.load_state_dict({k: v for k, v in sd.items()}, strict=False)
+            rm.eval()
+            lfn = ref_lik.get_likelihood_fn(ref_sde.subVPSDE(0.1, 20., N=1000), lambda v: v, rtol=1e-5, atol=1e-5, eps=1e-5)
+            Bl = 32
+            xl = (synthetic.toy_poses()[:Bl] - mean) / std
+            t0 = time.perf_counter()
+            _, _, nfe = lfn(rm, xl)
+            dt = time.perf_counter() - t0
+            res['f2_likelihood'] = {'value': Bl / dt, 'unit': 'poses/s', 'cores': os.cpu_count(), 'kind': 'reference',
+                                    'sample': f'{Bl} poses, {nfe} function evaluations (autograd divergence, scipy RK45), {dt:.1f} s'}
+    except Exception as e:                                     # the staged reference is optional
+        res['f2_likelihood'] = {'error': repr(e)[:160]}
     # training step: the oracle restatement (autograd on the host cores; pinned to the real losses.get_step_fn by
     # tests/golden/train_golden.npz) at the reference's batch size
     from oracle import train_ref

@@ -1,8 +1,9 @@
 """Log-likelihood / latent code under the probability-flow ODE with the reference's call surface
 (lib/algorithms/advanced/likelihood.py:40-113).
 
-``get_likelihood_fn(sde, inverse_scaler, ...)`` returns ``likelihood_fn(model, data) -> (bpd, z, nfe)``.  scipy's RK45
-drives the ODE on the host exactly like the reference; every function evaluation is ONE native call,
+``get_likelihood_fn(sde, inverse_scaler, ...)`` returns ``likelihood_fn(model, data) -> (bpd, z, nfe)``.  ``method='RK45'``
+(the reference's) integrates on the device (ode.py: scipy's controller, native stage / error kernels); other methods fall
+back to scipy on the host over the same function evaluation.  Every function evaluation is ONE native call,
 ``dpb_score_jvp``: the score net and its forward-mode derivative along the Hutchinson probe (split-fp16 tcgen05 GEMMs).  The
 reference gets ``eps . (J^T eps)`` from autograd (likelihood.py:26-37); the same scalar is ``eps . (J eps)``, so no
 backward pass through the network is needed.  drift and divergence follow from the affine form of the reverse SDE:
@@ -58,21 +59,30 @@ def get_likelihood_fn(sde, inverse_scaler, hutchinson_type='Rademacher', rtol=1e
                 else:
                     raise NotImplementedError(f"Hutchinson type {hutchinson_type} unknown.")
             epsilon = epsilon.to(device=data.device, dtype=torch.float32)
-            h = model.handle()
-            ws = torch.empty(int(L.load().dpb_score_jvp_workspace_bytes(h.ptr, shape[0])), dtype=torch.uint8,
-                             device=data.device)
+            if method == 'RK45':
+                # device-side Dormand-Prince (ode.py): state [x | logp] in fp64 on the GPU, scipy's controller on the host,
+                # one scalar read back per attempted step
+                from . import ode
+                be = ode.PFOdeBackend(model, sde, data, epsilon)
+                nfe, _ = ode.solve_rk45(be, eps, sde.T, rtol=rtol, atol=atol)
+                z = be.y[:be.nx].view(shape).to(torch.float32)
+                delta_logp = be.y[be.nx:].to(torch.float32)
+            else:
+                h = model.handle()
+                ws = torch.empty(int(L.load().dpb_score_jvp_workspace_bytes(h.ptr, shape[0])), dtype=torch.uint8,
+                                 device=data.device)
 
-            def ode_func(t, x):
-                sample = mutils.from_flattened_numpy(x[:-shape[0]], shape).to(data.device).type(torch.float32)
-                drift, div = drift_and_div(model, sde, sample, t, epsilon, ws)
-                return np.concatenate([mutils.to_flattened_numpy(drift), mutils.to_flattened_numpy(div)], axis=0)
+                def ode_func(t, x):
+                    sample = mutils.from_flattened_numpy(x[:-shape[0]], shape).to(data.device).type(torch.float32)
+                    drift, div = drift_and_div(model, sde, sample, t, epsilon, ws)
+                    return np.concatenate([mutils.to_flattened_numpy(drift), mutils.to_flattened_numpy(div)], axis=0)
 
-            init = np.concatenate([mutils.to_flattened_numpy(data), np.zeros((shape[0],))], axis=0)
-            solution = integrate.solve_ivp(ode_func, (eps, sde.T), init, rtol=rtol, atol=atol, method=method)
-            nfe = solution.nfev
-            zp = solution.y[:, -1]
-            z = mutils.from_flattened_numpy(zp[:-shape[0]], shape).to(data.device).type(torch.float32)
-            delta_logp = mutils.from_flattened_numpy(zp[-shape[0]:], (shape[0],)).to(data.device).type(torch.float32)
+                init = np.concatenate([mutils.to_flattened_numpy(data), np.zeros((shape[0],))], axis=0)
+                solution = integrate.solve_ivp(ode_func, (eps, sde.T), init, rtol=rtol, atol=atol, method=method)
+                nfe = solution.nfev
+                zp = solution.y[:, -1]
+                z = mutils.from_flattened_numpy(zp[:-shape[0]], shape).to(data.device).type(torch.float32)
+                delta_logp = mutils.from_flattened_numpy(zp[-shape[0]:], (shape[0],)).to(data.device).type(torch.float32)
             prior_logp = sde.prior_logp(z)
             bpd = -(prior_logp + delta_logp) / np.log(2)
             bpd = bpd / np.prod(shape[1:])

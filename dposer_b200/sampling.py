@@ -143,7 +143,8 @@ def _langevin_loop(model, sde, x, coef, table, t_run, obs, mask, noise, seed, st
 
 def get_ode_sampler(sde, shape, inverse_scaler, denoise=False, rtol=1e-5, atol=1e-5, method='RK45', eps=1e-3,
                     device='cuda'):
-    """sampling.py:471-542: scipy RK45 on the host drives the probability-flow drift evaluated on the GPU."""
+    """sampling.py:471-542.  ``method='RK45'`` (the reference's default) integrates on the device (ode.py: scipy's step-size
+    controller on the host, native stage / error kernels, fp64 state); other methods run scipy on the host over the GPU drift."""
     device = torch.device(device)
 
     def drift_fn(model, x, t):
@@ -153,21 +154,28 @@ def get_ode_sampler(sde, shape, inverse_scaler, denoise=False, rtol=1e-5, atol=1
     def ode_sampler(model, z=None):
         with torch.no_grad():
             x = (sde.prior_sampling(shape) if z is None else z).to(device)
+            if method == 'RK45' and device.type == 'cuda':
+                # device-side Dormand-Prince (ode.py): fp64 state on the GPU, one scalar read back per attempted step
+                from . import ode
+                be = ode.PFOdeBackend(model, sde, x.to(torch.float32))
+                nfev, _ = ode.solve_rk45(be, sde.T, eps, rtol=rtol, atol=atol)
+                x = be.y.view(shape).to(torch.float32)
+            else:
+                def ode_func(t, xf):
+                    xx = mutils.from_flattened_numpy(xf, shape).to(device).type(torch.float32)
+                    vec_t = torch.ones(shape[0], device=device) * t
+                    return mutils.to_flattened_numpy(drift_fn(model, xx, vec_t))
 
-            def ode_func(t, xf):
-                xx = mutils.from_flattened_numpy(xf, shape).to(device).type(torch.float32)
-                vec_t = torch.ones(shape[0], device=device) * t
-                return mutils.to_flattened_numpy(drift_fn(model, xx, vec_t))
-
-            sol = integrate.solve_ivp(ode_func, (sde.T, eps), mutils.to_flattened_numpy(x), rtol=rtol, atol=atol,
-                                      method=method)
-            x = torch.tensor(sol.y[:, -1]).reshape(shape).to(device).type(torch.float32)
+                sol = integrate.solve_ivp(ode_func, (sde.T, eps), mutils.to_flattened_numpy(x), rtol=rtol, atol=atol,
+                                          method=method)
+                nfev = sol.nfev
+                x = torch.tensor(sol.y[:, -1]).reshape(shape).to(device).type(torch.float32)
             if denoise:
                 # one reverse-diffusion predictor step without noise (sampling.py:492-499)
                 vec_eps = torch.ones(x.shape[0], device=device) * eps
                 score_fn = mutils.get_score_fn(sde, model, train=False, continuous=True)
                 f, G = sde.reverse(score_fn, probability_flow=False).discretize(x, vec_eps)
                 x = x - f
-            return sol.nfev, inverse_scaler(x)
+            return nfev, inverse_scaler(x)
 
     return ode_sampler

@@ -305,6 +305,25 @@ int dpb_joint_map_scatter(const float* g_out, int n_map, const int32_t* map, int
                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Probability-flow ODE on the device (replaces scipy.integrate.solve_ivp(method='RK45') as driven by
+ * lib/algorithms/advanced/likelihood.py:93-101 and sampling.py:520-524): Dormand-Prince stages and error norm on DEVICE
+ * vectors, fp64 state, fp32 stage derivatives k [7, n]; the host keeps scipy's step-size controller and reads one scalar
+ * per attempted step.
+ * ---------------------------------------------------------------------------------------- */
+/* stage 1..5: y + h sum_j a[stage][j] k_j;  stage 6: the 5th-order solution y + h sum_j b_j k_j.
+ * y_out DEVICE fp64 [n] and / or x_out DEVICE fp32 [nx] (the first nx entries, the network's input), either may be NULL */
+int dpb_rk45_stage(const double* y, const float* k, int64_t n, double h, int stage, double* y_out, float* x_out,
+                   int64_t nx, void* stream);
+/* ((double*)scratch)[0] = sum_i (h sum_j e_j k_j[i] / (atol + rtol max(|y_i|, |y_new_i|)))^2, fixed summation order */
+size_t dpb_rk45_scratch_bytes(void);
+int dpb_rk45_error(const double* y, const double* y_new, const float* k, int64_t n, double h, double rtol, double atol,
+                   void* scratch, void* stream);
+/* k_out[b,c] = fx x - 0.5 g2 score (drift of the reverse ODE, sde_lib.py:98-106 with probability_flow) and, with jv / eps,
+ * k_out[B*63 + b] = fx sum_c eps^2 - 0.5 g2 sum_c jv eps (Hutchinson divergence, likelihood.py:26-37) */
+int dpb_pf_ode_rhs(const float* x, const float* score, const float* jv, const float* eps, float fx, float g2, float* k_out,
+                   int64_t B, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training step of the score network (replaces loss_fn + loss.backward() + optimize_fn + ema.update of
  * lib/algorithms/advanced/losses.py:31-57,61-137,187-275 with model.py:141-196 in train mode and
  * lib/algorithms/ema.py:35-50).  Every contraction of the forward and backward pass is a split-fp16 tcgen05 GEMM.

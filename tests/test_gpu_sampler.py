@@ -285,7 +285,8 @@ def test_likelihood_vs_reference_golden(gpu_model):
     bpd, z, nfe = fn(gpu_model, torch.tensor(g['lik_data']).cuda(), epsilon=torch.tensor(g['lik_eps']).cuda())
     assert max_rel(bpd, g['lik_bpd']) < 2e-3
     assert max_rel(z, g['lik_z']) < 5e-3
-    assert abs(nfe - int(g['lik_nfe'])) <= 0.25 * int(g['lik_nfe']), (nfe, int(g['lik_nfe']))
+    # device-side RK45 with scipy's controller: the step sequence follows the reference's to within a few evaluations
+    assert abs(nfe - int(g['lik_nfe'])) <= 0.02 * int(g['lik_nfe']), (nfe, int(g['lik_nfe']))
 
 
 def test_small_batch_engine_matches_whole_tile_engine(gpu_model, monkeypatch):

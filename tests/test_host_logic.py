@@ -258,3 +258,59 @@ def test_rot6d_transforms_properties():
     assert float((T.axis_angle_to_mat3x3(back) - R).abs().max()) < 2e-5      # same rotation (axis-angle is 2-to-1 at pi)
     small = aa.norm(dim=1) < 3.0
     assert float((back[small] - aa[small]).abs().max()) < 2e-5
+
+
+def test_rk45_controller_reproduces_scipy_solve_ivp():
+    """dposer_b200.ode: the host-side step-size controller (scipy's RungeKutta._step_impl / select_initial_step restated)
+    over a numpy stand-in for the native stage / error kernels lands on solve_ivp(method='RK45') itself: same number of
+    function evaluations, same final state; and the Butcher tableau the kernels carry equals scipy's."""
+    import re
+    from scipy import integrate
+    from dposer_b200 import ode
+    RK = integrate.RK45
+    src = open(os.path.join(ROOT, 'dposer_b200', 'csrc', 'rk45.cu')).read()
+
+    def table(name):
+        body = re.search(name + r'\[[^\]]*\](?:\[[^\]]*\])?\s*=\s*\{(.*?)\};', src, re.S).group(1)
+        return [eval(x.replace('.0', '.0')) for x in re.sub(r'[{}\s]', '', body).split(',') if x]
+    A = np.array(table('A')).reshape(6, 5)
+    assert np.allclose(A, RK.A, rtol=0, atol=1e-16) and np.allclose(table('Bc'), RK.B, atol=1e-16)
+    assert np.allclose(table('Ec'), RK.E, atol=1e-16) and np.allclose(ode.C_NODES, RK.C, atol=1e-16)
+
+    class NumpyBackend(ode.Backend):
+        def __init__(self, fun, y0):
+            self.fun, self.y, self.n = fun, np.array(y0, float), len(y0)
+            self.k = np.zeros((7, self.n))
+
+        def eval_initial(self, t):
+            self.k[0] = self.fun(t, self.y)
+
+        def eval_stage(self, s, t, h):
+            self.k[s] = self.fun(t, self.y + np.dot(self.k[:s].T, RK.A[s, :s]) * h)
+
+        def eval_candidate(self, t, h):
+            self.y_new = self.y + h * np.dot(self.k[:-1].T, RK.B)
+            self.k[6] = self.fun(t, self.y_new)
+
+        def error_norm(self, h, rtol, atol):
+            scale = atol + np.maximum(np.abs(self.y), np.abs(self.y_new)) * rtol
+            e = np.dot(self.k.T, RK.E) * h / scale
+            return np.linalg.norm(e) / e.size ** 0.5
+
+        def accept(self):
+            self.y, self.k[0] = self.y_new, self.k[6]
+
+        def initial_step_norms(self, t0, direction, rtol, atol, interval):
+            return ode.select_initial_step(self.y, self.k[0].copy(), self.fun, t0, direction, rtol, atol, interval)
+
+    W = np.random.default_rng(0).standard_normal((12, 12)) * 0.7
+
+    def fun(t, y):                                  # stiff-ish nonlinear system, time dependent
+        return np.tanh(W @ y) * (1 + 3 * t) - 0.5 * y + np.sin(5 * t)
+    y0 = np.linspace(-1, 1, 12)
+    for (t0, t1, rtol, atol) in [(1e-5, 1.0, 1e-5, 1e-5), (1.0, 1e-3, 1e-5, 1e-5), (0.0, 2.0, 1e-3, 1e-6)]:
+        ref = integrate.solve_ivp(fun, (t0, t1), y0, rtol=rtol, atol=atol, method='RK45')
+        be = NumpyBackend(fun, y0)
+        nfev, attempts = ode.solve_rk45(be, t0, t1, rtol=rtol, atol=atol)
+        assert nfev == ref.nfev, (nfev, ref.nfev)
+        assert np.abs(be.y - ref.y[:, -1]).max() <= 1e-12 * max(1.0, np.abs(ref.y[:, -1]).max())
