@@ -63,3 +63,12 @@ for (M, N, K) in [(257, 129, 200), (63, 1024, 96)]:
     ws = torch.empty(int(lib.dpb_gemm_nt_workspace_bytes(M, N, K)), dtype=torch.uint8, device='cuda')
     L.check(lib.dpb_gemm_nt(L.ptr(A), L.ptr(Bm), None, L.ptr(out), M, N, K, L.ptr(ws), ws.numel(), L.current_stream(A.device)))
     torch.cuda.synchronize(); print('gemm ok', float((out - A @ Bm.T).abs().max()))
+# device-side RK45 + tensor-core JVP: a short likelihood integration (loose tolerance) and the ODE sampler
+from dposer_b200 import likelihood as lk
+lfn = lk.get_likelihood_fn(sde1k, lambda v: v, rtol=1e-2, atol=1e-2, eps=1e-3)
+model.eval()
+bpd, zz, nfe = lfn(model, synthetic.toy_poses()[:70].cuda())
+torch.cuda.synchronize(); print('likelihood rk45 ok', nfe, bool(torch.isfinite(bpd).all()))
+ofn = sampling.get_ode_sampler(sde1k, (33, 63), lambda v: v, rtol=1e-2, atol=1e-2, eps=1e-3, device='cuda')
+nfe, xo = ofn(model, z=torch.randn(33, 63))
+torch.cuda.synchronize(); print('ode sampler rk45 ok', nfe, bool(torch.isfinite(xo).all()))
