@@ -47,7 +47,7 @@ EXPORTS = ['dpb_version', 'dpb_last_error', 'dpb_device_info', 'dpb_score_create
            'dpb_lbs_backward', 'dpb_lbs_backward_scratch_bytes', 'dpb_lbs_backward_scratch_bytes_joints', 'dpb_apd_partial', 'dpb_mean_point_error', 'dpb_fit_loss',
            'dpb_motion_loss', 'dpb_camera_fit_loss', 'dpb_adam_step', 'dpb_affine_cols', 'dpb_joint_map_gather',
            'dpb_joint_map_scatter', 'dpb_masked_mse_grad', 'dpb_train_create', 'dpb_train_destroy',
-           'dpb_train_loss_grad', 'dpb_train_adam_scratch_bytes', 'dpb_train_grad_norm', 'dpb_train_adam', 'dpb_ema_update', 'dpb_train_set_seed_pointer', 'dpb_gemm_nt_workspace_bytes', 'dpb_gemm_nt', 'dpb_rk45_stage', 'dpb_rk45_scratch_bytes', 'dpb_rk45_error',
+           'dpb_train_loss_grad', 'dpb_train_adam_scratch_bytes', 'dpb_train_grad_norm', 'dpb_train_adam', 'dpb_ema_update', 'dpb_train_set_seed_pointer', 'dpb_gemm_nt_workspace_bytes', 'dpb_gemm_nt', 'dpb_train_forward', 'dpb_train_backward', 'dpb_rows_axpby', 'dpb_weighted_sqdiff', 'dpb_rk45_stage', 'dpb_rk45_scratch_bytes', 'dpb_rk45_error',
            'dpb_pf_ode_rhs']
 
 _lib = None
@@ -120,6 +120,10 @@ def load():
     lib.dpb_train_loss_grad.argtypes = [vp, C.POINTER(ScoreWeights), C.POINTER(ScoreWeights), vp, vp, vp, vp, f32, u64, vp,
                                         vp, vp]
     lib.dpb_train_adam_scratch_bytes.restype = sz
+    lib.dpb_train_forward.argtypes = [vp, C.POINTER(ScoreWeights), vp, vp, vp, f32, u64, vp, vp]
+    lib.dpb_train_backward.argtypes = [vp, C.POINTER(ScoreWeights), C.POINTER(ScoreWeights), vp, vp, f32, u64, C.c_int, vp, vp]
+    lib.dpb_rows_axpby.argtypes = [vp, vp, vp, vp, vp, C.c_int, i64, vp]
+    lib.dpb_weighted_sqdiff.argtypes = [vp, vp, vp, i64, i64, f32, vp, vp, vp, vp]
     lib.dpb_train_grad_norm.argtypes = [vp, i64, vp, vp]
     lib.dpb_train_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp, vp, vp]
     lib.dpb_train_set_seed_pointer.argtypes = [vp, vp]

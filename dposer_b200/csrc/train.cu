@@ -26,7 +26,7 @@ struct dpb_train {
   float *xp, *z, *temb0, *q, *temb, *tproj, *u[5], *act[5], *res, *gres, *Gall, *gA, *gB, *gtemb, *gq, *t1, *t2;
   float *mean[5], *rstd[5], *loss_rows;
   dpb::Op16 xp16, xpT16, temb0_16, temb0T16, temb16, tembT16, X16[5], XT16[5], G16, GT16, gres16, gresT16, gqT16;
-  dpb::Op16 Wpre16, W16[4], WT16[4], Wpost16, WpostT16, Ws16, Wt16, WtT16;
+  dpb::Op16 Wpre16, WpreT16, W16[4], WT16[4], Wpost16, WpostT16, Ws16, Wt16, WtT16;
   const uint64_t* seed_dev = nullptr;     // when set, the Philox seed is read from device memory (graph replay)
   cudaStream_t side = nullptr;            // weight-gradient GEMMs run beside the cotangent chain
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(256) gn_act_bwd_kernel(const float* __restrict
 
 // dst[c] = scale * sum_r src[r, c], rows added in a fixed order (32 row lanes, then a fixed tree)
 __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ src, int64_t R, int Cc, int64_t ld,
-                                                      float scale, float* __restrict__ dst1, float* __restrict__ dst2) {
+                                                      float scale, float* __restrict__ dst1, float* __restrict__ dst2,
+                                                      int acc) {
   __shared__ float part[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += part[i][threadIdx.x];
     t *= scale;
-    dst1[c] = t;
-    if (dst2) dst2[c] = t;
+    dst1[c] = acc ? dst1[c] + t : t;
+    if (dst2) dst2[c] = acc ? dst2[c] + t : t;
   }
 }
 
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(1024) colsum3_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
                                                        const float* __restrict__ s2, int64_t ld2, int64_t R,
                                                        float* __restrict__ d0, float* __restrict__ d1,
-                                                       float* __restrict__ d2a, float* __restrict__ d2b) {
+                                                       float* __restrict__ d2a, float* __restrict__ d2b, int acc) {
   __shared__ float part[32][33];
   const int which = blockIdx.y;
   const float* src = which == 0 ? s0 : which == 1 ? s1 : s2;
@@ -192,9 +193,9 @@ __global__ void __launch_bounds__(1024) colsum3_kernel(const float* __restrict__
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += part[i][threadIdx.x];
-    if (which == 0) d0[c] = t;
-    else if (which == 1) d1[c] = t;
-    else { d2a[c] = t; d2b[c] = t; }
+    if (which == 0) d0[c] = acc ? d0[c] + t : t;
+    else if (which == 1) d1[c] = acc ? d1[c] + t : t;
+    else { d2a[c] = acc ? d2a[c] + t : t; d2b[c] = acc ? d2b[c] + t : t; }
   }
 }
 
@@ -307,7 +308,7 @@ static size_t layout(dpb_train* h, void* base, size_t cap) {
   h->G16 = carve16(ws, B, NL * H); h->GT16 = carve16(ws, NL * H, Bp);
   h->gres16 = carve16(ws, B, DP); h->gresT16 = carve16(ws, DP, Bp);
   h->gqT16 = carve16(ws, E, Bp);
-  h->Wpre16 = carve16(ws, H, DP);
+  h->Wpre16 = carve16(ws, H, DP); h->WpreT16 = carve16(ws, DP, H);
   for (int l = 0; l < 4; ++l) { h->W16[l] = carve16(ws, H, H); h->WT16[l] = carve16(ws, H, H); }
   h->Wpost16 = carve16(ws, DP, H); h->WpostT16 = carve16(ws, H, DP);
   h->Ws16 = carve16(ws, E, E);
@@ -358,6 +359,149 @@ extern "C" int dpb_train_destroy(dpb_train* h) {
   return DPB_OK;
 }
 
+namespace dpb {
+namespace trn {
+
+// x [B,63] -> xp [B,64] (pad column zero); sinusoidal embedding of the per-row label
+__global__ void __launch_bounds__(256) prep_given_kernel(const float* __restrict__ x, const float* __restrict__ labels,
+                                                         const float* __restrict__ freqs, float* __restrict__ xp,
+                                                         float* __restrict__ temb0, int64_t B) {
+  const int64_t b = blockIdx.x;
+  const int t = threadIdx.x;
+  if (t < DP) xp[b * DP + t] = t < D ? x[b * D + t] : 0.f;
+  const float arg = labels[b] * freqs[t];
+  temb0[b * E + t] = sinf(arg);
+  temb0[b * E + E / 2 + t] = cosf(arg);
+}
+
+// [B,63] <-> [B,64] copies of the network output / its cotangent
+__global__ void pad_cols_kernel(const float* __restrict__ src, int ls, float* __restrict__ dst, int ld, int cols, int64_t B) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * ld) return;
+  const int64_t b = i / ld;
+  const int c = (int)(i % ld);
+  dst[i] = c < cols ? src[b * ls + c] : 0.f;
+}
+
+struct Ptrs {
+  const float *Wl[4], *Wt[5], *bl[5], *bt[5], *gam[5], *bet[5];
+  explicit Ptrs(const dpb_train_tensors* P) {
+    for (int l = 0; l < 4; ++l) Wl[l] = P->blk_w[l];
+    Wt[0] = P->pre_t_w; bl[0] = P->pre_b; bt[0] = P->pre_t_b; gam[0] = P->pre_gn_w; bet[0] = P->pre_gn_b;
+    for (int l = 0; l < 4; ++l) {
+      Wt[l + 1] = P->blk_t_w[l]; bl[l + 1] = P->blk_b[l]; bt[l + 1] = P->blk_t_b[l];
+      gam[l + 1] = P->blk_gn_w[l]; bet[l + 1] = P->blk_gn_b[l];
+    }
+  }
+};
+
+#define TRY(expr) do { rc = (expr); if (rc != DPB_OK) return rc; } while (0)
+
+// fp16 [hi | lo] operands of the current weights (they change every step); `back`: the transposed copies too
+static int weight_operands(dpb_train* h, const dpb_train_tensors* P, bool back, cudaStream_t st) {
+  int rc = DPB_OK;
+  const Ptrs w(P);
+  TRY(split16(P->pre_w, H, D, D, &h->Wpre16, back ? &h->WpreT16 : nullptr, st));
+  for (int l = 0; l < 4; ++l) TRY(split16(w.Wl[l], H, H, H, &h->W16[l], back ? &h->WT16[l] : nullptr, st));
+  TRY(split16(P->post_w, D, H, H, &h->Wpost16, back ? &h->WpostT16 : nullptr, st));
+  TRY(split16(P->temb_w, E, E, E, &h->Ws16, nullptr, st));
+  for (int s = 0; s < NL; ++s) {
+    const Op16 r = h->Wt16.block(s * H, 0), c = h->WtT16.block(0, s * H);
+    TRY(split16(w.Wt[s], H, E, E, &r, back ? &c : nullptr, st));
+  }
+  return DPB_OK;
+}
+
+// h->xp, h->temb0 -> h->res (activations and, with `back`, the transposed operands stay in the handle)
+static int forward(dpb_train* h, const dpb_train_tensors* P, const uint8_t* mask_given, float drop_p, uint64_t seed,
+                   bool back, cudaStream_t st) {
+  int rc = DPB_OK;
+  const Ptrs w(P);
+  const int64_t B = h->B;
+  const int Bi = (int)B;
+  const unsigned gw = (unsigned)((B * 32 + 7) / 8);
+  TRY(split16(h->xp, Bi, DP, DP, &h->xp16, back ? &h->xpT16 : nullptr, st));
+  TRY(split16(h->temb0, Bi, E, E, &h->temb0_16, back ? &h->temb0T16 : nullptr, st));
+  TRY(gemm_tc(h->temb0_16, h->Ws16, Bi, E, E, h->q, E, P->temb_b, nullptr, nullptr, 0, st));
+  silu_fwd_kernel<<<(unsigned)((B * E + 255) / 256), 256, 0, st>>>(h->q, h->temb, B * E);
+  TRY(split16(h->temb, Bi, E, E, &h->temb16, back ? &h->tembT16 : nullptr, st));
+  TRY(gemm_tc(h->temb16, h->Wt16, Bi, NL * H, E, h->tproj, NL * H, nullptr, nullptr, nullptr, 0, st));
+  for (int s = 0; s < NL; ++s) {
+    const Op16& in = s == 0 ? h->xp16 : h->X16[s - 1];
+    const Op16& wop = s == 0 ? h->Wpre16 : h->W16[s - 1];
+    TRY(gemm_tc(in, wop, Bi, H, s == 0 ? DP : H, h->u[s], H, w.bl[s], w.bt[s], h->tproj + (size_t)s * H, NL * H, st));
+    const float* resid = (s == 2) ? h->act[0] : (s == 4) ? h->act[2] : nullptr;
+    gn_act_fwd_kernel<<<gw, 256, 0, st>>>(h->u[s], w.gam[s], w.bet[s], resid, h->act[s], h->mean[s], h->rstd[s], mask_given,
+                                          seed, h->seed_dev, s, drop_p, B);
+    TRY(split16(h->act[s], Bi, H, H, &h->X16[s], back ? &h->XT16[s] : nullptr, st));
+  }
+  TRY(gemm_tc(h->X16[4], h->Wpost16, Bi, D, H, h->res, DP, P->post_b, nullptr, nullptr, 0, st));
+  return DPB_OK;
+}
+
+// h->gres (cotangent of res) -> every parameter gradient (overwritten, or added to with `acc`) and, if asked, the
+// cotangent of the network input g_x [B,63]
+static int backward(dpb_train* h, const dpb_train_tensors* P, const dpb_train_tensors* G, const uint8_t* mask_given,
+                    float drop_p, uint64_t seed, bool acc, float* g_x, cudaStream_t st) {
+  int rc = DPB_OK;
+  const Ptrs w(P);
+  const int64_t B = h->B;
+  const int Bi = (int)B;
+  const unsigned gw = (unsigned)((B * 32 + 7) / 8);
+  float* gWl[4] = {(float*)G->blk_w[0], (float*)G->blk_w[1], (float*)G->blk_w[2], (float*)G->blk_w[3]};
+  float* gWt[5] = {(float*)G->pre_t_w, (float*)G->blk_t_w[0], (float*)G->blk_t_w[1], (float*)G->blk_t_w[2], (float*)G->blk_t_w[3]};
+  float* gbl[5] = {(float*)G->pre_b, (float*)G->blk_b[0], (float*)G->blk_b[1], (float*)G->blk_b[2], (float*)G->blk_b[3]};
+  float* gbt[5] = {(float*)G->pre_t_b, (float*)G->blk_t_b[0], (float*)G->blk_t_b[1], (float*)G->blk_t_b[2], (float*)G->blk_t_b[3]};
+  float* ggam[5] = {(float*)G->pre_gn_w, (float*)G->blk_gn_w[0], (float*)G->blk_gn_w[1], (float*)G->blk_gn_w[2], (float*)G->blk_gn_w[3]};
+  float* gbet[5] = {(float*)G->pre_gn_b, (float*)G->blk_gn_b[0], (float*)G->blk_gn_b[1], (float*)G->blk_gn_b[2], (float*)G->blk_gn_b[3]};
+  const dim3 cs(32, 32);
+  const int ia = acc ? 1 : 0;
+  auto addc = [&](float* c) -> const float* { return acc ? c : nullptr; };      // C += ... through the GEMM's added matrix
+  TRY(split16(h->gres, Bi, DP, DP, &h->gres16, &h->gresT16, st));
+  // weight-gradient GEMMs leave the critical path (the cotangent chain): they run on a side stream, forked after the
+  // operand they read is written and joined at the end (works the same under stream capture)
+  cudaStream_t sd = h->side ? h->side : st;
+  auto fork = [&]() { if (sd != st) { cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(sd, h->ev_fork, 0); } };
+  fork();
+  TRY(gemm_tc(h->gresT16, h->XT16[4], D, H, Bi, (float*)G->post_w, H, nullptr, nullptr, addc((float*)G->post_w), H, sd));   // dW_post
+  colsum_kernel<<<2, cs, 0, st>>>(h->gres, B, D, DP, 1.0f, (float*)G->post_b, nullptr, ia);
+  TRY(gemm_tc(h->gres16, h->WpostT16, Bi, H, DP, h->gA, H, nullptr, nullptr, nullptr, 0, st));                   // d h''
+  // cotangent buffers: gA carries d h'' -> d h' -> d h (outputs of the even stages), gB the odd stages' outputs
+  for (int s = NL - 1; s >= 0; --s) {
+    float* gu = h->Gall + (size_t)s * H;
+    const float* gout = (s & 1) ? h->gB : h->gA;
+    gn_act_bwd_kernel<<<gw, 256, 0, st>>>(gout, h->u[s], w.gam[s], w.bet[s], h->mean[s], h->rstd[s], gu, NL * H, h->t1, h->t2,
+                                          mask_given, seed, h->seed_dev, s, drop_p, B);
+    colsum3_kernel<<<dim3(H / 32, 3), cs, 0, st>>>(h->t1, h->t2, gu, NL * H, B, gbet[s], ggam[s], gbl[s], gbt[s], ia);
+    const Op16 grow = h->G16.block(0, s * H), gcol = h->GT16.block(s * H, 0);
+    TRY(split16(gu, Bi, H, NL * H, &grow, &gcol, st));
+    fork();
+    if (s == 0) {
+      TRY(gemm_tc(gcol, h->xpT16, H, D, Bi, (float*)G->pre_w, D, nullptr, nullptr, addc((float*)G->pre_w), D, sd));   // dW_pre
+      if (g_x) TRY(gemm_tc(grow, h->WpreT16, Bi, D, H, g_x, D, nullptr, nullptr, nullptr, 0, st));                    // d x
+    } else {
+      TRY(gemm_tc(gcol, h->XT16[s - 1], H, H, Bi, gWl[s - 1], H, nullptr, nullptr, addc(gWl[s - 1]), H, sd));         // dW_s
+      if (s & 1)     // input of stage 3 / 1 is h' / h, which also feeds the residual: d h' = g_u3 W_3 + d h''  (in place)
+        TRY(gemm_tc(grow, h->WT16[s - 1], Bi, H, H, h->gA, H, nullptr, nullptr, h->gA, H, st));
+      else           // input of stage 4 / 2 is a_3 / a_1
+        TRY(gemm_tc(grow, h->WT16[s - 1], Bi, H, H, h->gB, H, nullptr, nullptr, nullptr, 0, st));
+    }
+    TRY(gemm_tc(gcol, h->tembT16, H, E, Bi, gWt[s], E, nullptr, nullptr, addc(gWt[s]), E, sd));                       // dWt_s
+  }
+  // time path: d temb = sum_s g_u_s Wt_s (one GEMM over the concatenated cotangents), through SiLU, into the shared layer
+  TRY(gemm_tc(h->G16, h->WtT16, Bi, E, NL * H, h->gtemb, E, nullptr, nullptr, nullptr, 0, st));
+  silu_bwd_kernel<<<(unsigned)((B * E + 255) / 256), 256, 0, st>>>(h->q, h->gtemb, h->gq, B * E);
+  TRY(split16(h->gq, Bi, E, E, nullptr, &h->gqT16, st));
+  TRY(gemm_tc(h->gqT16, h->temb0T16, E, E, Bi, (float*)G->temb_w, E, nullptr, nullptr, addc((float*)G->temb_w), E, st));  // dW_s
+  colsum_kernel<<<E / 32, cs, 0, st>>>(h->gq, B, E, E, 1.0f, (float*)G->temb_b, nullptr, ia);
+  if (sd != st) { cudaEventRecord(h->ev_join, sd); cudaStreamWaitEvent(st, h->ev_join, 0); }
+  return DPB_OK;
+}
+#undef TRY
+
+}  // namespace trn
+}  // namespace dpb
+
 extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, const dpb_train_tensors* G, const float* batch,
                                    const float* rows, const float* z_given, const uint8_t* mask_given, float drop_p,
                                    uint64_t seed, float* loss, float* loss_rows, void* stream) {
@@ -366,98 +510,110 @@ extern "C" int dpb_train_loss_grad(dpb_train* h, const dpb_train_tensors* P, con
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t B = h->B;
-  const int Bi = (int)B;
-  const unsigned gw = (unsigned)((B * 32 + 7) / 8);
-  auto ew = [](int64_t n) { return (unsigned)((n + 255) / 256); };
-  int rc = DPB_OK;
-#define TRY(expr) do { rc = (expr); if (rc != DPB_OK) return rc; } while (0)
-  const float* Wl[4] = {P->blk_w[0], P->blk_w[1], P->blk_w[2], P->blk_w[3]};
-  const float* Wt[5] = {P->pre_t_w, P->blk_t_w[0], P->blk_t_w[1], P->blk_t_w[2], P->blk_t_w[3]};
-  const float* bl[5] = {P->pre_b, P->blk_b[0], P->blk_b[1], P->blk_b[2], P->blk_b[3]};
-  const float* bt[5] = {P->pre_t_b, P->blk_t_b[0], P->blk_t_b[1], P->blk_t_b[2], P->blk_t_b[3]};
-  const float* gam[5] = {P->pre_gn_w, P->blk_gn_w[0], P->blk_gn_w[1], P->blk_gn_w[2], P->blk_gn_w[3]};
-  const float* bet[5] = {P->pre_gn_b, P->blk_gn_b[0], P->blk_gn_b[1], P->blk_gn_b[2], P->blk_gn_b[3]};
-
-  // ---- operands of the current weights (they change every step)
-  TRY(split16(P->pre_w, H, D, D, &h->Wpre16, nullptr, st));
-  for (int l = 0; l < 4; ++l) TRY(split16(Wl[l], H, H, H, &h->W16[l], G ? &h->WT16[l] : nullptr, st));
-  TRY(split16(P->post_w, D, H, H, &h->Wpost16, G ? &h->WpostT16 : nullptr, st));
-  TRY(split16(P->temb_w, E, E, E, &h->Ws16, nullptr, st));
-  for (int s = 0; s < NL; ++s) {
-    const Op16 r = h->Wt16.block(s * H, 0), c = h->WtT16.block(0, s * H);
-    TRY(split16(Wt[s], H, E, E, &r, G ? &c : nullptr, st));
-  }
-  // ---- forward
+  int rc = trn::weight_operands(h, P, G != nullptr, st);
+  if (rc != DPB_OK) return rc;
   trn::prep_kernel<<<(unsigned)B, 256, 0, st>>>(batch, rows, z_given, seed, h->seed_dev, P->emb_freqs, h->xp, h->z, h->temb0, B);
-  TRY(split16(h->xp, Bi, DP, DP, &h->xp16, G ? &h->xpT16 : nullptr, st));
-  TRY(split16(h->temb0, Bi, E, E, &h->temb0_16, G ? &h->temb0T16 : nullptr, st));
-  TRY(gemm_tc(h->temb0_16, h->Ws16, Bi, E, E, h->q, E, P->temb_b, nullptr, nullptr, 0, st));
-  trn::silu_fwd_kernel<<<ew(B * E), 256, 0, st>>>(h->q, h->temb, B * E);
-  TRY(split16(h->temb, Bi, E, E, &h->temb16, G ? &h->tembT16 : nullptr, st));
-  TRY(gemm_tc(h->temb16, h->Wt16, Bi, NL * H, E, h->tproj, NL * H, nullptr, nullptr, nullptr, 0, st));
-  for (int s = 0; s < NL; ++s) {
-    const Op16& in = s == 0 ? h->xp16 : h->X16[s - 1];
-    const Op16& w = s == 0 ? h->Wpre16 : h->W16[s - 1];
-    TRY(gemm_tc(in, w, Bi, H, s == 0 ? DP : H, h->u[s], H, bl[s], bt[s], h->tproj + (size_t)s * H, NL * H, st));
-    const float* resid = (s == 2) ? h->act[0] : (s == 4) ? h->act[2] : nullptr;
-    trn::gn_act_fwd_kernel<<<gw, 256, 0, st>>>(h->u[s], gam[s], bet[s], resid, h->act[s], h->mean[s], h->rstd[s],
-                                               mask_given, seed, h->seed_dev, s, drop_p, B);
-    TRY(split16(h->act[s], Bi, H, H, &h->X16[s], G ? &h->XT16[s] : nullptr, st));
-  }
-  TRY(gemm_tc(h->X16[4], h->Wpost16, Bi, D, H, h->res, DP, P->post_b, nullptr, nullptr, 0, st));
+  if ((rc = trn::forward(h, P, mask_given, drop_p, seed, G != nullptr, st)) != DPB_OK) return rc;
   float* lrows = loss_rows ? loss_rows : h->loss_rows;
   trn::loss_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(h->res, h->z, rows, h->gres, lrows, B);
-  trn::colsum_kernel<<<1, dim3(32, 32), 0, st>>>(lrows, B, 1, 1, 1.0f / (float)B, loss, nullptr);
+  trn::colsum_kernel<<<1, dim3(32, 32), 0, st>>>(lrows, B, 1, 1, 1.0f / (float)B, loss, nullptr, 0);
   DPB_CUDA_CHECK(cudaGetLastError());
   if (!G) return DPB_OK;
-
-  // ---- backward
-  float* gWl[4] = {(float*)G->blk_w[0], (float*)G->blk_w[1], (float*)G->blk_w[2], (float*)G->blk_w[3]};
-  float* gWt[5] = {(float*)G->pre_t_w, (float*)G->blk_t_w[0], (float*)G->blk_t_w[1], (float*)G->blk_t_w[2], (float*)G->blk_t_w[3]};
-  float* gbl[5] = {(float*)G->pre_b, (float*)G->blk_b[0], (float*)G->blk_b[1], (float*)G->blk_b[2], (float*)G->blk_b[3]};
-  float* gbt[5] = {(float*)G->pre_t_b, (float*)G->blk_t_b[0], (float*)G->blk_t_b[1], (float*)G->blk_t_b[2], (float*)G->blk_t_b[3]};
-  float* ggam[5] = {(float*)G->pre_gn_w, (float*)G->blk_gn_w[0], (float*)G->blk_gn_w[1], (float*)G->blk_gn_w[2], (float*)G->blk_gn_w[3]};
-  float* gbet[5] = {(float*)G->pre_gn_b, (float*)G->blk_gn_b[0], (float*)G->blk_gn_b[1], (float*)G->blk_gn_b[2], (float*)G->blk_gn_b[3]};
-  const dim3 cs(32, 32);
-  TRY(split16(h->gres, Bi, DP, DP, &h->gres16, &h->gresT16, st));
-  // weight-gradient GEMMs leave the critical path (the cotangent chain): they run on a side stream, forked after the
-  // operand they read is written and joined at the end (works the same under stream capture)
-  cudaStream_t sd = h->side ? h->side : st;
-  auto fork = [&]() { if (sd != st) { cudaEventRecord(h->ev_fork, st); cudaStreamWaitEvent(sd, h->ev_fork, 0); } };
-  fork();
-  TRY(gemm_tc(h->gresT16, h->XT16[4], D, H, Bi, (float*)G->post_w, H, nullptr, nullptr, nullptr, 0, sd));       // dW_post
-  trn::colsum_kernel<<<2, cs, 0, st>>>(h->gres, B, D, DP, 1.0f, (float*)G->post_b, nullptr);
-  TRY(gemm_tc(h->gres16, h->WpostT16, Bi, H, DP, h->gA, H, nullptr, nullptr, nullptr, 0, st));                   // d h''
-  // cotangent buffers: gA carries d h'' -> d h' -> d h (outputs of the even stages), gB the odd stages' outputs
-  for (int s = NL - 1; s >= 0; --s) {
-    float* gu = h->Gall + (size_t)s * H;
-    const float* gout = (s & 1) ? h->gB : h->gA;
-    trn::gn_act_bwd_kernel<<<gw, 256, 0, st>>>(gout, h->u[s], gam[s], bet[s], h->mean[s], h->rstd[s], gu, NL * H, h->t1,
-                                               h->t2, mask_given, seed, h->seed_dev, s, drop_p, B);
-    trn::colsum3_kernel<<<dim3(H / 32, 3), cs, 0, st>>>(h->t1, h->t2, gu, NL * H, B, gbet[s], ggam[s], gbl[s], gbt[s]);
-    const Op16 grow = h->G16.block(0, s * H), gcol = h->GT16.block(s * H, 0);
-    TRY(split16(gu, Bi, H, NL * H, &grow, &gcol, st));
-    fork();
-    if (s == 0) {
-      TRY(gemm_tc(gcol, h->xpT16, H, D, Bi, (float*)G->pre_w, D, nullptr, nullptr, nullptr, 0, sd));             // dW_pre
-    } else {
-      TRY(gemm_tc(gcol, h->XT16[s - 1], H, H, Bi, gWl[s - 1], H, nullptr, nullptr, nullptr, 0, sd));             // dW_s
-      if (s & 1)     // input of stage 3 / 1 is h' / h, which also feeds the residual: d h' = g_u3 W_3 + d h''  (in place)
-        TRY(gemm_tc(grow, h->WT16[s - 1], Bi, H, H, h->gA, H, nullptr, nullptr, h->gA, H, st));
-      else           // input of stage 4 / 2 is a_3 / a_1
-        TRY(gemm_tc(grow, h->WT16[s - 1], Bi, H, H, h->gB, H, nullptr, nullptr, nullptr, 0, st));
-    }
-    TRY(gemm_tc(gcol, h->tembT16, H, E, Bi, gWt[s], E, nullptr, nullptr, nullptr, 0, sd));                       // dWt_s
-  }
-  // time path: d temb = sum_s g_u_s Wt_s (one GEMM over the concatenated cotangents), through SiLU, into the shared layer
-  TRY(gemm_tc(h->G16, h->WtT16, Bi, E, NL * H, h->gtemb, E, nullptr, nullptr, nullptr, 0, st));
-  trn::silu_bwd_kernel<<<ew(B * E), 256, 0, st>>>(h->q, h->gtemb, h->gq, B * E);
-  TRY(split16(h->gq, Bi, E, E, nullptr, &h->gqT16, st));
-  TRY(gemm_tc(h->gqT16, h->temb0T16, E, E, Bi, (float*)G->temb_w, E, nullptr, nullptr, nullptr, 0, st));         // dW_s
-  trn::colsum_kernel<<<E / 32, cs, 0, st>>>(h->gq, B, E, E, 1.0f, (float*)G->temb_b, nullptr);
-  if (sd != st) { cudaEventRecord(h->ev_join, sd); cudaStreamWaitEvent(st, h->ev_join, 0); }
+  if ((rc = trn::backward(h, P, G, mask_given, drop_p, seed, false, nullptr, st)) != DPB_OK) return rc;
   DPB_CUDA_CHECK(cudaGetLastError());
-#undef TRY
+  return DPB_OK;
+}
+
+// The two halves on their own, for losses that chain several network evaluations (the auxiliary loss of losses.py:91-106,
+// 244-258: a DDIM chain under the optimiser).  One handle = the activations of ONE evaluation.
+extern "C" int dpb_train_forward(dpb_train* h, const dpb_train_tensors* P, const float* x, const float* labels,
+                                 const uint8_t* mask_given, float drop_p, uint64_t seed, float* res, void* stream) {
+  DPB_REQUIRE(h && P && x && labels && res, "dpb_train_forward: bad argument");
+  DPB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dpb_train_forward: dropout probability must be in [0, 1)");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t B = h->B;
+  int rc = trn::weight_operands(h, P, true, st);
+  if (rc != DPB_OK) return rc;
+  trn::prep_given_kernel<<<(unsigned)B, 256, 0, st>>>(x, labels, P->emb_freqs, h->xp, h->temb0, B);
+  if ((rc = trn::forward(h, P, mask_given, drop_p, seed, true, st)) != DPB_OK) return rc;
+  trn::pad_cols_kernel<<<(unsigned)((B * D + 255) / 256), 256, 0, st>>>(h->res, DP, res, D, D, B);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+extern "C" int dpb_train_backward(dpb_train* h, const dpb_train_tensors* P, const dpb_train_tensors* G, const float* g_res,
+                                  const uint8_t* mask_given, float drop_p, uint64_t seed, int accumulate, float* g_x,
+                                  void* stream) {
+  DPB_REQUIRE(h && P && G && g_res, "dpb_train_backward: bad argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t B = h->B;
+  trn::pad_cols_kernel<<<(unsigned)((B * DP + 255) / 256), 256, 0, st>>>(g_res, D, h->gres, DP, D, B);
+  int rc = trn::backward(h, P, G, mask_given, drop_p, seed, accumulate != 0, g_x, st);
+  if (rc != DPB_OK) return rc;
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+namespace dpb {
+namespace trn {
+
+// out[b,c] = a[b] x[b,c] + b[b] y[b,c]  (y may be null): the DDIM chain's affine steps and their adjoints
+__global__ void rows_axpby_kernel(const float* __restrict__ a, const float* __restrict__ x, const float* __restrict__ bb,
+                                  const float* __restrict__ y, float* __restrict__ out, int cols, int64_t B) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * cols) return;
+  const int64_t b = i / cols;
+  float v = a[b] * x[i];
+  if (y) v += bb[b] * y[i];
+  out[i] = v;
+}
+
+// row_loss[b] = w[b] sum_i (p[b,i] - q[b,i])^2 ;  grad_q[b,i] = -2 scale w[b] (p - q)   (weighted MSE of losses.py:253-254)
+__global__ void __launch_bounds__(256) wsqdiff_kernel(const float* __restrict__ p, const float* __restrict__ q,
+                                                      const float* __restrict__ w, int64_t n, float scale,
+                                                      float* __restrict__ row_loss, float* __restrict__ grad_q) {
+  __shared__ float sh[256];
+  const int64_t b = blockIdx.x;
+  const float wb = w[b];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const float d = p[b * n + i] - q[b * n + i];
+    s += d * d;
+    if (grad_q) grad_q[b * n + i] = -2.0f * scale * wb * d;
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) row_loss[b] = wb * sh[0];
+}
+
+}  // namespace trn
+}  // namespace dpb
+
+extern "C" int dpb_rows_axpby(const float* a, const float* x, const float* b, const float* y, float* out, int cols,
+                              int64_t B, void* stream) {
+  DPB_REQUIRE(a && x && out && cols > 0 && B >= 0 && (!y || b), "dpb_rows_axpby: bad argument");
+  if (B == 0) return DPB_OK;
+  PtrDeviceGuard guard(out);
+  trn::rows_axpby_kernel<<<(unsigned)((B * cols + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, x, b, y, out, cols, B);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+// loss[0] = scale * sum_b w[b] sum_i (p - q)^2 (rows added in a fixed order); grad_q optional; row_scratch DEVICE [B]
+extern "C" int dpb_weighted_sqdiff(const float* p, const float* q, const float* w, int64_t B, int64_t n, float scale,
+                                   float* loss, float* grad_q, float* row_scratch, void* stream) {
+  DPB_REQUIRE(p && q && w && loss && row_scratch && B > 0 && n > 0, "dpb_weighted_sqdiff: bad argument");
+  PtrDeviceGuard guard(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  trn::wsqdiff_kernel<<<(unsigned)B, 256, 0, st>>>(p, q, w, n, scale, row_scratch, grad_q);
+  trn::colsum_kernel<<<1, dim3(32, 32), 0, st>>>(row_scratch, B, 1, 1, scale, loss, nullptr, 0);
+  DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }
 

@@ -349,6 +349,23 @@ int dpb_train_destroy(dpb_train_t* h);
 int dpb_train_loss_grad(dpb_train_t* h, const dpb_train_tensors* params, const dpb_train_tensors* grads,
                         const float* batch, const float* rows, const float* z_given, const uint8_t* mask_given,
                         float drop_p, uint64_t seed, float* loss, float* loss_rows, void* stream);
+/* The two halves of dpb_train_loss_grad on their own, for losses that chain several network evaluations under the
+ * optimiser (the auxiliary loss: multi_step_denoise of losses.py:91-106 feeding the body model, :244-258).  One handle holds
+ * the activations of ONE evaluation: forward stores them, backward consumes them (same mask / drop_p / seed).
+ *   x DEVICE [B,63] network input, labels DEVICE [B] (= 999 t), res DEVICE [B,63] post_dense output (before the sigma division)
+ *   g_res DEVICE [B,63] cotangent of res; accumulate != 0 adds to the gradients instead of overwriting them;
+ *   g_x DEVICE [B,63] cotangent of x, or NULL */
+int dpb_train_forward(dpb_train_t* h, const dpb_train_tensors* params, const float* x, const float* labels,
+                      const uint8_t* mask_given, float drop_p, uint64_t seed, float* res, void* stream);
+int dpb_train_backward(dpb_train_t* h, const dpb_train_tensors* params, const dpb_train_tensors* grads, const float* g_res,
+                       const uint8_t* mask_given, float drop_p, uint64_t seed, int accumulate, float* g_x, void* stream);
+/* out[b,c] = a[b] x[b,c] + b[b] y[b,c] (y may be NULL): the affine steps of the DDIM chain and their adjoints */
+int dpb_rows_axpby(const float* a, const float* x, const float* b, const float* y, float* out, int cols, int64_t B,
+                   void* stream);
+/* loss[0] = scale sum_b w[b] sum_i (p[b,i] - q[b,i])^2, grad_q = -2 scale w[b] (p - q) (optional): the weighted v2v / j2j
+ * terms of losses.py:253-254; row_scratch DEVICE fp32 [B] */
+int dpb_weighted_sqdiff(const float* p, const float* q, const float* w, int64_t B, int64_t n, float scale, float* loss,
+                        float* grad_q, float* row_scratch, void* stream);
 /* C[M,N] = A[M,K] B[N,K]^T (+ bias[n]) on the split-fp16 tcgen05 GEMM the training step is built from (DEVICE fp32,
  * row-major, ~1e-6 relative); utility / unit-test entry, the operands are converted on every call */
 size_t dpb_gemm_nt_workspace_bytes(int M, int N, int K);
