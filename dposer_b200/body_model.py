@@ -69,9 +69,12 @@ class _LbsFn(torch.autograd.Function):
         t = None if transl is None else transl.detach().to(torch.float32).contiguous()
         verts = torch.empty(B, core.V, 3, dtype=torch.float32, device=dev) if need_verts else None
         joints = torch.empty(B, core.n_out, 3, dtype=torch.float32, device=dev)
-        ws = core.workspace(B, dev)
+        wants_grad = betas.requires_grad or full_pose.requires_grad or (transl is not None and transl.requires_grad)
+        # the workspace carries what backward reads: a forward that a backward may follow gets its own (another forward of
+        # the same module must not overwrite it); grad mode is always off inside Function.forward, so ask the inputs
+        ws = core.workspace(B, dev, fresh=wants_grad)
         flags = core.engine | (L.LBS_CONST_TAIL if (const_tail and core.tail is not None) else 0)
-        if not (betas.requires_grad or full_pose.requires_grad or (transl is not None and transl.requires_grad)):
+        if not wants_grad:
             flags |= L.LBS_NO_SAVE      # no backward will follow: skip the per-pose fp32 side outputs
         L.check(L.load().dpb_lbs_forward(h.ptr, L.ptr(b), L.ptr(p), L.ptr(t), L.ptr(verts), L.ptr(joints), B,
                                          flags, L.ptr(ws), ws.numel(), L.current_stream(dev)))
@@ -187,10 +190,10 @@ class LbsCore:
             self._declare_tail(h)
         return h
 
-    def workspace(self, B, device):
-        """A fresh workspace per call when autograd may keep it alive; cached otherwise."""
+    def workspace(self, B, device, fresh=False):
+        """A fresh workspace per call when autograd will keep it alive (``fresh``); cached otherwise."""
         n = L.load().dpb_lbs_workspace_bytes(self.handle(device).ptr, int(B), 0)
-        if torch.is_grad_enabled():
+        if fresh:
             return torch.empty(int(n), dtype=torch.uint8, device=device)
         key = (int(B), str(device))
         ws = self._ws.get(key)

@@ -10,7 +10,9 @@ What differs from the reference, by construction:
   * the per-row time draws ``t`` come from torch's CPU generator (the schedule scalars are evaluated on the host in fp32
     like everywhere else in this package); ``z`` and the dropout masks come from Philox on the device.  All three can be
     passed in (``t=``, ``z=``, ``drop_mask=``) -- that is how the parity tests replay the reference's draws;
-  * the auxiliary v2v / j2j loss (``return_data=True``, "not recommended" in the reference's config) is not built.
+  * the auxiliary v2v / j2j loss ("not recommended" in the reference's config) runs as a whole inside ``step_fn``
+    (:func:`auxiliary_loss_grad`): the DDIM chain keeps one native engine per network evaluation and is walked backwards
+    by hand; only ``denormalize`` + the body model (a native autograd function) go through torch autograd.
 """
 import ctypes as C
 
@@ -250,7 +252,8 @@ def get_sde_loss_fn(sde, train, reduce_mean=False, continuous=True, likelihood_w
                     return_data=False, denoise_steps=5):
     """losses.py:61-137.  ``loss_fn(model, batch, condition, mask, t=None, z=None, drop_mask=None)``."""
     if return_data:
-        raise NotImplementedError('the auxiliary (multi-step denoise + body model) loss is not built')
+        raise NotImplementedError('without autograd the estimate cannot carry gradients out of loss_fn: the auxiliary loss '
+                                  'runs as a whole in get_step_fn(auxiliary_loss=True) / losses.auxiliary_loss_grad')
     red = (1.0 / _DATA_DIM) if reduce_mean else 0.5
 
     def make_rows(model, B, t=None):
@@ -316,6 +319,120 @@ def get_ddpm_loss_fn(vpsde, train, reduce_mean=True):
     return loss_fn
 
 
+# ---------------------------------------------------------------------------------------------
+# auxiliary loss: DDIM chain under the optimiser + body model (losses.py:91-106,117-121,244-258)
+# ---------------------------------------------------------------------------------------------
+def _rows_axpby(a, x, b=None, y=None):
+    """out[r,c] = a[r] x[r,c] (+ b[r] y[r,c]) -- native, device fp32."""
+    out = torch.empty_like(x)
+    L.check(L.load().dpb_rows_axpby(L.ptr(a), L.ptr(x), L.ptr(b), L.ptr(y), L.ptr(out), x.shape[1], x.shape[0],
+                                    L.current_stream(x.device)))
+    return out
+
+
+def _weighted_sqdiff(p, q, w, scale, want_grad=True):
+    """(scale * sum_b w[b] sum (p - q)^2 as a [1] tensor, d/dq or None) -- native."""
+    B = p.shape[0]
+    n = p[0].numel()
+    loss = torch.empty(1, device=p.device)
+    grad = torch.empty_like(q) if want_grad else None
+    scratch = torch.empty(B, device=p.device)
+    L.check(L.load().dpb_weighted_sqdiff(L.ptr(p), L.ptr(q), L.ptr(w), B, n, float(scale), L.ptr(loss), L.ptr(grad),
+                                         L.ptr(scratch), L.current_stream(p.device)))
+    return loss, grad
+
+
+def auxiliary_loss_grad(model, sde, batch, denormalize, body_model, denoise_steps=5, reduce_mean=False, continuous=True,
+                        eps=1e-5, t=None, z=None, drop_mask=None, score_scale=1.0):
+    """Loss of get_step_fn(auxiliary_loss=True) (losses.py:244-258) and every parameter gradient, without autograd through
+    the network: ``denoise_steps`` network evaluations of multi_step_denoise (each on its own native engine, activations
+    kept), the estimate through ``denormalize`` + ``body_model`` (torch autograd over the native LBS function), weighted
+    v2v / j2j terms, then the chain backwards -- every evaluation's backward adds into the same flat gradient buffers.
+    ``drop_mask``: [denoise_steps, 5, B, 1024] keep-masks (parity mode); ``score_scale`` multiplies the score-matching term
+    (tests switch it off to look at the body-model terms alone).  Returns a dict of [] device tensors."""
+    from .misc import linear_interpolation
+    L.require_cuda(batch, 'batch')
+    lib = L.load()
+    dev, B, N = batch.device, batch.shape[0], int(denoise_steps)
+    st = L.current_stream(dev)
+    p_drop = float(model.config.model.dropout)
+    engines = getattr(model, '_aux_engines', None)
+    if engines is None or len(engines) != N or engines[0].B != B or engines[0].device != dev:
+        engines = model._aux_engines = [_Engine(model, B, dev) for _ in range(N)]
+    for prm in model.parameters():
+        if prm.grad is None:
+            prm.grad = torch.zeros_like(prm)
+    P = _tensor_struct(model, lambda q: q.data)
+    P.emb_freqs = _f32p(engines[0].freqs)
+    G = _tensor_struct(model, lambda q: q.grad)
+    up = lambda v: v.to(device=dev, dtype=torch.float32).contiguous()                 # noqa: E731
+    # ---- host scalars of the chain (fp32 torch expressions of the reference)
+    if t is None:
+        t = torch.rand(B) * (sde.T - eps) + eps
+    t = t.detach().to('cpu', torch.float32)
+    traj = linear_interpolation(t, t / (2 * N), N + 1)                                 # losses.py:92,120
+    coef0, _ = mutils.em_coefficients(sde, model, t, probability_flow=True, continuous=continuous)
+    mean_c, std0, m0 = coef0[:, 3], coef0[:, 4], coef0[:, 5]
+    alpha0, sigma0 = sde.return_alpha_sigma(t)
+    weight = torch.log(1.0 + alpha0[:, 0] / sigma0)                                    # log(1 + SNR), losses.py:246
+    labels, c1s, c2s = [], [], []
+    for i in range(N):
+        tc, tb = traj[i], traj[i + 1]
+        a_c, s_c = sde.return_alpha_sigma(tc)
+        a_b, s_b = sde.return_alpha_sigma(tb)
+        cf, lab = mutils.em_coefficients(sde, model, tc, probability_flow=True, continuous=continuous)
+        c1 = (a_b / a_c)[:, 0]
+        labels.append(up(lab))
+        c1s.append(up(c1))
+        c2s.append(up(-(s_b - c1 * s_c) * cf[:, 5] * s_c))          # x' = c1 x + (s_b - c1 s_c) noise, noise = -m res s_c
+    ones = torch.ones(B, device=dev)
+    # ---- forward chain
+    batch = batch.detach().to(torch.float32).contiguous()
+    if z is None:
+        z = torch.empty(B, _DATA_DIM, device=dev)
+        L.check(lib.dpb_normal_fill(L.ptr(z), B, C.c_uint64(_draw_seed()), C.c_uint64(0), 0, st))
+    else:
+        z = up(z)
+    x = _rows_axpby(up(mean_c), batch, up(std0), z)                                    # perturbed data, losses.py:113-115
+    seeds = [_draw_seed() for _ in range(N)]
+    masks = [None] * N if drop_mask is None else [drop_mask[i].to(device=dev, dtype=torch.uint8).contiguous() for i in range(N)]
+    res0 = None
+    for i in range(N):
+        res = torch.empty(B, _DATA_DIM, device=dev)
+        L.check(lib.dpb_train_forward(engines[i].ptr, C.byref(P), L.ptr(x), L.ptr(labels[i]), L.ptr(masks[i]), p_drop,
+                                      C.c_uint64(seeds[i]), L.ptr(res), st))
+        if i == 0:
+            res0 = res
+        x = _rows_axpby(c1s[i], x, c2s[i], res)
+    # ---- score-matching term on the first evaluation: (score std + z)^2 = rc^2 (res - (-z / rc))^2, rc = m std
+    red = (1.0 / _DATA_DIM) if reduce_mean else 0.5
+    rc = m0 * std0
+    target = _rows_axpby(up(-1.0 / rc), z)
+    score_loss, g_res_score = _weighted_sqdiff(target, res0, up(red * rc * rc), float(score_scale) / B)
+    # ---- body-model terms on the estimate (torch autograd over denormalize + the native LBS function)
+    wdev = up(weight)
+    with torch.no_grad():                      # the target first: the body model keeps ONE saved forward state per module
+        gt = body_model(pose_body=denormalize(batch))
+        gt_v, gt_j = gt.v.clone(), gt.Jtr.clone()
+    with torch.enable_grad():
+        leaf = x.detach().requires_grad_(True)
+        pred = body_model(pose_body=denormalize(leaf))
+        loss_v2v, g_v = _weighted_sqdiff(gt_v, pred.v.detach().contiguous(), wdev, 1.0 / (B * pred.v.shape[1]))
+        loss_j2j, g_j = _weighted_sqdiff(gt_j, pred.Jtr.detach().contiguous(), wdev, 1.0 / (B * pred.Jtr.shape[1]))
+        torch.autograd.backward([pred.v, pred.Jtr], [g_v.view_as(pred.v), g_j.view_as(pred.Jtr)])
+    g_x = leaf.grad.contiguous()
+    # ---- chain backwards: the first call overwrites the gradients, the others add
+    for i in reversed(range(N)):
+        g_res = _rows_axpby(c2s[i], g_x, ones, g_res_score) if i == 0 else _rows_axpby(c2s[i], g_x)
+        g_in = torch.empty(B, _DATA_DIM, device=dev) if i > 0 else None
+        L.check(lib.dpb_train_backward(engines[i].ptr, C.byref(P), C.byref(G), L.ptr(g_res), L.ptr(masks[i]), p_drop,
+                                       C.c_uint64(seeds[i]), 0 if i == N - 1 else 1, L.ptr(g_in), st))
+        if i > 0:
+            g_x = _rows_axpby(c1s[i], g_x, ones, g_in)
+    loss = score_loss + loss_v2v + loss_j2j
+    return {'step_loss': loss[0], 'score_loss': score_loss[0], 'v2v_loss': loss_v2v[0], 'j2j_loss': loss_j2j[0]}
+
+
 class _GraphedStep:
     """loss + backward + clip + Adam + EMA of one batch size as ONE captured CUDA graph.  What changes from step to step --
     the per-row schedule scalars, the Philox seed, Adam's step size / bias correction, the EMA decay -- lives in one
@@ -370,7 +487,11 @@ def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True
     trains on one GPU (run/train.py), this is the collective SURVEY 8(e)/(f)3 names for scaling it out."""
     from . import dist as D
     if auxiliary_loss:
-        raise NotImplementedError('the auxiliary (multi-step denoise + body model) loss is not built')
+        assert denormalize is not None and body_model is not None
+        if rot_rep != 'axis':
+            raise NotImplementedError("the auxiliary loss is built for rot_rep='axis' (the 63-D network input)")
+        if not continuous or likelihood_weighting:
+            raise NotImplementedError('the auxiliary loss goes with the continuous, unweighted SDE loss')
     if continuous:
         loss_fn = get_sde_loss_fn(sde, train, reduce_mean=reduce_mean, continuous=True,
                                   likelihood_weighting=likelihood_weighting)
@@ -387,7 +508,7 @@ def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True
 
     def step_fn(state, batch, condition=None, mask=None, **draws):
         model = state['model']
-        if train and graph and not data_parallel and 'z' not in draws and 'drop_mask' not in draws:
+        if train and graph and not data_parallel and not auxiliary_loss and 'z' not in draws and 'drop_mask' not in draws:
             optimizer, ema, B = state['optimizer'], state['ema'], batch.shape[0]
             L.require_cuda(batch, 'batch')
             g = graphs.get(B)
@@ -399,6 +520,17 @@ def get_step_fn(sde, train, optimize_fn=None, reduce_mean=False, continuous=True
             loss = g.run(optimizer, ema, batch.detach().to(torch.float32), rows, lr_t)
             state['step'] += 1
             model.mark_updated()
+        elif train and auxiliary_loss:
+            optimizer = state['optimizer']
+            ld = auxiliary_loss_grad(model, sde, batch, denormalize, body_model, denoise_steps=denoise_steps,
+                                     reduce_mean=reduce_mean, **draws)
+            if data_parallel:
+                D.all_reduce_mean_(optimizer.flat_g)
+            optimize_fn(optimizer, model.parameters(), step=state['step'])
+            state['step'] += 1
+            model.mark_updated()
+            state['ema'].update(model.parameters())
+            return ld
         elif train:
             optimizer = state['optimizer']
             optimizer.zero_grad()

@@ -60,6 +60,35 @@ def sde_loss(sd, sde, batch, t, z, masks=None, p=0.0, reduce_mean=True, likeliho
     return losses.mean()
 
 
+def aux_loss(sd, sde, batch, t, z, masks, p, denormalize, body_fn, n_steps, reduce_mean=True):
+    """losses.py:91-121,244-258: score loss on the first evaluation + log(1 + SNR)-weighted v2v / j2j terms on the estimate
+    of an ``n_steps`` DDIM chain (t -> t / (2 n_steps)); masks [n_steps, 5, B, 1024]; body_fn(pose) -> (verts, joints)."""
+    mean, std = sde.marginal(batch, t)
+    x = mean + std[:, None] * z
+    alpha0, sigma0 = sde.alpha_sigma(t)
+    snr = alpha0 / sigma0[:, None]
+    lin = torch.linspace(0, 1, n_steps + 1)[:, None]
+    traj = (1 - lin) * t + lin * (t / (2 * n_steps))
+    score0 = None
+    for i in range(n_steps):
+        tc, tb = traj[i], traj[i + 1]
+        a_c, s_c = sde.alpha_sigma(tc)
+        a_b, s_b = sde.alpha_sigma(tb)
+        score = -forward_train(sd, x, tc * 999, None if masks is None else masks[i], p) / sde.marginal(x, tc)[1][:, None]
+        if i == 0:
+            score0 = score
+        noise = -score * s_c[:, None]
+        x = a_b / a_c * (x - s_c[:, None] * noise) + s_b[:, None] * noise
+    red = (lambda v: v.mean(dim=-1)) if reduce_mean else (lambda v: 0.5 * v.sum(dim=-1))
+    score_loss = red(torch.square(score0 * std[:, None] + z)).mean()
+    weight = torch.log(1.0 + snr)
+    gv, gj = body_fn(denormalize(batch))
+    pv, pj = body_fn(denormalize(x))
+    v2v = torch.mean(weight * ((gv - pv) ** 2).sum(dim=-1))
+    j2j = torch.mean(weight * ((gj - pj) ** 2).sum(dim=-1))
+    return score_loss + v2v + j2j, score_loss, v2v, j2j
+
+
 def clip_coef(grads, max_norm):
     """torch.nn.utils.clip_grad_norm_: max_norm / (||g|| + 1e-6), clamped to 1."""
     total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()

@@ -282,3 +282,25 @@ def test_lbs_joints_only_tensor_core_path(mt, B):
         ref, got = leaf[k].grad, dl[k].grad.cpu()
         scale = ref.abs().max().clamp_min(1e-12)
         assert float((got - ref).abs().max() / scale) < 2e-4, k
+
+
+@pytest.mark.parametrize('B', [5, 130])
+def test_lbs_interleaved_forwards_keep_their_saved_state(B):
+    """A second forward of the same BodyModel between a forward and its backward (gt body / predicted body, as in
+    losses.py:251-252) must not disturb the first one's gradient: every differentiable forward owns its workspace."""
+    bm = BodyModel(synthetic.make_body_tensors('smplx'), num_betas=10, batch_size=B, model_type='smplx').cuda()
+    g = torch.Generator().manual_seed(1)
+    pa, pb = torch.randn(B, 63, generator=g).cuda() * 0.3, torch.randn(B, 63, generator=g).cuda() * 0.3
+    gv = torch.randn(B, 10475, 3, generator=g).cuda()
+    grads = []
+    for mode in ('plain', 'nograd_between', 'grad_between'):
+        leaf = pa.clone().requires_grad_(True)
+        pred = bm(pose_body=leaf)
+        if mode == 'nograd_between':
+            with torch.no_grad():
+                bm(pose_body=pb)
+        elif mode == 'grad_between':
+            bm(pose_body=pb.clone().requires_grad_(True))
+        torch.autograd.backward([pred.v, pred.Jtr], [gv, torch.ones_like(pred.Jtr)])
+        grads.append(leaf.grad.clone())
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])

@@ -262,3 +262,77 @@ def test_checkpoint_resume_continues_identically(tmp_path):
     assert all(torch.equal(x, y) for x, y in zip(a['ema'].shadow_params, b['ema'].shadow_params))
     # the EMA update after a load runs on the re-allocated flat shadow buffer too
     assert b['ema']._flat.numel() == a['ema']._flat.numel()
+
+
+def _aux_setup(B):
+    from dposer_b200.body_model import BodyModel
+    from dposer_b200.misc import Posenormalizer
+    model = synthetic.make_score_model(42).cuda()
+    model.train()
+    bm = BodyModel(synthetic.make_body_tensors('smplx'), num_betas=10, batch_size=B, model_type='smplx').cuda()
+    norm = Posenormalizer(None, device='cuda', normalize=True, min_max=False, rot_rep='axis')
+    return model, bm, norm
+
+
+def test_auxiliary_loss_step_vs_reference_golden():
+    """get_step_fn(auxiliary_loss=True) (losses.py:91-121,244-258: DDIM chain under the optimiser + body model) against the
+    REAL reference (train_aux_golden.npz: its step_fn run with a BodyModel-compatible object over the LBS restatement):
+    the four losses, the gradient norm and sampled gradients, with the reference's t, z and 15 dropout masks replayed."""
+    g = golden('train_aux_golden.npz')
+    B, N = g['data'].shape[0], int(g['nsteps'])
+    cfg = synthetic.default_config()
+    model, bm, norm = _aux_setup(B)
+    state = _state(cfg, model)
+    state['step'] = 4000
+    sde = sde_lib.subVPSDE(0.1, 20., 1000)
+    step_fn = losses.get_step_fn(sde, train=True, optimize_fn=lambda *a, **k: None, reduce_mean=True, continuous=True,
+                                 auxiliary_loss=True, denormalize=norm.offline_denormalize, body_model=bm, rot_rep='axis',
+                                 denoise_steps=N)
+    masks = torch.tensor(np.unpackbits(g['masks'], axis=-1)).reshape(N, 5, B, 1024)
+    ld = step_fn(state, torch.tensor(g['data']).cuda(), t=torch.tensor(g['t']), z=torch.tensor(g['z']), drop_mask=masks)
+    for k, tol in (('step_loss', 3e-4), ('score_loss', 3e-4), ('v2v_loss', 2e-3), ('j2j_loss', 2e-3)):
+        assert abs(float(ld[k]) - float(g[k])) < tol * abs(float(g[k])), (k, float(ld[k]), float(g[k]))
+    assert abs(state['optimizer'].grad_norm() - float(g['gnorm'])) < 3e-4 * float(g['gnorm'])
+    for n, p in model.named_parameters():
+        if f'g_{n}' not in g.files:
+            continue
+        flat = p.grad.reshape(-1)
+        got = flat[sample_idx(flat.numel()).cuda()].cpu()
+        assert float((got - torch.tensor(g[f'g_{n}'])).abs().max()) < 5e-4 * float(g[f'gmax_{n}']), n
+
+
+def test_auxiliary_body_terms_vs_oracle():
+    """The body-model terms alone (score term switched off, so that the chain's backward pass is what is measured): native
+    gradients against autograd through the CPU oracle (DDIM chain + LBS restatement)."""
+    from oracle import lbs_ref
+    from oracle import score_ref as S
+    from oracle import train_ref as T
+    B, N = 5, 3
+    model, bm, norm = _aux_setup(B)
+    sde, osde = sde_lib.subVPSDE(0.1, 20., 1000), S.SubVP(0.1, 20., 1000)
+    gen = torch.Generator().manual_seed(12)
+    batch = norm.offline_normalize(synthetic.toy_poses()[:B].cuda()).cpu()
+    t = torch.rand(B, generator=gen) * 0.6 + 0.2
+    z = torch.randn(B, 63, generator=gen)
+    masks = (torch.rand(N, 5, B, 1024, generator=gen) >= 0.1).to(torch.uint8)
+    ld = losses.auxiliary_loss_grad(model, sde, batch.cuda(), norm.offline_denormalize, bm, denoise_steps=N, reduce_mean=True,
+                                    t=t, z=z, drop_mask=masks, score_scale=0.0)
+    m = synthetic.make_body_tensors('smplx')
+    mean, std = norm.mean_poses.cpu(), norm.std_poses.cpu()
+
+    def body_fn(pose):
+        full = torch.cat([torch.zeros(B, 3), pose, torch.zeros(B, 99)], 1)
+        return lbs_ref.body_forward(m, torch.zeros(B, m['shapedirs'].shape[2]), full)
+    sd = S.make_state_dict(42)
+    names = T.param_names(sd)
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    full = dict(sd)
+    full.update(leaves)
+    _, _, ov, oj = T.aux_loss(full, osde, batch, t, z, masks, 0.1, lambda v: v * std + mean, body_fn, N, reduce_mean=True)
+    used = [k for k in names if not k.startswith('pre_dense_cond')]
+    og = dict(zip(used, torch.autograd.grad(ov + oj, [leaves[k] for k in used])))
+    ov, oj = ov.detach(), oj.detach()
+    assert abs(float(ld['v2v_loss']) - float(ov)) < 2e-3 * float(ov) and abs(float(ld['j2j_loss']) - float(oj)) < 2e-3 * float(oj)
+    for n, p in model.named_parameters():
+        if n in og:
+            assert rel(p.grad, og[n]) < 2e-3, n
