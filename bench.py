@@ -434,10 +434,40 @@ def bench_configs(args, dev, model, peaks, flush, cpu_per_row_step):
         'finite': bool(torch.isfinite(bpd).all())}
     del ldata, bpd
 
+    # the auxiliary variant (losses.py:244-258): 10-step DDIM chain under the optimiser + SMPL-X v2v / j2j terms
+    from dposer_b200.body_model import BodyModel as _BM
+    Bt = cfg.training.batch_size
+    tm = synthetic.make_score_model(42).to(dev)
+    tm.train()
+    abm = _BM(mx, num_betas=10, batch_size=Bt, model_type='smplx').to(dev)
+    state = dict(optimizer=losses.get_optimizer(cfg, tm.parameters()), model=tm,
+                 ema=ExponentialMovingAverage(tm.parameters(), decay=cfg.model.ema_rate), step=0)
+    aux_fn = losses.get_step_fn(sde, True, losses.optimization_manager(cfg), reduce_mean=cfg.training.reduce_mean,
+                                auxiliary_loss=True, denormalize=norm.offline_denormalize, body_model=abm, rot_rep='axis',
+                                denoise_steps=cfg.training.denoise_steps)
+    toy = synthetic.toy_poses()
+    data = norm.offline_normalize(toy[torch.randint(0, toy.shape[0], (Bt,))].to(dev))
+    for _ in range(3):
+        aux_fn(state, data)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        ld = aux_fn(state, data)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_aux = e0.elapsed_time(e1) / 20
+    tr['auxiliary'] = {'batch': Bt, 'denoise_steps': cfg.training.denoise_steps, 'ms_per_step': ms_aux, 'value': Bt / (ms_aux * 1e-3),
+                       'unit': 'poses/s', 'finite': bool(torch.isfinite(ld['step_loss'])),
+                       'note': 'training.auxiliary_loss = True: 10 network evaluations forward + backward, two SMPL-X LBS '
+                               'forwards (10475 vertices) and one LBS backward per step'}
+    del state, tm, abm, data
+    torch.cuda.empty_cache()
+
     out['f3_train_step'] = {
         'workload': 'SURVEY 8(f)3: one training step of ScoreModelFC (sub-VP denoising score matching, per-row t, dropout 0.1, '
                     'grad clip 1.0, Adam, EMA) -- 27 tcgen05 GEMMs + elementwise kernels per step, replayed as one CUDA graph; AMASS toy poses',
-        'flop_per_row_step': FLOP_ROW, **tr['reference_batch'], 'large_batch': tr['large_batch']}
+        'flop_per_row_step': FLOP_ROW, **tr['reference_batch'], 'large_batch': tr['large_batch'], 'auxiliary': tr['auxiliary']}
     return out
 
 

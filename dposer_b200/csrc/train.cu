@@ -1,5 +1,6 @@
 // Training step of the score network on the device: denoising score-matching loss with per-row random times, its
-// gradient with respect to every parameter, Adam with warm-up / gradient clipping, and the EMA update.
+// gradient with respect to every parameter, Adam with warm-up / gradient clipping, the EMA update, and the forward /
+// backward halves + small kernels the auxiliary (DDIM chain + body model) loss chains together.
 // Reference: lib/algorithms/advanced/losses.py:31-57 (optimizer, optimize_fn), :61-137 (get_sde_loss_fn), :187-275
 // (get_step_fn), lib/algorithms/advanced/model.py:141-196 (forward in train mode, dropout active),
 // lib/algorithms/ema.py:10-98.  The reference differentiates with autograd; here the backward pass is written out:

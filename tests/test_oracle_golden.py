@@ -282,3 +282,37 @@ def test_training_oracle_reproduces_reference_steps():
         assert float((d[idx(d.numel())] - torch.tensor(g[f'dp_{n}'])).abs().max()) <= 2e-2 * dmax + 1e-12, n
         e = (ema[n] - sd0[n]).reshape(-1)
         assert float((e[idx(e.numel())] - torch.tensor(g[f'dema_{n}'])).abs().max()) <= 2e-2 * dmax + 1e-12, n
+
+
+def test_training_oracle_auxiliary_loss_reproduces_reference():
+    """oracle/train_ref.aux_loss against the REAL reference's step_fn(auxiliary_loss=True) (train_aux_golden.npz): the four
+    loss values and sampled gradients (DDIM chain of three evaluations under autograd + LBS restatement)."""
+    from dposer_b200 import synthetic
+    from oracle import lbs_ref
+    from oracle import score_ref as S
+    from oracle import train_ref as T
+    g = golden('train_aux_golden.npz')
+    B, N = g['data'].shape[0], int(g['nsteps'])
+    stats = np.load(os.path.join(os.path.dirname(synthetic.__file__), 'data', 'amass_stats.npz'))
+    mean, std = torch.tensor(stats['mean_poses']), torch.tensor(stats['std_poses'])
+    m = synthetic.make_body_tensors('smplx')
+
+    def body_fn(pose):
+        full = torch.cat([torch.zeros(B, 3), pose, torch.zeros(B, 99)], 1)
+        return lbs_ref.body_forward(m, torch.zeros(B, m['shapedirs'].shape[2]), full)
+    sd = S.make_state_dict(42)
+    names = T.param_names(sd)
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    full = dict(sd)
+    full.update(leaves)
+    masks = torch.tensor(np.unpackbits(g['masks'], axis=-1)).reshape(N, 5, B, 1024)
+    ol, osc, ov, oj = T.aux_loss(full, S.SubVP(0.1, 20., 1000), torch.tensor(g['data']), torch.tensor(g['t']), torch.tensor(g['z']),
+                                 masks, 0.1, lambda v: v * std + mean, body_fn, N, reduce_mean=True)
+    for a, k in ((ol, 'step_loss'), (osc, 'score_loss'), (ov, 'v2v_loss'), (oj, 'j2j_loss')):
+        assert abs(float(a.detach()) - float(g[k])) <= 2e-5 * abs(float(g[k])), k
+    used = [k for k in names if not k.startswith('pre_dense_cond')]
+    og = dict(zip(used, torch.autograd.grad(ol, [leaves[k] for k in used])))
+    idx = lambda n: torch.linspace(0, n - 1, min(48, n)).long()     # noqa: E731
+    for n in used:
+        flat = og[n].reshape(-1)
+        assert float((flat[idx(flat.numel())] - torch.tensor(g[f'g_{n}'])).abs().max()) <= 2e-4 * float(g[f'gmax_{n}']) + 1e-10, n
