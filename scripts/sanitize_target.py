@@ -72,3 +72,14 @@ torch.cuda.synchronize(); print('likelihood rk45 ok', nfe, bool(torch.isfinite(b
 ofn = sampling.get_ode_sampler(sde1k, (33, 63), lambda v: v, rtol=1e-2, atol=1e-2, eps=1e-3, device='cuda')
 nfe, xo = ofn(model, z=torch.randn(33, 63))
 torch.cuda.synchronize(); print('ode sampler rk45 ok', nfe, bool(torch.isfinite(xo).all()))
+# auxiliary training loss: DDIM chain (forward / backward halves, gradient accumulation) + SMPL-X body terms
+from dposer_b200.body_model import BodyModel as _BM2
+from dposer_b200.misc import Posenormalizer
+tm.train()
+abm = _BM2(synthetic.make_body_tensors('smplx'), num_betas=10, batch_size=70, model_type='smplx').cuda()
+anorm = Posenormalizer(None, device='cuda', normalize=True, min_max=False, rot_rep='axis')
+afn = losses.get_step_fn(sde1k, True, losses.optimization_manager(cfg), reduce_mean=True, auxiliary_loss=True,
+                         denormalize=anorm.offline_denormalize, body_model=abm, rot_rep='axis', denoise_steps=3)
+for _ in range(2):
+    ld = afn(state, anorm.offline_normalize(synthetic.toy_poses()[:70].cuda()))
+torch.cuda.synchronize(); print('auxiliary step ok', float(ld['step_loss']), float(ld['v2v_loss']))
