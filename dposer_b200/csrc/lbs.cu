@@ -55,7 +55,7 @@ __device__ __forceinline__ void compose(const float* __restrict__ P, const float
 template <int SLOTS>
 __global__ void __launch_bounds__(128) lbs_pose_kernel(
     const float* __restrict__ betas, const float* __restrict__ pose, const float* __restrict__ transl,
-    const float* __restrict__ j_template, const float* __restrict__ j_shapedirs,
+    const float* __restrict__ j_template, const float* __restrict__ j_shapedirsT,
     const int32_t* __restrict__ parents, const int32_t* __restrict__ depth, int J, int S, int max_depth,
     float* __restrict__ A_out, float* __restrict__ G_out, float* __restrict__ feat_out,
     float* __restrict__ jrest_out, float* __restrict__ joints_out, int n_out, int64_t B,
@@ -68,7 +68,16 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
   // written straight to global they were ~60 two-byte stores per lane and the kernel took 0.28 ms per 65 536 poses.
   __shared__ __align__(16) __half stage_f[4][1024];       // [hi | lo] blend operand row (2 * Kp <= 1024)
   __shared__ __align__(16) __half stage_s[4][12 * 128];   // 12 transform rows x [hi | lo] (2 * Jp <= 128)
+  // fp32 side outputs (A, G, feat: what the backward reads) leave through a per-warp staging row as well: written from the
+  // registers each store instruction touched 32 lanes x 4 bytes at a 48- / 36-byte stride (every sector 9-12 times)
+  __shared__ float stage_x[4][64 * 12];
   if (b >= B) return;  // warp-uniform
+  float* xs = stage_x[threadIdx.x >> 5];
+  auto flush = [&](float* __restrict__ dst, int n) {      // staging row -> global, 128 contiguous bytes per instruction
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) dst[i] = xs[i];
+    __syncwarp();
+  };
   const int P = (J - 1) * 9;
   __half* fs = stage_f[threadIdx.x >> 5];
   __half* ss = stage_s[threadIdx.x >> 5];
@@ -83,8 +92,25 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
       if (k < S) put_split(frow, k, Kp, betas[b * S + k]);
       else if (k >= S + p_feat) put_split(frow, k, Kp, k == S + p_feat ? 1.0f : 0.f);
   }
+  // rest joints J_template + J_shapedirs . beta (== J_regressor . v_shaped): lanes walk the (joint, coordinate) pairs, so
+  // every load of the transposed table and the jrest store are contiguous (per joint-lane the table is a 12 S-byte stride:
+  // 32 cache lines per load instruction, which was most of this kernel's time)
+  for (int q = lane; q < 3 * J; q += 32) {
+    float acc = j_template[q];
+    for (int k = 0; k < S; ++k) acc = fmaf(j_shapedirsT[k * 3 * J + q], betas[b * S + k], acc);
+    xs[q] = acc;
+    if (jrest_out) jrest_out[b * J * 3 + q] = acc;
+  }
+  __syncwarp();
   float M[SLOTS][12], G[SLOTS][12], jr[SLOTS][3];
   int par[SLOTS], dep[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    const int j = lane + 32 * s;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) jr[s][c] = j < J ? xs[j * 3 + c] : 0.f;
+  }
+  __syncwarp();                      // the staging row is reused for the pose features below
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
     const int j = lane + 32 * s;
@@ -92,30 +118,22 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
     dep[s] = -1;
 #pragma unroll
     for (int e = 0; e < 12; ++e) M[s][e] = G[s][e] = 0.f;
-    jr[s][0] = jr[s][1] = jr[s][2] = 0.f;
     if (j < J) {
       par[s] = parents[j];
       dep[s] = depth[j];
-      // rest joint: J_template + J_shapedirs . beta   (== J_regressor . v_shaped)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float acc = j_template[j * 3 + c];
-        for (int k = 0; k < S; ++k) acc = fmaf(j_shapedirs[(j * 3 + c) * S + k], betas[b * S + k], acc);
-        jr[s][c] = acc;
-        if (jrest_out) jrest_out[(b * J + j) * 3 + c] = acc;
-      }
       rodrigues(pose + (b * J + j) * 3, M[s]);
       if (j > 0) {
 #pragma unroll
         for (int e = 0; e < 9; ++e)
         {
           const float f = M[s][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
-          if (feat_out) feat_out[b * P + (j - 1) * 9 + e] = f;
+          if (feat_out) xs[(j - 1) * 9 + e] = f;
           if (featop && (j - 1) * 9 + e < p_feat) put_split(fs, S + (j - 1) * 9 + e, Kp, f);
         }
       }
     }
   }
+  if (feat_out) flush(feat_out + b * P, P);
   // relative joint offsets need the parent's rest joint: fetch by shuffle
 #pragma unroll
   for (int s = 0; s < SLOTS; ++s) {
@@ -173,11 +191,9 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       Ao[9 + i] = G[s][9 + i] - (G[s][i * 3 + 0] * jr[s][0] + G[s][i * 3 + 1] * jr[s][1] + G[s][i * 3 + 2] * jr[s][2]);
-    if (A_out) {   // fp32 copies for the backward pass / the fp32 vertex kernel (skipped on forward-only fused calls)
-      float* Ag = A_out + (b * J + j) * 12;
-      float* Go = G_out + (b * J + j) * 12;
+    if (A_out) {   // fp32 copy for the backward pass / the fp32 vertex kernel (skipped on forward-only fused calls)
 #pragma unroll
-      for (int e = 0; e < 12; ++e) { Go[e] = G[s][e]; Ag[e] = Ao[e]; }
+      for (int e = 0; e < 12; ++e) xs[j * 12 + e] = Ao[e];
     }
     if (skinop) {
 #pragma unroll
@@ -187,6 +203,18 @@ __global__ void __launch_bounds__(128) lbs_pose_kernel(
     jo[0] = G[s][9] + tx;
     jo[1] = G[s][10] + ty;
     jo[2] = G[s][11] + tz;
+  }
+  if (A_out) {
+    flush(A_out + b * J * 12, J * 12);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const int j = lane + 32 * s;
+      if (j < J) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) xs[j * 12 + e] = G[s][e];
+      }
+    }
+    flush(G_out + b * J * 12, J * 12);
   }
   // shared-memory operand rows -> global, 16 bytes per lane per step
   if (featop || skinop) __syncwarp();
@@ -472,6 +500,10 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
   UP(posedirs, m->posedirs, (size_t)h->P * V * 3);
   UP(j_template, jt.data(), J * 3);
   UP(j_shapedirs, js.data(), (size_t)J * 3 * S);
+  std::vector<float> jsT((size_t)S * 3 * J);
+  for (int q = 0; q < 3 * J; ++q)
+    for (int k = 0; k < S; ++k) jsT[(size_t)k * 3 * J + q] = js[(size_t)q * S + k];
+  UP(j_shapedirsT, jsT.data(), (size_t)S * 3 * J);
   UP(parents, m->parents, J);
   UP(depth, depth.data(), J);
   UP(ell_idx, eidx.data(), (size_t)nnz * V);
@@ -523,7 +555,7 @@ extern "C" int dpb_lbs_destroy(dpb_lbs_t* h) {
   lbs_bwd_release(h);
   lbs_bwd_tc_release(h);
   lbs_skin_bwd_tc_release(h);
-  void* ptrs[] = {h->v_template, h->shapedirs, h->posedirs, h->j_template, h->j_shapedirs, h->parents, h->depth,
+  void* ptrs[] = {h->v_template, h->shapedirs, h->posedirs, h->j_template, h->j_shapedirs, h->j_shapedirsT, h->parents, h->depth,
                   h->ell_idx, h->ell_w, h->extra_vids, h->lmk_faces, h->lmk_bary, h->need_vids, h->extra_pos,
                   h->lmk_pos, h->need_index};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -599,11 +631,11 @@ extern "C" int dpb_lbs_forward(dpb_lbs_t* h, const float* betas, const float* fu
   float* jrest_o = no_save ? nullptr : w.jrest;
   const unsigned pose_grid = (unsigned)((B + 3) / 4);
   if (h->J > 32)
-    lbs_pose_kernel<2><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirs, h->parents,
+    lbs_pose_kernel<2><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirsT, h->parents,
                                                    h->depth, h->J, h->S, h->max_depth, A_o, G_o, feat_o, jrest_o,
                                                    joints, h->n_out, B, fop, var.kext / 2, var.p_feat, sop, h->jp);
   else
-    lbs_pose_kernel<1><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirs, h->parents,
+    lbs_pose_kernel<1><<<pose_grid, 128, 0, st>>>(betas, full_pose, transl, h->j_template, h->j_shapedirsT, h->parents,
                                                    h->depth, h->J, h->S, h->max_depth, A_o, G_o, feat_o, jrest_o,
                                                    joints, h->n_out, B, fop, var.kext / 2, var.p_feat, sop, h->jp);
   DPB_CUDA_CHECK(cudaGetLastError());

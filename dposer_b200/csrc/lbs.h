@@ -31,6 +31,7 @@ struct dpb_lbs {
   float* posedirs = nullptr;      // [P,3V]
   float* j_template = nullptr;    // [J,3]     J_regressor . v_template
   float* j_shapedirs = nullptr;   // [J,3,S]   J_regressor . shapedirs
+  float* j_shapedirsT = nullptr;  // [S, 3J]   the same, transposed: lanes walk (joint, coordinate) pairs contiguously
   int32_t* parents = nullptr;     // [J]
   int32_t* depth = nullptr;       // [J]
   int32_t* ell_idx = nullptr;     // [nnz,V]

@@ -383,7 +383,7 @@ __device__ __forceinline__ void rodrigues_fwd(const float* __restrict__ p, float
 __global__ void __launch_bounds__(128) lbs_pose_bwd_kernel(
     const float* __restrict__ pose, const float* __restrict__ G, const float* __restrict__ jrest,
     const float* __restrict__ gA, const float* __restrict__ gfeat, const float* __restrict__ gbt,
-    const float* __restrict__ g_joints, const float* __restrict__ j_shapedirs, const int32_t* __restrict__ parents,
+    const float* __restrict__ g_joints, const float* __restrict__ j_shapedirsT, const int32_t* __restrict__ parents,
     const int32_t* __restrict__ depth, int J, int S, int max_depth, int n_out, float* __restrict__ g_pose,
     float* __restrict__ g_betas, float* __restrict__ g_transl, int64_t B) {
   extern __shared__ float smem[];
@@ -478,9 +478,7 @@ __global__ void __launch_bounds__(128) lbs_pose_bwd_kernel(
   if (g_betas) {
     for (int s = 0; s < S; ++s) {
       float part = 0.f;
-      for (int j = lane; j < J; j += 32)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) part = fmaf(j_shapedirs[(j * 3 + c) * S + s], gJ[j * 3 + c], part);
+      for (int q = lane; q < 3 * J; q += 32) part = fmaf(j_shapedirsT[s * 3 * J + q], gJ[q], part);   // contiguous rows
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
       if (lane == 0) g_betas[b * S + s] = part + gbt[b * (S + 3) + s];
     }
@@ -662,7 +660,7 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
   }
   size_t psmem = (size_t)4 * J * 15 * 4;
   lbs_pose_bwd_kernel<<<(unsigned)((B + 3) / 4), 128, psmem, st>>>(full_pose, w.G, w.jrest, w.gA, w.gfeat, w.gbeta,
-                                                                    g_joints, h->j_shapedirs, h->parents, h->depth, J,
+                                                                    g_joints, h->j_shapedirsT, h->parents, h->depth, J,
                                                                     S, h->max_depth, h->n_out, g_pose, g_betas,
                                                                     g_transl, B);
   DPB_CUDA_CHECK(cudaGetLastError());
