@@ -506,6 +506,15 @@ extern "C" int dpb_lbs_create(dpb_lbs_t** out, const dpb_body_tensors* m, int de
   UP(j_shapedirsT, jsT.data(), (size_t)S * 3 * J);
   UP(parents, m->parents, J);
   UP(depth, depth.data(), J);
+  std::vector<int32_t> cptr(J + 1, 0), cidx(J > 1 ? J - 1 : 1, 0);
+  for (int j = 1; j < J; ++j) cptr[m->parents[j] + 1]++;
+  for (int j = 0; j < J; ++j) cptr[j + 1] += cptr[j];
+  {
+    std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
+    for (int j = 1; j < J; ++j) cidx[fill[m->parents[j]]++] = j;
+  }
+  UP(child_ptr, cptr.data(), J + 1);
+  UP(child_idx, cidx.data(), J > 1 ? J - 1 : 1);
   UP(ell_idx, eidx.data(), (size_t)nnz * V);
   UP(ell_w, ew.data(), (size_t)nnz * V);
   UP(extra_vids, m->extra_vids, m->n_extra);
@@ -555,7 +564,7 @@ extern "C" int dpb_lbs_destroy(dpb_lbs_t* h) {
   lbs_bwd_release(h);
   lbs_bwd_tc_release(h);
   lbs_skin_bwd_tc_release(h);
-  void* ptrs[] = {h->v_template, h->shapedirs, h->posedirs, h->j_template, h->j_shapedirs, h->j_shapedirsT, h->parents, h->depth,
+  void* ptrs[] = {h->v_template, h->shapedirs, h->posedirs, h->j_template, h->j_shapedirs, h->j_shapedirsT, h->parents, h->depth, h->child_ptr, h->child_idx,
                   h->ell_idx, h->ell_w, h->extra_vids, h->lmk_faces, h->lmk_bary, h->need_vids, h->extra_pos,
                   h->lmk_pos, h->need_index};
   for (void* p : ptrs) if (p) cudaFree(p);

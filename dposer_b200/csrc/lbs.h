@@ -34,6 +34,8 @@ struct dpb_lbs {
   float* j_shapedirsT = nullptr;  // [S, 3J]   the same, transposed: lanes walk (joint, coordinate) pairs contiguously
   int32_t* parents = nullptr;     // [J]
   int32_t* depth = nullptr;       // [J]
+  int32_t* child_ptr = nullptr;   // [J+1]  CSR of each joint's children (the backward sweep pulls instead of using atomics)
+  int32_t* child_idx = nullptr;   // [J-1]
   int32_t* ell_idx = nullptr;     // [nnz,V]
   float* ell_w = nullptr;         // [nnz,V]
   int32_t* extra_vids = nullptr;  // [n_extra]

@@ -384,16 +384,28 @@ __global__ void __launch_bounds__(128) lbs_pose_bwd_kernel(
     const float* __restrict__ pose, const float* __restrict__ G, const float* __restrict__ jrest,
     const float* __restrict__ gA, const float* __restrict__ gfeat, const float* __restrict__ gbt,
     const float* __restrict__ g_joints, const float* __restrict__ j_shapedirsT, const int32_t* __restrict__ parents,
-    const int32_t* __restrict__ depth, int J, int S, int max_depth, int n_out, float* __restrict__ g_pose,
-    float* __restrict__ g_betas, float* __restrict__ g_transl, int64_t B) {
+    const int32_t* __restrict__ depth, const int32_t* __restrict__ child_ptr, const int32_t* __restrict__ child_idx, int J,
+    int S, int max_depth, int n_out, float* __restrict__ g_pose, float* __restrict__ g_betas, float* __restrict__ g_transl,
+    int64_t B) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + warp;
   if (b >= B) return;
-  float* gG = smem + (size_t)warp * J * 15;
+  float* gG = smem + (size_t)warp * J * 30;
   float* gJ = gG + (size_t)J * 12;
+  float* ctb = gJ + (size_t)J * 3;                     // [J,15] what joint j hands to its parent (gG part, gJ part)
   const int P = (J - 1) * 9;
   float gt[3] = {0.f, 0.f, 0.f};
+  // The kernel is issue-bound (ncu: 8.8 k warp instructions per pose at 12 of 32 lanes active, a third of them in the
+  // compare-and-swap loops that fp32 shared-memory atomics compile to: ATOMS.CAST.SPIN).  So: no atomics -- children
+  // publish their contribution, parents pull it through a child list; the tree tables stay in registers; the sweep skips
+  // (level, lane-slot) pairs that hold no joint.
+  int dep[2] = {-1, -1}, par[2] = {0, 0}, c0[2] = {0, 0}, c1[2] = {0, 0};
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int j = lane + 32 * s;
+    if (j < J) { dep[s] = depth[j]; par[s] = parents[j]; c0[s] = child_ptr[j]; c1[s] = child_ptr[j + 1]; }
+  }
   for (int j = lane; j < J; j += 32) {
     const float* a = gA + (b * J + j) * 12;
     const float* g = G + (b * J + j) * 12;
@@ -415,11 +427,15 @@ __global__ void __launch_bounds__(128) lbs_pose_bwd_kernel(
     for (int k = 0; k < 3; ++k) gJ[j * 3 + k] = -(g[0 * 3 + k] * a[9] + g[1 * 3 + k] * a[10] + g[2 * 3 + k] * a[11]);
   }
   __syncwarp();
-  // reverse sweep: children (depth d) push into their parents
+  // reverse sweep: level d publishes, level d - 1 pulls
   for (int d = max_depth; d >= 1; --d) {
-    for (int j = lane; j < J; j += 32) {
-      if (depth[j] != d) continue;
-      const int p = parents[j];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int j = lane + 32 * s;
+      const bool mine = dep[s] == d;
+      if (!__any_sync(0xffffffffu, mine)) continue;      // warp-uniform: no joint of this slot sits at this level
+      if (!mine) continue;
+      const int p = par[s];
       float R[9];
       rodrigues_fwd(pose + (b * J + j) * 3, R);
       const float* gp = G + (b * J + p) * 12;
@@ -428,16 +444,14 @@ __global__ void __launch_bounds__(128) lbs_pose_bwd_kernel(
       for (int k = 0; k < 3; ++k) rel[k] = jrest[(b * J + j) * 3 + k] - jrest[(b * J + p) * 3 + k];
 #pragma unroll
       for (int e = 0; e < 12; ++e) gg[e] = gG[j * 12 + e];
-      // parent: gG_R,p += gG_R,j R_j^T + gG_t,j (x) rel ; gG_t,p += gG_t,j
+      // for the parent: gG_R,p += gG_R,j R_j^T + gG_t,j (x) rel ; gG_t,p += gG_t,j
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float t = gg[i * 3 + 0] * R[k * 3 + 0] + gg[i * 3 + 1] * R[k * 3 + 1] + gg[i * 3 + 2] * R[k * 3 + 2] +
-                    gg[9 + i] * rel[k];
-          atomicAdd(gG + p * 12 + i * 3 + k, t);
-        }
-        atomicAdd(gG + p * 12 + 9 + i, gg[9 + i]);
+        for (int k = 0; k < 3; ++k)
+          ctb[j * 15 + i * 3 + k] = gg[i * 3 + 0] * R[k * 3 + 0] + gg[i * 3 + 1] * R[k * 3 + 1] + gg[i * 3 + 2] * R[k * 3 + 2] +
+                                    gg[9 + i] * rel[k];
+        ctb[j * 15 + 9 + i] = gg[9 + i];
       }
       // own local transform: g_R_j = G_R,p^T gG_R,j (kept in place), g_rel = G_R,p^T gG_t,j
       float gl[12];
@@ -452,9 +466,31 @@ __global__ void __launch_bounds__(128) lbs_pose_bwd_kernel(
       for (int e = 0; e < 12; ++e) gG[j * 12 + e] = gl[e];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        atomicAdd(gJ + j * 3 + k, gl[9 + k]);
-        atomicAdd(gJ + p * 3 + k, -gl[9 + k]);
+        gJ[j * 3 + k] += gl[9 + k];                       // own slot: nobody else writes it at this level
+        ctb[j * 15 + 12 + k] = -gl[9 + k];
       }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int j = lane + 32 * s;
+      const bool mine = dep[s] == d - 1 && c1[s] > c0[s];
+      if (!__any_sync(0xffffffffu, mine)) continue;
+      if (!mine) continue;
+      float acc[15];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) acc[e] = gG[j * 12 + e];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc[12 + k] = gJ[j * 3 + k];
+      for (int ci = c0[s]; ci < c1[s]; ++ci) {            // children in index order: a fixed summation order
+        const float* cb = ctb + child_idx[ci] * 15;
+#pragma unroll
+        for (int e = 0; e < 15; ++e) acc[e] += cb[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) gG[j * 12 + e] = acc[e];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gJ[j * 3 + k] = acc[12 + k];
     }
     __syncwarp();
   }
@@ -658,9 +694,11 @@ extern "C" int dpb_lbs_backward(dpb_lbs_t* h, const float* betas, const float* f
                                                      w.gfeat, w.gbeta, B);
     DPB_CUDA_CHECK(cudaGetLastError());
   }
-  size_t psmem = (size_t)4 * J * 15 * 4;
+  DPB_REQUIRE(J <= 64, "dpb_lbs_backward: the pose kernel handles up to 64 joints");
+  size_t psmem = (size_t)4 * J * 30 * 4;
   lbs_pose_bwd_kernel<<<(unsigned)((B + 3) / 4), 128, psmem, st>>>(full_pose, w.G, w.jrest, w.gA, w.gfeat, w.gbeta,
-                                                                    g_joints, h->j_shapedirsT, h->parents, h->depth, J,
+                                                                    g_joints, h->j_shapedirsT, h->parents, h->depth, h->child_ptr, h->child_idx,
+                                                                    J,
                                                                     S, h->max_depth, h->n_out, g_pose, g_betas,
                                                                     g_transl, B);
   DPB_CUDA_CHECK(cudaGetLastError());
