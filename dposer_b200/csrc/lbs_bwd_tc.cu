@@ -180,18 +180,18 @@ lbs_blendT_tc_kernel(const __grid_constant__ Params p, const __grid_constant__ C
 }
 
 // gfeat[b, k] += sum_s C[s, b, k] (k < P);  gbeta[b, k - P] += ... (P <= k < P + S): splits added in a fixed order
-__global__ void blendT_unpack_kernel(const float* __restrict__ C, int splits, int Kp, int P, int S,
-                                     const float* __restrict__ scale, float* __restrict__ gfeat,
-                                     float* __restrict__ gbt, int64_t B) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * (P + S)) return;
-  const int64_t b = i / (P + S);
-  const int k = (int)(i % (P + S));
-  float v = 0.f;
-  for (int s = 0; s < splits; ++s) v += C[((size_t)s * B + b) * Kp + k];
-  if (scale) v /= scale[b];                             // the operand was scaled into fp16 range by a power of two
-  if (k < P) gfeat[b * P + k] += v;
-  else gbt[b * (S + 3) + (k - P)] += v;
+__global__ void __launch_bounds__(256) blendT_unpack_kernel(const float* __restrict__ C, int splits, int Kp, int P, int S,
+                                                            const float* __restrict__ scale, float* __restrict__ gfeat,
+                                                            float* __restrict__ gbt, int64_t B) {
+  const int64_t b = blockIdx.x;                         // one pose row per block: no per-thread 64-bit division
+  const float inv = scale ? 1.0f / scale[b] : 1.0f;     // the operand was scaled into fp16 range by a power of two (exact)
+  for (int k = threadIdx.x; k < P + S; k += 256) {
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += C[((size_t)s * B + b) * Kp + k];
+    v *= inv;
+    if (k < P) gfeat[b * P + k] += v;
+    else gbt[b * (S + 3) + (k - P)] += v;
+  }
 }
 
 }  // namespace lbt
@@ -259,7 +259,7 @@ int lbs_blendT_tc(dpb_lbs* h, const __half* gvp16, const float* scale, float* cp
   else
     lbt::lbs_blendT_tc_kernel<4><<<grid, lbt::NUM_THREADS, lbt::SMEM_BYTES, st>>>(p, h->tm_bT, tm_g);
   const int64_t n = B * (h->P + h->S);
-  lbt::blendT_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cpart, p.splits, p.Kp, h->P, h->S, scale, gfeat, gbeta, B);
+  lbt::blendT_unpack_kernel<<<(unsigned)B, 256, 0, st>>>(cpart, p.splits, p.Kp, h->P, h->S, scale, gfeat, gbeta, B);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }
