@@ -559,20 +559,42 @@ lbs_skin_tc_kernel(const __grid_constant__ SkinParams p, const __grid_constant__
 // per-pose transforms A[b,j,12] -> operand rows (b*12 + e) = [A[b,:,e] hi (Jp) | lo (Jp)] fp16
 // If J < Jp the spare joint slot J carries the translation: its weight is 1 for every vertex (lbs_tc_prepare) and
 // its "transform" is [0 | transl], so T_t already includes + transl and the epilogue does not add it.
-__global__ void lbs_skinop_kernel(const float* __restrict__ A, const float* __restrict__ transl, int J, int Jp,
-                                  __half* __restrict__ op, int64_t B, int64_t B_pad) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B_pad * 12 * Jp) return;
-  const int j = (int)(i % Jp);
-  const int64_t r = i / Jp;          // row = b*12 + e
-  const int64_t b = r / 12;
-  const int e = (int)(r % 12);
-  float x = 0.f;
-  if (b < B && j < J) x = A[(b * J + j) * 12 + e];
-  else if (b < B && j == J && e >= 9 && transl) x = transl[b * 3 + (e - 9)];
-  const __half hi = __float2half_rn(x);
-  op[r * (2 * Jp) + j] = hi;
-  op[r * (2 * Jp) + Jp + j] = __float2half_rn(x - __half2float(hi));
+// One warp per pose: the pose's transforms A[b] (J x 12 floats, contiguous) are read once, coalesced; the 12 operand rows
+// [hi | lo] (12 x 2 Jp halves, contiguous in `op`) are assembled in shared memory and leave as 16-byte vectors.  (The
+// thread-per-element version issued two 2-byte stores per element and re-read every sector of A twelve times.)
+__global__ void __launch_bounds__(128) lbs_skinop_kernel(const float* __restrict__ A, const float* __restrict__ transl, int J,
+                                                         int Jp, __half* __restrict__ op, int64_t B, int64_t B_pad) {
+  __shared__ __align__(16) __half stage[4][12 * 128];      // 2 * Jp <= 128
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * 4 + w;
+  if (b >= B_pad) return;                                   // warp-uniform
+  __half* ss = stage[w];
+  const int n_el = 12 * Jp;
+  if (b < B) {
+    for (int i = lane; i < 12 * Jp; i += 32) {              // zero-fill, then the valid entries below overwrite
+      const int e = i / Jp, j = i - e * Jp;
+      float x = 0.f;
+      if (j == J && e >= 9 && transl) x = transl[b * 3 + (e - 9)];
+      const __half hi = __float2half_rn(x);
+      ss[e * 2 * Jp + j] = hi;
+      ss[e * 2 * Jp + Jp + j] = __float2half_rn(x - __half2float(hi));
+    }
+    __syncwarp();
+    const float* a = A + b * J * 12;
+    for (int i = lane; i < J * 12; i += 32) {               // contiguous read of the pose's transforms
+      const int j = i / 12, e = i - j * 12;
+      const float x = a[i];
+      const __half hi = __float2half_rn(x);
+      ss[e * 2 * Jp + j] = hi;
+      ss[e * 2 * Jp + Jp + j] = __float2half_rn(x - __half2float(hi));
+    }
+  } else {
+    for (int i = lane; i < 2 * n_el; i += 32) ss[i] = __float2half_rn(0.f);
+  }
+  __syncwarp();
+  const uint4* src = reinterpret_cast<const uint4*>(ss);
+  uint4* dst = reinterpret_cast<uint4*>(op + (size_t)b * 12 * 2 * Jp);
+  for (int i = lane; i < 3 * Jp; i += 32) dst[i] = src[i];  // 12 rows x 2 Jp halves = 3 Jp vectors of 16 bytes
 }
 
 
@@ -996,7 +1018,7 @@ int lbs_tc_skin(dpb_lbs* h, const float* A, const float* transl, __half* skinop,
   const int64_t B_pad = (B + ltc::SK_GROUP - 1) / ltc::SK_GROUP * ltc::SK_GROUP;   // operand rows (64 | 32 both divide)
   {
     const int64_t n = B_pad * 12 * Jp;
-    ltc::lbs_skinop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, transl, h->J, Jp, skinop, B, B_pad);
+    ltc::lbs_skinop_kernel<<<(unsigned)((B_pad + 3) / 4), 128, 0, st>>>(A, transl, h->J, Jp, skinop, B, B_pad);
     DPB_CUDA_CHECK(cudaGetLastError());
   }
   CUtensorMap tm_s;
@@ -1032,7 +1054,7 @@ int lbs_tc_skin_adjoint(dpb_lbs* h, const float* A, __half* skinop, const float*
   const int64_t B_pad = (B + ltc::SK_GROUP - 1) / ltc::SK_GROUP * ltc::SK_GROUP;
   {
     const int64_t n = B_pad * 12 * Jp;
-    ltc::lbs_skinop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A, nullptr, h->J, Jp, skinop, B, B_pad);
+    ltc::lbs_skinop_kernel<<<(unsigned)((B_pad + 3) / 4), 128, 0, st>>>(A, nullptr, h->J, Jp, skinop, B, B_pad);
     DPB_CUDA_CHECK(cudaGetLastError());
   }
   CUtensorMap tm_s;
@@ -1083,7 +1105,7 @@ int lbs_tc_fused(dpb_lbs* h, const float* betas, const float* feat, __half* feat
     const int64_t n = B_pad * Kp;
     ltc::lbs_featop_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(betas, feat, h->S, h->P, h->P, Kp, featop, B, B_pad);
     const int64_t n2 = B_pad * 12 * Jp;
-    ltc::lbs_skinop_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(A, transl, h->J, Jp, skinop, B, B_pad);
+    ltc::lbs_skinop_kernel<<<(unsigned)((B_pad + 3) / 4), 128, 0, st>>>(A, transl, h->J, Jp, skinop, B, B_pad);
     DPB_CUDA_CHECK(cudaGetLastError());
   }
   CUtensorMap tm_feat, tm_s;
