@@ -202,6 +202,18 @@ __global__ void joint_scatter_kernel(const float* __restrict__ g_out, int n_map,
   for (int k = 0; k < n_map; ++k) gi[map[k] * 3] += g_out[(b * n_map + k) * 3 + c];
 }
 
+// zero-padded 3-tap smoothing along the frames of each sequence (gaussian_smoothing(window_size=3), lib/utils/misc.py:84-95,
+// as applied per sequence by run/motion_denoising.py:281-285); the first / last frame of a sequence keep their values
+__global__ void seq_smooth3_kernel(const float* __restrict__ x, float* __restrict__ out, int L, int C, float w0, float w1,
+                                   float w2, int keep_ends, int64_t rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int64_t r = i / C;
+  const int f = (int)(r % L);
+  const float xm = f > 0 ? x[i - C] : 0.f, xp = f < L - 1 ? x[i + C] : 0.f, x0 = x[i];
+  out[i] = (keep_ends && (f == 0 || f == L - 1)) ? x0 : w0 * xm + w1 * x0 + w2 * xp;
+}
+
 }  // namespace dpb
 
 using namespace dpb;
@@ -295,6 +307,16 @@ extern "C" int dpb_joint_map_scatter(const float* g_out, int n_map, const int32_
   PtrDeviceGuard guard(g_out);
   const int64_t n = B * 3;
   joint_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g_out, n_map, map, n_in, g_in, B);
+  DPB_CUDA_CHECK(cudaGetLastError());
+  return DPB_OK;
+}
+
+extern "C" int dpb_seq_smooth3(const float* x, float* out, int64_t rows, int seq_len, int cols, float w0, float w1, float w2,
+                               int keep_ends, void* stream) {
+  DPB_REQUIRE(x && out && x != out && rows > 0 && seq_len > 0 && cols > 0 && rows % seq_len == 0, "dpb_seq_smooth3: bad argument");
+  PtrDeviceGuard guard(x);
+  const int64_t n = rows * cols;
+  seq_smooth3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, seq_len, cols, w0, w1, w2, keep_ends, rows);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }

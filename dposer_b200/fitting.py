@@ -21,7 +21,6 @@ import torch
 from . import _lib as L
 from . import steps as S
 from . import utils as mutils
-from .misc import gaussian_smoothing
 from .prior import MotionPrior
 
 # constants.JOINT_IDS of ['OP Neck', 'OP RHip', 'OP LHip', 'Right Hip', 'Left Hip'] (run/smplify.py:136-137)
@@ -150,10 +149,13 @@ class MotionDenoise(MotionPrior):
             sg.run(k, lambda k=k: one_step(k))
         with torch.no_grad():
             pose_final = b['full_pose'][:, 3:66].clone()
-            ps = pose_final.view(self.n_seq, self.seq_len, -1)
-            smooth = torch.stack([gaussian_smoothing(s, window_size=3, sigma=2) for s in ps])
-            smooth[:, 0], smooth[:, -1] = ps[:, 0], ps[:, -1]                    # :283-285
-            smooth = smooth.reshape(-1, ps.shape[-1])
+            # gaussian_smoothing(window_size=3, sigma=2) per sequence, first / last frame kept (:281-285): one native launch
+            kk = torch.exp(-0.5 * ((torch.arange(3).float() - 1) / 2.0) ** 2)
+            kk = kk / kk.sum()
+            smooth = torch.empty_like(pose_final)
+            L.check(L.load().dpb_seq_smooth3(L.ptr(pose_final), L.ptr(smooth), pose_final.shape[0], self.seq_len,
+                                             pose_final.shape[1], float(kk[0]), float(kk[1]), float(kk[2]), 1,
+                                             L.current_stream(pose_final.device)))
             final = bm(betas=self.betas, pose_body=smooth)
             results = {'pose_body': smooth, 'pose_body_raw': pose_final}
             if smpl_gt is not None:

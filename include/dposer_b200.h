@@ -298,6 +298,11 @@ int dpb_masked_mse_grad(const float* x, const float* obs, const float* mask, flo
  * score weights use it to bring the sampler's output into a plausible angle range before the body model. */
 int dpb_affine_cols(const float* x, int64_t ldx, const float* mean, const float* std, float* out, int64_t ldo,
                     int64_t rows, int cols, int inverse, float squash, void* stream);
+/* out[r,c] = w0 x[r-1,c] + w1 x[r,c] + w2 x[r+1,c] inside each sequence of seq_len rows, zero-padded at its ends
+ * (gaussian_smoothing(window_size=3), lib/utils/misc.py:84-95, per sequence as in run/motion_denoising.py:281-285);
+ * keep_ends != 0 copies the first and last row of every sequence instead.  out must not alias x. */
+int dpb_seq_smooth3(const float* x, float* out, int64_t rows, int seq_len, int cols, float w0, float w1, float w2,
+                    int keep_ends, void* stream);
 /* joints[:, joint_map] (lib/body_model/smpl.py:70) and its adjoint (g_in is overwritten; repeated map entries add) */
 int dpb_joint_map_gather(const float* joints, int n_in, const int32_t* map, int n_map, float* out, int64_t B,
                          void* stream);
