@@ -314,3 +314,44 @@ def test_rk45_controller_reproduces_scipy_solve_ivp():
         nfev, attempts = ode.solve_rk45(be, t0, t1, rtol=rtol, atol=atol)
         assert nfev == ref.nfev, (nfev, ref.nfev)
         assert np.abs(be.y - ref.y[:, -1]).max() <= 1e-12 * max(1.0, np.abs(ref.y[:, -1]).max())
+
+
+def test_training_host_surface_without_a_gpu():
+    """losses / ema on the host: no CPU fallback (loudly), argument errors, the EMA decay schedule and Adam's scalars."""
+    from dposer_b200 import ema as ema_mod
+    from dposer_b200 import losses
+    cfg = synthetic.default_config()
+    model = synthetic.make_score_model(42)                     # CPU parameters
+    with pytest.raises(RuntimeError):
+        losses.get_optimizer(cfg, model.parameters())          # flat buffers live on the device
+    sde = sde_lib.subVPSDE(0.1, 20., 1000)
+    with pytest.raises(NotImplementedError):
+        losses.get_sde_loss_fn(sde, True, return_data=True)
+    with pytest.raises(ValueError):
+        losses.get_step_fn(sde_lib.subVPSDE(0.1, 20., 1000), True, continuous=False)      # discrete training: VE / VP only
+    with pytest.raises(NotImplementedError):
+        losses.get_step_fn(sde, True, auxiliary_loss=True, denormalize=lambda v: v, body_model=object(), rot_rep='rot6d')
+    fn = losses.get_sde_loss_fn(sde, True, reduce_mean=True)
+    with pytest.raises(RuntimeError):
+        fn(model, torch.zeros(4, 63), None, None)              # batch on the CPU
+    # per-row scalars of the three loss families (host fp32, the reference's expressions)
+    t = torch.tensor([0.25, 0.5, 1.0])
+    rows = fn.make_rows(model, 3, t)
+    mean, std = sde.marginal_prob(torch.ones(3, 1), t)
+    assert rows.shape == (6, 3) and torch.equal(rows[0], t * 999) and torch.equal(rows[1], mean[:, 0]) and torch.equal(rows[2], std)
+    sig = mutils.sigma_at(model, t * 999)
+    assert torch.allclose(rows[3], -1.0 / sig, rtol=1e-6) and torch.equal(rows[4], torch.ones(3))        # e = -res / sigma + z
+    assert torch.allclose(rows[5], torch.full((3,), 1.0 / 63))
+    lw = losses.get_sde_loss_fn(sde, True, reduce_mean=False, likelihood_weighting=True).make_rows(model, 3, t)
+    g2 = sde.sde(torch.zeros(3, 1), t)[1] ** 2
+    assert torch.allclose(lw[5], 0.5 * g2) and torch.allclose(lw[4], 1.0 / std)
+    with pytest.raises(ValueError):
+        ema_mod.ExponentialMovingAverage(model.parameters(), decay=1.5)
+    e = ema_mod.ExponentialMovingAverage(model.parameters(), decay=0.9999)
+    seq = []
+    for n in range(1, 6):
+        seq.append(e.next_one_minus_decay())
+        e.num_updates += 1
+    assert np.allclose(seq, [1 - min(0.9999, (1 + n) / (10 + n)) for n in range(1, 6)])
+    sd = e.state_dict()
+    assert set(sd) == {'decay', 'num_updates', 'shadow_params'} and len(sd['shadow_params']) == len(list(model.parameters()))
