@@ -11,6 +11,8 @@
 //   warp 0     TMA producer: per k-block the four tiles A_hi, A_lo, B_hi, B_lo (64 KB stage, 3 stages)
 //   warp 1     TMEM allocator + MMA issuer: 12 UMMAs (M = 128, N = 128, K = 16) per stage
 //   warps 2-5  epilogue: TMEM -> registers -> 32 x 32 transpose in shared memory -> C (a warp stores whole row segments)
+// Persistent: a CTA walks tiles blockIdx.x, + gridDim.x, ... with two TMEM accumulators, so that the epilogue of one tile
+// overlaps the main loop of the next (matters once a GEMM has more tiles than the chip has SMs).
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 
@@ -29,9 +31,11 @@ constexpr int BK = 64;
 constexpr int TILE = 128 * BK * 2;      // 16 KB: [128 rows x 64 k] fp16, SWIZZLE_128B
 constexpr int ST = 3;                   // stages of four tiles
 constexpr int NUM_THREADS = 192;
-constexpr int OFF_BAR = ST * 4 * TILE;
-constexpr int NBARS = 2 * ST + 1;
+constexpr int OFF_TR = ST * 4 * TILE;            // 4 x [32][33] fp32 transpose buffers of the epilogue warps
+constexpr int OFF_BAR = OFF_TR + 4 * 32 * 33 * 4 + 512;
+constexpr int NBARS = 2 * ST + 4;                // operand stages full / empty, accumulator full / empty x 2
 constexpr int SMEM_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;
+static_assert(OFF_BAR % 8 == 0 && SMEM_BYTES <= 232448, "shared memory layout");
 
 struct Params {
   int M, N, kt;              // valid output extent, k-blocks of 64 per product
@@ -44,6 +48,7 @@ struct Params {
   const float* add;          // [M, ldadd] or null (may alias C)
   int64_t ldadd;
   int bias_rows;             // the biases apply to rows < bias_rows (stacked [primal ; tangent] rows of the JVP)
+  int mt, n_tiles;           // m-tiles, all tiles: a CTA walks tiles blockIdx.x, + gridDim.x, ... (persistent)
 };
 
 template <int BN>      // output tile 128 x BN: BN = 64 doubles the CTA count of the small GEMMs (a step at batch 1280 is latency-bound)
@@ -58,25 +63,31 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
   const uint32_t bar = sb + OFF_BAR;
   auto full = [&](uint32_t s) { return bar + 8u * s; };
   auto empty = [&](uint32_t s) { return bar + 8u * (ST + s); };
-  const uint32_t dfull = bar + 8u * (2 * ST);
+  auto dfull = [&](uint32_t b) { return bar + 8u * (2 * ST + b); };
+  auto dempty = [&](uint32_t b) { return bar + 8u * (2 * ST + 2 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBARS * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
-    ptx::mbar_init(dfull, 1);
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(dfull(b), 1); ptx::mbar_init(dempty(b), 4); }   // dempty: the four epilogue warps
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), BN);
+  // Two accumulators: the epilogue of tile i (TMEM -> transpose -> global) overlaps the main loop of tile i + 1 when a CTA
+  // owns several tiles (large batches); with one tile per CTA the second accumulator is simply never used.
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 2 * BN);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  auto tile_m0 = [&](int t) { return (t % p.mt) * 128; };
+  auto tile_n0 = [&](int t) { return (t / p.mt) * BN; };
 
   if (warp == 0) {
     if (lane == 0) { ptx::prefetch_tmap(&tm_a); ptx::prefetch_tmap(&tm_b); }
     __syncwarp();
     uint32_t s = 0, ph = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    const int m0 = tile_m0(t), n0 = tile_n0(t);
     for (int k = 0; k < p.kt; ++k) {
       ptx::mbar_wait(empty(s), ph ^ 1);
       if (ptx::elect_one()) {
@@ -90,8 +101,13 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
       __syncwarp();
       if (++s == ST) { s = 0; ph ^= 1; }
     }
+    }
   } else if (warp == 1) {
-    uint32_t s = 0, ph = 0;
+    uint32_t s = 0, ph = 0, it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+    const uint32_t buf = it & 1, acc = tmem_base + buf * BN;
+    ptx::mbar_wait(dempty(buf), ((it >> 1) & 1) ^ 1);          // the epilogue has read this accumulator's previous tile
+    ptx::tc_fence_after();
     for (int k = 0; k < p.kt; ++k) {
       ptx::mbar_wait(full(s), ph);
       ptx::tc_fence_after();
@@ -100,23 +116,29 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
         const uint64_t bhi = alo + (uint64_t)(TILE >> 4), blo = bhi + (uint64_t)(TILE >> 4);
 #pragma unroll
         for (int j = 0; j < BK / 16; ++j) {
-          ptx::mma_f16_ss(tmem_base, alo + 2 * j, bhi + 2 * j, IDESC, (k == 0 && j == 0) ? 0u : 1u);
-          ptx::mma_f16_ss(tmem_base, ahi + 2 * j, blo + 2 * j, IDESC, 1u);
-          ptx::mma_f16_ss(tmem_base, ahi + 2 * j, bhi + 2 * j, IDESC, 1u);
+          ptx::mma_f16_ss(acc, alo + 2 * j, bhi + 2 * j, IDESC, (k == 0 && j == 0) ? 0u : 1u);
+          ptx::mma_f16_ss(acc, ahi + 2 * j, blo + 2 * j, IDESC, 1u);
+          ptx::mma_f16_ss(acc, ahi + 2 * j, bhi + 2 * j, IDESC, 1u);
         }
         ptx::mma_commit(empty(s));
       }
       __syncwarp();
       if (++s == ST) { s = 0; ph ^= 1; }
     }
-    if (ptx::elect_one()) ptx::mma_commit(dfull);
+    if (ptx::elect_one()) ptx::mma_commit(dfull(buf));
     __syncwarp();
+    }
   } else {
     const int q = warp & 3;                                   // TMEM lane quarter this warp may read
-    // Each 32 x 32 block is transposed through shared memory (the operand stages are idle by then) so that a warp writes
+    // Each 32 x 32 block is transposed through shared memory (a buffer of its own: the operand stages already hold the next
+    // tile) so that a warp writes
     // 128 contiguous bytes of one output row per instruction.  Everything the epilogue reads from global memory (bias,
     // the added matrix) is requested BEFORE the accumulator is waited for / loaded: the loads of a block are independent.
-    float* tr = reinterpret_cast<float*>(smem) + q * (32 * 33);
+    float* tr = reinterpret_cast<float*>(smem + OFF_TR) + q * (32 * 33);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+    const int m0 = tile_m0(t), n0 = tile_n0(t);
+    const uint32_t buf = it & 1, acc = tmem_base + buf * BN;
     const int mrow0 = m0 + q * 32;
     const int rmax = min(32, p.M - mrow0);
     float bsum[BN / 32];
@@ -137,13 +159,18 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
     };
     float a[32];
     load_add(0, a);
-    ptx::mbar_wait(dfull, 0);
+    ptx::mbar_wait(dfull(buf), (it >> 1) & 1);
     ptx::tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+      ptx::tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + c * 32, v);
       ptx::tmem_ld_wait();
+      if (c == BN / 32 - 1) {                  // this warp's last read of the accumulator: hand it back to the issuer
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(dempty(buf));
+      }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = __uint_as_float(v[i]);
@@ -159,12 +186,13 @@ gemm_split_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
           if (r < rmax) p.C[(size_t)(mrow0 + r) * p.ldc + n] = o[r];
       }
     }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, BN);
+    ptx::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -229,7 +257,16 @@ int gemm_tc(const Op16& A, const Op16& B, int M, int N, int K, float* C, int64_t
   p.b_r0 = B.r0; p.b_k0 = B.k0; p.b_lo = B.lo;
   p.C = C; p.ldc = ldc; p.bias1 = bias1; p.bias2 = bias2; p.add = add; p.ldadd = ldadd;
   p.bias_rows = bias_rows;
-  dim3 grid((unsigned)mt, (unsigned)((N + bn - 1) / bn));
+  p.mt = mt;
+  p.n_tiles = mt * ((N + bn - 1) / bn);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  dim3 grid((unsigned)(p.n_tiles < sm_count ? p.n_tiles : sm_count));
   if (bn == 64)
     gtc::gemm_split_kernel<64><<<grid, gtc::NUM_THREADS, gtc::SMEM_BYTES, st>>>(p, ta, tb);
   else
