@@ -286,43 +286,68 @@ namespace lsb {
 // prologue and drain there (2.1 ms per 131 072 poses for three slabs per CTA).  One block per pose; the pose's cotangents
 // and blended vertices sit in shared memory; thread = one of the J x 12 outputs walks the joint's vertex list (CSR of the
 // sparse weights, ascending vertex order: deterministic).
+// The kernel is issue-bound (ncu: 7.7 k warp instructions per pose at 87 % issue utilisation), so the per-list-element
+// work is cut down: the outer products q_v = g_v (x) [x_v | 1] are formed once per vertex, a block serves PB poses with
+// one walk of the index / weight lists, and the walk is one shared-memory load and one FMA per pose.
+template <int PB>
 __global__ void __launch_bounds__(256) lbs_skin_bwd_small_kernel(
     const float* __restrict__ vposed, const float* __restrict__ g_verts, const int32_t* __restrict__ csr_ptr,
     const int32_t* __restrict__ csr_v, const float* __restrict__ csr_w, int V, int J, int S, float* __restrict__ gA,
     float* __restrict__ gbt, int64_t B) {
-  extern __shared__ float sm[];
-  float* g = sm;               // [V,3]
-  float* x = sm + (size_t)V * 3;
-  const int64_t b = blockIdx.x;
-  for (int i = threadIdx.x; i < V * 3; i += 256) {
-    g[i] = g_verts[(size_t)b * V * 3 + i];
-    x[i] = vposed[(size_t)b * V * 3 + i];
+  extern __shared__ float sm[];                     // q [PB][V,12]
+  const int64_t b0 = (int64_t)blockIdx.x * PB;
+  for (int i = threadIdx.x; i < PB * V; i += 256) {
+    const int pb = i / V, v = i - pb * V;
+    const int64_t b = b0 + pb;
+    float* q = sm + ((size_t)pb * V + v) * 12;
+    if (b < B) {
+      const float* gp = g_verts + ((size_t)b * V + v) * 3;
+      const float* xp = vposed + ((size_t)b * V + v) * 3;
+      const float g0 = gp[0], g1 = gp[1], g2 = gp[2], x0 = xp[0], x1 = xp[1], x2 = xp[2];
+      q[0] = g0 * x0; q[1] = g0 * x1; q[2] = g0 * x2;
+      q[3] = g1 * x0; q[4] = g1 * x1; q[5] = g1 * x2;
+      q[6] = g2 * x0; q[7] = g2 * x1; q[8] = g2 * x2;
+      q[9] = g0; q[10] = g1; q[11] = g2;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 12; ++e) q[e] = 0.f;
+    }
   }
   __syncthreads();
   for (int o = threadIdx.x; o < J * 12; o += 256) {
-    const int j = o / 12, e = o % 12;
-    const int a = e < 9 ? e / 3 : e - 9, c = e % 3;
-    float acc = 0.f;
-    for (int k = csr_ptr[j]; k < csr_ptr[j + 1]; ++k) {
-      const int v = csr_v[k];
-      const float t = csr_w[k] * g[v * 3 + a];
-      acc = fmaf(t, e < 9 ? x[v * 3 + c] : 1.0f, acc);
+    const int j = o / 12, e = o - j * 12;
+    float acc[PB];
+#pragma unroll
+    for (int pb = 0; pb < PB; ++pb) acc[pb] = 0.f;
+    const int k1 = csr_ptr[j + 1];
+    for (int k = csr_ptr[j]; k < k1; ++k) {          // ascending vertex order: deterministic
+      const float w = csr_w[k];
+      const float* q = sm + (size_t)csr_v[k] * 12 + e;
+#pragma unroll
+      for (int pb = 0; pb < PB; ++pb) acc[pb] = fmaf(w, q[(size_t)pb * V * 12], acc[pb]);
     }
-    gA[((size_t)b * J + j) * 12 + e] = acc;
+#pragma unroll
+    for (int pb = 0; pb < PB; ++pb)
+      if (b0 + pb < B) gA[((size_t)(b0 + pb) * J) * 12 + o] = acc[pb];
   }
-  if (threadIdx.x < 3) {       // translation cotangent = sum_v g (ascending vertex order)
-    float acc = 0.f;
-    for (int v = 0; v < V; ++v) acc += g[v * 3 + threadIdx.x];
-    gbt[(size_t)b * (S + 3) + S + threadIdx.x] += acc;
+  if (threadIdx.x < 3 * PB) {  // translation cotangent = sum_v g (ascending vertex order)
+    const int pb = threadIdx.x / 3, c = threadIdx.x - pb * 3;
+    if (b0 + pb < B) {
+      float acc = 0.f;
+      for (int v = 0; v < V; ++v) acc += sm[((size_t)pb * V + v) * 12 + 9 + c];
+      gbt[(size_t)(b0 + pb) * (S + 3) + S + c] += acc;
+    }
   }
 }
 }  // namespace lsb
 
 int lbs_skin_bwd_small(dpb_lbs* h, const float* vposed, const float* g_verts, float* gA, float* gbt, int64_t B,
                        cudaStream_t st) {
-  const size_t smem = (size_t)h->V * 6 * 4;
-  lsb::lbs_skin_bwd_small_kernel<<<(unsigned)B, 256, smem, st>>>(vposed, g_verts, h->csr_ptr, h->csr_v, h->csr_w, h->V,
-                                                               h->J, h->S, gA, gbt, B);
+  constexpr int PB = 2;                                       // poses per block: one walk of the joint lists serves both
+  const size_t smem = (size_t)PB * h->V * 12 * 4;             // V <= 1024 (prepare): at most 96 KB
+  DPB_CUDA_CHECK(cudaFuncSetAttribute(lsb::lbs_skin_bwd_small_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  lsb::lbs_skin_bwd_small_kernel<PB><<<(unsigned)((B + PB - 1) / PB), 256, smem, st>>>(vposed, g_verts, h->csr_ptr, h->csr_v,
+                                                                                   h->csr_w, h->V, h->J, h->S, gA, gbt, B);
   DPB_CUDA_CHECK(cudaGetLastError());
   return DPB_OK;
 }
