@@ -774,7 +774,7 @@ def run_gpu_arm(args):
         rf['lbs'] = roof_lbs
     line['roofline'] = rf
     cpu_per_row_step = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:        # the CPU arm is timed on rank 0 at N = 1 only
         line['cpu_baseline'] = cpu_reference(wl, budget_s=args.cpu_budget)
     if configs:
         if not args.no_cpu:

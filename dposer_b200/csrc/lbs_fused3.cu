@@ -56,7 +56,9 @@ struct Params {
   long long n_items;         // pose groups x tile pairs
   float* verts;              // [B,V,3]
   int debug;                 // timing experiments only (DPB_LBS_DEBUG; results are garbage): 1 = epilogue loads T / D but
-                             // skips math + stores, 2 = no blend MMAs, 4 = one skinning MMA per chunk, 8 = no TMEM loads
+                             // skips math + stores, 2 = no blend MMAs, 4 = one skinning MMA per chunk, 8 = no TMEM loads;
+                             // 16 / 32 keep the results: 16 = no L2::evict_last on basis / weight loads, 32 = plain
+                             // (not st.global.cs) vertex stores
 };
 
 template <int JSLABS, int ASTAGES, int SSTAGES>
@@ -127,6 +129,14 @@ lbs_fused3_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
   auto load = [&](uint32_t dst, const CUtensorMap* tm, uint32_t fullbar, int c0, int c1) {
     ptx::tma_load_2d_2sm(dst, tm, ptx::mapa(fullbar, 0), c0, c1);
   };
+  // operands every pose group re-reads (blend basis, skinning weights) load with L2::evict_last, the write-once vertices
+  // leave with st.global.cs: 3.14 -> 3.06 ms per 65 536 SMPL poses, bit-identical (p.debug & 16 / & 32 switch them off, A/B)
+  const bool keep_hint = (p.debug & 16) == 0;
+  const uint64_t keep_pol = ptx::l2_policy_evict_last();
+  auto load_keep = [&](uint32_t dst, const CUtensorMap* tm, uint32_t fullbar, int c0, int c1) {
+    if (keep_hint) ptx::tma_load_2d_2sm_hint(dst, tm, ptx::mapa(fullbar, 0), c0, c1, keep_pol);
+    else ptx::tma_load_2d_2sm(dst, tm, ptx::mapa(fullbar, 0), c0, c1);
+  };
   const long long i0 = p.n_items * worker / n_workers, i1 = p.n_items * (worker + 1) / n_workers;
   const int n_my = (int)(i1 - i0);                 // items of this pair
   const int grp0 = (int)(i0 / p.n_tp), tp0 = (int)(i0 % p.n_tp);
@@ -194,7 +204,7 @@ lbs_fused3_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
             ptx::mbar_wait(aempty(stage), phase ^ 1);
             if (ptx::elect_one()) {
               expect(afull(stage), A_SLAB);
-              load(a_base + stage * A_SLAB, &tm_dirs, afull(stage), i * BK, c * p.V_pad + tile * TILE_V);
+              load_keep(a_base + stage * A_SLAB, &tm_dirs, afull(stage), i * BK, c * p.V_pad + tile * TILE_V);
             }
             __syncwarp();
             if (++stage == ASTAGES) { stage = 0; phase ^= 1; }
@@ -214,7 +224,7 @@ lbs_fused3_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
           expect(wfull(wb), JSLABS * A_SLAB);
 #pragma unroll
           for (int i = 0; i < JSLABS; ++i)
-            load(w_base + (wb * JSLABS + i) * A_SLAB, &tm_w, wfull(wb), i * BK, tile * TILE_V);
+            load_keep(w_base + (wb * JSLABS + i) * A_SLAB, &tm_w, wfull(wb), i * BK, tile * TILE_V);
         }
         __syncwarp();
         const int row0 = grp * NP * 12 + (int)crank * (NS / 2);
@@ -350,9 +360,8 @@ lbs_fused3_kernel(const __grid_constant__ Params p, const __grid_constant__ CUte
             const float oz = fmaf(T[6], x, fmaf(T[7], y, fmaf(T[8], z, T[11])));
             if (i < n_ok) {
               float* w = dst + (size_t)i * pstride;
-              w[0] = ox;
-              w[1] = oy;
-              w[2] = oz;
+              if (!(p.debug & 32)) { __stcs(w, ox); __stcs(w + 1, oy); __stcs(w + 2, oz); }   // streaming stores
+              else { w[0] = ox; w[1] = oy; w[2] = oz; }
             }
           }
         }
