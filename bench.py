@@ -38,9 +38,10 @@ LBS_BYTES_PER_POSE = 83560            # verts 6890*12 + joints 45*1
 # DRAM traffic from the committed `ncu --set full` capture (profiles/r2_ncu_full_summary.md):
 #   fused sampler: 60.5 MB read + 255.7 MB written for 18 944 rows x 4 steps (write-back of the L2-resident activation
 #   scratch; 1.201 GB per 37 888 x 4 before the evict_last hints)
-#   LBS: lt3::lbs_fused3_kernel 326 MB read + 1.311 GB written for 16 384 poses (the output plus operand refills)
+#   LBS: lt3::lbs_fused3_kernel 547 MB read + 5.377 GB written for 65 536 poses (profiles/r2_ncu_fused3_l2_hints.md: the
+#   output plus operand refills; 1.474 GB read without the L2 hints; 326 MB + 1.311 GB per 16 384 poses before them)
 SAMPLER_DRAM_BYTES_PER_ROW_STEP = (60.514e6 + 255.652e6) / (18944 * 4)
-LBS_DRAM_BYTES_PER_POSE = (326.14e6 + 1310.56e6) / 16384
+LBS_DRAM_BYTES_PER_POSE = (546.978e6 + 5377.018e6) / 65536
 # tensor floor of the LBS forward at three fp16 products: (63 blend + 38.4 skinning) tensor-pipe cycles per (pose,
 # 128-vertex tile), 54 tiles, 148 SMs, 1.92 GHz (LBS design)
 LBS_TENSOR_FLOOR_MS = 65536 * 54 * 101.4 / 148 / 1.92e9 * 1e3
