@@ -355,3 +355,33 @@ def test_training_host_surface_without_a_gpu():
     assert np.allclose(seq, [1 - min(0.9999, (1 + n) / (10 + n)) for n in range(1, 6)])
     sd = e.state_dict()
     assert set(sd) == {'decay', 'num_updates', 'shadow_params'} and len(sd['shadow_params']) == len(list(model.parameters()))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's CPU arm): rank 0 prints ONE JSON line with the contract's keys, the
+    cpu_baseline that describes the run and a zero-copy e2e equal to the line's own value; other ranks print nothing and
+    exit 0.  On this container oracle/_ref is staged by build(), so the arm is the reference's own sampler."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
+                        '--warmup', '1'], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ''
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '1', '--steps', '1',
+                        '--warmup', '1'], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['unit'] == 'poses/s' and d['higher_is_better'] is True and d['vs_baseline'] is None
+    assert d['metric'].startswith('poses/sec') and 'workload' in d['config'] and 'model' not in d['config']
+    cb = d['cpu_baseline']
+    assert cb['value'] == d['value'] > 0 and cb['cores'] >= 1 and cb['kind'] in ('reference', 'port') and cb['sample']
+    if os.path.isdir(os.path.join(ROOT, 'oracle', '_ref', 'lib')):
+        assert cb['kind'] == 'reference'
+    assert d['e2e'] == {'value': d['value'], 'unit': 'poses/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
