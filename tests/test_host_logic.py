@@ -260,6 +260,18 @@ def test_rot6d_transforms_properties():
     assert float((back[small] - aa[small]).abs().max()) < 2e-5
 
 
+def test_rot6d_gram_schmidt_vs_reference_golden():
+    """lib/utils/transforms.py:225-234 (`rot6d_to_mat3x3`, pure torch in the reference): bit-exact against the fixture the
+    real reference wrote (tests/golden/make_rot6d_golden.py), including non-orthonormal, tiny and huge inputs."""
+    from dposer_b200 import transforms as T
+    gd = golden('rot6d_golden.npz')
+    R = T.rot6d_to_mat3x3(torch.from_numpy(gd['rot6d']))
+    assert torch.equal(R, torch.from_numpy(gd['mat']))
+    # the axis-angle leg (torchgeometry in the reference: unpinned) must at least describe the same rotation
+    aa = T.rot6d_to_axis_angle(torch.from_numpy(gd['rot6d']))
+    assert float((T.axis_angle_to_mat3x3(aa) - R).abs().max()) < 2e-5
+
+
 def test_rk45_controller_reproduces_scipy_solve_ivp():
     """dposer_b200.ode: the host-side step-size controller (scipy's RungeKutta._step_impl / select_initial_step restated)
     over a numpy stand-in for the native stage / error kernels lands on solve_ivp(method='RK45') itself: same number of
