@@ -272,6 +272,35 @@ def test_rot6d_gram_schmidt_vs_reference_golden():
     assert float((T.axis_angle_to_mat3x3(aa) - R).abs().max()) < 2e-5
 
 
+def test_rot6d_helpers_vs_torchgeometry_restatement():
+    """The legs of lib/utils/transforms.py:197-258 that call torchgeometry (absent; oracle/tgm_ref.py restates its published
+    0.1.2 algorithms, parity unpinned): the product helpers agree with them to fp32 rounding.  torchgeometry's axis is
+    `aa / (theta + 1e-6)` -- a relative 1e-6 / theta shortening the product does not reproduce: tolerance 4e-6 on matrix
+    entries.  Small components must survive the matrix -> axis-angle leg (a sqrt(1 +- Rii)-only extraction loses ~3e-4)."""
+    from dposer_b200 import transforms as T
+    from oracle import tgm_ref as G
+    g = torch.Generator().manual_seed(5)
+    aa = torch.randn(4000, 3, generator=g) * 1.2
+    aa[0] = 0.
+    aa[1] = torch.tensor([1e-8, 0., 0.])
+    aa[2] = torch.tensor([3.1, 0.1, -0.05])
+    aa[3] = torch.tensor([5e-4, 5e-4, 5e-4])                      # below torchgeometry's Taylor threshold (theta^2 <= 1e-6)
+    aa[4] = torch.tensor([1.0923, 1.3298, -2.98e-4])              # one tiny component
+    aa[5] = torch.tensor([0., -3.1415, 1e-3])                     # next to pi
+    assert float((T.axis_angle_to_mat3x3(aa) - G.axis_angle_to_mat3x3(aa)).abs().max()) < 4e-6
+    assert float((T.axis_angle_to_rot6d(aa) - G.axis_angle_to_rot6d(aa)).abs().max()) < 4e-6
+    r6 = T.axis_angle_to_rot6d(aa)
+    ours, ref = T.rot6d_to_axis_angle(r6.clone()), G.rot6d_to_axis_angle(r6.clone())
+    below_pi = aa.norm(dim=1) < 3.0                               # at pi the two sign conventions may differ
+    assert float((ours - ref)[below_pi].abs().max()) < 5e-6
+    assert float((ours - aa)[below_pi].abs().max()) < 5e-6        # incl. the -2.98e-4 component of row 4
+    R = T.axis_angle_to_mat3x3(aa)
+    assert float((T.axis_angle_to_mat3x3(ours) - R).abs().max()) < 5e-6
+    assert float((T.axis_angle_to_mat3x3(ref) - R).abs().max()) < 5e-6
+    deg = torch.zeros(2, 6)                                       # degenerate input: NaN -> 0 like the reference
+    assert torch.equal(T.rot6d_to_axis_angle(deg), torch.zeros(2, 3))
+
+
 def test_rk45_controller_reproduces_scipy_solve_ivp():
     """dposer_b200.ode: the host-side step-size controller (scipy's RungeKutta._step_impl / select_initial_step restated)
     over a numpy stand-in for the native stage / error kernels lands on solve_ivp(method='RK45') itself: same number of
