@@ -26,6 +26,10 @@ def _worker(rank, world, port, total, q):
     s, n = D.my_shard(total)
     gathered = D.all_gather_rows(full[s:s + n].clone(), total)
     ok = torch.equal(gathered, full)
+    # the preallocated-buffer form bench.py's e2e region uses: same result, and when the shards are equal the buffer IS the result
+    buf = torch.empty(world * ((total + world - 1) // world), 3)
+    g2 = D.all_gather_rows(full[s:s + n].clone(), total, out=buf)
+    ok = ok and torch.equal(g2, full) and (total % world != 0 or g2.data_ptr() == buf.data_ptr())
     # whole 60-frame sequences stay on one rank
     s2, n2 = D.my_shard(7 * 60, units=60)
     ok = ok and s2 % 60 == 0 and n2 % 60 == 0
